@@ -1,0 +1,27 @@
+"""argtypes / restype of the plain-argument entry points (include/countr_b200.h)."""
+from ctypes import c_double, c_float, c_int32, c_int64, c_void_p
+
+P, I, L, F = c_void_p, c_int32, c_int64, c_float
+
+SIGS = {
+    "countr_layernorm_fwd": [P, P, P, P, P, P, P, I, I, F, I, P],
+    "countr_layernorm_bwd": [P, P, P, P, P, P, P, P, I, I, I, P],
+    "countr_attention_fwd": [P, P, P, I, I, I, I, F, I, P],
+    "countr_cross_attn_core": [P, P, P, P, P, I, I, I, I, I, F, I, P],
+    "countr_cast_f32_to_16": [P, P, L, F, I, P],
+    "countr_cast_transpose_f32_to_16": [P, P, I, I, I, P],
+    "countr_patchify": [P, I, L, L, L, L, P, I, I, I, I, I, I, P],
+    "countr_conv_weight_pack": [P, P, I, I, I, I, P],
+    "countr_gn_relu_upsample2x": [P, P, P, P, P, I, I, I, I, I, F, I, P],
+    "countr_gn_relu_conv1x1": [P, P, P, P, P, P, P, I, I, I, I, F, I, P],
+    "countr_upsample2x_f32": [P, P, I, I, I, I, P],
+    "countr_exemplar_conv1": [P, I, L, L, L, L, L, P, P, P, I, I, I, I, I, P],
+    "countr_inorm_relu_pool": [P, P, P, P, P, I, I, I, I, F, I, I, P],
+}
+
+
+def declare(lib):
+    for name, args in SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = c_int32

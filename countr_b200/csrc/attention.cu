@@ -1,0 +1,315 @@
+// countr_b200 — fused multi-head self-attention forward (flash-style, tcgen05 + TMEM).
+//
+//   out[b, q, h*dh:(h+1)*dh] = softmax_k( scale * Q[b,h,q,:] . K[b,h,k,:] ) @ V[b,h,:,:]
+//
+// replaces: Attention.forward lines models_crossvit.py:87-91 (q@k^T * scale, softmax, attn@v,
+// transpose/reshape) for both the ViT encoder blocks (dh=64, H=12) and the FIM self-attention
+// (dh=32, H=16).  The [B,H,L,L] score tensor the reference materialises never leaves the SM.
+//
+// One CTA (4 warps) = one (batch, head, 128-query tile).  K/V are streamed in 128-key chunks by
+// TMA straight out of the packed qkv GEMM output [B][L][3][H][dh] (no permute / copy):
+//   S  = Q K_c^T        tcgen05.mma  (A,B K-major in smem)      -> TMEM columns [64,192)
+//   P  = exp2(S*c - m)  thread == row, online max/sum in fp32   -> smem (fp16, SWIZZLE_128B)
+//   O += P V_c          tcgen05.mma  (B = V chunk, MN-major)    -> TMEM columns [0,dh)
+// Two CTAs are co-resident per SM (80 KB smem, 256 TMEM columns each) so one CTA's softmax
+// (MUFU-bound: 128x576 exp2 per tile) overlaps the other's MMA/TMA.
+#include "../../include/countr_b200.h"
+#include "common.cuh"
+#include "tma.h"
+
+namespace countr {
+namespace {
+
+constexpr int BQ = 128;   // query rows per CTA
+constexpr int KC = 128;   // keys per chunk
+constexpr int kThreads = 128;
+constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kTmemS = 64;  // S starts at this column; O occupies [0, dh)
+
+template <int DH>
+struct AttnSmem {
+  static constexpr uint32_t kRowBytes = DH * 2;               // 128 (SW128) or 64 (SW64)
+  static constexpr uint32_t kQBytes = BQ * kRowBytes;
+  static constexpr uint32_t kKBytes = KC * kRowBytes;
+  static constexpr uint32_t kPBytes = BQ * KC * 2;            // 2 column blocks of [128 x 128 B]
+  static constexpr uint32_t kOffQ = 0;
+  static constexpr uint32_t kOffK = kQBytes;
+  static constexpr uint32_t kOffV = kOffK + kKBytes;
+  static constexpr uint32_t kOffP = kOffV + kKBytes;
+  static constexpr uint32_t kOffBar = kOffP + kPBytes;
+  static constexpr uint32_t kTotal = kOffBar + 64 + 1024;
+};
+
+// shared-memory matrix descriptor with explicit swizzle mode (2 = 128B, 4 = 64B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo & 0x3FFFFu) >> 4) << 16;
+  d |= static_cast<uint64_t>((sbo & 0x3FFFFu) >> 4) << 32;
+  d |= 1ull << 46;
+  d |= static_cast<uint64_t>(layout) << 61;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
+  uint32_t r;
+  if (bf16)
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
+struct AttnArgs {
+  uint16_t* out;   // [B][L][H*dh]
+  float* lse;      // [B][H][L] natural-log sum-exp of the scaled scores (optional)
+  int B, L, H;
+  float scale_log2;  // scale * log2(e)
+  int bf16;
+  int q_tiles;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(kThreads, 2)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
+                     const AttnArgs p) {
+  using SM = AttnSmem<DH>;
+  constexpr uint32_t kLayout = DH == 64 ? 2u : 4u;            // SWIZZLE_128B : SWIZZLE_64B
+  constexpr uint32_t kSboK = DH == 64 ? 1024u : 512u;         // 8 rows of the K-major tiles
+  constexpr uint32_t kVStep = 16 * SM::kRowBytes;             // 16 key rows per k-step of P.V
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + SM::kOffQ;
+  uint8_t* sK = smem + SM::kOffK;
+  uint8_t* sV = smem + SM::kOffV;
+  uint8_t* sP = smem + SM::kOffP;
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
+  uint64_t* bar_k = bar_q + 1;
+  uint64_t* bar_v = bar_q + 2;
+  uint64_t* bar_s = bar_q + 3;
+  uint64_t* bar_o = bar_q + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_q + 5);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int qt = blockIdx.x % p.q_tiles;
+  const int h = (blockIdx.x / p.q_tiles) % p.H;
+  const int b = blockIdx.x / (p.q_tiles * p.H);
+  const int q0 = qt * BQ;
+  const int nchunks = (p.L + KC - 1) / KC;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_kv);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, SM::kQBytes);
+    tma_load_4d(sQ, &tma_q, bar_q, 0, q0, h, b);
+    mbar_arrive_expect_tx(bar_k, SM::kKBytes);
+    tma_load_4d(sK, &tma_kv, bar_k, 0, 0, p.H + h, b);
+  }
+
+  const uint32_t idesc_s = make_idesc_f16(BQ, KC, false, false, p.bf16 != 0);
+  const uint32_t idesc_o = make_idesc_f16(BQ, DH, false, true, p.bf16 != 0);
+
+  float m_run = -INFINITY;  // running max (log2 domain, already scaled)
+  float l_run = 0.f;        // running sum
+  const int row = warp * 32 + (tid & 31);
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int valid = min(KC, p.L - c * KC);          // keys in this chunk
+    const int groups = (valid + 31) / 32;             // 32-column groups that hold any valid key
+    if (tid == 0) {
+      if (c == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, c & 1);
+      tc_fence_after();
+      const uint64_t a_desc = make_desc(smem_u32(sQ), 16, kSboK, kLayout);
+      const uint64_t b_desc = make_desc(smem_u32(sK), 16, kSboK, kLayout);
+#pragma unroll
+      for (int k = 0; k < DH / 16; ++k)
+        umma_f16_ss(tmem_base + kTmemS, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k),
+                    idesc_s, k != 0);
+      umma_commit(bar_s);
+    }
+    // S_c ready  (=> every earlier MMA, in particular P.V of chunk c-1, has completed:
+    // the K and V buffers and the P tile are free again)
+    mbar_wait(bar_s, c & 1);
+    tc_fence_after();
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar_v, SM::kKBytes);
+      tma_load_4d(sV, &tma_kv, bar_v, 0, c * KC, 2 * p.H + h, b);
+      if (c + 1 < nchunks) {
+        mbar_arrive_expect_tx(bar_k, SM::kKBytes);
+        tma_load_4d(sK, &tma_kv, bar_k, 0, (c + 1) * KC, p.H + h, b);
+      }
+    }
+
+    // ---- pass 1: row maximum of this chunk ----
+    float mx = -INFINITY;
+    for (int g = 0; g < groups; ++g) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_lane + kTmemS + g * 32, r);
+      tmem_ld_wait();
+      const int lim = valid - g * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < lim) mx = fmaxf(mx, __uint_as_float(r[j]));
+    }
+    const float m_new = fmaxf(m_run, mx * p.scale_log2);
+    const float corr = exp2f(m_run - m_new);  // 0 on the first chunk (m_run = -inf)
+    m_run = m_new;
+
+    // ---- pass 2: P = exp2(S*c - m), row sum, fp16 P tile into swizzled smem ----
+    float lsum = 0.f;
+    for (int g = 0; g < groups; ++g) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_lane + kTmemS + g * 32, r);
+      tmem_ld_wait();
+      const int lim = valid - g * 32;
+      float pv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float e = exp2f(fmaf(__uint_as_float(r[j]), p.scale_log2, -m_new));
+        pv[j] = (j < lim) ? e : 0.f;
+        lsum += pv[j];
+      }
+      // group g covers key columns [32g, 32g+32) = 16-byte chunks (g&1)*4 .. +3 of column block g>>1
+      uint8_t* prow = sP + (g >> 1) * (BQ * 128) + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = pack2(pv[8 * q + 0], pv[8 * q + 1], p.bf16);
+        o.y = pack2(pv[8 * q + 2], pv[8 * q + 3], p.bf16);
+        o.z = pack2(pv[8 * q + 4], pv[8 * q + 5], p.bf16);
+        o.w = pack2(pv[8 * q + 6], pv[8 * q + 7], p.bf16);
+        const int chunk16 = (g & 1) * 4 + q;
+        *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (row & 7)) << 4)) = o;
+      }
+    }
+    l_run = l_run * corr + lsum;
+
+    // ---- rescale the running output (TMEM) when the maximum moved ----
+    if (c > 0) {
+#pragma unroll
+      for (int d0 = 0; d0 < DH; d0 += 16) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_lane + d0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * corr);
+        tmem_st_32x32b_x16(t_lane + d0, r);
+      }
+      tmem_st_wait();
+    }
+
+    fence_proxy_async_smem();  // P tile (generic-proxy stores) -> visible to the tensor core
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(bar_v, c & 1);
+      tc_fence_after();
+      const int ksteps = groups * 2;
+      for (int k = 0; k < ksteps; ++k) {
+        const uint64_t a_desc = make_desc(smem_u32(sP) + (k >> 2) * (BQ * 128) + (k & 3) * 32, 16, 1024, 2u);
+        const uint64_t b_desc = make_desc(smem_u32(sV) + k * kVStep, 16, kSboK, kLayout);
+        umma_f16_ss(tmem_base, a_desc, b_desc, idesc_o, (c | k) != 0);
+      }
+      if (c == nchunks - 1) umma_commit(bar_o);
+    }
+  }
+
+  // ---- epilogue: O / l -> 16-bit, one contiguous dh-wide row segment per thread ----
+  mbar_wait(bar_o, 0);
+  tc_fence_after();
+  const float inv_l = 1.f / l_run;
+  const int q = q0 + row;
+  uint16_t* orow = p.out + (static_cast<long long>(b) * p.L + q) * (p.H * DH) + h * DH;
+#pragma unroll
+  for (int d0 = 0; d0 < DH; d0 += 16) {
+    uint32_t r[16];
+    tmem_ld_32x32b_x16(t_lane + d0, r);
+    tmem_ld_wait();
+    if (q < p.L) {
+      uint4 o0, o1;
+      o0.x = pack2(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l, p.bf16);
+      o0.y = pack2(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l, p.bf16);
+      o0.z = pack2(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l, p.bf16);
+      o0.w = pack2(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l, p.bf16);
+      o1.x = pack2(__uint_as_float(r[8]) * inv_l, __uint_as_float(r[9]) * inv_l, p.bf16);
+      o1.y = pack2(__uint_as_float(r[10]) * inv_l, __uint_as_float(r[11]) * inv_l, p.bf16);
+      o1.z = pack2(__uint_as_float(r[12]) * inv_l, __uint_as_float(r[13]) * inv_l, p.bf16);
+      o1.w = pack2(__uint_as_float(r[14]) * inv_l, __uint_as_float(r[15]) * inv_l, p.bf16);
+      *reinterpret_cast<uint4*>(orow + d0) = o0;
+      *reinterpret_cast<uint4*>(orow + d0 + 8) = o1;
+    }
+  }
+  if (p.lse != nullptr && q < p.L)
+    p.lse[(static_cast<long long>(b) * p.H + h) * p.L + q] = (m_run + log2f(l_run)) * 0.69314718055994531f;
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+template <int DH>
+int launch_attention(const void* qkv, void* out, float* lse, int B, int L, int H, float scale, int bf16,
+                     cudaStream_t stream) {
+  using SM = AttnSmem<DH>;
+  CUtensorMap tq, tkv;
+  const uint64_t dims[4] = {(uint64_t)DH, (uint64_t)L, (uint64_t)(3 * H), (uint64_t)B};
+  const uint64_t str[4] = {1, (uint64_t)(3 * H * DH), (uint64_t)DH, (uint64_t)L * 3 * H * DH};
+  const uint32_t boxq[4] = {DH, BQ, 1, 1}, boxk[4] = {DH, KC, 1, 1};
+  const TmapSwizzle sw = DH == 64 ? TMAP_SW_128 : TMAP_SW_64;
+  int rc = make_tmap_4d_16b(&tq, qkv, dims, str, boxq, sw);
+  if (rc) return rc;
+  rc = make_tmap_4d_16b(&tkv, qkv, dims, str, boxk, sw);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    COUNTR_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+    attr_set = true;
+  }
+  AttnArgs p;
+  p.out = reinterpret_cast<uint16_t*>(out);
+  p.lse = lse;
+  p.B = B; p.L = L; p.H = H;
+  p.scale_log2 = scale * 1.44269504088896340736f;
+  p.bf16 = bf16;
+  p.q_tiles = (L + BQ - 1) / BQ;
+  const int grid = B * H * p.q_tiles;
+  attention_fwd_kernel<DH><<<grid, kThreads, SM::kTotal, stream>>>(tq, tkv, p);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+}  // namespace
+}  // namespace countr
+
+extern "C" int countr_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int dh, float scale,
+                                    int bf16, countr_stream_t stream_) {
+  using namespace countr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(qkv && out, "null pointer");
+  COUNTR_REQUIRE(B > 0 && L > 0 && H > 0, "bad shape B=%d L=%d H=%d", B, L, H);
+  if (dh == 64) return launch_attention<64>(qkv, out, lse, B, L, H, scale, bf16, stream);
+  if (dh == 32) return launch_attention<32>(qkv, out, lse, B, L, H, scale, bf16, stream);
+  return set_error(COUNTR_ERR_UNSUPPORTED, "attention head_dim %d not supported (32 or 64)", dh);
+}

@@ -1,0 +1,586 @@
+// countr_b200 — HBM-bound layout / normalisation / resampling kernels around the tensor-core ops.
+//
+// None of these is GEMM shaped; they are coalesced, 16-byte-vectorised streaming kernels whose
+// job is to touch every activation exactly once between two tensor-core kernels.
+#include "../../include/countr_b200.h"
+#include "common.cuh"
+
+namespace countr {
+namespace {
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
+  uint32_t r;
+  if (bf16)
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(uint32_t v, int bf16) {
+  if (bf16) return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+  __half2 h = *reinterpret_cast<__half2*>(&v);
+  return __half22float2(h);
+}
+__device__ __forceinline__ float load_any(const void* p, long long i, int dtype) {
+  // dtype: 0 fp32, 1 fp16, 2 bf16
+  if (dtype == 0) return reinterpret_cast<const float*>(p)[i];
+  const uint16_t u = reinterpret_cast<const uint16_t*>(p)[i];
+  if (dtype == 1) return __half2float(__ushort_as_half(u));
+  return __uint_as_float(static_cast<uint32_t>(u) << 16);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8], int bf16) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack2(w[i], bf16);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], int bf16) {
+  uint4 o;
+  o.x = pack2(f[0], f[1], bf16);
+  o.y = pack2(f[2], f[3], bf16);
+  o.z = pack2(f[4], f[5], bf16);
+  o.w = pack2(f[6], f[7], bf16);
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 -> 16-bit casts (weights each step, gradients into GEMM operands)
+// ------------------------------------------------------------------------------------------
+__global__ void cast_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n, float scale,
+                            int bf16) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = *reinterpret_cast<const float4*>(src + i), b = *reinterpret_cast<const float4*>(src + i + 4);
+    uint4 o;
+    o.x = pack2(a.x * scale, a.y * scale, bf16);
+    o.y = pack2(a.z * scale, a.w * scale, bf16);
+    o.z = pack2(b.x * scale, b.y * scale, bf16);
+    o.w = pack2(b.z * scale, b.w * scale, bf16);
+    *reinterpret_cast<uint4*>(dst + i) = o;
+  } else {
+    for (long long j = i; j < n; ++j) dst[j] = static_cast<uint16_t>(pack2(src[j] * scale, 0.f, bf16) & 0xffffu);
+  }
+}
+
+// dst[c][r] = src[r][c]   (fp32 [R][C] -> 16-bit [C][R]); 32x32 tiles through padded smem
+__global__ void cast_transpose_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int R, int C,
+                                      int bf16) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? src[static_cast<size_t>(r) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) dst[static_cast<size_t>(c) * R + r] = static_cast<uint16_t>(pack2(tile[threadIdx.x][i], 0.f, bf16) & 0xffffu);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// PatchEmbed gather: NCHW image (any float dtype, any strides) -> A[B*gh*gw][C*P*P] 16-bit,
+// column order (c, ky, kx) == Conv2d weight.view(out, -1)   (models_mae_cross.py:27,138)
+// ------------------------------------------------------------------------------------------
+__global__ void patchify_kernel(const void* __restrict__ img, int dtype, long long sb, long long sc, long long sh,
+                                long long sw, uint16_t* __restrict__ out, int B, int C, int H, int W, int P, int bf16) {
+  // one thread = 8 consecutive kx of one (patch, c, ky)
+  const int gw = W / P, gh = H / P;
+  const int vec_per_row = P / 8;
+  const long long total = static_cast<long long>(B) * gh * gw * C * P * vec_per_row;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  long long t = idx;
+  const int kxv = t % vec_per_row; t /= vec_per_row;
+  const int ky = t % P; t /= P;
+  const int c = t % C; t /= C;
+  const int px = t % gw; t /= gw;
+  const int py = t % gh; t /= gh;
+  const int b = static_cast<int>(t);
+  const long long src = b * sb + c * sc + static_cast<long long>(py * P + ky) * sh + static_cast<long long>(px * P + kxv * 8) * sw;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = load_any(img, src + j * sw, dtype);
+  const long long row = (static_cast<long long>(b) * gh + py) * gw + px;
+  const long long col = (static_cast<long long>(c) * P + ky) * P + kxv * 8;
+  *reinterpret_cast<uint4*>(out + row * (static_cast<long long>(C) * P * P) + col) = pack8(f, bf16);
+}
+
+// ------------------------------------------------------------------------------------------
+// Conv2d 3x3 weight [Cout][Cin][3][3] fp32 -> GEMM B operand, 16-bit:
+//   mode 0 (forward):  out[co][(ky*3+kx)*Cin + ci] = w[co][ci][ky][kx]
+//   mode 1 (dX):       out[ci][((2-ky)*3+(2-kx))*Cout + co] = w[co][ci][ky][kx]
+//                      (correlation with the flipped, channel-transposed filter)
+// ------------------------------------------------------------------------------------------
+__global__ void conv_weight_pack_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cout, int Cin,
+                                        int mode, int bf16) {
+  const long long n = static_cast<long long>(Cout) * Cin * 9;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // iterate in OUTPUT order so the stores coalesce
+  long long t = i;
+  if (mode == 0) {
+    const int ci = t % Cin; t /= Cin;
+    const int tap = t % 9; t /= 9;
+    const int co = static_cast<int>(t);
+    out[i] = static_cast<uint16_t>(pack2(w[(static_cast<long long>(co) * Cin + ci) * 9 + tap], 0.f, bf16) & 0xffffu);
+  } else {
+    const int co = t % Cout; t /= Cout;
+    const int tap = t % 9; t /= 9;
+    const int ci = static_cast<int>(t);
+    out[i] = static_cast<uint16_t>(pack2(w[(static_cast<long long>(co) * Cin + ci) * 9 + (8 - tap)], 0.f, bf16) & 0xffffu);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm(apply) + ReLU + bilinear x2 (align_corners=False), NHWC 16-bit -> NHWC 16-bit.
+//   y = up2( relu( (x - mean_g) * rstd_g * gamma_c + beta_c ) )
+// replaces: nn.GroupNorm(8,256) + ReLU + F.interpolate(x2) (models_mae_cross.py:80-95,189-194)
+// stats: [B][G][2] double (sum, sumsq) accumulated by the conv epilogue.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_relu_up2_kernel(const uint16_t* __restrict__ x, const double* __restrict__ stats,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           uint16_t* __restrict__ y, int H, int W, int C, int G, float eps,
+                                                           int bf16) {
+  extern __shared__ float sm_ab[];  // [2][C]
+  float* sa = sm_ab;
+  float* sb = sm_ab + C;
+  const int b = blockIdx.y;
+  const int cpg = C / G;
+  const double cnt = static_cast<double>(H) * W * cpg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double s = stats[(static_cast<long long>(b) * G + g) * 2], ss = stats[(static_cast<long long>(b) * G + g) * 2 + 1];
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = rsqrtf(static_cast<float>(var) + eps);
+    const float a = rstd * gamma[c];
+    sa[c] = a;
+    sb[c] = beta[c] - static_cast<float>(mean) * a;
+  }
+  __syncthreads();
+  const int vecs = C / 8;
+  const int OW = 2 * W, OH = 2 * H;
+  const long long total = static_cast<long long>(OH) * OW * vecs;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = idx % vecs;
+    const long long pix = idx / vecs;
+    const int ox = pix % OW, oy = pix / OW;
+    // source taps: even o=2i -> (i-1: .25, i: .75); odd o=2i+1 -> (i: .75, i+1: .25); indices clamped
+    const int ix = ox >> 1, iy = oy >> 1;
+    const int x0 = (ox & 1) ? ix : max(ix - 1, 0), x1 = (ox & 1) ? min(ix + 1, W - 1) : ix;
+    const int y0 = (oy & 1) ? iy : max(iy - 1, 0), y1 = (oy & 1) ? min(iy + 1, H - 1) : iy;
+    const float wx1 = (ox & 1) ? 0.25f : 0.75f, wy1 = (oy & 1) ? 0.25f : 0.75f;
+    const float wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+    const uint16_t* xb = x + static_cast<long long>(b) * H * W * C + cv * 8;
+    float f00[8], f01[8], f10[8], f11[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(xb + (static_cast<long long>(y0) * W + x0) * C), f00, bf16);
+    unpack8(*reinterpret_cast<const uint4*>(xb + (static_cast<long long>(y0) * W + x1) * C), f01, bf16);
+    unpack8(*reinterpret_cast<const uint4*>(xb + (static_cast<long long>(y1) * W + x0) * C), f10, bf16);
+    unpack8(*reinterpret_cast<const uint4*>(xb + (static_cast<long long>(y1) * W + x1) * C), f11, bf16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = sa[cv * 8 + j], bb = sb[cv * 8 + j];
+      const float v00 = fmaxf(f00[j] * a + bb, 0.f), v01 = fmaxf(f01[j] * a + bb, 0.f);
+      const float v10 = fmaxf(f10[j] * a + bb, 0.f), v11 = fmaxf(f11[j] * a + bb, 0.f);
+      o[j] = wy0 * (wx0 * v00 + wx1 * v01) + wy1 * (wx0 * v10 + wx1 * v11);
+    }
+    *reinterpret_cast<uint4*>(y + ((static_cast<long long>(b) * OH + oy) * OW + ox) * C + cv * 8) = pack8(o, bf16);
+  }
+}
+
+// GroupNorm + ReLU + Conv2d 1x1 (C -> 1): one warp per pixel.   (models_mae_cross.py:96-100)
+__global__ void __launch_bounds__(256) gn_relu_dot_kernel(const uint16_t* __restrict__ x, const double* __restrict__ stats,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           float* __restrict__ out, int HW, int C, int G, float eps,
+                                                           int bf16) {
+  extern __shared__ float sm_abw[];  // [3][C]
+  float* sa = sm_abw;
+  float* sb = sm_abw + C;
+  float* sw = sm_abw + 2 * C;
+  const int b = blockIdx.y;
+  const int cpg = C / G;
+  const double cnt = static_cast<double>(HW) * cpg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double s = stats[(static_cast<long long>(b) * G + g) * 2], ss = stats[(static_cast<long long>(b) * G + g) * 2 + 1];
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = rsqrtf(static_cast<float>(var) + eps);
+    const float a = rstd * gamma[c];
+    sa[c] = a;
+    sb[c] = beta[c] - static_cast<float>(mean) * a;
+    sw[c] = w[c];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float b0 = bias[0];
+  for (int pix = blockIdx.x * 8 + warp; pix < HW; pix += gridDim.x * 8) {
+    const uint16_t* xp = x + (static_cast<long long>(b) * HW + pix) * C;
+    float acc = 0.f;
+    for (int c0 = lane * 8; c0 < C; c0 += 256) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(xp + c0), f, bf16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += fmaxf(f[j] * sa[c0 + j] + sb[c0 + j], 0.f) * sw[c0 + j];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[static_cast<long long>(b) * HW + pix] = acc + b0;
+  }
+}
+
+// bilinear x2 of a single-channel fp32 map [B][H][W] -> out (fp32 / fp16 / bf16) [B][2H][2W]
+__global__ void up2_f32_kernel(const float* __restrict__ x, void* __restrict__ y, int B, int H, int W, int out_dtype) {
+  const int OW = 2 * W, OH = 2 * H;
+  const long long total = static_cast<long long>(B) * OH * OW;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = idx % OW;
+  const int oy = (idx / OW) % OH;
+  const int b = idx / (static_cast<long long>(OW) * OH);
+  const int ix = ox >> 1, iy = oy >> 1;
+  const int x0 = (ox & 1) ? ix : max(ix - 1, 0), x1 = (ox & 1) ? min(ix + 1, W - 1) : ix;
+  const int y0 = (oy & 1) ? iy : max(iy - 1, 0), y1 = (oy & 1) ? min(iy + 1, H - 1) : iy;
+  const float wx1 = (ox & 1) ? 0.25f : 0.75f, wy1 = (oy & 1) ? 0.25f : 0.75f;
+  const float wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+  const float* xb = x + static_cast<long long>(b) * H * W;
+  const float v = wy0 * (wx0 * xb[y0 * W + x0] + wx1 * xb[y0 * W + x1]) + wy1 * (wx0 * xb[y1 * W + x0] + wx1 * xb[y1 * W + x1]);
+  if (out_dtype == 0)
+    reinterpret_cast<float*>(y)[idx] = v;
+  else
+    reinterpret_cast<uint16_t*>(y)[idx] = static_cast<uint16_t>(pack2(v, 0.f, out_dtype == 2) & 0xffffu);
+}
+
+// ------------------------------------------------------------------------------------------
+// Exemplar CNN stage 1: Conv2d(3,64,3,p=1) on [B][K][3][64][64] boxes (first S of K used),
+// direct fp32 FMA (27 MACs per output; not worth a tensor-core tile) -> NHWC 16-bit raw output.
+// replaces: decoder_proj1[0] (models_mae_cross.py:47-48,166); sample index n = b*S + s.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) exemplar_conv1_kernel(const void* __restrict__ boxes, int dtype, long long sB,
+                                                              long long sK, long long sC, long long sH, long long sW,
+                                                              const float* __restrict__ w, const float* __restrict__ bias,
+                                                              uint16_t* __restrict__ out, int S, int HW, int Cout, int bf16) {
+  __shared__ float sw[27 * 64];
+  __shared__ float sbias[64];
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
+    const int co = i % Cout, k = i / Cout;  // k = ci*9 + tap
+    sw[k * Cout + co] = w[co * 27 + k];
+  }
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sbias[i] = bias[i];
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int b = n / S, s = n % S;
+  const int pix = blockIdx.x * 32 + (threadIdx.x >> 3);
+  const int cg = threadIdx.x & 7;  // 8 output channels
+  const int H = HW, W = HW;
+  const int py = pix / W, px = pix % W;
+  float in[27];
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int yy = py + ky - 1, xx = px + kx - 1;
+        float v = 0.f;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = load_any(boxes, b * sB + s * sK + ci * sC + yy * sH + xx * sW, dtype);
+        in[ci * 9 + ky * 3 + kx] = v;
+      }
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = sbias[cg * 8 + j];
+#pragma unroll
+  for (int k = 0; k < 27; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += in[k] * sw[k * Cout + cg * 8 + j];
+  *reinterpret_cast<uint4*>(out + (static_cast<long long>(n) * H * W + pix) * Cout + cg * 8) = pack8(acc, bf16);
+}
+
+// ------------------------------------------------------------------------------------------
+// InstanceNorm2d (no affine, eps, biased var) + ReLU + {MaxPool2d(2) | global average pool},
+// NHWC 16-bit in.  One CTA per (sample, 64-channel block).
+// replaces: decoder_proj{1..4}[1:4] (models_mae_cross.py:49-51,55-57,61-63,67-69).
+// mode 0: y16 [N][H/2][W/2][C];  mode 1: y32 [N][C] (+ optional 16-bit copy y16 [N][C])
+// Also stores mean/rstd [N][C] for the backward pass when asked.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) inorm_relu_pool_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y16,
+                                                               float* __restrict__ y32, float* __restrict__ mean_out,
+                                                               float* __restrict__ rstd_out, int H, int W, int C,
+                                                               float eps, int mode, int bf16) {
+  __shared__ float red[2][8][64];
+  __shared__ float s_mean[64], s_rstd[64];
+  const int n = blockIdx.y, c0 = blockIdx.x * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int HW = H * W;
+  const uint16_t* xb = x + static_cast<long long>(n) * HW * C + c0 + lane * 2;
+  float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+  for (int p = warp; p < HW; p += 8) {
+    const float2 f = unpack2(*reinterpret_cast<const uint32_t*>(xb + static_cast<long long>(p) * C), bf16);
+    s1a += f.x; s1b += f.y; s2a += f.x * f.x; s2b += f.y * f.y;
+  }
+  red[0][warp][lane * 2] = s1a; red[0][warp][lane * 2 + 1] = s1b;
+  red[1][warp][lane * 2] = s2a; red[1][warp][lane * 2 + 1] = s2b;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float a = 0.f, q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a += red[0][k][threadIdx.x]; q += red[1][k][threadIdx.x]; }
+    const float mean = a / HW;
+    const float var = fmaxf(q / HW - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rstd;
+    if (mean_out) mean_out[static_cast<long long>(n) * C + c0 + threadIdx.x] = mean;
+    if (rstd_out) rstd_out[static_cast<long long>(n) * C + c0 + threadIdx.x] = rstd;
+  }
+  __syncthreads();
+  const float ma = s_mean[lane * 2], mb = s_mean[lane * 2 + 1], ra = s_rstd[lane * 2], rb = s_rstd[lane * 2 + 1];
+  if (mode == 0) {
+    const int OH = H / 2, OW = W / 2;
+    uint16_t* yb = y16 + static_cast<long long>(n) * OH * OW * C + c0 + lane * 2;
+    for (int p = warp; p < OH * OW; p += 8) {
+      const int oy = p / OW, ox = p % OW;
+      const uint16_t* q = xb + (static_cast<long long>(2 * oy) * W + 2 * ox) * C;
+      const float2 f0 = unpack2(*reinterpret_cast<const uint32_t*>(q), bf16);
+      const float2 f1 = unpack2(*reinterpret_cast<const uint32_t*>(q + C), bf16);
+      const float2 f2 = unpack2(*reinterpret_cast<const uint32_t*>(q + static_cast<long long>(W) * C), bf16);
+      const float2 f3 = unpack2(*reinterpret_cast<const uint32_t*>(q + static_cast<long long>(W) * C + C), bf16);
+      const float va = fmaxf(fmaxf(f0.x, f1.x), fmaxf(f2.x, f3.x)), vb = fmaxf(fmaxf(f0.y, f1.y), fmaxf(f2.y, f3.y));
+      *reinterpret_cast<uint32_t*>(yb + static_cast<long long>(p) * C) =
+          pack2(fmaxf((va - ma) * ra, 0.f), fmaxf((vb - mb) * rb, 0.f), bf16);
+    }
+  } else {
+    float aa = 0.f, ab = 0.f;
+    for (int p = warp; p < HW; p += 8) {
+      const float2 f = unpack2(*reinterpret_cast<const uint32_t*>(xb + static_cast<long long>(p) * C), bf16);
+      aa += fmaxf((f.x - ma) * ra, 0.f);
+      ab += fmaxf((f.y - mb) * rb, 0.f);
+    }
+    __syncthreads();
+    red[0][warp][lane * 2] = aa; red[0][warp][lane * 2 + 1] = ab;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a += red[0][k][threadIdx.x];
+      a /= HW;
+      const long long o = static_cast<long long>(n) * C + c0 + threadIdx.x;
+      if (y32) y32[o] = a;
+      if (y16) y16[o] = static_cast<uint16_t>(pack2(a, 0.f, bf16) & 0xffffu);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Cross-attention core (tiny K/V): per token, per head: softmax_s(q.k_s * scale) . v_s
+// replaces: CrossAttention.forward lines models_crossvit.py:122-126 (attn, softmax, attn @ v).
+// q16 [M][D] 16-bit (wq output), k32/v32 [B][S][D] fp32 (wk/wv outputs), out16 [M][D] 16-bit,
+// probs [M][Hh][S] fp32 (optional, saved for backward).  dh == 32, D % 512 == 0, S <= 8.
+// One warp per token: lane l owns channels [16l,16l+16) of each 512-chunk (= half a head).
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxShots = 8;
+__global__ void __launch_bounds__(256) cross_attn_core_kernel(const uint16_t* __restrict__ q16, const float* __restrict__ k32,
+                                                               const float* __restrict__ v32, uint16_t* __restrict__ out16,
+                                                               float* __restrict__ probs, int L, int S, int D, float scale,
+                                                               int tokens_per_block, int bf16) {
+  extern __shared__ float skv[];  // [2][S][D]
+  const int tok0 = blockIdx.x * tokens_per_block;
+  const int b = tok0 / L;
+  float* sk = skv;
+  float* sv = skv + S * D;
+  for (int i = threadIdx.x; i < S * D; i += blockDim.x) {
+    sk[i] = k32[static_cast<long long>(b) * S * D + i];
+    sv[i] = v32[static_cast<long long>(b) * S * D + i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Hh = D / 32;
+  for (int t = warp; t < tokens_per_block; t += 8) {
+    const long long tok = tok0 + t;
+    for (int c0 = 0; c0 < D; c0 += 512) {
+      const int ch = c0 + lane * 16;
+      float q[16];
+      {
+        const uint4 u0 = *reinterpret_cast<const uint4*>(q16 + tok * D + ch);
+        const uint4 u1 = *reinterpret_cast<const uint4*>(q16 + tok * D + ch + 8);
+        float a[8], c[8];
+        unpack8(u0, a, bf16);
+        unpack8(u1, c, bf16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { q[j] = a[j]; q[8 + j] = c[j]; }
+      }
+      float sc[kMaxShots];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int s = 0; s < kMaxShots; ++s) {
+        if (s < S) {
+          float d = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) d += q[j] * sk[s * D + ch + j];
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          sc[s] = d * scale;
+          mx = fmaxf(mx, sc[s]);
+        }
+      }
+      float den = 0.f;
+#pragma unroll
+      for (int s = 0; s < kMaxShots; ++s)
+        if (s < S) { sc[s] = __expf(sc[s] - mx); den += sc[s]; }
+      const float inv = 1.f / den;
+      float o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = 0.f;
+#pragma unroll
+      for (int s = 0; s < kMaxShots; ++s) {
+        if (s < S) {
+          const float pr = sc[s] * inv;
+          if (probs && (lane & 1) == 0) probs[(tok * Hh + (ch >> 5)) * S + s] = pr;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] += pr * sv[s * D + ch + j];
+        }
+      }
+      float a[8], c[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] = o[j]; c[j] = o[8 + j]; }
+      *reinterpret_cast<uint4*>(out16 + tok * D + ch) = pack8(a, bf16);
+      *reinterpret_cast<uint4*>(out16 + tok * D + ch + 8) = pack8(c, bf16);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace countr
+
+using namespace countr;
+
+extern "C" int countr_cast_f32_to_16(const float* src, void* dst, int64_t n, float scale, int bf16, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(src && dst && n > 0, "bad arguments");
+  COUNTR_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0, "pointers must be 16-byte aligned");
+  const long long threads = (n + 7) / 8;
+  cast_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(src, reinterpret_cast<uint16_t*>(dst), n, scale, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_cast_transpose_f32_to_16(const float* src, void* dst, int R, int C, int bf16, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(src && dst && R > 0 && C > 0, "bad arguments");
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  cast_transpose_kernel<<<grid, block, 0, stream>>>(src, reinterpret_cast<uint16_t*>(dst), R, C, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_patchify(const void* img, int dtype, int64_t sb, int64_t sc, int64_t sh, int64_t sw, void* out,
+                               int B, int C, int H, int W, int P, int bf16, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(img && out, "null pointer");
+  COUNTR_REQUIRE(dtype >= 0 && dtype <= 2, "image dtype code %d", dtype);
+  COUNTR_REQUIRE(P % 8 == 0 && H % P == 0 && W % P == 0, "patch size %d must be a multiple of 8 dividing %dx%d", P, H, W);
+  const long long total = static_cast<long long>(B) * (H / P) * (W / P) * C * P * (P / 8);
+  patchify_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(img, dtype, sb, sc, sh, sw,
+                                                                                 reinterpret_cast<uint16_t*>(out), B, C, H, W, P, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_conv_weight_pack(const float* w, void* out, int Cout, int Cin, int mode, int bf16, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(w && out && Cout > 0 && Cin > 0 && (mode == 0 || mode == 1), "bad arguments");
+  const long long n = static_cast<long long>(Cout) * Cin * 9;
+  conv_weight_pack_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(w, reinterpret_cast<uint16_t*>(out), Cout, Cin, mode, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_gn_relu_upsample2x(const void* x, const double* stats, const float* gamma, const float* beta, void* y,
+                                         int B, int H, int W, int C, int G, float eps, int bf16, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(x && stats && gamma && beta && y, "null pointer");
+  COUNTR_REQUIRE(C % 8 == 0 && C % G == 0 && C <= 4096, "bad channel count %d / groups %d", C, G);
+  const long long total = 4ll * H * W * (C / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = 148ll * 8 * 4;
+  if (blocks * B > cap) blocks = (cap + B - 1) / B;
+  if (blocks < 1) blocks = 1;
+  dim3 grid(static_cast<unsigned>(blocks), B);
+  gn_relu_up2_kernel<<<grid, 256, 2 * C * sizeof(float), stream>>>(reinterpret_cast<const uint16_t*>(x), stats, gamma, beta,
+                                                                   reinterpret_cast<uint16_t*>(y), H, W, C, G, eps, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_gn_relu_conv1x1(const void* x, const double* stats, const float* gamma, const float* beta, const float* w,
+                                      const float* bias, float* out, int B, int HW, int C, int G, float eps, int bf16,
+                                      countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(x && stats && gamma && beta && w && bias && out, "null pointer");
+  COUNTR_REQUIRE(C % 8 == 0 && C % G == 0 && C <= 4096, "bad channel count %d / groups %d", C, G);
+  long long blocks = (HW + 7) / 8;
+  const long long cap = 148ll * 8 * 2;
+  if (blocks * B > cap) blocks = (cap + B - 1) / B;
+  if (blocks < 1) blocks = 1;
+  dim3 grid(static_cast<unsigned>(blocks), B);
+  gn_relu_dot_kernel<<<grid, 256, 3 * C * sizeof(float), stream>>>(reinterpret_cast<const uint16_t*>(x), stats, gamma, beta, w, bias,
+                                                                   out, HW, C, G, eps, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_upsample2x_f32(const float* x, void* y, int B, int H, int W, int out_dtype, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(x && y && out_dtype >= 0 && out_dtype <= 2, "bad arguments");
+  const long long total = 4ll * B * H * W;
+  up2_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x, y, B, H, W, out_dtype);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_exemplar_conv1(const void* boxes, int dtype, int64_t sB, int64_t sK, int64_t sC, int64_t sH, int64_t sW,
+                                     const float* w, const float* bias, void* out, int B, int S, int HW, int Cout, int bf16,
+                                     countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(boxes && w && bias && out, "null pointer");
+  COUNTR_REQUIRE(Cout == 64 && HW % 32 == 0 && B > 0 && S > 0, "exemplar conv1 expects Cout=64 (got %d), side %% 32 == 0", Cout);
+  dim3 grid(HW * HW / 32, B * S);
+  exemplar_conv1_kernel<<<grid, 256, 0, stream>>>(boxes, dtype, sB, sK, sC, sH, sW, w, bias, reinterpret_cast<uint16_t*>(out), S, HW,
+                                                  Cout, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_inorm_relu_pool(const void* x, void* y16, float* y32, float* mean, float* rstd, int N, int H, int W, int C,
+                                      float eps, int mode, int bf16, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(x && (y16 || y32), "null pointer");
+  COUNTR_REQUIRE(C % 64 == 0 && (mode == 1 || (H % 2 == 0 && W % 2 == 0 && y16)), "bad shape C=%d H=%d W=%d mode=%d", C, H, W, mode);
+  dim3 grid(C / 64, N);
+  inorm_relu_pool_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(x), reinterpret_cast<uint16_t*>(y16), y32, mean,
+                                                   rstd, H, W, C, eps, mode, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_cross_attn_core(const void* q16, const float* k32, const float* v32, void* out16, float* probs, int B, int L,
+                                      int S, int D, int dh, float scale, int bf16, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(q16 && k32 && v32 && out16, "null pointer");
+  COUNTR_REQUIRE(dh == 32 && D % 512 == 0, "cross-attention core supports head_dim 32 and D %% 512 == 0 (got dh=%d D=%d)", dh, D);
+  COUNTR_REQUIRE(S >= 1 && S <= kMaxShots, "exemplar count %d outside [1,%d]", S, kMaxShots);
+  int tpb = 32;
+  while (L % tpb) tpb >>= 1;
+  const int blocks = B * L / tpb;
+  const size_t smem = 2ull * S * D * sizeof(float);
+  cross_attn_core_kernel<<<blocks, 256, smem, stream>>>(reinterpret_cast<const uint16_t*>(q16), k32, v32,
+                                                       reinterpret_cast<uint16_t*>(out16), probs, L, S, D, scale, tpb, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}

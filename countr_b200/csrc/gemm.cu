@@ -1,0 +1,526 @@
+// countr_b200 — persistent, warp-specialised tcgen05 GEMM / implicit-GEMM 3x3 convolution.
+//
+//   warp 0      : TMA producer (one elected lane) — fills a 4-deep ring of {A 128x64, B bn x64}
+//                 fp16 tiles in SWIZZLE_128B shared memory
+//   warp 1      : TMEM allocator + MMA issuer (one lane) — tcgen05.mma kind::f16, M=128, N=bn,
+//                 fp32 accumulators double-buffered in tensor memory (2 x 256 columns)
+//   warps 2..5  : epilogue — tcgen05.ld the accumulator (thread == row), apply
+//                 alpha/bias/GELU/GELU'/residual/GroupNorm statistics, store fp16 or fp32
+//
+// Conv mode re-uses the whole pipeline: the A tile of k-block (tap, cin-block) is the TMA box of
+// the NHWC activation shifted by the tap offset; the TMA unit zero-fills the halo, so there is no
+// im2col buffer and no padding copy.
+//
+// Reference arithmetic replaced: nn.Linear / Conv2d(3x3, s1, p1) call sites listed in
+// include/countr_b200.h (models_crossvit.py:55-92,104-127; models_mae_cross.py:39,53-100,152).
+#include "../../include/countr_b200.h"
+#include "common.cuh"
+#include "tma.h"
+
+namespace countr {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kStages = 4;
+constexpr int kMaxBN = 256;
+constexpr uint32_t kABytes = BM * BK * 2;       // 16 KB
+constexpr uint32_t kBBytes = kMaxBN * BK * 2;   // 32 KB
+constexpr uint32_t kStageBytes = kABytes + kBBytes;
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kThreads = 192;
+
+struct GemmArgs {
+  int M, N, K;
+  int nb2;            // inner batch count (batch = b1 * nb2 + b2)
+  int bn;             // N tile
+  int a_mn, b_mn;
+  int bf16;
+  int split_k, k_per_split;
+  int m_tiles, n_tiles, total_tiles;
+  // conv mode
+  int conv, H, W, cin_blocks, bx, by, tiles_x;
+  // epilogue
+  void* C;
+  long long ldc, sc1, sc2;
+  int out_f32, atomic;
+  float alpha;
+  const float* bias;
+  int act;
+  void* aux;
+  long long ldaux;
+  const float* residual;
+  long long ldr;
+  int res_mod;
+  double* gn_stats;
+};
+
+struct TileCoord {
+  int m, n, s, b1, b2;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int idx) {
+  TileCoord t;
+  t.m = idx % p.m_tiles;
+  idx /= p.m_tiles;
+  t.n = idx % p.n_tiles;
+  idx /= p.n_tiles;
+  t.s = idx % p.split_k;
+  idx /= p.split_k;
+  t.b2 = idx % p.nb2;
+  t.b1 = idx / p.nb2;
+  return t;
+}
+
+__device__ __forceinline__ uint32_t pack_16b(float a, float b, int bf16) {
+  uint32_t r;
+  if (bf16)
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_16b(uint32_t v, int bf16) {
+  if (bf16) return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+  __half2 h = *reinterpret_cast<__half2*>(&v);
+  return __half22float2(h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const GemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full = bars;                      // [kStages]
+  uint64_t* empty = bars + kStages;           // [kStages]
+  uint64_t* tmem_full = bars + 2 * kStages;   // [2]
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * BK * 2;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int k_begin = t.s * p.k_per_split;
+        const int k_end = min(p.K, k_begin + p.k_per_split);
+        const int nkb = (k_end - k_begin + BK - 1) / BK;
+        int x0 = 0, y0 = 0;
+        if (p.conv) {
+          x0 = (t.m % p.tiles_x) * p.bx;
+          y0 = (t.m / p.tiles_x) * p.by;
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_arrive_expect_tx(&full[stage], kABytes + b_bytes);
+          const int k = k_begin + kb * BK;
+          if (p.conv) {
+            const int tap = kb / p.cin_blocks;
+            const int cb = kb - tap * p.cin_blocks;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            tma_load_4d(sa, &tma_a, &full[stage], cb * BK, x0 + kx - 1, y0 + ky - 1, t.b1);
+          } else if (!p.a_mn) {
+            tma_load_4d(sa, &tma_a, &full[stage], k, t.m * BM, t.b2, t.b1);
+          } else {
+            tma_load_4d(sa, &tma_a, &full[stage], t.m * BM, k, t.b2, t.b1);
+            tma_load_4d(sa + 8192, &tma_a, &full[stage], t.m * BM + 64, k, t.b2, t.b1);
+          }
+          if (!p.b_mn) {
+            tma_load_4d(sb, &tma_b, &full[stage], k, t.n * p.bn, p.conv ? 0 : t.b2, p.conv ? 0 : t.b1);
+          } else {
+            for (int i = 0; i < p.bn / 64; ++i)
+              tma_load_4d(sb + i * 8192, &tma_b, &full[stage], t.n * p.bn + i * 64, k, t.b2, t.b1);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer -------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(BM, p.bn, p.a_mn != 0, p.b_mn != 0, p.bf16 != 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int k_begin = t.s * p.k_per_split;
+        const int k_end = min(p.K, k_begin + p.k_per_split);
+        const int nkb = (k_end - k_begin + BK - 1) / BK;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kMaxBN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+          // K-major : 8-row groups 1024 B apart; +32 B per 16-element k-step inside the swizzle atom
+          // MN-major: 64-wide MN blocks 8192 B apart (LBO), 8-row k groups 1024 B apart (SBO);
+          //           +2048 B per 16-row k-step
+          const uint64_t a_desc = p.a_mn ? make_smem_desc_sw128(sa, 8192, 1024) : make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t b_desc = p.b_mn ? make_smem_desc_sw128(sb, 8192, 1024) : make_smem_desc_sw128(sb, 16, 1024);
+          const uint32_t a_step = p.a_mn ? (2048u >> 4) : (32u >> 4);
+          const uint32_t b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_ss(d_tmem, a_desc + static_cast<uint64_t>(a_step * k), b_desc + static_cast<uint64_t>(b_step * k),
+                        idesc, (kb | k) != 0);
+          umma_commit(&empty[stage]);
+          if (kb == nkb - 1) umma_commit(&tmem_full[acc]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------- epilogue -------------------------------
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
+    const int r_in_tile = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      bool row_valid;
+      long long row;        // logical row (for residual / aux addressing)
+      long long c_off;      // element offset of (row, 0) inside C
+      if (p.conv) {
+        const int x = (t.m % p.tiles_x) * p.bx + r_in_tile % p.bx;
+        const int y = (t.m / p.tiles_x) * p.by + r_in_tile / p.bx;
+        row_valid = (x < p.W) && (y < p.H);
+        row = static_cast<long long>(y) * p.W + x;
+        c_off = t.b1 * p.sc1 + row * p.ldc;
+      } else {
+        row = static_cast<long long>(t.m) * BM + r_in_tile;
+        row_valid = row < p.M;
+        c_off = t.b1 * p.sc1 + t.b2 * p.sc2 + row * p.ldc;
+      }
+      const int n0 = t.n * p.bn;
+      const bool first_split = (t.s == 0);
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kMaxBN;
+
+      for (int c = 0; c < p.bn / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        const int ncols = min(32, p.N - col0);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+
+        const bool full32 = (ncols == 32);
+        if (p.bias != nullptr && first_split && ncols > 0) {
+          if (full32) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
+          }
+        }
+
+        if (p.gn_stats != nullptr) {
+          // GroupNorm statistics of this 32-channel group over the 32 pixels of this warp.
+          float s1 = 0.f, s2 = 0.f;
+          if (row_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              s1 += v[j];
+              s2 += v[j] * v[j];
+            }
+          }
+          s1 = warp_sum(s1);
+          s2 = warp_sum(s2);
+          if (lane == 0 && ncols > 0) {
+            double* st = p.gn_stats + (static_cast<long long>(t.b1) * (p.N / 32) + col0 / 32) * 2;
+            atomicAdd(st, static_cast<double>(s1));
+            atomicAdd(st + 1, static_cast<double>(s2));
+          }
+        }
+
+        if (row_valid && ncols > 0) {
+          if (p.act == 1) {
+            if (p.aux != nullptr) {
+              uint16_t* ap = reinterpret_cast<uint16_t*>(p.aux) + row * p.ldaux + col0;
+              if (full32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 o;
+                  o.x = pack_16b(v[j], v[j + 1], p.bf16);
+                  o.y = pack_16b(v[j + 2], v[j + 3], p.bf16);
+                  o.z = pack_16b(v[j + 4], v[j + 5], p.bf16);
+                  o.w = pack_16b(v[j + 6], v[j + 7], p.bf16);
+                  *reinterpret_cast<uint4*>(ap + j) = o;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) ap[j] = static_cast<uint16_t>(pack_16b(v[j], 0.f, p.bf16) & 0xffffu);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.act == 2) {
+            const uint16_t* ap = reinterpret_cast<const uint16_t*>(p.aux) + row * p.ldaux + col0;
+            if (full32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 a = *reinterpret_cast<const uint4*>(ap + j);
+                const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 f = unpack_16b(w[q], p.bf16);
+                  v[j + 2 * q] *= gelu_erf_grad(f.x);
+                  v[j + 2 * q + 1] *= gelu_erf_grad(f.y);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] *= gelu_erf_grad(unpack_16b(ap[j], p.bf16).x);
+            }
+          }
+
+          if (p.residual != nullptr && first_split) {
+            const long long rr = p.res_mod > 0 ? (row % p.res_mod) : row;
+            const float* rp = p.residual + rr * p.ldr + col0;
+            if (full32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 x = *reinterpret_cast<const float4*>(rp + j);
+                v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] += rp[j];
+            }
+          }
+
+          if (p.out_f32) {
+            float* cp = reinterpret_cast<float*>(p.C) + c_off + col0;
+            if (p.atomic) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) atomicAdd(cp + j, v[j]);
+            } else if (full32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) cp[j] = v[j];
+            }
+          } else {
+            uint16_t* cp = reinterpret_cast<uint16_t*>(p.C) + c_off + col0;
+            if (full32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 o;
+                o.x = pack_16b(v[j], v[j + 1], p.bf16);
+                o.y = pack_16b(v[j + 2], v[j + 3], p.bf16);
+                o.z = pack_16b(v[j + 4], v[j + 5], p.bf16);
+                o.w = pack_16b(v[j + 6], v[j + 7], p.bf16);
+                *reinterpret_cast<uint4*>(cp + j) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) cp[j] = static_cast<uint16_t>(pack_16b(v[j], 0.f, p.bf16) & 0xffffu);
+            }
+          }
+        }
+      }
+      // accumulator drained: hand the TMEM stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+int pick_bn(int m_tiles, int N, int other, int b_mn, int sms) {
+  // Choose the N tile that minimises (waves * tile cost); larger tiles win ties (more operand reuse).
+  int best = 0;
+  double best_cost = 1e30;
+  const int cands[4] = {256, 192, 128, 64};
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    if (b_mn && (bn % 64)) continue;
+    if (bn > 64 && bn >= 2 * N && N > 0) continue;  // grossly oversized
+    const long long n_tiles = (N + bn - 1) / bn;
+    const long long tiles = n_tiles * m_tiles * other;
+    const long long waves = (tiles + sms - 1) / sms;
+    // per-tile cost ~ MMA time (bn) plus a fixed per-tile overhead
+    const double cost = static_cast<double>(waves) * (bn + 24);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+}  // namespace
+
+}  // namespace countr
+
+extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
+  using namespace countr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(d != nullptr, "null descriptor");
+  COUNTR_REQUIRE(d->a && d->b && d->c, "null operand pointer");
+  COUNTR_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "bad GEMM shape M=%d N=%d K=%d", d->M, d->N, d->K);
+  const int nb1 = d->nb1 > 0 ? d->nb1 : 1, nb2 = d->nb2 > 0 ? d->nb2 : 1;
+  const bool conv = d->conv_h > 0;
+  const int sms = num_sms();
+  COUNTR_REQUIRE(sms > 0, "no CUDA device");
+
+  GemmArgs p{};
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.nb2 = nb2;
+  p.a_mn = d->a_mn; p.b_mn = d->b_mn; p.bf16 = d->bf16;
+  p.conv = conv ? 1 : 0;
+  if (conv) {
+    COUNTR_REQUIRE(!d->a_mn && !d->b_mn, "conv mode needs K-major operands");
+    COUNTR_REQUIRE(d->conv_cin % BK == 0, "conv Cin=%d must be a multiple of %d", d->conv_cin, BK);
+    COUNTR_REQUIRE(d->conv_bx * d->conv_by == BM, "conv tile %dx%d must cover %d pixels", d->conv_bx, d->conv_by, BM);
+    COUNTR_REQUIRE(d->K == 9 * d->conv_cin, "conv K=%d must equal 9*Cin", d->K);
+    p.H = d->conv_h; p.W = d->conv_w; p.bx = d->conv_bx; p.by = d->conv_by;
+    p.cin_blocks = d->conv_cin / BK;
+    p.tiles_x = (p.W + p.bx - 1) / p.bx;
+    p.m_tiles = p.tiles_x * ((p.H + p.by - 1) / p.by);
+  } else {
+    p.m_tiles = (d->M + BM - 1) / BM;
+  }
+  const int split_k = d->split_k > 1 ? d->split_k : 1;
+  COUNTR_REQUIRE(split_k == 1 || (d->atomic && d->out_f32), "split_k > 1 needs atomic fp32 output");
+  COUNTR_REQUIRE(!d->atomic || (d->out_f32 && d->act == 0), "atomic output must be fp32 without activation");
+  int kps = ((d->K + split_k - 1) / split_k + BK - 1) / BK * BK;
+  p.k_per_split = kps;
+  p.split_k = (d->K + kps - 1) / kps;  // drop empty splits
+  int bn = d->bn;
+  if (bn <= 0) bn = pick_bn(p.m_tiles, d->N, p.split_k * nb1 * nb2, d->b_mn, sms);
+  COUNTR_REQUIRE(bn >= 32 && bn <= kMaxBN && bn % 32 == 0 && (!d->b_mn || bn % 64 == 0), "bad N tile %d", bn);
+  p.bn = bn;
+  p.n_tiles = (d->N + bn - 1) / bn;
+  p.total_tiles = p.m_tiles * p.n_tiles * p.split_k * nb1 * nb2;
+
+  p.C = d->c; p.ldc = d->ldc; p.sc1 = d->sc1; p.sc2 = d->sc2;
+  p.out_f32 = d->out_f32; p.atomic = d->atomic;
+  p.alpha = d->alpha;
+  p.bias = d->bias;
+  p.act = d->act; p.aux = d->aux; p.ldaux = d->ldaux;
+  p.residual = d->residual; p.ldr = d->ldr; p.res_mod = d->res_mod;
+  p.gn_stats = d->gn_stats;
+  COUNTR_REQUIRE(d->act != 2 || d->aux != nullptr, "act=2 needs aux");
+  COUNTR_REQUIRE(d->ldc > 0, "ldc must be positive");
+  COUNTR_REQUIRE(d->bias == nullptr || (reinterpret_cast<uintptr_t>(d->bias) & 15u) == 0, "bias must be 16-byte aligned");
+  const int c_align = d->out_f32 ? 4 : 8;
+  COUNTR_REQUIRE(d->ldc % c_align == 0 && (reinterpret_cast<uintptr_t>(d->c) & 15u) == 0,
+                 "C must be 16-byte aligned with ldc %% %d == 0", c_align);
+  COUNTR_REQUIRE(d->gn_stats == nullptr || (conv && d->N % 32 == 0), "gn_stats needs conv mode with N %% 32 == 0");
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (conv) {
+    const uint64_t dims[4] = {(uint64_t)d->conv_cin, (uint64_t)d->conv_w, (uint64_t)d->conv_h, (uint64_t)nb1};
+    const uint64_t str[4] = {1, (uint64_t)d->lda, (uint64_t)d->lda * d->conv_w, (uint64_t)d->sa1};
+    const uint32_t box[4] = {BK, (uint32_t)d->conv_bx, (uint32_t)d->conv_by, 1};
+    rc = make_tmap_4d_16b(&ta, d->a, dims, str, box, TMAP_SW_128);
+  } else if (!d->a_mn) {
+    const uint64_t dims[4] = {(uint64_t)d->K, (uint64_t)d->M, (uint64_t)nb2, (uint64_t)nb1};
+    const uint64_t str[4] = {1, (uint64_t)d->lda, (uint64_t)(nb2 > 1 ? d->sa2 : d->lda), (uint64_t)(nb1 > 1 ? d->sa1 : d->lda)};
+    const uint32_t box[4] = {BK, BM, 1, 1};
+    rc = make_tmap_4d_16b(&ta, d->a, dims, str, box, TMAP_SW_128);
+  } else {
+    const uint64_t dims[4] = {(uint64_t)d->M, (uint64_t)d->K, (uint64_t)nb2, (uint64_t)nb1};
+    const uint64_t str[4] = {1, (uint64_t)d->lda, (uint64_t)(nb2 > 1 ? d->sa2 : d->lda), (uint64_t)(nb1 > 1 ? d->sa1 : d->lda)};
+    const uint32_t box[4] = {64, BK, 1, 1};
+    rc = make_tmap_4d_16b(&ta, d->a, dims, str, box, TMAP_SW_128);
+  }
+  if (rc) return rc;
+  const int bnb1 = conv ? 1 : nb1, bnb2 = conv ? 1 : nb2;
+  if (!d->b_mn) {
+    const uint64_t dims[4] = {(uint64_t)d->K, (uint64_t)d->N, (uint64_t)bnb2, (uint64_t)bnb1};
+    const uint64_t str[4] = {1, (uint64_t)d->ldb, (uint64_t)(bnb2 > 1 ? d->sb2 : d->ldb), (uint64_t)(bnb1 > 1 ? d->sb1 : d->ldb)};
+    const uint32_t box[4] = {BK, (uint32_t)bn, 1, 1};
+    rc = make_tmap_4d_16b(&tb, d->b, dims, str, box, TMAP_SW_128);
+  } else {
+    const uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->K, (uint64_t)bnb2, (uint64_t)bnb1};
+    const uint64_t str[4] = {1, (uint64_t)d->ldb, (uint64_t)(bnb2 > 1 ? d->sb2 : d->ldb), (uint64_t)(bnb1 > 1 ? d->sb1 : d->ldb)};
+    const uint32_t box[4] = {64, BK, 1, 1};
+    rc = make_tmap_4d_16b(&tb, d->b, dims, str, box, TMAP_SW_128);
+  }
+  if (rc) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    COUNTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}

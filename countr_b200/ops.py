@@ -1,0 +1,173 @@
+"""Thin tensor-level wrappers over the C ABI (include/countr_b200.h).
+
+Every function enqueues hand-written sm_100a kernels on torch's current CUDA stream and
+returns immediately.  PyTorch is used for memory ownership only: no ATen math runs here.
+"""
+import ctypes
+
+import torch
+
+from ._lib import GemmDesc, check, lib
+
+F16 = torch.float16
+BF16 = torch.bfloat16
+_DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _is_bf16(t):
+    return 1 if t.dtype == BF16 else 0
+
+
+LAUNCHES = [0]  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n=1):
+    LAUNCHES[0] += n
+
+
+def gemm(a, b, c, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, nb1=1, nb2=1,
+         sa=(0, 0), sb=(0, 0), sc=(0, 0), bias=None, act=0, aux=None, ldaux=0, residual=None, ldr=0,
+         res_mod=0, alpha=1.0, atomic=False, split_k=1, bn=0, conv=None, gn_stats=None):
+    """C = epilogue(alpha * A @ B^T); see countr_gemm_desc for the layout rules."""
+    assert a.dtype in (F16, BF16) and b.dtype == a.dtype
+    d = GemmDesc()
+    d.a, d.b = a.data_ptr(), b.data_ptr()
+    d.lda, d.sa1, d.sa2 = lda, sa[0], sa[1]
+    d.ldb, d.sb1, d.sb2 = ldb, sb[0], sb[1]
+    d.a_mn, d.b_mn = int(a_mn), int(b_mn)
+    d.M, d.N, d.K = M, N, K
+    d.nb1, d.nb2 = nb1, nb2
+    d.bf16 = _is_bf16(a)
+    d.bn, d.split_k = bn, split_k
+    if conv is not None:
+        d.conv_h, d.conv_w, d.conv_cin, d.conv_bx, d.conv_by = conv
+    d.c = c.data_ptr()
+    d.ldc, d.sc1, d.sc2 = ldc, sc[0], sc[1]
+    d.out_f32 = 1 if c.dtype == torch.float32 else 0
+    d.atomic = int(atomic)
+    d.alpha = alpha
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.act = act
+    d.aux = aux.data_ptr() if aux is not None else None
+    d.ldaux = ldaux
+    d.residual = residual.data_ptr() if residual is not None else None
+    d.ldr = ldr
+    d.res_mod = res_mod
+    d.gn_stats = gn_stats.data_ptr() if gn_stats is not None else None
+    check(lib().countr_gemm(ctypes.byref(d), _stream()))
+    _count()
+    return c
+
+
+def linear(x16, w16, out, bias=None, act=0, aux=None, residual=None, res_mod=0, alpha=1.0):
+    """out[M,N] = epi(x16[M,K] @ w16[N,K]^T); residual is fp32 [M or res_mod, N] (may alias out)."""
+    M, K = x16.shape
+    N = w16.shape[0]
+    assert w16.shape[1] == K and out.shape == (M, N)
+    return gemm(x16, w16, out, M, N, K, lda=x16.stride(0), ldb=w16.stride(0), ldc=out.stride(0), bias=bias,
+                act=act, aux=aux, ldaux=aux.stride(0) if aux is not None else 0, residual=residual,
+                ldr=residual.stride(0) if residual is not None else 0, res_mod=res_mod, alpha=alpha)
+
+
+def conv3x3(x16, w16, out, bias=None, gn_stats=None):
+    """NHWC implicit-GEMM conv: x16 [B,H,W,Cin], w16 [Cout, 9*Cin] (ky,kx,ci), out [B,H,W,Cout]."""
+    B, H, W, Cin = x16.shape
+    Cout = w16.shape[0]
+    bx = next((t for t in (128, 64, 32, 16, 8) if W % t == 0), 8)
+    by = 128 // bx
+    return gemm(x16, w16, out, B * H * W, Cout, 9 * Cin, lda=Cin, ldb=w16.stride(0), ldc=Cout, nb1=B,
+                sa=(H * W * Cin, 0), sc=(H * W * Cout, 0), bias=bias, conv=(H, W, Cin, bx, by), gn_stats=gn_stats)
+
+
+def layernorm_fwd(x, gamma, beta, eps, y16=None, y32=None, mean=None, rstd=None):
+    rows, D = x.shape
+    check(lib().countr_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y16), _ptr(y32), _ptr(mean), _ptr(rstd),
+                                     rows, D, eps, _is_bf16(y16) if y16 is not None else 0, _stream()))
+    _count()
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma=None, dbeta=None, accumulate=False):
+    rows, D = x.shape
+    check(lib().countr_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dgamma),
+                                     _ptr(dbeta), rows, D, int(accumulate), _stream()))
+    _count()
+
+
+def attention_fwd(qkv16, out16, B, L, H, dh, scale, lse=None):
+    check(lib().countr_attention_fwd(_ptr(qkv16), _ptr(out16), _ptr(lse), B, L, H, dh, scale, _is_bf16(qkv16), _stream()))
+    _count()
+
+
+def cross_attn_core(q16, k32, v32, out16, B, L, S, D, dh, scale, probs=None):
+    check(lib().countr_cross_attn_core(_ptr(q16), _ptr(k32), _ptr(v32), _ptr(out16), _ptr(probs), B, L, S, D, dh, scale,
+                                       _is_bf16(q16), _stream()))
+    _count()
+
+
+def cast16(src32, dst16, scale=1.0):
+    check(lib().countr_cast_f32_to_16(_ptr(src32), _ptr(dst16), src32.numel(), scale, _is_bf16(dst16), _stream()))
+    _count()
+
+
+def cast16_transpose(src32, dst16):
+    R, C = src32.shape
+    check(lib().countr_cast_transpose_f32_to_16(_ptr(src32), _ptr(dst16), R, C, _is_bf16(dst16), _stream()))
+    _count()
+
+
+def patchify(img, out16, P):
+    B, C, H, W = img.shape
+    sb, sc, sh, sw = img.stride()
+    check(lib().countr_patchify(_ptr(img), _DTYPE_CODE[img.dtype], sb, sc, sh, sw, _ptr(out16), B, C, H, W, P,
+                                _is_bf16(out16), _stream()))
+    _count()
+
+
+def conv_weight_pack(w32, out16, mode=0):
+    Cout, Cin = w32.shape[0], w32.shape[1]
+    check(lib().countr_conv_weight_pack(_ptr(w32), _ptr(out16), Cout, Cin, mode, _is_bf16(out16), _stream()))
+    _count()
+
+
+def gn_relu_upsample2x(x16, stats, gamma, beta, y16, G, eps):
+    B, H, W, C = x16.shape
+    check(lib().countr_gn_relu_upsample2x(_ptr(x16), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(y16), B, H, W, C, G, eps,
+                                          _is_bf16(x16), _stream()))
+    _count()
+
+
+def gn_relu_conv1x1(x16, stats, gamma, beta, w, bias, out32, G, eps):
+    B, H, W, C = x16.shape
+    check(lib().countr_gn_relu_conv1x1(_ptr(x16), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(w), _ptr(bias), _ptr(out32), B,
+                                       H * W, C, G, eps, _is_bf16(x16), _stream()))
+    _count()
+
+
+def upsample2x_f32(x32, y):
+    B, H, W = x32.shape
+    check(lib().countr_upsample2x_f32(_ptr(x32), _ptr(y), B, H, W, _DTYPE_CODE[y.dtype], _stream()))
+    _count()
+
+
+def exemplar_conv1(boxes, S, w, bias, out16):
+    B, K, C, H, W = boxes.shape
+    assert C == 3 and H == W and S <= K
+    sB, sK, sC, sH, sW = boxes.stride()
+    check(lib().countr_exemplar_conv1(_ptr(boxes), _DTYPE_CODE[boxes.dtype], sB, sK, sC, sH, sW, _ptr(w), _ptr(bias),
+                                      _ptr(out16), B, S, H, w.shape[0], _is_bf16(out16), _stream()))
+    _count()
+
+
+def inorm_relu_pool(x16, mode, eps, y16=None, y32=None, mean=None, rstd=None):
+    N, H, W, C = x16.shape
+    check(lib().countr_inorm_relu_pool(_ptr(x16), _ptr(y16), _ptr(y32), _ptr(mean), _ptr(rstd), N, H, W, C, eps, mode,
+                                       _is_bf16(x16), _stream()))
+    _count()

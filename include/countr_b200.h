@@ -1,0 +1,170 @@
+/* countr_b200 — C ABI of the sm_100a kernel library (libcountr_sm100.so).
+ *
+ * The reference (Verg-Avesta/CounTR) is pure PyTorch and has no FFI of its own: every device
+ * operation on its hot path is an implicit ATen call made from models_mae_cross.py /
+ * models_crossvit.py.  Each entry point below replaces one family of those
+ * call sites; the citation after "replaces:" is the reference line whose arithmetic it performs.
+ * The Python modules in countr_b200/ (same class names and state_dict keys as the reference)
+ * are the only callers; INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes; no torch types; every pointer is DEVICE memory owned by the caller
+ *   - nothing here allocates, frees or synchronises; work is enqueued on `stream`
+ *   - return 0 on success, <0 on error (countr_last_error() gives the message, thread-local)
+ *   - 16-bit activations are IEEE fp16 unless the descriptor says bf16; accumulation is fp32
+ */
+#ifndef COUNTR_B200_H_
+#define COUNTR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* countr_stream_t; /* cudaStream_t */
+
+const char* countr_last_error(void);
+const char* countr_version(void);
+int countr_check_device(void);
+int countr_num_sms(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core GEMM / implicit-GEMM 3x3 convolution (tcgen05.mma, TMA-fed, TMEM accumulators)
+ *
+ *   C[b][m][n] = epilogue( alpha * sum_k A[b][m][k] * B[b][n][k] )
+ *
+ * replaces: every nn.Linear on the path — Attention.qkv/proj (models_crossvit.py:77,79,84,92),
+ *   Mlp.fc1/fc2 (:55,58,62,65), CrossAttention.wq/wk/wv/proj (:104-108,115-127),
+ *   decoder_embed (models_mae_cross.py:39,152), PatchEmbed.proj as a patch GEMM (:27,138);
+ *   the bmm's of the attention backward; and, in conv mode, the Conv2d 3x3 of decode_head0..3
+ *   (:80-100) and decoder_proj2..4 (:53-71) plus their dX.
+ *
+ * Operand layouts (16-bit):
+ *   a_mn == 0 : A[m][k] at a + m*lda + k      (K contiguous,  "K-major")
+ *   a_mn == 1 : A[m][k] at a + k*lda + m      (M contiguous, "MN-major"; used for dW = dY^T X)
+ *   b_mn likewise for B[n][k].   lda/ldb/batch strides must be multiples of 8 elements.
+ * Batch index = b1*nb2 + b2 with independent strides (so a [B,L,3,H,dh] qkv buffer can be
+ * addressed per (batch, head) without a copy).
+ *
+ * conv mode (conv_h > 0): A is an NHWC activation [nb1=B][H][W][Cin] read through shifted
+ * TMA boxes (zero-filled halo = padding 1); B is the weight as [N=Cout][9*Cin] with k ordered
+ * (ky, kx, cin); M tiles are conv_bx x conv_by pixel rectangles (bx*by == 128); C is NHWC
+ * [B][H][W][ldc].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct countr_gemm_desc {
+  const void* a;
+  const void* b;
+  int64_t lda, sa1, sa2; /* elements */
+  int64_t ldb, sb1, sb2;
+  int32_t a_mn, b_mn;
+  int32_t M, N, K;
+  int32_t nb1, nb2;
+  int32_t bf16; /* 0: fp16 operands/outputs, 1: bf16 */
+  /* tiling */
+  int32_t bn;      /* N tile: 0 = choose; else multiple of 32 (64 if b_mn), <= 256 */
+  int32_t split_k; /* >= 1; > 1 requires atomic == 1 */
+  /* conv mode */
+  int32_t conv_h, conv_w, conv_cin, conv_bx, conv_by;
+  /* epilogue */
+  void* c;
+  int64_t ldc, sc1, sc2;
+  int32_t out_f32;       /* 1: C is fp32, 0: C is 16-bit */
+  int32_t atomic;        /* 1: C (fp32, pre-zeroed by caller) += result via red.global.add */
+  float alpha;
+  const float* bias;     /* [N] fp32 or NULL */
+  int32_t act;           /* 0 none, 1 GELU(erf), 2 multiply by GELU'(aux) */
+  void* aux;             /* 16-bit [M][ldaux]: act==1 -> pre-activation is stored here (may be NULL);
+                            act==2 -> pre-activation is read from here */
+  int64_t ldaux;
+  const float* residual; /* fp32, added last; row index = m % res_mod when res_mod > 0 */
+  int64_t ldr;
+  int32_t res_mod;
+  double* gn_stats;      /* conv mode: [B][N/32][2] (sum, sum of squares) += over 32-channel groups */
+} countr_gemm_desc;
+
+int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm on the fp32 residual stream.  y16 (16-bit GEMM operand) and/or y32 are written;
+ * mean/rstd ([rows], optional) are saved for the backward pass.
+ * replaces: nn.LayerNorm call sites — timm Block.norm1/norm2, SupervisedMAE.norm / decoder_norm
+ *   (models_mae_cross.py:32-35,78,146,182; eps=1e-6 via :214), CrossAttentionBlock.norm0/1/2
+ *   (models_crossvit.py:137,142,147,153-155).  Backward: native_layer_norm_backward.
+ * ------------------------------------------------------------------------------------------ */
+int countr_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y16, float* y32,
+                         float* mean, float* rstd, int rows, int D, float eps, int bf16,
+                         countr_stream_t stream);
+/* dx (+)= LN'(dy); dgamma/dbeta (optional, pre-zeroed or carrying earlier contributions) += */
+int countr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
+                         const float* rstd, float* dx, float* dgamma, float* dbeta, int rows, int D,
+                         int accumulate, countr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused multi-head self-attention forward: softmax(scale * Q K^T) V, flash-style on tcgen05.
+ * qkv is the packed output of the qkv Linear, [B][L][3][H][dh] 16-bit; out is [B][L][H*dh].
+ * lse ([B][H][L] fp32, optional) receives log-sum-exp of the scaled scores.
+ * replaces: Attention.forward, models_crossvit.py:85-91 (reshape/permute, q@k^T*scale, softmax,
+ *   attn@v, transpose) — used by the 12 encoder blocks and the FIM self-attention.
+ * ------------------------------------------------------------------------------------------ */
+int countr_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int dh, float scale,
+                         int bf16, countr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Cross-attention core for a handful of exemplar tokens (S <= 8): per token and head
+ * softmax_s(scale * q . k_s) applied to v_s.   q16 [B*L][D] 16-bit, k32/v32 [B][S][D] fp32,
+ * out16 [B*L][D] 16-bit, probs [B*L][D/dh][S] fp32 (optional, kept for backward).
+ * replaces: CrossAttention.forward, models_crossvit.py:122-126.
+ * ------------------------------------------------------------------------------------------ */
+int countr_cross_attn_core(const void* q16, const float* k32, const float* v32, void* out16, float* probs,
+                           int B, int L, int S, int D, int dh, float scale, int bf16, countr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout / cast helpers (HBM-bound streaming kernels).
+ * ------------------------------------------------------------------------------------------ */
+/* dst16[i] = (16-bit) (src[i] * scale) : fp32 master weights / gradients -> GEMM operands */
+int countr_cast_f32_to_16(const float* src, void* dst, int64_t n, float scale, int bf16, countr_stream_t stream);
+/* dst16[c][r] = src[r][c] : W^T operand for dX = dY W */
+int countr_cast_transpose_f32_to_16(const float* src, void* dst, int R, int C, int bf16, countr_stream_t stream);
+/* PatchEmbed gather (timm PatchEmbed.proj as a GEMM; models_mae_cross.py:27,138): NCHW image of
+ * dtype code {0 fp32, 1 fp16, 2 bf16} with element strides (sb,sc,sh,sw) -> out16 [B*gh*gw][C*P*P],
+ * columns ordered (c, ky, kx) like Conv2d.weight.view(out, -1). */
+int countr_patchify(const void* img, int dtype, int64_t sb, int64_t sc, int64_t sh, int64_t sw, void* out,
+                    int B, int C, int H, int W, int P, int bf16, countr_stream_t stream);
+/* Conv2d 3x3 weight [Cout][Cin][3][3] fp32 -> B operand of the implicit GEMM:
+ * mode 0: [Cout][(ky,kx,ci)] (forward);  mode 1: [Cin][(2-ky,2-kx,co)] (dX = conv with flipped filter) */
+int countr_conv_weight_pack(const float* w, void* out, int Cout, int Cin, int mode, int bf16, countr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Density-head glue (models_mae_cross.py:80-100,189-197); activations NHWC 16-bit,
+ * stats = [B][G][2] doubles (sum, sum of squares) produced by the conv epilogue (gn_stats).
+ * ------------------------------------------------------------------------------------------ */
+/* y = bilinear_x2( relu( GroupNorm(x) ) ),  [B][H][W][C] -> [B][2H][2W][C]
+ * replaces: nn.GroupNorm(8,256)+ReLU (:82-83,87-88,92-93) + F.interpolate(x2, bilinear) (:189-194) */
+int countr_gn_relu_upsample2x(const void* x, const double* stats, const float* gamma, const float* beta, void* y,
+                              int B, int H, int W, int C, int G, float eps, int bf16, countr_stream_t stream);
+/* out[b][p] = bias + sum_c w[c] * relu(GroupNorm(x))[b][p][c]   (GN + ReLU + Conv2d 1x1 C->1, :97-99) */
+int countr_gn_relu_conv1x1(const void* x, const double* stats, const float* gamma, const float* beta, const float* w,
+                           const float* bias, float* out, int B, int HW, int C, int G, float eps, int bf16,
+                           countr_stream_t stream);
+/* single-channel bilinear x2 [B][H][W] fp32 -> [B][2H][2W] of dtype code {0 fp32,1 fp16,2 bf16}
+ * (last F.interpolate + squeeze, :195-197) */
+int countr_upsample2x_f32(const float* x, void* y, int B, int H, int W, int out_dtype, countr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Exemplar encoder glue (models_mae_cross.py:47-71,157-177); sample n = b*S + s.
+ * ------------------------------------------------------------------------------------------ */
+/* decoder_proj1[0]: Conv2d(3,64,3,p=1) on boxes [B][K][3][HW][HW] (first S of K) -> NHWC 16-bit raw */
+int countr_exemplar_conv1(const void* boxes, int dtype, int64_t sB, int64_t sK, int64_t sC, int64_t sH, int64_t sW,
+                          const float* w, const float* bias, void* out, int B, int S, int HW, int Cout, int bf16,
+                          countr_stream_t stream);
+/* InstanceNorm2d(eps, no affine) + ReLU + MaxPool2d(2) (mode 0 -> y16 [N][H/2][W/2][C]) or
+ * AdaptiveAvgPool2d(1) (mode 1 -> y32 [N][C] and/or y16 [N][C]); mean/rstd [N][C] optional */
+int countr_inorm_relu_pool(const void* x, void* y16, float* y32, float* mean, float* rstd, int N, int H, int W, int C,
+                           float eps, int mode, int bf16, countr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COUNTR_B200_H_ */
