@@ -1,0 +1,160 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Runs only in the build container (the GPU box has no /root/reference).  The reference needs
+timm==0.4.9, which is not installed and cannot be (no network): a minimal shim provides
+`timm.models.vision_transformer.{PatchEmbed,Block}` built from the reference's OWN
+models_crossvit.Attention / Mlp (verbatim copies of timm's, models_crossvit.py:46-94), and
+`np.float` is aliased for util/pos_embed.py:56 under numpy >= 1.24.  Nothing is copied from the
+reference; its files are imported by path.
+
+    python scripts/gen_golden.py
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+from oracle import synth  # noqa: E402
+from oracle import countr_oracle as O  # noqa: E402
+
+
+def import_reference():
+    if not hasattr(np, "float"):
+        np.float = float
+    sys.path.insert(0, REF)
+    import models_crossvit as ref_xvit  # the reference's own file
+
+    class PatchEmbed(nn.Module):  # timm 0.4.9 vision_transformer.PatchEmbed
+        def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=768):
+            super().__init__()
+            self.img_size = (img_size, img_size)
+            self.patch_size = (patch_size, patch_size)
+            self.num_patches = (img_size // patch_size) ** 2
+            self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+        def forward(self, x):
+            B, C, H, W = x.shape
+            assert H == self.img_size[0] and W == self.img_size[1]
+            return self.proj(x).flatten(2).transpose(1, 2)
+
+    class Block(nn.Module):  # timm 0.4.9 vision_transformer.Block (drop_path=0 -> identity)
+        def __init__(self, dim, num_heads, mlp_ratio=4., qkv_bias=False, qk_scale=None, drop=0., attn_drop=0.,
+                     drop_path=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+            super().__init__()
+            self.norm1 = norm_layer(dim)
+            self.attn = ref_xvit.Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, qk_scale=qk_scale,
+                                           attn_drop=attn_drop, proj_drop=drop)
+            self.drop_path = nn.Identity()
+            self.norm2 = norm_layer(dim)
+            self.mlp = ref_xvit.Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+
+        def forward(self, x):
+            x = x + self.drop_path(self.attn(self.norm1(x)))
+            x = x + self.drop_path(self.mlp(self.norm2(x)))
+            return x
+
+    timm = types.ModuleType("timm")
+    timm.__version__ = "0.4.9"
+    timm.models = types.ModuleType("timm.models")
+    vt = types.ModuleType("timm.models.vision_transformer")
+    vt.PatchEmbed, vt.Block = PatchEmbed, Block
+    timm.models.vision_transformer = vt
+    sys.modules.update({"timm": timm, "timm.models": timm.models, "timm.models.vision_transformer": vt})
+    if "torchvision" not in sys.modules:
+        try:
+            import torchvision  # noqa: F401
+        except Exception:
+            tv = types.ModuleType("torchvision")
+            tv.utils = types.ModuleType("torchvision.utils")
+            sys.modules.update({"torchvision": tv, "torchvision.utils": tv.utils})
+    spec = importlib.util.spec_from_file_location("ref_models_mae_cross", os.path.join(REF, "models_mae_cross.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def build_ref_model(ref, cfg, sd):
+    from functools import partial
+    m = ref.SupervisedMAE(img_size=cfg["img_size"], patch_size=cfg["patch_size"], embed_dim=cfg["embed_dim"],
+                          depth=cfg["depth"], num_heads=cfg["num_heads"], decoder_embed_dim=cfg["decoder_embed_dim"],
+                          decoder_depth=cfg["decoder_depth"], decoder_num_heads=cfg["decoder_num_heads"],
+                          mlp_ratio=cfg["mlp_ratio"], norm_layer=partial(nn.LayerNorm, eps=cfg["eps"]))
+    # the synthetic spec must reproduce the reference's key set, order and shapes exactly
+    ref_sd = m.state_dict()
+    assert list(ref_sd.keys()) == list(sd.keys()), "state_dict key order differs from the reference"
+    for k in ref_sd:
+        assert tuple(ref_sd[k].shape) == tuple(sd[k].shape), k
+    # the sin-cos tables of the oracle must equal the reference's bit for bit
+    assert torch.equal(ref_sd["pos_embed"], sd["pos_embed"]) and torch.equal(ref_sd["decoder_pos_embed"], sd["decoder_pos_embed"])
+    m.load_state_dict(sd, strict=True)
+    return m
+
+
+def pool8(x):
+    return torch.nn.functional.avg_pool2d(x[:, None], 8)[:, 0]
+
+
+def main():
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.manual_seed(0)
+    ref = import_reference()
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+
+    # ---- C1: base model, one image, 3 exemplars, eval, fp32 (demo.py path) ----
+    cfg = synth.CONFIGS["base"]
+    sd = synth.make_state_dict(cfg, seed=0)
+    m = build_ref_model(ref, cfg, sd).eval()
+    imgs, boxes = synth.make_inputs(1, seed=1234)
+    with torch.no_grad():
+        latent = m.forward_encoder(imgs)
+        out = m(imgs, boxes, 3)
+        out0 = m(imgs, torch.empty(1, 0), 0)
+    np.savez_compressed(os.path.join(out_dir, "base_c1.npz"), out=out.numpy(), out_zero_pool8=pool8(out0).numpy(),
+                        out_zero_sum=out0.sum().numpy(), latent_head=latent[0, :8, :32].numpy(),
+                        latent_mean=latent.mean().numpy(), latent_std=latent.std().numpy(),
+                        latent_rowsum=latent[0].sum(-1).numpy())
+    print("base_c1: count=%.4f zero-shot count=%.4f" % (out.sum().item() / 60, out0.sum().item() / 60))
+
+    # ---- small model: every shot count, B=2, plus decoder gradients of the fine-tune loss ----
+    cfg = synth.CONFIGS["small"]
+    sd = synth.make_state_dict(cfg, seed=1)
+    m = build_ref_model(ref, cfg, sd).train()   # train(): no dropout / BN in the model, same arithmetic as eval
+    imgs, boxes = synth.make_inputs(2, seed=77, shots=5)
+    gt, mask = synth.make_targets(2, seed=78)
+    fwd, grads = {}, {}
+    for shot in (0, 1, 2, 3, 5):
+        m.zero_grad(set_to_none=True)
+        bx = boxes if shot > 0 else torch.empty(2, 0)
+        out = m(imgs, bx, shot)
+        loss = O.finetune_loss(out, gt, mask)
+        loss.backward()
+        fwd[f"out_pool8_s{shot}"] = pool8(out.detach()).numpy()
+        fwd[f"out_rows_s{shot}"] = out.detach()[:, [0, 100, 383]].numpy()
+        fwd[f"sum_s{shot}"] = out.detach().sum((1, 2)).numpy()
+        fwd[f"loss_s{shot}"] = loss.detach().numpy()
+        if shot in (0, 3):
+            for name, p in m.named_parameters():
+                if p.grad is None:
+                    continue
+                gflat = p.grad.flatten()
+                grads[f"s{shot}/{name}/norm"] = gflat.norm().numpy()
+                grads[f"s{shot}/{name}/sum"] = gflat.sum().numpy()
+                grads[f"s{shot}/{name}/head"] = gflat[:16].numpy()
+        print(f"small shot={shot}: loss={loss.item():.6f} sums={out.detach().sum((1,2)).tolist()}")
+    np.savez_compressed(os.path.join(out_dir, "small_fwd.npz"), **fwd)
+    np.savez_compressed(os.path.join(out_dir, "small_grads.npz"), **grads)
+    for f in sorted(os.listdir(out_dir)):
+        print(f, os.path.getsize(os.path.join(out_dir, f)))
+
+
+if __name__ == "__main__":
+    main()

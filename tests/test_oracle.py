@@ -1,0 +1,77 @@
+"""CPU tests: the oracle restatement (oracle/countr_oracle.py) against golden vectors produced by
+the reference itself (scripts/gen_golden.py, run in the build container).  fp32 on CPU is
+reproducible to ~1e-6 relative across thread counts, so the tolerance is 2e-5 (matrix-level)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import countr_oracle as O
+from oracle import synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def test_state_dict_spec_counts():
+    """99,690,625 parameters in the reference base model."""
+    n = sum(int(np.prod(s)) for _, s, _ in synth.state_dict_spec(synth.CONFIGS["base"]))
+    assert n == 99_690_625
+
+
+def test_base_c1_forward_matches_reference():
+    g = np.load(os.path.join(GOLD, "base_c1.npz"))
+    cfg = synth.CONFIGS["base"]
+    sd = synth.make_state_dict(cfg, seed=0)
+    imgs, boxes = synth.make_inputs(1, seed=1234)
+    taps = {}
+    with torch.no_grad():
+        out = O.forward(sd, cfg, imgs, boxes, 3, taps)
+        out0 = O.forward(sd, cfg, imgs, torch.empty(1, 0), 0)
+    assert out.shape == (1, 384, 384)
+    assert rel(out, g["out"]) < 2e-5
+    assert rel(taps["latent"][0, :8, :32], g["latent_head"]) < 2e-5
+    assert rel(taps["latent"][0].sum(-1), g["latent_rowsum"]) < 2e-4
+    assert abs(out.sum().item() / 60 - g["out"].sum() / 60) < 1e-2          # the count
+    assert rel(torch.nn.functional.avg_pool2d(out0[:, None], 8)[:, 0], g["out_zero_pool8"]) < 2e-5
+
+
+@pytest.mark.parametrize("shot", [0, 1, 2, 3, 5])
+def test_small_forward_and_loss_match_reference(shot):
+    g = np.load(os.path.join(GOLD, "small_fwd.npz"))
+    cfg = synth.CONFIGS["small"]
+    sd = synth.make_state_dict(cfg, seed=1)
+    imgs, boxes = synth.make_inputs(2, seed=77, shots=5)
+    gt, mask = synth.make_targets(2, seed=78)
+    with torch.no_grad():
+        out = O.forward(sd, cfg, imgs, boxes if shot else torch.empty(2, 0), shot)
+    assert rel(torch.nn.functional.avg_pool2d(out[:, None], 8)[:, 0], g[f"out_pool8_s{shot}"]) < 2e-5
+    assert rel(out[:, [0, 100, 383]], g[f"out_rows_s{shot}"]) < 2e-5
+    assert rel(out.sum((1, 2)), g[f"sum_s{shot}"]) < 2e-5
+    assert rel(O.finetune_loss(out, gt, mask), g[f"loss_s{shot}"]) < 2e-5
+
+
+@pytest.mark.parametrize("shot", [0, 3])
+def test_small_decoder_grads_match_reference(shot):
+    g = np.load(os.path.join(GOLD, "small_grads.npz"))
+    cfg = synth.CONFIGS["small"]
+    sd = synth.make_state_dict(cfg, seed=1)
+    names = O.decoder_param_names(sd, shot)
+    for n in names:
+        sd[n] = sd[n].clone().requires_grad_(True)
+    imgs, boxes = synth.make_inputs(2, seed=77, shots=5)
+    gt, mask = synth.make_targets(2, seed=78)
+    out = O.forward(sd, cfg, imgs, boxes if shot else torch.empty(2, 0), shot)
+    O.finetune_loss(out, gt, mask).backward()
+    golden_names = sorted({k.split("/")[1] for k in g.files if k.startswith(f"s{shot}/")})
+    assert sorted(names) == golden_names          # exactly the parameters the reference gives a grad
+    for n in names:
+        gr = sd[n].grad.flatten()
+        ref_norm = float(g[f"s{shot}/{n}/norm"])
+        assert abs(gr.norm().item() - ref_norm) <= 5e-4 * ref_norm + 1e-12, n
+        assert rel(gr[:16], g[f"s{shot}/{n}/head"]) < 1e-3 or ref_norm < 1e-10, n
