@@ -4,10 +4,11 @@ from ctypes import c_double, c_float, c_int32, c_int64, c_void_p
 P, I, L, F = c_void_p, c_int32, c_int64, c_float
 
 SIGS = {
+    "countr_memset_zero": [P, c_int64, P],
     "countr_layernorm_fwd": [P, P, P, P, P, P, P, I, I, F, I, P],
     "countr_layernorm_bwd": [P, P, P, P, P, P, P, P, I, I, I, P],
     "countr_attention_fwd": [P, P, P, I, I, I, I, F, I, P],
-    "countr_cross_attn_core": [P, P, P, P, P, I, I, I, I, I, F, I, P],
+    "countr_cross_attn_core": [P, P, P, P, P, I, I, I, I, I, F, I, I, P],
     "countr_cast_f32_to_16": [P, P, L, F, I, P],
     "countr_cast_transpose_f32_to_16": [P, P, I, I, I, P],
     "countr_patchify": [P, I, L, L, L, L, P, I, I, I, I, I, I, P],

@@ -106,4 +106,10 @@ int countr_check_device(void) {
 
 int countr_num_sms(void) { return countr::num_sms(); }
 
+int countr_memset_zero(void* ptr, size_t bytes, countr_stream_t stream) {
+  if (cudaMemsetAsync(ptr, 0, bytes, reinterpret_cast<cudaStream_t>(stream)) != cudaSuccess)
+    return countr::set_error(countr::COUNTR_ERR_CUDA, "cudaMemsetAsync failed");
+  return 0;
+}
+
 }  // extern "C"

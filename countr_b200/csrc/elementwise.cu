@@ -389,15 +389,15 @@ constexpr int kMaxShots = 8;
 __global__ void __launch_bounds__(256) cross_attn_core_kernel(const uint16_t* __restrict__ q16, const float* __restrict__ k32,
                                                                const float* __restrict__ v32, uint16_t* __restrict__ out16,
                                                                float* __restrict__ probs, int L, int S, int D, float scale,
-                                                               int tokens_per_block, int bf16) {
+                                                               int tokens_per_block, int bf16, long long kv_bstride) {
   extern __shared__ float skv[];  // [2][S][D]
   const int tok0 = blockIdx.x * tokens_per_block;
   const int b = tok0 / L;
   float* sk = skv;
   float* sv = skv + S * D;
   for (int i = threadIdx.x; i < S * D; i += blockDim.x) {
-    sk[i] = k32[static_cast<long long>(b) * S * D + i];
-    sv[i] = v32[static_cast<long long>(b) * S * D + i];
+    sk[i] = k32[b * kv_bstride + i];
+    sv[i] = v32[b * kv_bstride + i];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -570,7 +570,7 @@ extern "C" int countr_inorm_relu_pool(const void* x, void* y16, float* y32, floa
 }
 
 extern "C" int countr_cross_attn_core(const void* q16, const float* k32, const float* v32, void* out16, float* probs, int B, int L,
-                                      int S, int D, int dh, float scale, int bf16, countr_stream_t stream_) {
+                                      int S, int D, int dh, float scale, int bf16, int kv_broadcast, countr_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(q16 && k32 && v32 && out16, "null pointer");
   COUNTR_REQUIRE(dh == 32 && D % 512 == 0, "cross-attention core supports head_dim 32 and D %% 512 == 0 (got dh=%d D=%d)", dh, D);
@@ -580,7 +580,8 @@ extern "C" int countr_cross_attn_core(const void* q16, const float* k32, const f
   const int blocks = B * L / tpb;
   const size_t smem = 2ull * S * D * sizeof(float);
   cross_attn_core_kernel<<<blocks, 256, smem, stream>>>(reinterpret_cast<const uint16_t*>(q16), k32, v32,
-                                                       reinterpret_cast<uint16_t*>(out16), probs, L, S, D, scale, tpb, bf16);
+                                                       reinterpret_cast<uint16_t*>(out16), probs, L, S, D, scale, tpb, bf16,
+                                                       kv_broadcast ? 0ll : static_cast<long long>(S) * D);
   COUNTR_CHECK_CUDA(cudaGetLastError());
   return COUNTR_OK;
 }

@@ -1,0 +1,294 @@
+"""Kernel schedules of the CounTR hot path (host side).
+
+`encoder_forward` / `decoder_forward` / `decoder_backward` enqueue the sm_100a kernels of
+libcountr_sm100.so in order on torch's current stream.  torch is used for buffer ownership only.
+
+Data layout in HBM (per step, B images, L = 576 tokens, M = B*L):
+  residual stream          fp32  [M, D]              (updated in place in eval; chained in training)
+  GEMM / conv operands     fp16  [M, K] row-major / NHWC (TMA SWIZZLE_128B tiles)
+  qkv                      fp16  [B, L, 3, H, dh]    (read in place by the attention kernel)
+  weights                  fp16 copies of the fp32 master parameters, refreshed when a parameter's
+                           version counter changes (every optimizer step for the decoder, never for
+                           the frozen encoder)
+
+Reference correspondence: encoder_forward = SupervisedMAE.forward_encoder (models_mae_cross.py:
+136-148); decoder_forward = forward_decoder (:150-199).
+"""
+import math
+
+import torch
+
+from . import ops
+
+F16 = torch.float16
+F32 = torch.float32
+
+
+class Workspace:
+    """Named device buffers reused across steps (no allocator traffic on the hot path)."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, name, shape, dtype, device):
+        key = (name, tuple(shape), dtype, str(device))
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=device)
+            self.bufs[key] = t
+        return t
+
+
+class WeightCache:
+    """16-bit GEMM-operand copies of fp32 master parameters."""
+
+    def __init__(self):
+        self.cache = {}
+
+    def _lookup(self, p, kind, shape, fill):
+        key = (id(p), kind)
+        ent = self.cache.get(key)
+        ver = (p.data_ptr(), p._version)
+        if ent is None or ent[0] != ver or ent[1].device != p.device:
+            buf = ent[1] if (ent is not None and ent[1].device == p.device and ent[1].shape == torch.Size(shape)) else \
+                torch.empty(shape, dtype=F16, device=p.device)
+            fill(p.detach(), buf)
+            ent = (ver, buf)
+            self.cache[key] = ent
+        return ent[1]
+
+    def w16(self, p):
+        """[N, K] row-major copy (B operand of y = x W^T)."""
+        shape = (p.shape[0], p.numel() // p.shape[0])
+        return self._lookup(p, "w", shape, lambda src, dst: ops.cast16(src, dst))
+
+    def w16_t(self, p):
+        """[K, N] transposed copy (B operand of dX = dY W)."""
+        n, k = p.shape[0], p.numel() // p.shape[0]
+        return self._lookup(p, "wt", (k, n), lambda src, dst: ops.cast16_transpose(src.reshape(n, k), dst))
+
+    def conv16(self, p, mode=0):
+        cout, cin = p.shape[0], p.shape[1]
+        shape = (cout, 9 * cin) if mode == 0 else (cin, 9 * cout)
+        return self._lookup(p, "c%d" % mode, shape, lambda src, dst: ops.conv_weight_pack(src, dst, mode))
+
+    def v16(self, p):
+        return self._lookup(p, "v", tuple(p.shape), lambda src, dst: ops.cast16(src, dst))
+
+
+def _contig32(p):
+    t = p.detach()
+    assert t.dtype == F32 and t.is_contiguous(), "countr_b200 expects contiguous fp32 parameters"
+    return t
+
+
+class Engine:
+    def __init__(self):
+        self.ws = Workspace()
+        self.wc = WeightCache()
+
+    # ------------------------------------------------------------------ encoder
+    def encoder_forward(self, m, imgs):
+        """m: SupervisedMAE-like module (patch_embed, pos_embed, blocks, norm).
+        Returns (latent fp32 [B, L, D], latent fp16 [B*L, D])."""
+        ops_ = ops
+        dev = imgs.device
+        B, C, Himg, Wimg = imgs.shape
+        P = m.patch_embed.patch_size[0]
+        assert Himg == m.patch_embed.img_size[0] and Wimg == m.patch_embed.img_size[1], \
+            f"Input image size ({Himg}*{Wimg}) doesn't match model ({m.patch_embed.img_size[0]}*{m.patch_embed.img_size[1]})."
+        L = (Himg // P) * (Wimg // P)
+        M = B * L
+        D = m.pos_embed.shape[-1]
+        ws, wc = self.ws, self.wc
+        patches = ws.get("patches", (M, C * P * P), F16, dev)
+        ops_.patchify(imgs, patches, P)
+        x = ws.get("enc_x", (M, D), F32, dev)
+        pe = m.patch_embed.proj
+        ops_.linear(patches, wc.w16(pe.weight), x, bias=_contig32(pe.bias), residual=_contig32(m.pos_embed).reshape(L, D),
+                    res_mod=L)
+        h = ws.get("enc_h", (M, D), F16, dev)
+        for blk in m.blocks:
+            H = blk.attn.num_heads
+            dh = D // H
+            hid = blk.mlp.fc1.weight.shape[0]
+            qkv = ws.get("enc_qkv", (M, 3 * D), F16, dev)
+            att = ws.get("enc_att", (M, D), F16, dev)
+            u = ws.get("enc_u", (M, hid), F16, dev)
+            ops_.layernorm_fwd(x, _contig32(blk.norm1.weight), _contig32(blk.norm1.bias), blk.norm1.eps, y16=h)
+            ops_.linear(h, wc.w16(blk.attn.qkv.weight), qkv, bias=_contig32(blk.attn.qkv.bias))
+            ops_.attention_fwd(qkv, att, B, L, H, dh, blk.attn.scale)
+            ops_.linear(att, wc.w16(blk.attn.proj.weight), x, bias=_contig32(blk.attn.proj.bias), residual=x)
+            ops_.layernorm_fwd(x, _contig32(blk.norm2.weight), _contig32(blk.norm2.bias), blk.norm2.eps, y16=h)
+            ops_.linear(h, wc.w16(blk.mlp.fc1.weight), u, bias=_contig32(blk.mlp.fc1.bias), act=1)
+            ops_.linear(u, wc.w16(blk.mlp.fc2.weight), x, bias=_contig32(blk.mlp.fc2.bias), residual=x)
+        lat32 = torch.empty(B, L, D, dtype=F32, device=dev)
+        lat16 = ws.get("lat16", (M, D), F16, dev)
+        ops_.layernorm_fwd(x, _contig32(m.norm.weight), _contig32(m.norm.bias), m.norm.eps, y16=lat16, y32=lat32.view(M, D))
+        return lat32, lat16
+
+    # ------------------------------------------------------------------ exemplar encoder
+    def exemplar_forward(self, m, boxes, S, save):
+        """decoder_proj1..4 on the first S boxes of every image -> y32 [B*S, C], y16 [B*S, C]."""
+        dev = boxes.device
+        B = boxes.shape[0]
+        N = B * S
+        ws, wc = self.ws, self.wc
+        get = (lambda name, shape, dt: torch.empty(shape, dtype=dt, device=dev)) if save is not None else \
+            (lambda name, shape, dt: ws.get(name, shape, dt, dev))
+        c1 = m.decoder_proj1[0]
+        side = boxes.shape[-1]
+        raw = get("ex_raw1", (N, side, side, c1.weight.shape[0]), F16)
+        ops.exemplar_conv1(boxes, S, _contig32(c1.weight), _contig32(c1.bias), raw)
+        stages = [m.decoder_proj2[0], m.decoder_proj3[0], m.decoder_proj4[0]]
+        saved = {"raw": [raw], "pooled": [], "mean": [], "rstd": []}
+        cur = raw
+        for i, conv in enumerate(stages):
+            n, hh, ww, cc = cur.shape
+            pooled = get(f"ex_pool{i}", (n, hh // 2, ww // 2, cc), F16)
+            mean = get(f"ex_mean{i}", (n, cc), F32) if save is not None else None
+            rstd = get(f"ex_rstd{i}", (n, cc), F32) if save is not None else None
+            ops.inorm_relu_pool(cur, 0, 1e-5, y16=pooled, mean=mean, rstd=rstd)
+            cout = conv.weight.shape[0]
+            nxt = get(f"ex_raw{i + 2}", (n, hh // 2, ww // 2, cout), F16)
+            ops.conv3x3(pooled, wc.conv16(conv.weight), nxt, bias=_contig32(conv.bias))
+            saved["pooled"].append(pooled); saved["mean"].append(mean); saved["rstd"].append(rstd); saved["raw"].append(nxt)
+            cur = nxt
+        n, hh, ww, cc = cur.shape
+        y32 = get("ex_y32", (N, cc), F32)
+        y16 = get("ex_y16", (N, cc), F16)
+        mean = get("ex_mean3", (n, cc), F32) if save is not None else None
+        rstd = get("ex_rstd3", (n, cc), F32) if save is not None else None
+        ops.inorm_relu_pool(cur, 1, 1e-5, y16=y16, y32=y32, mean=mean, rstd=rstd)
+        saved["mean"].append(mean); saved["rstd"].append(rstd)
+        if save is not None:
+            save["exemplar"] = saved
+        return y32, y16
+
+    # ------------------------------------------------------------------ decoder
+    def decoder_forward(self, m, lat16, boxes, shot_num, B, out_dtype, save=None):
+        """lat16: fp16 [B*L, D] encoder output.  Returns the density map [B, 2^4*h, 2^4*w]."""
+        dev = lat16.device
+        ws, wc = self.ws, self.wc
+        M, D = lat16.shape
+        L = M // B
+        Dd = m.decoder_embed.weight.shape[0]
+        train = save is not None
+        # in training every activation the backward needs gets its own buffer
+        get = (lambda name, shape, dt: torch.empty(shape, dtype=dt, device=dev)) if train else \
+            (lambda name, shape, dt: ws.get(name, shape, dt, dev))
+
+        x = get("dec_x", (M, Dd), F32)
+        ops.linear(lat16, wc.w16(m.decoder_embed.weight), x, bias=_contig32(m.decoder_embed.bias),
+                   residual=_contig32(m.decoder_pos_embed).reshape(L, Dd), res_mod=L)
+
+        if shot_num > 0:
+            assert boxes.dim() == 5 and boxes.shape[1] >= shot_num, "boxes must be [N, K>=shot_num, 3, 64, 64]"
+            S = shot_num
+            y32, y16 = self.exemplar_forward(m, boxes, S, save)
+            kv_broadcast = False
+        else:
+            S = 1
+            y16 = wc.v16(m.shot_token).reshape(1, Dd)     # same token for every image (models_mae_cross.py:176)
+            kv_broadcast = True
+        ny = y16.shape[0]
+
+        blocks_saved = []
+        for blk in m.decoder_blocks:
+            H = blk.selfattn.num_heads
+            dh = Dd // H
+            hid = blk.mlp.fc1.weight.shape[0]
+            sv = {}
+            # --- self attention
+            h0 = get("dec_h0", (M, Dd), F16)
+            mean0 = get("m0", (M,), F32) if train else None
+            rstd0 = get("r0", (M,), F32) if train else None
+            ops.layernorm_fwd(x, _contig32(blk.norm0.weight), _contig32(blk.norm0.bias), blk.norm0.eps, y16=h0, mean=mean0, rstd=rstd0)
+            qkv = get("dec_qkv", (M, 3 * Dd), F16)
+            ops.linear(h0, wc.w16(blk.selfattn.qkv.weight), qkv, bias=_contig32(blk.selfattn.qkv.bias))
+            att = get("dec_att", (M, Dd), F16)
+            lse = get("dec_lse", (B, H, L), F32) if train else None
+            ops.attention_fwd(qkv, att, B, L, H, dh, blk.selfattn.scale, lse=lse)
+            x1 = get("dec_x1", (M, Dd), F32) if train else x
+            ops.linear(att, wc.w16(blk.selfattn.proj.weight), x1, bias=_contig32(blk.selfattn.proj.bias), residual=x)
+            # --- cross attention with the exemplar tokens
+            h1 = get("dec_h1", (M, Dd), F16)
+            mean1 = get("m1", (M,), F32) if train else None
+            rstd1 = get("r1", (M,), F32) if train else None
+            ops.layernorm_fwd(x1, _contig32(blk.norm1.weight), _contig32(blk.norm1.bias), blk.norm1.eps, y16=h1, mean=mean1, rstd=rstd1)
+            q16 = get("dec_q", (M, Dd), F16)
+            ops.linear(h1, wc.w16(blk.attn.wq.weight), q16, bias=_contig32(blk.attn.wq.bias))
+            k32 = get("dec_k", (ny, Dd), F32)
+            v32 = get("dec_v", (ny, Dd), F32)
+            ops.linear(y16, wc.w16(blk.attn.wk.weight), k32, bias=_contig32(blk.attn.wk.bias))
+            ops.linear(y16, wc.w16(blk.attn.wv.weight), v32, bias=_contig32(blk.attn.wv.bias))
+            c16 = get("dec_c", (M, Dd), F16)
+            probs = get("dec_probs", (M, H, S), F32) if train else None
+            ops.cross_attn_core(q16, k32, v32, c16, B, L, S, Dd, dh, blk.attn.scale, probs=probs, kv_broadcast=kv_broadcast)
+            x2 = get("dec_x2", (M, Dd), F32) if train else x1
+            ops.linear(c16, wc.w16(blk.attn.proj.weight), x2, bias=_contig32(blk.attn.proj.bias), residual=x1)
+            # --- MLP
+            h2 = get("dec_h2", (M, Dd), F16)
+            mean2 = get("m2", (M,), F32) if train else None
+            rstd2 = get("r2", (M,), F32) if train else None
+            ops.layernorm_fwd(x2, _contig32(blk.norm2.weight), _contig32(blk.norm2.bias), blk.norm2.eps, y16=h2, mean=mean2, rstd=rstd2)
+            u = get("dec_u", (M, hid), F16)
+            pre = get("dec_pre", (M, hid), F16) if train else None
+            ops.linear(h2, wc.w16(blk.mlp.fc1.weight), u, bias=_contig32(blk.mlp.fc1.bias), act=1, aux=pre)
+            x3 = get("dec_x3", (M, Dd), F32) if train else x2
+            ops.linear(u, wc.w16(blk.mlp.fc2.weight), x3, bias=_contig32(blk.mlp.fc2.bias), residual=x2)
+            if train:
+                sv.update(x0=x, h0=h0, mean0=mean0, rstd0=rstd0, qkv=qkv, att=att, lse=lse, x1=x1, h1=h1, mean1=mean1,
+                          rstd1=rstd1, q16=q16, k32=k32, v32=v32, c16=c16, probs=probs, x2=x2, h2=h2, mean2=mean2,
+                          rstd2=rstd2, u=u, pre=pre)
+                blocks_saved.append(sv)
+            x = x3
+
+        f16 = get("dec_f", (M, Dd), F16)
+        meanf = get("mf", (M,), F32) if train else None
+        rstdf = get("rf", (M,), F32) if train else None
+        ops.layernorm_fwd(x, _contig32(m.decoder_norm.weight), _contig32(m.decoder_norm.bias), m.decoder_norm.eps, y16=f16,
+                          mean=meanf, rstd=rstdf)
+
+        # --- density head: tokens [B, L, C] are already NHWC [B, h, w, C]
+        hgt = wdt = int(math.sqrt(L))
+        cur = f16.view(B, hgt, wdt, Dd)
+        heads = [m.decode_head0, m.decode_head1, m.decode_head2, m.decode_head3]
+        head_saved = []
+        out = None
+        for i, head in enumerate(heads):
+            conv, gn = head[0], head[1]
+            cout = conv.weight.shape[0]
+            G = gn.num_groups
+            assert cout // G == 32, "GroupNorm statistics are fused for 32-channel groups"
+            raw = get(f"head_raw{i}", (B, hgt, wdt, cout), F16)
+            stats = get(f"head_stats{i}", (B, G, 2), torch.float64)
+            ops.zero_(stats)
+            ops.conv3x3(cur, wc.conv16(conv.weight), raw, bias=_contig32(conv.bias), gn_stats=stats)
+            head_saved.append(dict(inp=cur, raw=raw, stats=stats))
+            if i < 3:
+                nxt = get(f"head_in{i + 1}", (B, 2 * hgt, 2 * wdt, cout), F16)
+                ops.gn_relu_upsample2x(raw, stats, _contig32(gn.weight), _contig32(gn.bias), nxt, G, gn.eps)
+                cur = nxt
+                hgt, wdt = 2 * hgt, 2 * wdt
+            else:
+                c1 = head[3]
+                dmap = get("head_dmap", (B, hgt, wdt), F32)
+                ops.gn_relu_conv1x1(raw, stats, _contig32(gn.weight), _contig32(gn.bias), _contig32(c1.weight).reshape(-1),
+                                    _contig32(c1.bias), dmap, G, gn.eps)
+                out = torch.empty(B, 2 * hgt, 2 * wdt, dtype=out_dtype, device=dev)
+                ops.upsample2x_f32(dmap, out)
+        if train:
+            save.update(blocks=blocks_saved, x_final=x, meanf=meanf, rstdf=rstdf, f16=f16, heads=head_saved, lat16=lat16,
+                        y16=y16, S=S, kv_broadcast=kv_broadcast, B=B, L=L, shot_num=shot_num)
+        return out
+
+
+_ENGINE = None
+
+
+def engine():
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = Engine()
+    return _ENGINE

@@ -106,9 +106,9 @@ def attention_fwd(qkv16, out16, B, L, H, dh, scale, lse=None):
     _count()
 
 
-def cross_attn_core(q16, k32, v32, out16, B, L, S, D, dh, scale, probs=None):
+def cross_attn_core(q16, k32, v32, out16, B, L, S, D, dh, scale, probs=None, kv_broadcast=False):
     check(lib().countr_cross_attn_core(_ptr(q16), _ptr(k32), _ptr(v32), _ptr(out16), _ptr(probs), B, L, S, D, dh, scale,
-                                       _is_bf16(q16), _stream()))
+                                       _is_bf16(q16), int(kv_broadcast), _stream()))
     _count()
 
 
@@ -171,3 +171,8 @@ def inorm_relu_pool(x16, mode, eps, y16=None, y32=None, mean=None, rstd=None):
     check(lib().countr_inorm_relu_pool(_ptr(x16), _ptr(y16), _ptr(y32), _ptr(mean), _ptr(rstd), N, H, W, C, eps, mode,
                                        _is_bf16(x16), _stream()))
     _count()
+
+
+def zero_(t):
+    check(lib().countr_memset_zero(_ptr(t), t.numel() * t.element_size(), _stream()))
+    return t

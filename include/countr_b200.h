@@ -29,6 +29,8 @@ const char* countr_last_error(void);
 const char* countr_version(void);
 int countr_check_device(void);
 int countr_num_sms(void);
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream` (statistics / split-K accumulators) */
+int countr_memset_zero(void* ptr, size_t bytes, countr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Tensor-core GEMM / implicit-GEMM 3x3 convolution (tcgen05.mma, TMA-fed, TMEM accumulators)
@@ -115,10 +117,12 @@ int countr_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, i
  * Cross-attention core for a handful of exemplar tokens (S <= 8): per token and head
  * softmax_s(scale * q . k_s) applied to v_s.   q16 [B*L][D] 16-bit, k32/v32 [B][S][D] fp32,
  * out16 [B*L][D] 16-bit, probs [B*L][D/dh][S] fp32 (optional, kept for backward).
+ * kv_broadcast != 0: k32/v32 are [S][D], shared by every image (zero-shot shot_token, :176).
  * replaces: CrossAttention.forward, models_crossvit.py:122-126.
  * ------------------------------------------------------------------------------------------ */
 int countr_cross_attn_core(const void* q16, const float* k32, const float* v32, void* out16, float* probs,
-                           int B, int L, int S, int D, int dh, float scale, int bf16, countr_stream_t stream);
+                           int B, int L, int S, int D, int dh, float scale, int bf16, int kv_broadcast,
+                           countr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Layout / cast helpers (HBM-bound streaming kernels).
