@@ -28,6 +28,7 @@ class GemmDesc(Structure):
         ("bf16", c_int32),
         ("bn", c_int32), ("split_k", c_int32),
         ("conv_h", c_int32), ("conv_w", c_int32), ("conv_cin", c_int32), ("conv_bx", c_int32), ("conv_by", c_int32),
+        ("conv_dw", c_int32), ("conv_batch", c_int32),
         ("c", c_void_p),
         ("ldc", c_int64), ("sc1", c_int64), ("sc2", c_int64),
         ("out_f32", c_int32), ("atomic", c_int32),

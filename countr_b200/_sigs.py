@@ -6,7 +6,7 @@ P, I, L, F = c_void_p, c_int32, c_int64, c_float
 SIGS = {
     "countr_memset_zero": [P, c_int64, P],
     "countr_layernorm_fwd": [P, P, P, P, P, P, P, I, I, F, I, P],
-    "countr_layernorm_bwd": [P, P, P, P, P, P, P, P, I, I, I, P],
+    "countr_layernorm_bwd": [P, P, P, P, P, P, P, P, P, I, I, I, I, P],
     "countr_attention_fwd": [P, P, P, I, I, I, I, F, I, P],
     "countr_cross_attn_core": [P, P, P, P, P, I, I, I, I, I, F, I, I, P],
     "countr_cast_f32_to_16": [P, P, L, F, I, P],
@@ -18,6 +18,15 @@ SIGS = {
     "countr_upsample2x_f32": [P, P, I, I, I, I, P],
     "countr_exemplar_conv1": [P, I, L, L, L, L, L, P, P, P, I, I, I, I, I, P],
     "countr_inorm_relu_pool": [P, P, P, P, P, I, I, I, I, F, I, I, P],
+    "countr_upsample2x_bwd": [P, I, P, I, I, I, P],
+    "countr_gn_relu_bwd_reduce": [P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, F, I, P],
+    "countr_gn_bwd_apply": [P, P, P, P, P, P, P, I, I, I, I, F, I, P],
+    "countr_colsum": [P, I, P, L, I, L, P],
+    "countr_softmax_bwd_rows": [P, P, P, L, I, F, I, P],
+    "countr_cross_attn_core_bwd": [P, P, P, P, P, P, P, P, I, I, I, I, I, F, I, I, P],
+    "countr_inorm_relu_pool_bwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, P],
+    "countr_exemplar_conv1_dw": [P, I, L, L, L, L, L, P, P, I, I, I, I, P],
+    "countr_conv_dw_unpack": [P, P, I, I, P],
 }
 
 

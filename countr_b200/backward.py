@@ -1,0 +1,216 @@
+"""Decoder backward schedule of the fine-tune step (host side).
+
+Reverse of `Engine.decoder_forward`: density head -> decoder_norm -> FIM blocks -> decoder_embed,
+plus the exemplar CNN.  Every gradient is produced by the sm_100a kernels of libcountr_sm100.so:
+  dX of a Linear      tcgen05 GEMM against the transposed 16-bit weight copy
+  dW of a Linear      tcgen05 GEMM with both operands MN-major (dY^T X), split-K, fp32 atomics
+  dX / dW of Conv3x3  implicit GEMM with the flipped filter / pixels-as-K implicit GEMM
+  attention backward  batched GEMMs over materialised [B,H,L,L] scores + a row softmax-backward
+  everything else     the streaming kernels of csrc/backward.cu and csrc/norm.cu
+
+The reference obtains all of this from autograd (scaler.scale(loss).backward(),
+util/misc.py:266-270); which parameters receive a gradient follows models_mae_cross.py:150-207
+(encoder frozen under no_grad; shot_token only when shot_num == 0; decoder_proj* only when > 0).
+Parameter gradients are views into one flat fp32 arena (one memset, ready for a single
+all-reduce); they are returned to autograd, which accumulates them into `.grad` as usual.
+"""
+import torch
+
+from . import ops
+from .engine import F16, F32, _contig32
+
+
+def _dw_linear(dy16, x16, dw32):
+    """dw32[N_out, K_in] += dy16[M, N_out]^T @ x16[M, K_in]   (both operands MN-major, split-K)."""
+    Mtok, n_out = dy16.shape
+    k_in = x16.shape[1]
+    out_tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
+    kblocks = (Mtok + 63) // 64
+    split = max(1, min(kblocks, (2 * 148) // max(1, out_tiles)))
+    ops.gemm(dy16, x16, dw32, n_out, k_in, Mtok, lda=dy16.stride(0), ldb=x16.stride(0), ldc=k_in, a_mn=True, b_mn=True,
+             atomic=True, split_k=split)
+
+
+def attention_backward(qkv, lse, datt, B, L, H, dh, scale):
+    """qkv fp16 [B*L, 3*H*dh] (packed), lse fp32 [B,H,L], datt fp16 [B*L, H*dh] -> dqkv fp16 [B*L, 3*H*dh]."""
+    dev = qkv.device
+    D = H * dh
+    row = 3 * D
+    flat = qkv.view(-1)
+    q, k, v = flat, flat[D:], flat[2 * D:]
+    s16 = torch.empty(B, H, L, L, dtype=F16, device=dev)
+    dp16 = torch.empty(B, H, L, L, dtype=F16, device=dev)
+    bs = dict(nb1=B, nb2=H)
+    # S = scale * Q K^T ; dP = dO V^T
+    ops.gemm(q, k, s16, L, L, dh, lda=row, ldb=row, ldc=L, sa=(L * row, dh), sb=(L * row, dh), sc=(H * L * L, L * L),
+             alpha=scale, **bs)
+    ops.gemm(datt, v, dp16, L, L, dh, lda=D, ldb=row, ldc=L, sa=(L * D, dh), sb=(L * row, dh), sc=(H * L * L, L * L), **bs)
+    ops.softmax_bwd_rows(s16, dp16, lse, scale)          # s16 <- P, dp16 <- dS (already * scale)
+    dqkv = torch.empty(B * L, row, dtype=F16, device=dev)
+    dflat = dqkv.view(-1)
+    # dV = P^T dO
+    ops.gemm(s16, datt, dflat[2 * D:], L, dh, L, lda=L, ldb=D, ldc=row, a_mn=True, b_mn=True, sa=(H * L * L, L * L),
+             sb=(L * D, dh), sc=(L * row, dh), **bs)
+    # dQ = dS K
+    ops.gemm(dp16, k, dflat, L, dh, L, lda=L, ldb=row, ldc=row, b_mn=True, sa=(H * L * L, L * L), sb=(L * row, dh),
+             sc=(L * row, dh), **bs)
+    # dK = dS^T Q
+    ops.gemm(dp16, q, dflat[D:], L, dh, L, lda=L, ldb=row, ldc=row, a_mn=True, b_mn=True, sa=(H * L * L, L * L),
+             sb=(L * row, dh), sc=(L * row, dh), **bs)
+    return dqkv
+
+
+def _conv_grads(d_raw, inp, conv, grads, wc, dx_dtype):
+    """dW (+ unpack into Conv2d layout) and dX of a 3x3/p1 conv; d_raw, inp are NHWC fp16."""
+    cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+    name_w = grads["__names__"][id(conv.weight)]
+    dwp = torch.empty(cout, 9 * cin, dtype=F32, device=d_raw.device)
+    ops.zero_(dwp)
+    ops.conv3x3_dw(d_raw, inp, dwp)
+    ops.conv_dw_unpack(dwp, grads[name_w], cout, cin)
+    if dx_dtype is None:
+        return None
+    d_in = torch.empty(inp.shape, dtype=dx_dtype, device=d_raw.device)
+    ops.conv3x3(d_raw, wc.conv16(conv.weight, mode=1), d_in)
+    return d_in
+
+
+def decoder_backward(eng, m, sv, boxes, grad_out):
+    dev = grad_out.device
+    wc = eng.wc
+    B, L, shot_num, S = sv["B"], sv["L"], sv["shot_num"], sv["S"]
+    M = B * L
+    Dd = m.decoder_embed.weight.shape[0]
+
+    # ---- flat gradient arena
+    names, params = m._decoder_params(shot_num)
+    total = sum((p.numel() + 3) // 4 * 4 for p in params)
+    arena = torch.empty(total, dtype=F32, device=dev)
+    ops.zero_(arena)
+    grads, off = {"__names__": {}}, 0
+    for n, p in zip(names, params):
+        grads[n] = arena[off:off + p.numel()].view(p.shape)
+        grads["__names__"][id(p)] = n
+        off += (p.numel() + 3) // 4 * 4
+
+    def G(p):
+        return grads[grads["__names__"][id(p)]]
+
+    # ---- density head (models_mae_cross.py:189-197 reversed)
+    heads = [m.decode_head0, m.decode_head1, m.decode_head2, m.decode_head3]
+    hs = sv["heads"]
+    go = grad_out if grad_out.is_contiguous() else grad_out.contiguous()
+    raw3 = hs[3]["raw"]
+    dmap = torch.empty(B, raw3.shape[1], raw3.shape[2], dtype=F32, device=dev)
+    ops.upsample2x_bwd(go, dmap)
+    d_next = None
+    for i in (3, 2, 1, 0):
+        conv, gn = heads[i][0], heads[i][1]
+        raw, stats, inp = hs[i]["raw"], hs[i]["stats"], hs[i]["inp"]
+        dyh = torch.empty_like(raw)
+        gsum = torch.empty(B, gn.num_groups, 2, dtype=torch.float64, device=dev)
+        ops.zero_(gsum)
+        gamma, beta = _contig32(gn.weight), _contig32(gn.bias)
+        if i == 3:
+            c1 = heads[3][3]
+            ops.gn_relu_bwd_reduce(raw, stats, gamma, beta, dyh, G(gn.weight), G(gn.bias), gsum, gn.num_groups, gn.eps,
+                                   dmap=dmap, w1=_contig32(c1.weight).reshape(-1), dw1=G(c1.weight).view(-1), db1=G(c1.bias))
+        else:
+            ops.gn_relu_bwd_reduce(raw, stats, gamma, beta, dyh, G(gn.weight), G(gn.bias), gsum, gn.num_groups, gn.eps,
+                                   d_next=d_next)
+        ops.gn_bwd_apply(raw, dyh, stats, gsum, gamma, dyh, G(conv.bias), gn.num_groups, gn.eps)   # in place: dyh -> d_raw
+        d_next = _conv_grads(dyh, inp, conv, grads, wc, F32 if i == 0 else F16)
+
+    # ---- decoder_norm
+    g = torch.empty(M, Dd, dtype=F32, device=dev)       # gradient of the fp32 residual stream
+    g16 = torch.empty(M, Dd, dtype=F16, device=dev)
+    dn = m.decoder_norm
+    ops.layernorm_bwd(d_next.view(M, Dd), sv["x_final"], _contig32(dn.weight), sv["meanf"], sv["rstdf"], g, G(dn.weight),
+                      G(dn.bias), accumulate=False, dx16=g16)
+
+    # ---- FIM blocks (models_crossvit.py:152-156 reversed)
+    y16 = sv["y16"]
+    ny = y16.shape[0]
+    kvb = sv["kv_broadcast"]
+    if shot_num == 0:
+        dy32 = G(m.shot_token).view(1, Dd)              # accumulate straight into shot_token.grad
+    else:
+        dy32 = torch.empty(ny, Dd, dtype=F32, device=dev)
+        ops.zero_(dy32)
+    dh = torch.empty(M, Dd, dtype=F32, device=dev)
+    for blk, s in zip(reversed(list(m.decoder_blocks)), reversed(sv["blocks"])):
+        H = blk.selfattn.num_heads
+        dhd = Dd // H
+        hid = blk.mlp.fc1.weight.shape[0]
+        # --- MLP: x3 = x2 + fc2(gelu(fc1(LN2 x2)))
+        ops.colsum(g, G(blk.mlp.fc2.bias))
+        _dw_linear(g16, s["u"], G(blk.mlp.fc2.weight))
+        dpre = torch.empty(M, hid, dtype=F16, device=dev)
+        ops.linear(g16, wc.w16_t(blk.mlp.fc2.weight), dpre, act=2, aux=s["pre"])
+        ops.colsum(dpre, G(blk.mlp.fc1.bias))
+        _dw_linear(dpre, s["h2"], G(blk.mlp.fc1.weight))
+        ops.linear(dpre, wc.w16_t(blk.mlp.fc1.weight), dh)
+        ops.layernorm_bwd(dh, s["x2"], _contig32(blk.norm2.weight), s["mean2"], s["rstd2"], g, G(blk.norm2.weight),
+                          G(blk.norm2.bias), accumulate=True, dx16=g16)
+        # --- cross attention: x2 = x1 + proj(core(wq(LN1 x1), wk(y), wv(y)))
+        ca = blk.attn
+        ops.colsum(g, G(ca.proj.bias))
+        _dw_linear(g16, s["c16"], G(ca.proj.weight))
+        dc = torch.empty(M, Dd, dtype=F16, device=dev)
+        ops.linear(g16, wc.w16_t(ca.proj.weight), dc)
+        dq = torch.empty(M, Dd, dtype=F16, device=dev)
+        dk32 = torch.empty(ny, Dd, dtype=F32, device=dev)
+        dv32 = torch.empty(ny, Dd, dtype=F32, device=dev)
+        ops.zero_(dk32)
+        ops.zero_(dv32)
+        ops.cross_attn_core_bwd(s["q16"], s["k32"], s["v32"], s["probs"], dc, dq, dk32, dv32, B, L, S, Dd, dhd, ca.scale,
+                                kv_broadcast=kvb)
+        ops.colsum(dq, G(ca.wq.bias))
+        _dw_linear(dq, s["h1"], G(ca.wq.weight))
+        ops.linear(dq, wc.w16_t(ca.wq.weight), dh)
+        dk16 = torch.empty(ny, Dd, dtype=F16, device=dev)
+        dv16 = torch.empty(ny, Dd, dtype=F16, device=dev)
+        ops.cast16(dk32, dk16)
+        ops.cast16(dv32, dv16)
+        ops.colsum(dk32, G(ca.wk.bias))
+        ops.colsum(dv32, G(ca.wv.bias))
+        _dw_linear(dk16, y16, G(ca.wk.weight))
+        _dw_linear(dv16, y16, G(ca.wv.weight))
+        ops.linear(dk16, wc.w16_t(ca.wk.weight), dy32, residual=dy32)
+        ops.linear(dv16, wc.w16_t(ca.wv.weight), dy32, residual=dy32)
+        ops.layernorm_bwd(dh, s["x1"], _contig32(blk.norm1.weight), s["mean1"], s["rstd1"], g, G(blk.norm1.weight),
+                          G(blk.norm1.bias), accumulate=True, dx16=g16)
+        # --- self attention: x1 = x0 + proj(attn(qkv(LN0 x0)))
+        sa = blk.selfattn
+        ops.colsum(g, G(sa.proj.bias))
+        _dw_linear(g16, s["att"], G(sa.proj.weight))
+        datt = torch.empty(M, Dd, dtype=F16, device=dev)
+        ops.linear(g16, wc.w16_t(sa.proj.weight), datt)
+        dqkv = attention_backward(s["qkv"], s["lse"], datt, B, L, H, dhd, sa.scale)
+        ops.colsum(dqkv, G(sa.qkv.bias))
+        _dw_linear(dqkv, s["h0"], G(sa.qkv.weight))
+        ops.linear(dqkv, wc.w16_t(sa.qkv.weight), dh)
+        ops.layernorm_bwd(dh, s["x0"], _contig32(blk.norm0.weight), s["mean0"], s["rstd0"], g, G(blk.norm0.weight),
+                          G(blk.norm0.bias), accumulate=True, dx16=g16)
+
+    # ---- decoder_embed: weight / bias only (its input is the frozen encoder's output)
+    de = m.decoder_embed
+    ops.colsum(g, G(de.bias))
+    _dw_linear(g16, sv["lat16"], G(de.weight))
+
+    # ---- exemplar CNN (models_mae_cross.py:157-177 reversed)
+    if shot_num > 0:
+        ex = sv["exemplar"]
+        convs = [m.decoder_proj1[0], m.decoder_proj2[0], m.decoder_proj3[0], m.decoder_proj4[0]]
+        raw4 = ex["raw"][3]
+        d_raw = torch.empty_like(raw4)
+        ops.inorm_relu_pool_bwd(raw4, ex["mean"][3], ex["rstd"][3], d_raw, 1, dpool32=dy32, dbias=G(convs[3].bias))
+        for i in (3, 2, 1):
+            d_pool = _conv_grads(d_raw, ex["pooled"][i - 1], convs[i], grads, wc, F16)
+            raw = ex["raw"][i - 1]
+            d_raw = torch.empty_like(raw)
+            ops.inorm_relu_pool_bwd(raw, ex["mean"][i - 1], ex["rstd"][i - 1], d_raw, 0, dpool16=d_pool, dbias=G(convs[i - 1].bias))
+        ops.exemplar_conv1_dw(boxes, S, d_raw, G(convs[0].weight))
+    if eng.grad_allreduce is not None:
+        eng.grad_allreduce(arena)      # data-parallel mean of every decoder gradient in one collective
+    return grads

@@ -1,0 +1,734 @@
+// countr_b200 — backward-only streaming kernels of the fine-tune step (decoder side).
+//
+// The reference gets these from autograd (SURVEY.md §2.3 "Backward-only call sites"):
+// upsample_bilinear2d_backward, native_group_norm_backward + threshold_backward,
+// native_batch_norm_backward (InstanceNorm) + max_pool2d_with_indices_backward,
+// _softmax_backward_data, bias-gradient sums, and the tiny-K/V cross-attention backward.
+// All are HBM-bound: NHWC, 16-byte vector loads, per-block partial sums, one atomic per block.
+#include "../../include/countr_b200.h"
+#include "common.cuh"
+
+namespace countr {
+namespace {
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
+  uint32_t r;
+  if (bf16)
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(uint32_t v, int bf16) {
+  if (bf16) return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+  __half2 h = *reinterpret_cast<__half2*>(&v);
+  return __half22float2(h);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8], int bf16) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack2(w[i], bf16);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], int bf16) {
+  uint4 o;
+  o.x = pack2(f[0], f[1], bf16);
+  o.y = pack2(f[2], f[3], bf16);
+  o.z = pack2(f[4], f[5], bf16);
+  o.w = pack2(f[6], f[7], bf16);
+  return o;
+}
+__device__ __forceinline__ float load_any(const void* p, long long i, int dtype) {
+  if (dtype == 0) return reinterpret_cast<const float*>(p)[i];
+  const uint16_t u = reinterpret_cast<const uint16_t*>(p)[i];
+  if (dtype == 1) return __half2float(__ushort_as_half(u));
+  return __uint_as_float(static_cast<uint32_t>(u) << 16);
+}
+
+// adjoint taps of bilinear x2 (align_corners=False): input index i receives from outputs
+// 2i-1 (.25, i>=1), 2i (.75, or 1 at i==0), 2i+1 (.75, or 1 at i==n-1), 2i+2 (.25, i<=n-2)
+__device__ __forceinline__ void up2_adjoint_taps(int i, int n, int (&o)[4], float (&w)[4]) {
+  o[0] = 2 * i - 1; w[0] = i >= 1 ? 0.25f : 0.f;
+  o[1] = 2 * i;     w[1] = i == 0 ? 1.f : 0.75f;
+  o[2] = 2 * i + 1; w[2] = i == n - 1 ? 1.f : 0.75f;
+  o[3] = 2 * i + 2; w[3] = i <= n - 2 ? 0.25f : 0.f;
+  if (i < 1) o[0] = 0;
+  if (i > n - 2) o[3] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// d(dmap)[B][H][W] fp32 = adjoint of the last F.interpolate(x2) applied to dOut [B][2H][2W]
+// ------------------------------------------------------------------------------------------
+__global__ void up2_bwd_kernel(const void* __restrict__ dy, int dtype, float* __restrict__ dx, int B, int H, int W) {
+  const long long total = static_cast<long long>(B) * H * W;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ix = idx % W, iy = (idx / W) % H;
+  const long long b = idx / (static_cast<long long>(W) * H);
+  int ox[4], oy[4];
+  float wx[4], wy[4];
+  up2_adjoint_taps(ix, W, ox, wx);
+  up2_adjoint_taps(iy, H, oy, wy);
+  const long long base = b * 4ll * H * W;
+  float acc = 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    if (wy[a] == 0.f) continue;
+    float r = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (wx[c] != 0.f) r += wx[c] * load_any(dy, base + static_cast<long long>(oy[a]) * (2 * W) + ox[c], dtype);
+    acc += wy[a] * r;
+  }
+  dx[idx] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm + ReLU backward, pass A (reduce).  C == 256, 32-channel groups.
+//   mode 0: dz = up2-adjoint gather of d_next [B][2H][2W][C] (gradient w.r.t. the next conv's input)
+//   mode 1: dz = dmap[b][p] * w1[c]          (Conv2d 1x1 C->1 backward), also dw1/db1
+// writes dyh = dz * 1[y > 0] (16-bit), accumulates dgamma/dbeta (fp32) and, per (image, group),
+// S1 = sum dyh*gamma, S2 = sum dyh*gamma*xhat (double).
+// ------------------------------------------------------------------------------------------
+constexpr int kC = 256;
+__global__ void __launch_bounds__(256) gn_relu_bwd_reduce_kernel(
+    const uint16_t* __restrict__ raw, const double* __restrict__ stats, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const uint16_t* __restrict__ d_next, const float* __restrict__ dmap,
+    const float* __restrict__ w1, uint16_t* __restrict__ dyh, float* __restrict__ dgamma, float* __restrict__ dbeta,
+    float* __restrict__ dw1, float* __restrict__ db1, double* __restrict__ gsum, int H, int W, int G, float eps,
+    int mode, int bf16) {
+  __shared__ float s_mean[8], s_rstd[8];
+  __shared__ float red[8][kC + 8];
+  const int b = blockIdx.y;
+  const int HW = H * W;
+  const int cpg = kC / G;  // 32
+  if (threadIdx.x < G) {
+    const double cnt = static_cast<double>(HW) * cpg;
+    const double s = stats[(static_cast<long long>(b) * G + threadIdx.x) * 2];
+    const double ss = stats[(static_cast<long long>(b) * G + threadIdx.x) * 2 + 1];
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0) var = 0;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = rsqrtf(static_cast<float>(var) + eps);
+  }
+  __syncthreads();
+  const int cv = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c0 = cv * 8, g = c0 / cpg;
+  const float mean = s_mean[g], rstd = s_rstd[g];
+  float gam[8], bet[8], wv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gam[j] = gamma[c0 + j];
+    bet[j] = beta[c0 + j];
+    wv[j] = mode == 1 ? w1[c0 + j] : 0.f;
+  }
+  float a_dg[8], a_db[8], a_dw[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a_dg[j] = a_db[j] = a_dw[j] = 0.f;
+  float s1 = 0.f, s2 = 0.f, a_b1 = 0.f;
+  const uint16_t* rb = raw + static_cast<long long>(b) * HW * kC + c0;
+  uint16_t* ob = dyh + static_cast<long long>(b) * HW * kC + c0;
+  for (int pix = blockIdx.x * 8 + pl; pix < HW; pix += gridDim.x * 8) {
+    float x[8], dz[8];
+    unpack8(*reinterpret_cast<const uint4*>(rb + static_cast<long long>(pix) * kC), x, bf16);
+    if (mode == 1) {
+      const float dm = dmap[static_cast<long long>(b) * HW + pix];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dz[j] = dm * wv[j];
+      if (cv == 0) a_b1 += dm;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y = (x[j] - mean) * rstd * gam[j] + bet[j];
+        a_dw[j] += dm * fmaxf(y, 0.f);
+      }
+    } else {
+      const int ix = pix % W, iy = pix / W;
+      int ox[4], oy[4];
+      float wx[4], wy[4];
+      up2_adjoint_taps(ix, W, ox, wx);
+      up2_adjoint_taps(iy, H, oy, wy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dz[j] = 0.f;
+      const uint16_t* nb = d_next + static_cast<long long>(b) * 4 * HW * kC + c0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (wy[a] == 0.f) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (wx[c] == 0.f) continue;
+          float t[8];
+          unpack8(*reinterpret_cast<const uint4*>(nb + (static_cast<long long>(oy[a]) * (2 * W) + ox[c]) * kC), t, bf16);
+          const float ww = wy[a] * wx[c];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dz[j] += ww * t[j];
+        }
+      }
+    }
+    float dy[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (x[j] - mean) * rstd;
+      const float y = xh * gam[j] + bet[j];
+      dy[j] = y > 0.f ? dz[j] : 0.f;
+      a_dg[j] += dy[j] * xh;
+      a_db[j] += dy[j];
+      s1 += dy[j] * gam[j];
+      s2 += dy[j] * gam[j] * xh;
+    }
+    *reinterpret_cast<uint4*>(ob + static_cast<long long>(pix) * kC) = pack8(dy, bf16);
+  }
+  // group sums: 4 consecutive lanes share a group
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+  // cross-pixel-lane reductions through smem, one quantity at a time
+  for (int q = 0; q < 4; ++q) {
+    if (q == 2 && mode != 1) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[pl][c0 + j] = q == 0 ? a_dg[j] : q == 1 ? a_db[j] : q == 2 ? a_dw[j] : 0.f;
+    if (q == 3) {
+      red[pl][c0] = s1; red[pl][c0 + 1] = s2; red[pl][c0 + 2] = a_b1;
+    }
+    __syncthreads();
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += red[k][threadIdx.x];
+    if (q == 0) atomicAdd(dgamma + threadIdx.x, v);
+    else if (q == 1) atomicAdd(dbeta + threadIdx.x, v);
+    else if (q == 2) atomicAdd(dw1 + threadIdx.x, v);
+    else {
+      // threadIdx.x = cv*8 + {0: s1, 1: s2, 2: db1}; one representative lane per group (cv % 4 == 0)
+      const int cvv = threadIdx.x >> 3, which = threadIdx.x & 7;
+      if ((cvv & 3) == 0 && which < 2) atomicAdd(gsum + (static_cast<long long>(b) * G + (cvv >> 2)) * 2 + which, static_cast<double>(v));
+      if (mode == 1 && cvv == 0 && which == 2) atomicAdd(db1, v);
+    }
+    __syncthreads();
+  }
+}
+
+// pass B: d_raw = rstd * (dyh*gamma - S1/n - xhat*S2/n);  dbias[c] += sum d_raw
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint16_t* __restrict__ raw, const uint16_t* __restrict__ dyh,
+                                                            const double* __restrict__ stats, const double* __restrict__ gsum,
+                                                            const float* __restrict__ gamma, uint16_t* __restrict__ d_raw,
+                                                            float* __restrict__ dbias, int HW, int G, float eps, int bf16) {
+  __shared__ float s_mean[8], s_rstd[8], s_m1[8], s_m2[8];
+  __shared__ float red[8][kC + 8];
+  const int b = blockIdx.y;
+  const int cpg = kC / G;
+  if (threadIdx.x < G) {
+    const double cnt = static_cast<double>(HW) * cpg;
+    const long long o = (static_cast<long long>(b) * G + threadIdx.x) * 2;
+    const double mean = stats[o] / cnt;
+    double var = stats[o + 1] / cnt - mean * mean;
+    if (var < 0) var = 0;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = rsqrtf(static_cast<float>(var) + eps);
+    s_m1[threadIdx.x] = static_cast<float>(gsum[o] / cnt);
+    s_m2[threadIdx.x] = static_cast<float>(gsum[o + 1] / cnt);
+  }
+  __syncthreads();
+  const int cv = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c0 = cv * 8, g = c0 / cpg;
+  const float mean = s_mean[g], rstd = s_rstd[g], m1 = s_m1[g], m2 = s_m2[g];
+  float gam[8], a_b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gam[j] = gamma[c0 + j];
+    a_b[j] = 0.f;
+  }
+  const long long base = static_cast<long long>(b) * HW * kC + c0;
+  for (int pix = blockIdx.x * 8 + pl; pix < HW; pix += gridDim.x * 8) {
+    float x[8], dy[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(raw + base + static_cast<long long>(pix) * kC), x, bf16);
+    unpack8(*reinterpret_cast<const uint4*>(dyh + base + static_cast<long long>(pix) * kC), dy, bf16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (x[j] - mean) * rstd;
+      o[j] = rstd * (dy[j] * gam[j] - m1 - xh * m2);
+      a_b[j] += o[j];
+    }
+    *reinterpret_cast<uint4*>(d_raw + base + static_cast<long long>(pix) * kC) = pack8(o, bf16);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[pl][c0 + j] = a_b[j];
+  __syncthreads();
+  float v = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v += red[k][threadIdx.x];
+  atomicAdd(dbias + threadIdx.x, v);
+}
+
+// ------------------------------------------------------------------------------------------
+// out[n] += sum_r x[r][n] * scale   (bias gradients).  x is 16-bit or fp32.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x, int dtype, float* __restrict__ out, long long R,
+                                                      int N, long long ld, int rows_per_block) {
+  // thread = 2 columns; blockDim.x = 128 threads along N, blockDim.y = 2 row lanes
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (c >= N) return;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+  const long long r1 = min(R, r0 + rows_per_block);
+  float a0 = 0.f, a1 = 0.f;
+  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    if (dtype == 0) {
+      const float2 v = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(x) + r * ld + c);
+      a0 += v.x; a1 += v.y;
+    } else {
+      const float2 v = unpack2(*reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(x) + r * ld + c), dtype == 2);
+      a0 += v.x; a1 += v.y;
+    }
+  }
+  __shared__ float red[2][256];
+  red[threadIdx.y][threadIdx.x * 2] = a0;
+  red[threadIdx.y][threadIdx.x * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    atomicAdd(out + c, red[0][threadIdx.x * 2] + red[1][threadIdx.x * 2]);
+    if (c + 1 < N) atomicAdd(out + c + 1, red[0][threadIdx.x * 2 + 1] + red[1][threadIdx.x * 2 + 1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// softmax backward over materialised score rows (self-attention backward, unfused):
+//   P = exp(S - lse[row]);  dS = scale * P * (dP - sum_j P_j dP_j)   in place: S <- P, dP <- dS
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(uint16_t* __restrict__ s_io, uint16_t* __restrict__ dp_io,
+                                                                const float* __restrict__ lse, long long rows, int L,
+                                                                float scale, int bf16) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  uint32_t* sp = reinterpret_cast<uint32_t*>(s_io + row * L);
+  uint32_t* dp = reinterpret_cast<uint32_t*>(dp_io + row * L);
+  const float l = lse[row];
+  const int n2 = L / 2;
+  float dot = 0.f;
+  for (int i = lane; i < n2; i += 32) {
+    const float2 s = unpack2(sp[i], bf16), d = unpack2(dp[i], bf16);
+    const float p0 = __expf(s.x - l), p1 = __expf(s.y - l);
+    dot += p0 * d.x + p1 * d.y;
+  }
+  dot = warp_sum(dot);
+  for (int i = lane; i < n2; i += 32) {
+    const float2 s = unpack2(sp[i], bf16), d = unpack2(dp[i], bf16);
+    const float p0 = __expf(s.x - l), p1 = __expf(s.y - l);
+    sp[i] = pack2(p0, p1, bf16);
+    dp[i] = pack2(scale * p0 * (d.x - dot), scale * p1 * (d.y - dot), bf16);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// cross-attention core backward (S <= 8 exemplar tokens, dh == 32, D % 512 == 0).
+//   phase 1 (warp per token): dq16; ds (scaled) and p kept in smem
+//   phase 2 (thread per 2 channels): dk/dv of this block's tokens -> atomics into dk32/dv32 [B][S][D]
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxShots = 8;
+constexpr int kTokPerBlock = 32;
+__global__ void __launch_bounds__(256) cross_attn_core_bwd_kernel(
+    const uint16_t* __restrict__ q16, const float* __restrict__ k32, const float* __restrict__ v32,
+    const float* __restrict__ probs, const uint16_t* __restrict__ do16, uint16_t* __restrict__ dq16,
+    float* __restrict__ dk32, float* __restrict__ dv32, int L, int S, int D, float scale, long long kv_bstride, int bf16) {
+  extern __shared__ float sm[];
+  const int Hh = D / 32;
+  float* sk = sm;                       // [S][D]
+  float* sv = sk + S * D;               // [S][D]
+  float* sds = sv + S * D;              // [tokens][Hh][S]  (scaled ds)
+  float* spr = sds + kTokPerBlock * Hh * S;  // [tokens][Hh][S]
+  const int tok0 = blockIdx.x * kTokPerBlock;
+  const int b = tok0 / L;
+  for (int i = threadIdx.x; i < S * D; i += blockDim.x) {
+    sk[i] = k32[b * kv_bstride + i];
+    sv[i] = v32[b * kv_bstride + i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = warp; t < kTokPerBlock; t += 8) {
+    const long long tok = tok0 + t;
+    for (int c0 = 0; c0 < D; c0 += 512) {
+      const int ch = c0 + lane * 16;
+      const int hh = ch >> 5;
+      float dO[16];
+      {
+        float a[8], c[8];
+        unpack8(*reinterpret_cast<const uint4*>(do16 + tok * D + ch), a, bf16);
+        unpack8(*reinterpret_cast<const uint4*>(do16 + tok * D + ch + 8), c, bf16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { dO[j] = a[j]; dO[8 + j] = c[j]; }
+      }
+      float pr[kMaxShots], dpv[kMaxShots];
+      float dot = 0.f;
+#pragma unroll
+      for (int s = 0; s < kMaxShots; ++s) {
+        if (s < S) {
+          float d = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) d += dO[j] * sv[s * D + ch + j];
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          pr[s] = probs[(tok * Hh + hh) * S + s];
+          dpv[s] = d;
+          dot += pr[s] * d;
+        }
+      }
+      float dq[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dq[j] = 0.f;
+#pragma unroll
+      for (int s = 0; s < kMaxShots; ++s) {
+        if (s < S) {
+          const float ds = scale * pr[s] * (dpv[s] - dot);
+          if ((lane & 1) == 0) {
+            sds[(t * Hh + hh) * S + s] = ds;
+            spr[(t * Hh + hh) * S + s] = pr[s];
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dq[j] += ds * sk[s * D + ch + j];
+        }
+      }
+      float a[8], c[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] = dq[j]; c[j] = dq[8 + j]; }
+      *reinterpret_cast<uint4*>(dq16 + tok * D + ch) = pack8(a, bf16);
+      *reinterpret_cast<uint4*>(dq16 + tok * D + ch + 8) = pack8(c, bf16);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x * 2; c < D; c += blockDim.x * 2) {
+    const int hh = c >> 5;
+    float adk[kMaxShots][2], adv[kMaxShots][2];
+#pragma unroll
+    for (int s = 0; s < kMaxShots; ++s) adk[s][0] = adk[s][1] = adv[s][0] = adv[s][1] = 0.f;
+    for (int t = 0; t < kTokPerBlock; ++t) {
+      const long long tok = tok0 + t;
+      const float2 q = unpack2(*reinterpret_cast<const uint32_t*>(q16 + tok * D + c), bf16);
+      const float2 d = unpack2(*reinterpret_cast<const uint32_t*>(do16 + tok * D + c), bf16);
+#pragma unroll
+      for (int s = 0; s < kMaxShots; ++s) {
+        if (s < S) {
+          const float ds = sds[(t * Hh + hh) * S + s], p = spr[(t * Hh + hh) * S + s];
+          adk[s][0] += ds * q.x; adk[s][1] += ds * q.y;
+          adv[s][0] += p * d.x;  adv[s][1] += p * d.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < kMaxShots; ++s) {
+      if (s < S) {
+        const long long o = b * kv_bstride + static_cast<long long>(s) * D + c;
+        atomicAdd(dk32 + o, adk[s][0]); atomicAdd(dk32 + o + 1, adk[s][1]);
+        atomicAdd(dv32 + o, adv[s][0]); atomicAdd(dv32 + o + 1, adv[s][1]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// InstanceNorm + ReLU + {MaxPool2d(2) | global average} backward; one CTA per (sample, 64 channels)
+//   mode 0: dpool16 [N][H/2][W/2][C]; mode 1: dpool32 [N][C]     -> d_raw16 [N][H][W][C]
+// also accumulates the conv bias gradient dbias[c] += sum d_raw.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) inorm_relu_pool_bwd_kernel(const uint16_t* __restrict__ raw, const float* __restrict__ mean_in,
+                                                                   const float* __restrict__ rstd_in,
+                                                                   const uint16_t* __restrict__ dpool16,
+                                                                   const float* __restrict__ dpool32, uint16_t* __restrict__ d_raw,
+                                                                   float* __restrict__ dbias, int H, int W, int C, int mode,
+                                                                   int bf16) {
+  __shared__ float red[2][8][64];
+  __shared__ float s_a[64], s_b[64];
+  const int n = blockIdx.y, c0 = blockIdx.x * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int HW = H * W;
+  const int ca = c0 + lane * 2;
+  const float ma = mean_in[static_cast<long long>(n) * C + ca], mb = mean_in[static_cast<long long>(n) * C + ca + 1];
+  const float ra = rstd_in[static_cast<long long>(n) * C + ca], rb = rstd_in[static_cast<long long>(n) * C + ca + 1];
+  const uint16_t* xb = raw + static_cast<long long>(n) * HW * C + ca;
+  uint16_t* ob = d_raw + static_cast<long long>(n) * HW * C + ca;
+  const int OW = W / 2, OH = H / 2;
+  float ga = 0.f, gb = 0.f;
+  if (mode == 1) {
+    ga = dpool32[static_cast<long long>(n) * C + ca] / HW;
+    gb = dpool32[static_cast<long long>(n) * C + ca + 1] / HW;
+  }
+  // pass 1: A = sum dxhat, Bq = sum dxhat * xhat
+  float A0 = 0.f, A1 = 0.f, B0 = 0.f, B1 = 0.f;
+  if (mode == 0) {
+    for (int p = warp; p < OH * OW; p += 8) {
+      const int oy = p / OW, ox = p % OW;
+      const uint16_t* q = xb + (static_cast<long long>(2 * oy) * W + 2 * ox) * C;
+      const float2 f0 = unpack2(*reinterpret_cast<const uint32_t*>(q), bf16);
+      const float2 f1 = unpack2(*reinterpret_cast<const uint32_t*>(q + C), bf16);
+      const float2 f2 = unpack2(*reinterpret_cast<const uint32_t*>(q + static_cast<long long>(W) * C), bf16);
+      const float2 f3 = unpack2(*reinterpret_cast<const uint32_t*>(q + static_cast<long long>(W) * C + C), bf16);
+      const float va = fmaxf(fmaxf(f0.x, f1.x), fmaxf(f2.x, f3.x)), vb = fmaxf(fmaxf(f0.y, f1.y), fmaxf(f2.y, f3.y));
+      const float2 d = unpack2(*reinterpret_cast<const uint32_t*>(dpool16 + (static_cast<long long>(n) * OH * OW + p) * C + ca), bf16);
+      const float xa = (va - ma) * ra, xbb = (vb - mb) * rb;
+      if (xa > 0.f) { A0 += d.x; B0 += d.x * xa; }
+      if (xbb > 0.f) { A1 += d.y; B1 += d.y * xbb; }
+    }
+  } else {
+    for (int p = warp; p < HW; p += 8) {
+      const float2 f = unpack2(*reinterpret_cast<const uint32_t*>(xb + static_cast<long long>(p) * C), bf16);
+      const float xa = (f.x - ma) * ra, xbb = (f.y - mb) * rb;
+      if (xa > 0.f) { A0 += ga; B0 += ga * xa; }
+      if (xbb > 0.f) { A1 += gb; B1 += gb * xbb; }
+    }
+  }
+  red[0][warp][lane * 2] = A0; red[0][warp][lane * 2 + 1] = A1;
+  red[1][warp][lane * 2] = B0; red[1][warp][lane * 2 + 1] = B1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float a = 0.f, q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a += red[0][k][threadIdx.x]; q += red[1][k][threadIdx.x]; }
+    s_a[threadIdx.x] = a / HW;
+    s_b[threadIdx.x] = q / HW;
+  }
+  __syncthreads();
+  const float mA0 = s_a[lane * 2], mA1 = s_a[lane * 2 + 1], mB0 = s_b[lane * 2], mB1 = s_b[lane * 2 + 1];
+  // pass 2: d_raw = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat*xhat))
+  float sb0 = 0.f, sb1 = 0.f;
+  if (mode == 0) {
+    for (int p = warp; p < OH * OW; p += 8) {
+      const int oy = p / OW, ox = p % OW;
+      const long long o00 = (static_cast<long long>(2 * oy) * W + 2 * ox) * C;
+      const long long offs[4] = {o00, o00 + C, o00 + static_cast<long long>(W) * C, o00 + static_cast<long long>(W) * C + C};
+      float2 f[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) f[k] = unpack2(*reinterpret_cast<const uint32_t*>(xb + offs[k]), bf16);
+      // arg-max in window scan order; first maximum wins (max_pool2d semantics)
+      int ia = 0, ib = 0;
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        if (f[k].x > f[ia].x) ia = k;
+        if (f[k].y > f[ib].y) ib = k;
+      }
+      const float2 d = unpack2(*reinterpret_cast<const uint32_t*>(dpool16 + (static_cast<long long>(n) * OH * OW + p) * C + ca), bf16);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float xa = (f[k].x - ma) * ra, xbb = (f[k].y - mb) * rb;
+        const float da = (k == ia && xa > 0.f) ? d.x : 0.f, db = (k == ib && xbb > 0.f) ? d.y : 0.f;
+        const float oa = ra * (da - mA0 - xa * mB0), obv = rb * (db - mA1 - xbb * mB1);
+        sb0 += oa; sb1 += obv;
+        *reinterpret_cast<uint32_t*>(ob + offs[k]) = pack2(oa, obv, bf16);
+      }
+    }
+  } else {
+    for (int p = warp; p < HW; p += 8) {
+      const float2 f = unpack2(*reinterpret_cast<const uint32_t*>(xb + static_cast<long long>(p) * C), bf16);
+      const float xa = (f.x - ma) * ra, xbb = (f.y - mb) * rb;
+      const float oa = ra * ((xa > 0.f ? ga : 0.f) - mA0 - xa * mB0), obv = rb * ((xbb > 0.f ? gb : 0.f) - mA1 - xbb * mB1);
+      sb0 += oa; sb1 += obv;
+      *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(p) * C) = pack2(oa, obv, bf16);
+    }
+  }
+  if (dbias != nullptr) {
+    __syncthreads();
+    red[0][warp][lane * 2] = sb0; red[0][warp][lane * 2 + 1] = sb1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a += red[0][k][threadIdx.x];
+      atomicAdd(dbias + c0 + threadIdx.x, a);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// decoder_proj1[0] weight gradient: dW[co][ci][ky][kx] += sum_{n,y,x} d_raw[n,y,x,co] * box[n,ci,y+ky-1,x+kx-1]
+// (Cin = 3 -> K = 27: a direct smem-tiled reduction, not a tensor-core shape)
+// block = 128 pixels of one sample; thread (co = tid % 64, kq = tid / 64) owns taps kq, kq+4, ...
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) exemplar_conv1_dw_kernel(const void* __restrict__ boxes, int dtype, long long sB, long long sK,
+                                                                 long long sC, long long sH, long long sW,
+                                                                 const uint16_t* __restrict__ d_raw, float* __restrict__ dw, int S,
+                                                                 int HW, int bf16) {
+  constexpr int PX = 128;
+  __shared__ float s_in[PX][28];
+  __shared__ uint16_t s_d[PX][64 + 2];
+  const int n = blockIdx.y;
+  const int b = n / S, s = n % S;
+  const int p0 = blockIdx.x * PX;
+  const int H = HW, W = HW;
+  for (int i = threadIdx.x; i < PX * 27; i += blockDim.x) {
+    const int px = i / 27, k = i % 27;
+    const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
+    const int pix = p0 + px;
+    const int yy = pix / W + ky - 1, xx = pix % W + kx - 1;
+    float v = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = load_any(boxes, b * sB + s * sK + ci * sC + yy * sH + xx * sW, dtype);
+    s_in[px][k] = v;
+  }
+  for (int i = threadIdx.x; i < PX * 64; i += blockDim.x) {
+    const int px = i / 64, co = i % 64;
+    s_d[px][co] = d_raw[(static_cast<long long>(n) * H * W + p0 + px) * 64 + co];
+  }
+  __syncthreads();
+  const int co = threadIdx.x & 63, kq = threadIdx.x >> 6;
+  float acc[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) acc[j] = 0.f;
+  for (int px = 0; px < PX; ++px) {
+    const float d = bf16 ? __uint_as_float(static_cast<uint32_t>(s_d[px][co]) << 16) : __half2float(__ushort_as_half(s_d[px][co]));
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int k = kq + 4 * j;
+      if (k < 27) acc[j] += d * s_in[px][k];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int k = kq + 4 * j;
+    if (k < 27) atomicAdd(dw + co * 27 + k, acc[j]);
+  }
+}
+
+// dw_packed [Cout][9][Cin] fp32 -> grad [Cout][Cin][3][3] fp32 (overwrite)
+__global__ void conv_dw_unpack_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int Cin) {
+  const long long n = static_cast<long long>(Cout) * Cin * 9;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long t = i;
+  const int tap = t % 9; t /= 9;
+  const int ci = t % Cin; t /= Cin;
+  const int co = static_cast<int>(t);
+  dst[i] = src[(static_cast<long long>(co) * 9 + tap) * Cin + ci];
+}
+
+}  // namespace
+}  // namespace countr
+
+using namespace countr;
+
+extern "C" int countr_upsample2x_bwd(const void* dy, int dtype, float* dx, int B, int H, int W, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(dy && dx && dtype >= 0 && dtype <= 2, "bad arguments");
+  const long long total = static_cast<long long>(B) * H * W;
+  up2_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(dy, dtype, dx, B, H, W);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+static int gn_grid(int HW, int B, dim3* grid) {
+  long long blocks = (HW + 7) / 8;
+  const long long cap = 148ll * 8 * 2;
+  if (blocks * B > cap) blocks = (cap + B - 1) / B;
+  if (blocks < 1) blocks = 1;
+  *grid = dim3(static_cast<unsigned>(blocks), B);
+  return 0;
+}
+
+extern "C" int countr_gn_relu_bwd_reduce(const void* raw, const double* stats, const float* gamma, const float* beta,
+                                         const void* d_next, const float* dmap, const float* w1, void* dyh, float* dgamma,
+                                         float* dbeta, float* dw1, float* db1, double* gsum, int B, int H, int W, int C, int G,
+                                         float eps, int bf16, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(raw && stats && gamma && beta && dyh && dgamma && dbeta && gsum, "null pointer");
+  COUNTR_REQUIRE(C == kC && G == 8, "GroupNorm backward is built for C=256, G=8 (got %d, %d)", C, G);
+  const int mode = d_next ? 0 : 1;
+  COUNTR_REQUIRE(mode == 0 || (dmap && w1 && dw1 && db1), "1x1-conv mode needs dmap, w1, dw1, db1");
+  dim3 grid;
+  gn_grid(H * W, B, &grid);
+  gn_relu_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(raw), stats, gamma, beta,
+                                                      reinterpret_cast<const uint16_t*>(d_next), dmap, w1,
+                                                      reinterpret_cast<uint16_t*>(dyh), dgamma, dbeta, dw1, db1, gsum, H, W, G, eps,
+                                                      mode, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_gn_bwd_apply(const void* raw, const void* dyh, const double* stats, const double* gsum, const float* gamma,
+                                   void* d_raw, float* dbias, int B, int HW, int C, int G, float eps, int bf16,
+                                   countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(raw && dyh && stats && gsum && gamma && d_raw && dbias, "null pointer");
+  COUNTR_REQUIRE(C == kC && G == 8, "GroupNorm backward is built for C=256, G=8 (got %d, %d)", C, G);
+  dim3 grid;
+  gn_grid(HW, B, &grid);
+  gn_bwd_apply_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(raw), reinterpret_cast<const uint16_t*>(dyh), stats,
+                                                gsum, gamma, reinterpret_cast<uint16_t*>(d_raw), dbias, HW, G, eps, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_colsum(const void* x, int dtype, float* out, int64_t R, int N, int64_t ld, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(x && out && R > 0 && N > 0 && N % 2 == 0 && ld % 2 == 0 && dtype >= 0 && dtype <= 2, "bad arguments");
+  const int col_blocks = (N / 2 + 127) / 128;
+  long long row_blocks = (148 * 4 + col_blocks - 1) / col_blocks;
+  if (row_blocks > (R + 31) / 32) row_blocks = (R + 31) / 32;
+  if (row_blocks < 1) row_blocks = 1;
+  const int rpb = static_cast<int>((R + row_blocks - 1) / row_blocks);
+  dim3 grid(col_blocks, static_cast<unsigned>((R + rpb - 1) / rpb)), block(128, 2);
+  colsum_kernel<<<grid, block, 0, stream>>>(x, dtype, out, R, N, ld, rpb);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_softmax_bwd_rows(void* s_io, void* dp_io, const float* lse, int64_t rows, int L, float scale, int bf16,
+                                       countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(s_io && dp_io && lse && rows > 0 && L % 2 == 0, "bad arguments");
+  const long long blocks = (rows + 7) / 8;
+  softmax_bwd_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(reinterpret_cast<uint16_t*>(s_io),
+                                                                            reinterpret_cast<uint16_t*>(dp_io), lse, rows, L, scale, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_cross_attn_core_bwd(const void* q16, const float* k32, const float* v32, const float* probs, const void* do16,
+                                          void* dq16, float* dk32, float* dv32, int B, int L, int S, int D, int dh, float scale,
+                                          int bf16, int kv_broadcast, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(q16 && k32 && v32 && probs && do16 && dq16 && dk32 && dv32, "null pointer");
+  COUNTR_REQUIRE(dh == 32 && D % 512 == 0 && S >= 1 && S <= kMaxShots && L % kTokPerBlock == 0,
+                 "cross-attention backward supports dh=32, D%%512==0, S<=8, L%%32==0 (dh=%d D=%d S=%d L=%d)", dh, D, S, L);
+  const size_t smem = (2ull * S * D + 2ull * kTokPerBlock * (D / 32) * S) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    COUNTR_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  COUNTR_REQUIRE(smem <= 96 * 1024, "shared memory %zu too large", smem);
+  cross_attn_core_bwd_kernel<<<B * L / kTokPerBlock, 256, smem, stream>>>(
+      reinterpret_cast<const uint16_t*>(q16), k32, v32, probs, reinterpret_cast<const uint16_t*>(do16), reinterpret_cast<uint16_t*>(dq16),
+      dk32, dv32, L, S, D, scale, kv_broadcast ? 0ll : static_cast<long long>(S) * D, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_inorm_relu_pool_bwd(const void* raw, const float* mean, const float* rstd, const void* dpool16,
+                                          const float* dpool32, void* d_raw, float* dbias, int N, int H, int W, int C, int mode,
+                                          int bf16, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(raw && mean && rstd && d_raw && (mode == 0 ? dpool16 != nullptr : dpool32 != nullptr), "null pointer");
+  COUNTR_REQUIRE(C % 64 == 0 && (mode == 1 || (H % 2 == 0 && W % 2 == 0)), "bad shape");
+  dim3 grid(C / 64, N);
+  inorm_relu_pool_bwd_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(raw), mean, rstd,
+                                                       reinterpret_cast<const uint16_t*>(dpool16), dpool32,
+                                                       reinterpret_cast<uint16_t*>(d_raw), dbias, H, W, C, mode, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_exemplar_conv1_dw(const void* boxes, int dtype, int64_t sB, int64_t sK, int64_t sC, int64_t sH, int64_t sW,
+                                        const void* d_raw, float* dw, int B, int S, int HW, int bf16, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(boxes && d_raw && dw && (HW * HW) % 128 == 0, "bad arguments");
+  dim3 grid(HW * HW / 128, B * S);
+  exemplar_conv1_dw_kernel<<<grid, 256, 0, stream>>>(boxes, dtype, sB, sK, sC, sH, sW, reinterpret_cast<const uint16_t*>(d_raw), dw, S,
+                                                     HW, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_conv_dw_unpack(const float* src, float* dst, int Cout, int Cin, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(src && dst, "null pointer");
+  const long long n = static_cast<long long>(Cout) * Cin * 9;
+  conv_dw_unpack_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(src, dst, Cout, Cin);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}

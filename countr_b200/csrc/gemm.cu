@@ -40,7 +40,8 @@ struct GemmArgs {
   int split_k, k_per_split;
   int m_tiles, n_tiles, total_tiles;
   // conv mode
-  int conv, H, W, cin_blocks, bx, by, tiles_x;
+  int conv, H, W, cin_blocks, bx, by, tiles_x;   // conv: 0 none, 1 forward/dX implicit GEMM, 2 dW (pixels are K)
+  int tiles_per_img;
   // epilogue
   void* C;
   long long ldc, sc1, sc2;
@@ -134,7 +135,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const int k_end = min(p.K, k_begin + p.k_per_split);
         const int nkb = (k_end - k_begin + BK - 1) / BK;
         int x0 = 0, y0 = 0;
-        if (p.conv) {
+        if (p.conv == 1) {
           x0 = (t.m % p.tiles_x) * p.bx;
           y0 = (t.m / p.tiles_x) * p.by;
         }
@@ -144,7 +145,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           uint8_t* sb = sa + kABytes;
           mbar_arrive_expect_tx(&full[stage], kABytes + b_bytes);
           const int k = k_begin + kb * BK;
-          if (p.conv) {
+          if (p.conv == 2) {
+            // dW: k-block = one bx x by (= 64) pixel tile of image b; A = dY (M = Cout), B = X shifted by the tap
+            const int kbg = k / BK;
+            const int b = kbg / p.tiles_per_img;
+            const int r = kbg - b * p.tiles_per_img;
+            const int px0 = (r % p.tiles_x) * p.bx, py0 = (r / p.tiles_x) * p.by;
+            const int ky = t.b2 / 3, kx = t.b2 - ky * 3;
+            tma_load_4d(sa, &tma_a, &full[stage], t.m * BM, px0, py0, b);
+            tma_load_4d(sa + 8192, &tma_a, &full[stage], t.m * BM + 64, px0, py0, b);
+            for (int i = 0; i < p.bn / 64; ++i)
+              tma_load_4d(sb + i * 8192, &tma_b, &full[stage], t.n * p.bn + i * 64, px0 + kx - 1, py0 + ky - 1, b);
+          } else if (p.conv) {
             const int tap = kb / p.cin_blocks;
             const int cb = kb - tap * p.cin_blocks;
             const int ky = tap / 3, kx = tap - ky * 3;
@@ -155,7 +167,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             tma_load_4d(sa, &tma_a, &full[stage], t.m * BM, k, t.b2, t.b1);
             tma_load_4d(sa + 8192, &tma_a, &full[stage], t.m * BM + 64, k, t.b2, t.b1);
           }
-          if (!p.b_mn) {
+          if (p.conv == 2) {
+          } else if (!p.b_mn) {
             tma_load_4d(sb, &tma_b, &full[stage], k, t.n * p.bn, p.conv ? 0 : t.b2, p.conv ? 0 : t.b1);
           } else {
             for (int i = 0; i < p.bn / 64; ++i)
@@ -224,7 +237,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       bool row_valid;
       long long row;        // logical row (for residual / aux addressing)
       long long c_off;      // element offset of (row, 0) inside C
-      if (p.conv) {
+      if (p.conv == 1) {
         const int x = (t.m % p.tiles_x) * p.bx + r_in_tile % p.bx;
         const int y = (t.m / p.tiles_x) * p.by + r_in_tile / p.bx;
         row_valid = (x < p.W) && (y < p.H);
@@ -432,7 +445,8 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   COUNTR_REQUIRE(d->a && d->b && d->c, "null operand pointer");
   COUNTR_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "bad GEMM shape M=%d N=%d K=%d", d->M, d->N, d->K);
   const int nb1 = d->nb1 > 0 ? d->nb1 : 1, nb2 = d->nb2 > 0 ? d->nb2 : 1;
-  const bool conv = d->conv_h > 0;
+  const bool conv_dw = d->conv_h > 0 && d->conv_dw != 0;
+  const bool conv = d->conv_h > 0 && !conv_dw;
   const int sms = num_sms();
   COUNTR_REQUIRE(sms > 0, "no CUDA device");
 
@@ -452,6 +466,17 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
     p.m_tiles = p.tiles_x * ((p.H + p.by - 1) / p.by);
   } else {
     p.m_tiles = (d->M + BM - 1) / BM;
+  }
+  if (conv_dw) {
+    // M = Cout, N = Cin, K = (#pixel tiles) * 64, nb2 = 9 taps; both operands MN-major NHWC
+    COUNTR_REQUIRE(d->a_mn && d->b_mn && nb2 == 9 && nb1 == 1, "conv dW mode needs MN-major operands and nb2 == 9");
+    COUNTR_REQUIRE(d->conv_bx * d->conv_by == BK, "conv dW pixel tile %dx%d must cover %d pixels", d->conv_bx, d->conv_by, BK);
+    COUNTR_REQUIRE(d->M % 64 == 0 && d->N % 64 == 0, "conv dW needs Cout, Cin multiples of 64");
+    p.conv = 2;
+    p.H = d->conv_h; p.W = d->conv_w; p.bx = d->conv_bx; p.by = d->conv_by;
+    p.tiles_x = (p.W + p.bx - 1) / p.bx;
+    p.tiles_per_img = p.tiles_x * ((p.H + p.by - 1) / p.by);
+    COUNTR_REQUIRE(d->K == d->conv_batch * p.tiles_per_img * BK, "conv dW K=%d must equal batch*tiles*64", d->K);
   }
   const int split_k = d->split_k > 1 ? d->split_k : 1;
   COUNTR_REQUIRE(split_k == 1 || (d->atomic && d->out_f32), "split_k > 1 needs atomic fp32 output");
@@ -479,11 +504,16 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   const int c_align = d->out_f32 ? 4 : 8;
   COUNTR_REQUIRE(d->ldc % c_align == 0 && (reinterpret_cast<uintptr_t>(d->c) & 15u) == 0,
                  "C must be 16-byte aligned with ldc %% %d == 0", c_align);
-  COUNTR_REQUIRE(d->gn_stats == nullptr || (conv && d->N % 32 == 0), "gn_stats needs conv mode with N %% 32 == 0");
+  COUNTR_REQUIRE(d->gn_stats == nullptr || (conv && !conv_dw && d->N % 32 == 0), "gn_stats needs conv mode with N %% 32 == 0");
 
   CUtensorMap ta, tb;
   int rc;
-  if (conv) {
+  if (conv_dw) {
+    const uint64_t dims[4] = {(uint64_t)d->M, (uint64_t)d->conv_w, (uint64_t)d->conv_h, (uint64_t)d->conv_batch};
+    const uint64_t str[4] = {1, (uint64_t)d->lda, (uint64_t)d->lda * d->conv_w, (uint64_t)d->lda * d->conv_w * d->conv_h};
+    const uint32_t box[4] = {64, (uint32_t)d->conv_bx, (uint32_t)d->conv_by, 1};
+    rc = make_tmap_4d_16b(&ta, d->a, dims, str, box, TMAP_SW_128);
+  } else if (conv) {
     const uint64_t dims[4] = {(uint64_t)d->conv_cin, (uint64_t)d->conv_w, (uint64_t)d->conv_h, (uint64_t)nb1};
     const uint64_t str[4] = {1, (uint64_t)d->lda, (uint64_t)d->lda * d->conv_w, (uint64_t)d->sa1};
     const uint32_t box[4] = {BK, (uint32_t)d->conv_bx, (uint32_t)d->conv_by, 1};
@@ -501,7 +531,12 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   }
   if (rc) return rc;
   const int bnb1 = conv ? 1 : nb1, bnb2 = conv ? 1 : nb2;
-  if (!d->b_mn) {
+  if (conv_dw) {
+    const uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->conv_w, (uint64_t)d->conv_h, (uint64_t)d->conv_batch};
+    const uint64_t str[4] = {1, (uint64_t)d->ldb, (uint64_t)d->ldb * d->conv_w, (uint64_t)d->ldb * d->conv_w * d->conv_h};
+    const uint32_t box[4] = {64, (uint32_t)d->conv_bx, (uint32_t)d->conv_by, 1};
+    rc = make_tmap_4d_16b(&tb, d->b, dims, str, box, TMAP_SW_128);
+  } else if (!d->b_mn) {
     const uint64_t dims[4] = {(uint64_t)d->K, (uint64_t)d->N, (uint64_t)bnb2, (uint64_t)bnb1};
     const uint64_t str[4] = {1, (uint64_t)d->ldb, (uint64_t)(bnb2 > 1 ? d->sb2 : d->ldb), (uint64_t)(bnb1 > 1 ? d->sb1 : d->ldb)};
     const uint32_t box[4] = {BK, (uint32_t)bn, 1, 1};

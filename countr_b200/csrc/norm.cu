@@ -75,8 +75,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ mean_in,
                                                              const float* __restrict__ rstd_in, float* __restrict__ dx,
-                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                             int rows, int D, int accumulate, int rows_per_warp) {
+                                                             uint16_t* __restrict__ dx16, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, int rows, int D, int accumulate,
+                                                             int rows_per_warp, int bf16) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   float4 dg[NV], db[NV];
@@ -113,6 +114,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
       }
       dxr[lane + 32 * i] = o;
+      if (dx16) {
+        uint2 h;
+        h.x = pack2(o.x, o.y, bf16);
+        h.y = pack2(o.z, o.w, bf16);
+        reinterpret_cast<uint2*>(dx16 + static_cast<size_t>(row) * D)[lane + 32 * i] = h;
+      }
     }
   }
   // block-level reduction of dgamma/dbeta over the 8 warps, then one atomic per column per block
@@ -166,8 +173,8 @@ extern "C" int countr_layernorm_fwd(const float* x, const float* gamma, const fl
 }
 
 extern "C" int countr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
-                                    const float* rstd, float* dx, float* dgamma, float* dbeta, int rows, int D,
-                                    int accumulate, countr_stream_t stream_) {
+                                    const float* rstd, float* dx, void* dx16, float* dgamma, float* dbeta, int rows,
+                                    int D, int accumulate, int bf16, countr_stream_t stream_) {
   using namespace countr;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(dy && x && gamma && mean && rstd && dx, "null pointer");
@@ -181,8 +188,8 @@ extern "C" int countr_layernorm_bwd(const float* dy, const float* x, const float
   const int blocks = (warps + 7) / 8;
 #define LN_CASE(NV)                                                                                       \
   case NV:                                                                                                \
-    layernorm_bwd_kernel<NV><<<blocks, 256, 0, stream>>>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, D, \
-                                                         accumulate, rpw);                                \
+    layernorm_bwd_kernel<NV><<<blocks, 256, 0, stream>>>(dy, x, gamma, mean, rstd, dx, reinterpret_cast<uint16_t*>(dx16), \
+                                                         dgamma, dbeta, rows, D, accumulate, rpw, bf16);  \
     break;
   switch (D / 128) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(8) LN_CASE(10) LN_CASE(12)

@@ -86,6 +86,9 @@ class Engine:
     def __init__(self):
         self.ws = Workspace()
         self.wc = WeightCache()
+        # optional callable(arena): averages the flat fp32 gradient arena over the data-parallel ranks
+        # (one NCCL all-reduce per step, set by the trainer / bench when WORLD_SIZE > 1)
+        self.grad_allreduce = None
 
     # ------------------------------------------------------------------ encoder
     def encoder_forward(self, m, imgs):

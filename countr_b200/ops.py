@@ -35,7 +35,7 @@ def _count(n=1):
 
 def gemm(a, b, c, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, nb1=1, nb2=1,
          sa=(0, 0), sb=(0, 0), sc=(0, 0), bias=None, act=0, aux=None, ldaux=0, residual=None, ldr=0,
-         res_mod=0, alpha=1.0, atomic=False, split_k=1, bn=0, conv=None, gn_stats=None):
+         res_mod=0, alpha=1.0, atomic=False, split_k=1, bn=0, conv=None, gn_stats=None, conv_dw=None):
     """C = epilogue(alpha * A @ B^T); see countr_gemm_desc for the layout rules."""
     assert a.dtype in (F16, BF16) and b.dtype == a.dtype
     d = GemmDesc()
@@ -49,6 +49,9 @@ def gemm(a, b, c, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, nb1=1, nb2=
     d.bn, d.split_k = bn, split_k
     if conv is not None:
         d.conv_h, d.conv_w, d.conv_cin, d.conv_bx, d.conv_by = conv
+    if conv_dw is not None:
+        d.conv_h, d.conv_w, d.conv_bx, d.conv_by, d.conv_batch = conv_dw
+        d.conv_dw = 1
     d.c = c.data_ptr()
     d.ldc, d.sc1, d.sc2 = ldc, sc[0], sc[1]
     d.out_f32 = 1 if c.dtype == torch.float32 else 0
@@ -87,6 +90,21 @@ def conv3x3(x16, w16, out, bias=None, gn_stats=None):
                 sa=(H * W * Cin, 0), sc=(H * W * Cout, 0), bias=bias, conv=(H, W, Cin, bx, by), gn_stats=gn_stats)
 
 
+def conv3x3_dw(dy16, x16, dw32, split_k=0):
+    """dw32 [Cout, 9*Cin] fp32 (tap-major, PRE-ZEROED or accumulating) += dY^T (*) X over all pixels."""
+    B, H, W, Cout = dy16.shape
+    Cin = x16.shape[-1]
+    bx = next((t for t in (64, 32, 16, 8) if W % t == 0), 8)
+    by = 64 // bx
+    tiles = ((W + bx - 1) // bx) * ((H + by - 1) // by)
+    kblocks = B * tiles
+    if split_k <= 0:
+        out_tiles = 9 * ((Cout + 127) // 128) * ((Cin + 255) // 256)
+        split_k = max(1, min(kblocks, (2 * 148) // out_tiles))
+    return gemm(dy16, x16, dw32, Cout, Cin, kblocks * 64, lda=Cout, ldb=Cin, ldc=9 * Cin, a_mn=True, b_mn=True, nb2=9,
+                sc=(0, Cin), atomic=True, split_k=split_k, conv_dw=(H, W, bx, by, B))
+
+
 def layernorm_fwd(x, gamma, beta, eps, y16=None, y32=None, mean=None, rstd=None):
     rows, D = x.shape
     check(lib().countr_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y16), _ptr(y32), _ptr(mean), _ptr(rstd),
@@ -94,10 +112,10 @@ def layernorm_fwd(x, gamma, beta, eps, y16=None, y32=None, mean=None, rstd=None)
     _count()
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma=None, dbeta=None, accumulate=False):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma=None, dbeta=None, accumulate=False, dx16=None):
     rows, D = x.shape
-    check(lib().countr_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dgamma),
-                                     _ptr(dbeta), rows, D, int(accumulate), _stream()))
+    check(lib().countr_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dx16), _ptr(dgamma),
+                                     _ptr(dbeta), rows, D, int(accumulate), _is_bf16(dx16) if dx16 is not None else 0, _stream()))
     _count()
 
 
@@ -176,3 +194,65 @@ def inorm_relu_pool(x16, mode, eps, y16=None, y32=None, mean=None, rstd=None):
 def zero_(t):
     check(lib().countr_memset_zero(_ptr(t), t.numel() * t.element_size(), _stream()))
     return t
+
+
+def upsample2x_bwd(dy, dx32):
+    B, H, W = dx32.shape
+    check(lib().countr_upsample2x_bwd(_ptr(dy), _DTYPE_CODE[dy.dtype], _ptr(dx32), B, H, W, _stream()))
+    _count()
+
+
+def gn_relu_bwd_reduce(raw16, stats, gamma, beta, dyh16, dgamma, dbeta, gsum, G, eps, d_next=None, dmap=None, w1=None,
+                       dw1=None, db1=None):
+    B, H, W, C = raw16.shape
+    check(lib().countr_gn_relu_bwd_reduce(_ptr(raw16), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(d_next), _ptr(dmap), _ptr(w1),
+                                          _ptr(dyh16), _ptr(dgamma), _ptr(dbeta), _ptr(dw1), _ptr(db1), _ptr(gsum), B, H, W, C, G,
+                                          eps, _is_bf16(raw16), _stream()))
+    _count()
+
+
+def gn_bwd_apply(raw16, dyh16, stats, gsum, gamma, d_raw16, dbias, G, eps):
+    B, H, W, C = raw16.shape
+    check(lib().countr_gn_bwd_apply(_ptr(raw16), _ptr(dyh16), _ptr(stats), _ptr(gsum), _ptr(gamma), _ptr(d_raw16), _ptr(dbias), B,
+                                    H * W, C, G, eps, _is_bf16(raw16), _stream()))
+    _count()
+
+
+def colsum(x, out32):
+    """out32[n] += sum over all leading dims of x[..., n]"""
+    N = x.shape[-1]
+    R = x.numel() // N
+    check(lib().countr_colsum(_ptr(x), _DTYPE_CODE[x.dtype], _ptr(out32), R, N, N, _stream()))
+    _count()
+
+
+def softmax_bwd_rows(s16, dp16, lse, scale):
+    L = s16.shape[-1]
+    check(lib().countr_softmax_bwd_rows(_ptr(s16), _ptr(dp16), _ptr(lse), s16.numel() // L, L, scale, _is_bf16(s16), _stream()))
+    _count()
+
+
+def cross_attn_core_bwd(q16, k32, v32, probs, do16, dq16, dk32, dv32, B, L, S, D, dh, scale, kv_broadcast=False):
+    check(lib().countr_cross_attn_core_bwd(_ptr(q16), _ptr(k32), _ptr(v32), _ptr(probs), _ptr(do16), _ptr(dq16), _ptr(dk32),
+                                           _ptr(dv32), B, L, S, D, dh, scale, _is_bf16(q16), int(kv_broadcast), _stream()))
+    _count()
+
+
+def inorm_relu_pool_bwd(raw16, mean, rstd, d_raw16, mode, dpool16=None, dpool32=None, dbias=None):
+    N, H, W, C = raw16.shape
+    check(lib().countr_inorm_relu_pool_bwd(_ptr(raw16), _ptr(mean), _ptr(rstd), _ptr(dpool16), _ptr(dpool32), _ptr(d_raw16),
+                                           _ptr(dbias), N, H, W, C, mode, _is_bf16(raw16), _stream()))
+    _count()
+
+
+def exemplar_conv1_dw(boxes, S, d_raw16, dw32):
+    B, K, C, H, W = boxes.shape
+    sB, sK, sC, sH, sW = boxes.stride()
+    check(lib().countr_exemplar_conv1_dw(_ptr(boxes), _DTYPE_CODE[boxes.dtype], sB, sK, sC, sH, sW, _ptr(d_raw16), _ptr(dw32), B, S,
+                                         H, _is_bf16(d_raw16), _stream()))
+    _count()
+
+
+def conv_dw_unpack(src32, dst32, Cout, Cin):
+    check(lib().countr_conv_dw_unpack(_ptr(src32), _ptr(dst32), Cout, Cin, _stream()))
+    _count()

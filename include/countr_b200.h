@@ -54,6 +54,12 @@ int countr_memset_zero(void* ptr, size_t bytes, countr_stream_t stream);
  * TMA boxes (zero-filled halo = padding 1); B is the weight as [N=Cout][9*Cin] with k ordered
  * (ky, kx, cin); M tiles are conv_bx x conv_by pixel rectangles (bx*by == 128); C is NHWC
  * [B][H][W][ldc].
+ *
+ * conv weight-gradient mode (conv_h > 0 && conv_dw != 0): dW[co][tap][ci] += sum over pixels of
+ * dY[b,y,x,co] * X[b,y+ky-1,x+kx-1,ci].  A = dY NHWC [conv_batch][H][W][M=Cout] (lda = Cout),
+ * B = X NHWC [conv_batch][H][W][N=Cin] (ldb = Cin), both read as MN-major 64-pixel TMA boxes
+ * (conv_bx*conv_by == 64, B shifted by the tap); K = conv_batch * pixel_tiles * 64, nb2 = 9 taps,
+ * sc2 = Cin, ldc = 9*Cin, fp32 atomic output (split_k over the pixel tiles).
  * ------------------------------------------------------------------------------------------ */
 typedef struct countr_gemm_desc {
   const void* a;
@@ -69,6 +75,7 @@ typedef struct countr_gemm_desc {
   int32_t split_k; /* >= 1; > 1 requires atomic == 1 */
   /* conv mode */
   int32_t conv_h, conv_w, conv_cin, conv_bx, conv_by;
+  int32_t conv_dw, conv_batch; /* conv_dw != 0: weight-gradient mode, see below */
   /* epilogue */
   void* c;
   int64_t ldc, sc1, sc2;
@@ -98,10 +105,11 @@ int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream);
 int countr_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y16, float* y32,
                          float* mean, float* rstd, int rows, int D, float eps, int bf16,
                          countr_stream_t stream);
-/* dx (+)= LN'(dy); dgamma/dbeta (optional, pre-zeroed or carrying earlier contributions) += */
+/* dx (+)= LN'(dy); dx16 (optional) = 16-bit copy of the updated dx (next GEMM's operand);
+ * dgamma/dbeta (optional, pre-zeroed or carrying earlier contributions) += */
 int countr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
-                         const float* rstd, float* dx, float* dgamma, float* dbeta, int rows, int D,
-                         int accumulate, countr_stream_t stream);
+                         const float* rstd, float* dx, void* dx16, float* dgamma, float* dbeta, int rows, int D,
+                         int accumulate, int bf16, countr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused multi-head self-attention forward: softmax(scale * Q K^T) V, flash-style on tcgen05.
@@ -167,6 +175,45 @@ int countr_exemplar_conv1(const void* boxes, int dtype, int64_t sB, int64_t sK, 
  * AdaptiveAvgPool2d(1) (mode 1 -> y32 [N][C] and/or y16 [N][C]); mean/rstd [N][C] optional */
 int countr_inorm_relu_pool(const void* x, void* y16, float* y32, float* mean, float* rstd, int N, int H, int W, int C,
                            float eps, int mode, int bf16, countr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Backward-only kernels of the fine-tune step (autograd call sites listed in SURVEY.md §2.3).
+ * ------------------------------------------------------------------------------------------ */
+/* upsample_bilinear2d_backward of the last F.interpolate (models_mae_cross.py:195-196):
+ * dy [B][2H][2W] (dtype code) -> dx fp32 [B][H][W] */
+int countr_upsample2x_bwd(const void* dy, int dtype, float* dx, int B, int H, int W, countr_stream_t stream);
+/* GroupNorm(8,256)+ReLU backward, pass A.  The incoming gradient is either the bilinear-x2 adjoint
+ * of d_next [B][2H][2W][C] (stages 0-2) or dmap[b][p]*w1[c] (Conv2d 1x1 of decode_head3, then
+ * dw1/db1 are accumulated too).  Writes dyh = dz*1[y>0]; accumulates dgamma/dbeta [C] and the
+ * per-(image,group) sums gsum [B][G][2]. */
+int countr_gn_relu_bwd_reduce(const void* raw, const double* stats, const float* gamma, const float* beta,
+                              const void* d_next, const float* dmap, const float* w1, void* dyh, float* dgamma,
+                              float* dbeta, float* dw1, float* db1, double* gsum, int B, int H, int W, int C, int G,
+                              float eps, int bf16, countr_stream_t stream);
+/* pass B: d_raw (gradient w.r.t. the conv output) and the conv bias gradient dbias [C] += */
+int countr_gn_bwd_apply(const void* raw, const void* dyh, const double* stats, const double* gsum, const float* gamma,
+                        void* d_raw, float* dbias, int B, int HW, int C, int G, float eps, int bf16,
+                        countr_stream_t stream);
+/* out[n] += sum_r x[r][n]  (Linear bias gradients); dtype code of x: 0 fp32, 1 fp16, 2 bf16 */
+int countr_colsum(const void* x, int dtype, float* out, int64_t R, int N, int64_t ld, countr_stream_t stream);
+/* _softmax_backward_data on materialised rows (self-attention backward of the FIM):
+ * in place S <- P = exp(S - lse), dP <- dS = scale * P * (dP - sum_j P_j dP_j) */
+int countr_softmax_bwd_rows(void* s_io, void* dp_io, const float* lse, int64_t rows, int L, float scale, int bf16,
+                            countr_stream_t stream);
+/* backward of countr_cross_attn_core: dq16 [B*L][D]; dk32/dv32 [B][S][D] (or [S][D]) += */
+int countr_cross_attn_core_bwd(const void* q16, const float* k32, const float* v32, const float* probs, const void* do16,
+                               void* dq16, float* dk32, float* dv32, int B, int L, int S, int D, int dh, float scale,
+                               int bf16, int kv_broadcast, countr_stream_t stream);
+/* backward of countr_inorm_relu_pool (InstanceNorm + ReLU + MaxPool2d(2) | avg-pool);
+ * dbias [C] (optional) += sum d_raw = gradient of the preceding conv bias */
+int countr_inorm_relu_pool_bwd(const void* raw, const float* mean, const float* rstd, const void* dpool16,
+                               const float* dpool32, void* d_raw, float* dbias, int N, int H, int W, int C, int mode,
+                               int bf16, countr_stream_t stream);
+/* decoder_proj1[0] weight gradient dw [64][3][3][3] += (direct reduction, K = 27) */
+int countr_exemplar_conv1_dw(const void* boxes, int dtype, int64_t sB, int64_t sK, int64_t sC, int64_t sH, int64_t sW,
+                             const void* d_raw, float* dw, int B, int S, int HW, int bf16, countr_stream_t stream);
+/* [Cout][9][Cin] (implicit-GEMM dW layout) -> Conv2d.weight.grad layout [Cout][Cin][3][3] */
+int countr_conv_dw_unpack(const float* src, float* dst, int Cout, int Cin, countr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,9 @@ def cuda():
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    # the torch references must be real fp32 (TF32 would be less accurate than the kernels under test)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     from countr_b200 import _lib
     _lib.require_device()  # raises if the .so is missing or the device is not sm_100
     return torch.device("cuda:0")
