@@ -235,7 +235,7 @@ def test_decoder_gradients_match_oracle_and_golden(cuda, shot):
             if e > worst[0]:
                 worst = (e, n)
     total = (num / den) ** 0.5
-    lref = float(g[f"loss_s{shot}"])
+    lref = float(np.load(os.path.join(GOLD, "small_fwd.npz"))[f"loss_s{shot}"])
     print(f"\n[grad parity small shot={shot}] loss rel={abs(loss.item() - lref) / lref:.1e} "
           f"all-grads relL2={total:.3e} worst param {worst[1]} relL2={worst[0]:.3e}")
     assert abs(loss.item() - lref) / lref < 2e-3
