@@ -26,7 +26,7 @@ def _dw_linear(dy16, x16, dw32):
     k_in = x16.shape[1]
     out_tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
     kblocks = (Mtok + 63) // 64
-    split = max(1, min(kblocks, (2 * 148) // max(1, out_tiles)))
+    split = max(1, min(kblocks, 148 // max(1, out_tiles)))
     ops.gemm(dy16, x16, dw32, n_out, k_in, Mtok, lda=dy16.stride(0), ldb=x16.stride(0), ldc=k_in, a_mn=True, b_mn=True,
              atomic=True, split_k=split)
 

@@ -29,7 +29,8 @@ constexpr uint32_t kABytes = BM * BK * 2;       // 16 KB
 constexpr uint32_t kBBytes = kMaxBN * BK * 2;   // 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                     // 2 per TMEM lane quarter: they split the 32-column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 
 struct GemmArgs {
   int M, N, K;
@@ -112,7 +113,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -229,6 +230,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   } else {
     // ------------------------------- epilogue -------------------------------
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
+    const int egroup = (warp - 2) >> 2;  // which share of the column chunks this warp drains
     const int r_in_tile = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -255,7 +257,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kMaxBN;
 
-      for (int c = 0; c < p.bn / 32; ++c) {
+      for (int c = egroup; c < p.bn / 32; c += kEpiWarps / 4) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c * 32, r);
         tmem_ld_wait();
@@ -361,9 +363,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           if (p.out_f32) {
             float* cp = reinterpret_cast<float*>(p.C) + c_off + col0;
             if (p.atomic) {
+              if (full32) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) atomicAdd(cp + j, v[j]);
+                for (int j = 0; j < 32; j += 4)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + j), "f"(v[j]), "f"(v[j + 1]),
+                               "f"(v[j + 2]), "f"(v[j + 3])
+                               : "memory");
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) atomicAdd(cp + j, v[j]);
+              }
             } else if (full32) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)

@@ -100,7 +100,7 @@ def conv3x3_dw(dy16, x16, dw32, split_k=0):
     kblocks = B * tiles
     if split_k <= 0:
         out_tiles = 9 * ((Cout + 127) // 128) * ((Cin + 255) // 256)
-        split_k = max(1, min(kblocks, (2 * 148) // out_tiles))
+        split_k = max(1, min(kblocks, 148 // out_tiles))
     return gemm(dy16, x16, dw32, Cout, Cin, kblocks * 64, lda=Cout, ldb=Cin, ldc=9 * Cin, a_mn=True, b_mn=True, nb2=9,
                 sc=(0, Cin), atomic=True, split_k=split_k, conv_dw=(H, W, bx, by, B))
 

@@ -1,0 +1,109 @@
+"""Device-time microbenchmark of the GEMM / conv / attention kernels on the shapes of the B=8 fine-tune step."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from countr_b200 import ops
+
+dev = torch.device("cuda:0")
+B = int(os.environ.get("B", "8"))
+M = B * 576
+
+
+def timeit(fn, reps=20):
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3  # us
+
+
+def lin(name, m, n, k, mode, bn=0):
+    a = torch.randn(m, k, device=dev).half()
+    w = torch.randn(n, k, device=dev).half() * 0.05
+    bias = torch.zeros(n, device=dev)
+    if mode == "f16":
+        c = torch.empty(m, n, device=dev, dtype=torch.float16)
+        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, bn=bn)
+    elif mode == "gelu":
+        c = torch.empty(m, n, device=dev, dtype=torch.float16)
+        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, act=1, bn=bn)
+    elif mode == "gelubwd":
+        c = torch.empty(m, n, device=dev, dtype=torch.float16)
+        aux = torch.randn(m, n, device=dev).half()
+        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, act=2, aux=aux, ldaux=n, bn=bn)
+    elif mode == "res":
+        c = torch.zeros(m, n, device=dev)
+        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, residual=c, ldr=n, bn=bn)
+    elif mode == "f32":
+        c = torch.zeros(m, n, device=dev)
+        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bn=bn)
+    us = timeit(f)
+    print(f"{name:28s} M={m:6d} N={n:5d} K={k:5d} {mode:8s} bn={bn:3d}: {us:8.1f} us  {2.0*m*n*k/us/1e6:7.1f} TFLOP/s")
+
+
+def dw(name, m_tok, n_out, k_in, split):
+    dy = torch.randn(m_tok, n_out, device=dev).half()
+    x = torch.randn(m_tok, k_in, device=dev).half()
+    c = torch.zeros(n_out, k_in, device=dev)
+    f = lambda: ops.gemm(dy, x, c, n_out, k_in, m_tok, lda=n_out, ldb=k_in, ldc=k_in, a_mn=True, b_mn=True, atomic=True, split_k=split)
+    us = timeit(f)
+    print(f"{name:28s} dW [{n_out}x{k_in}] over {m_tok} split={split:2d}: {us:8.1f} us  {2.0*m_tok*n_out*k_in/us/1e6:7.1f} TFLOP/s")
+
+
+def conv(name, h, cin, cout):
+    x = torch.randn(B, h, h, cin, device=dev).half()
+    w = torch.randn(cout, 9 * cin, device=dev).half() * 0.02
+    y = torch.empty(B, h, h, cout, device=dev, dtype=torch.float16)
+    bias = torch.zeros(cout, device=dev)
+    stats = torch.zeros(B, cout // 32, 2, device=dev, dtype=torch.float64)
+    us = timeit(lambda: ops.conv3x3(x, w, y, bias=bias, gn_stats=stats))
+    fl = 2.0 * B * h * h * cout * 9 * cin
+    dyv = torch.randn(B, h, h, cout, device=dev).half()
+    dwp = torch.zeros(cout, 9 * cin, device=dev)
+    us2 = timeit(lambda: ops.conv3x3_dw(dyv, x, dwp))
+    print(f"{name:28s} conv {h}x{h} {cin}->{cout}: fwd {us:8.1f} us {fl/us/1e6:7.1f} TF | dW {us2:8.1f} us {fl/us2/1e6:7.1f} TF")
+
+
+def attn(name, H, dh):
+    qkv = torch.randn(B, 576, 3, H, dh, device=dev).half()
+    out = torch.empty(B, 576, H * dh, device=dev, dtype=torch.float16)
+    us = timeit(lambda: ops.attention_fwd(qkv, out, B, 576, H, dh, dh ** -0.5))
+    print(f"{name:28s} attention H={H} dh={dh}: {us:8.1f} us  {4.0*B*H*576*576*dh/us/1e6:7.1f} TFLOP/s")
+
+
+print(f"B={B}")
+lin("enc qkv", M, 2304, 768, "f16")
+lin("enc proj (+res)", M, 768, 768, "res")
+lin("enc proj (+res) bn=96", M, 768, 768, "res", 96)
+lin("enc proj (+res) bn=128", M, 768, 768, "res", 128)
+lin("enc proj (+res) bn=256", M, 768, 768, "res", 256)
+lin("enc fc1 (gelu)", M, 3072, 768, "gelu")
+lin("enc fc1 (gelu) bn=256", M, 3072, 768, "gelu", 256)
+lin("enc fc1 (gelu) bn=128", M, 3072, 768, "gelu", 128)
+lin("enc fc2 (+res)", M, 768, 3072, "res")
+lin("enc fc2 (+res) bn=128", M, 768, 3072, "res", 128)
+lin("enc qkv bn=256", M, 2304, 768, "f16", 256)
+lin("enc qkv bn=128", M, 2304, 768, "f16", 128)
+lin("fim qkv", M, 1536, 512, "f16")
+lin("fim proj (+res)", M, 512, 512, "res")
+lin("fim fc1 (gelu)", M, 2048, 512, "gelu")
+lin("fim fc2 (+res)", M, 512, 2048, "res")
+lin("fim fc2 dX (gelu bwd)", M, 2048, 512, "gelubwd")
+lin("fim fc1 dX (f32)", M, 512, 2048, "f32")
+lin("big square", 8192, 8192, 8192, "f16", 256)
+for sp in (1, 2, 4, 9):
+    dw("fim fc2 dW", M, 512, 2048, sp)
+dw("fim proj dW", M, 512, 512, 9)
+dw("fim proj dW", M, 512, 512, 4)
+dw("fim qkv dW", M, 1536, 512, 3)
+conv("head0", 24, 512, 256)
+conv("head1", 48, 256, 256)
+conv("head2", 96, 256, 256)
+conv("head3", 192, 256, 256)
+attn("encoder", 12, 64)
+attn("fim", 16, 32)

@@ -220,7 +220,7 @@ def test_decoder_gradients_match_oracle_and_golden(cuda, shot):
     # the overall gradient scale.
     all_ref = torch.cat([sd[n].grad.flatten().double() for n in names])
     floor = 1e-5 * all_ref.norm().item()
-    worst, num, den = (0.0, ""), 0.0, 0.0
+    num, den, table = 0.0, 0.0, []
     for n, p in m.named_parameters():
         if p.grad is None:
             continue
@@ -228,15 +228,21 @@ def test_decoder_gradients_match_oracle_and_golden(cuda, shot):
         ref = sd[n].grad.double()
         num += (got - ref).pow(2).sum().item()
         den += ref.pow(2).sum().item()
-        ref_norm = float(g[f"s{shot}/{n}/norm"])
-        assert abs(got.norm().item() - ref_norm) <= 3e-2 * ref_norm + floor, (n, got.norm().item(), ref_norm)
-        if ref.norm().item() > 10 * floor:
-            e = ((got - ref).norm() / ref.norm()).item()
-            if e > worst[0]:
-                worst = (e, n)
+        table.append((n, ref.norm().item(), (got - ref).norm().item(), float(g[f"s{shot}/{n}/norm"])))
     total = (num / den) ** 0.5
     lref = float(np.load(os.path.join(GOLD, "small_fwd.npz"))[f"loss_s{shot}"])
-    print(f"\n[grad parity small shot={shot}] loss rel={abs(loss.item() - lref) / lref:.1e} "
-          f"all-grads relL2={total:.3e} worst param {worst[1]} relL2={worst[0]:.3e}")
+    # per-parameter: error relative to the parameter's own gradient norm, with a floor tied to the overall
+    # gradient scale (wk.bias shifts every exemplar logit equally -> softmax-invariant -> true gradient 0)
+    worst = max(table, key=lambda t: t[2] / (t[1] + floor))
+    out_dir = os.path.join(os.path.dirname(GOLD), "..", "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, f"grad_parity_s{shot}.txt"), "w") as f:
+            for t in sorted(table, key=lambda t: -t[2] / (t[1] + floor)):
+                f.write(f"{t[0]:48s} ref_norm={t[1]:.3e} err_norm={t[2]:.3e} rel={t[2] / (t[1] + floor):.3e} golden_norm={t[3]:.3e}\n")
+    print(f"\n[grad parity small shot={shot}] loss rel={abs(loss.item() - lref) / lref:.1e} all-grads relL2={total:.3e} "
+          f"worst param {worst[0]} rel={worst[2] / (worst[1] + floor):.3e}")
     assert abs(loss.item() - lref) / lref < 2e-3
-    assert total < 1e-2 and worst[0] < 5e-2
+    assert total < 1e-2
+    for n, ref_norm, err_norm, gold_norm in table:
+        assert abs(ref_norm - gold_norm) <= 1e-3 * gold_norm + floor, n          # oracle autograd == reference autograd
+        assert err_norm <= 5e-2 * ref_norm + 20 * floor, (n, ref_norm, err_norm)
