@@ -6,7 +6,7 @@
 // transpose/reshape) for both the ViT encoder blocks (dh=64, H=12) and the FIM self-attention
 // (dh=32, H=16).  The [B,H,L,L] score tensor the reference materialises never leaves the SM.
 //
-// One CTA (4 warps) = one (batch, head, 128-query tile).  K/V are streamed in 128-key chunks by
+// One CTA (8 warps) = one (batch, head, 128-query tile).  K/V are streamed in 128-key chunks by
 // TMA straight out of the packed qkv GEMM output [B][L][3][H][dh] (no permute / copy):
 //   S  = Q K_c^T        tcgen05.mma  (A,B K-major in smem)      -> TMEM columns [64,192)
 //   P  = exp2(S*c - m)  thread == row, online max/sum in fp32   -> smem (fp16, SWIZZLE_128B)
@@ -22,7 +22,7 @@ namespace {
 
 constexpr int BQ = 128;   // query rows per CTA
 constexpr int KC = 128;   // keys per chunk
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
 constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kTmemS = 64;  // S starts at this column; O occupies [0, dh)
 
@@ -37,7 +37,8 @@ struct AttnSmem {
   static constexpr uint32_t kOffV = kOffK + kKBytes;
   static constexpr uint32_t kOffP = kOffV + kKBytes;
   static constexpr uint32_t kOffBar = kOffP + kPBytes;
-  static constexpr uint32_t kTotal = kOffBar + 64 + 1024;
+  static constexpr uint32_t kOffXchg = kOffBar + 64;                 // [2][BQ] floats: row max / row sum exchange
+  static constexpr uint32_t kTotal = kOffXchg + 2 * BQ * 4 + 1024;
 };
 
 // shared-memory matrix descriptor with explicit swizzle mode (2 = 128B, 4 = 64B)
@@ -69,6 +70,16 @@ struct AttnArgs {
   int q_tiles;
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 8 warps: warp w owns TMEM lane quarter (w & 3) — i.e. query rows 32*(w&3) .. +31 — and the column half
+// (w >> 2) of every 128-key chunk.  The two threads that share a row exchange their partial row maximum /
+// row sum through shared memory.  Twice the warps per SM of a thread-per-row design: the softmax is
+// latency-bound (MUFU + dependent FMAs), so it needs the extra warps to keep the issue slots busy.
 template <int DH>
 __global__ void __launch_bounds__(kThreads, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
@@ -77,6 +88,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   constexpr uint32_t kLayout = DH == 64 ? 2u : 4u;            // SWIZZLE_128B : SWIZZLE_64B
   constexpr uint32_t kSboK = DH == 64 ? 1024u : 512u;         // 8 rows of the K-major tiles
   constexpr uint32_t kVStep = 16 * SM::kRowBytes;             // 16 key rows per k-step of P.V
+  constexpr int kOHalf = DH / 2;                              // O columns rescaled / written per thread
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -90,9 +102,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   uint64_t* bar_s = bar_q + 3;
   uint64_t* bar_o = bar_q + 4;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_q + 5);
+  float* xchg = reinterpret_cast<float*>(smem + SM::kOffXchg);   // [2][BQ]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
+  const int quarter = warp & 3, half = warp >> 2;
   const int qt = blockIdx.x % p.q_tiles;
   const int h = (blockIdx.x / p.q_tiles) % p.H;
   const int b = blockIdx.x / (p.q_tiles * p.H);
@@ -114,7 +128,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_q, SM::kQBytes);
@@ -126,9 +140,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   const uint32_t idesc_s = make_idesc_f16(BQ, KC, false, false, p.bf16 != 0);
   const uint32_t idesc_o = make_idesc_f16(BQ, DH, false, true, p.bf16 != 0);
 
-  float m_run = -INFINITY;  // running max (log2 domain, already scaled)
-  float l_run = 0.f;        // running sum
-  const int row = warp * 32 + (tid & 31);
+  float m_run = -INFINITY;  // running max (log2 domain, already scaled) — identical in both threads of a row
+  float l_run = 0.f;        // running sum over this thread's columns
+  const int row = quarter * 32 + (tid & 31);
 
   for (int c = 0; c < nchunks; ++c) {
     const int valid = min(KC, p.L - c * KC);          // keys in this chunk
@@ -158,60 +172,84 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       }
     }
 
-    // ---- pass 1: row maximum of this chunk ----
+    // ---- pass 1: maximum over this thread's 64 columns, then over the row ----
     float mx = -INFINITY;
-    for (int g = 0; g < groups; ++g) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(t_lane + kTmemS + g * 32, r);
-      tmem_ld_wait();
-      const int lim = valid - g * 32;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < lim) mx = fmaxf(mx, __uint_as_float(r[j]));
+    for (int gi = 0; gi < 2; ++gi) {
+      const int g = half * 2 + gi;
+      if (g < groups) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_lane + kTmemS + g * 32, r);
+        tmem_ld_wait();
+        const int lim = valid - g * 32;
+        if (lim >= 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < lim) mx = fmaxf(mx, __uint_as_float(r[j]));
+        }
+      }
     }
+    xchg[half * BQ + row] = mx;
+    __syncthreads();
+    mx = fmaxf(mx, xchg[(half ^ 1) * BQ + row]);
     const float m_new = fmaxf(m_run, mx * p.scale_log2);
-    const float corr = exp2f(m_run - m_new);  // 0 on the first chunk (m_run = -inf)
+    const float corr = ex2_approx(m_run - m_new);  // 0 on the first chunk (m_run = -inf)
     m_run = m_new;
 
-    // ---- pass 2: P = exp2(S*c - m), row sum, fp16 P tile into swizzled smem ----
+    // ---- pass 2: P = exp2(S*c - m), partial row sum, fp16 P tile into swizzled smem ----
     float lsum = 0.f;
-    for (int g = 0; g < groups; ++g) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(t_lane + kTmemS + g * 32, r);
-      tmem_ld_wait();
-      const int lim = valid - g * 32;
-      float pv[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float e = exp2f(fmaf(__uint_as_float(r[j]), p.scale_log2, -m_new));
-        pv[j] = (j < lim) ? e : 0.f;
-        lsum += pv[j];
-      }
-      // group g covers key columns [32g, 32g+32) = 16-byte chunks (g&1)*4 .. +3 of column block g>>1
-      uint8_t* prow = sP + (g >> 1) * (BQ * 128) + (row >> 3) * 1024 + (row & 7) * 128;
+    for (int gi = 0; gi < 2; ++gi) {
+      const int g = half * 2 + gi;
+      if (g < groups) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_lane + kTmemS + g * 32, r);
+        tmem_ld_wait();
+        const int lim = valid - g * 32;
+        float pv[32];
+        if (lim >= 32) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 o;
-        o.x = pack2(pv[8 * q + 0], pv[8 * q + 1], p.bf16);
-        o.y = pack2(pv[8 * q + 2], pv[8 * q + 3], p.bf16);
-        o.z = pack2(pv[8 * q + 4], pv[8 * q + 5], p.bf16);
-        o.w = pack2(pv[8 * q + 6], pv[8 * q + 7], p.bf16);
-        const int chunk16 = (g & 1) * 4 + q;
-        *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (row & 7)) << 4)) = o;
+          for (int j = 0; j < 32; ++j) {
+            pv[j] = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -m_new));
+            lsum += pv[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float e = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -m_new));
+            pv[j] = (j < lim) ? e : 0.f;
+            lsum += pv[j];
+          }
+        }
+        // group g covers key columns [32g, 32g+32) = 16-byte chunks (g&1)*4 .. +3 of column block g>>1
+        uint8_t* prow = sP + (g >> 1) * (BQ * 128) + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack2(pv[8 * q + 0], pv[8 * q + 1], p.bf16);
+          o.y = pack2(pv[8 * q + 2], pv[8 * q + 3], p.bf16);
+          o.z = pack2(pv[8 * q + 4], pv[8 * q + 5], p.bf16);
+          o.w = pack2(pv[8 * q + 6], pv[8 * q + 7], p.bf16);
+          const int chunk16 = (g & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (row & 7)) << 4)) = o;
+        }
       }
     }
     l_run = l_run * corr + lsum;
 
-    // ---- rescale the running output (TMEM) when the maximum moved ----
+    // ---- rescale this thread's half of the running output (TMEM) when the maximum moved ----
     if (c > 0) {
 #pragma unroll
-      for (int d0 = 0; d0 < DH; d0 += 16) {
+      for (int d0 = 0; d0 < kOHalf; d0 += 16) {
         uint32_t r[16];
-        tmem_ld_32x32b_x16(t_lane + d0, r);
+        tmem_ld_32x32b_x16(t_lane + half * kOHalf + d0, r);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * corr);
-        tmem_st_32x32b_x16(t_lane + d0, r);
+        tmem_st_32x32b_x16(t_lane + half * kOHalf + d0, r);
       }
       tmem_st_wait();
     }
@@ -233,16 +271,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
     }
   }
 
-  // ---- epilogue: O / l -> 16-bit, one contiguous dh-wide row segment per thread ----
+  // ---- epilogue: O / l -> 16-bit; each thread writes its half of the dh-wide row segment ----
+  xchg[half * BQ + row] = l_run;
+  __syncthreads();
+  const float l_tot = l_run + xchg[(half ^ 1) * BQ + row];
   mbar_wait(bar_o, 0);
   tc_fence_after();
-  const float inv_l = 1.f / l_run;
+  const float inv_l = 1.f / l_tot;
   const int q = q0 + row;
-  uint16_t* orow = p.out + (static_cast<long long>(b) * p.L + q) * (p.H * DH) + h * DH;
+  uint16_t* orow = p.out + (static_cast<long long>(b) * p.L + q) * (p.H * DH) + h * DH + half * kOHalf;
 #pragma unroll
-  for (int d0 = 0; d0 < DH; d0 += 16) {
+  for (int d0 = 0; d0 < kOHalf; d0 += 16) {
     uint32_t r[16];
-    tmem_ld_32x32b_x16(t_lane + d0, r);
+    tmem_ld_32x32b_x16(t_lane + half * kOHalf + d0, r);
     tmem_ld_wait();
     if (q < p.L) {
       uint4 o0, o1;
@@ -258,8 +299,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       *reinterpret_cast<uint4*>(orow + d0 + 8) = o1;
     }
   }
-  if (p.lse != nullptr && q < p.L)
-    p.lse[(static_cast<long long>(b) * p.H + h) * p.L + q] = (m_run + log2f(l_run)) * 0.69314718055994531f;
+  if (p.lse != nullptr && q < p.L && half == 0)
+    p.lse[(static_cast<long long>(b) * p.H + h) * p.L + q] = (m_run + log2f(l_tot)) * 0.69314718055994531f;
 
   tc_fence_before();
   __syncthreads();

@@ -253,6 +253,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const int n0 = t.n * p.bn;
       const bool first_split = (t.s == 0);
 
+      // The residual does not depend on the MMA: fetch this warp's first chunk of it BEFORE waiting for the
+      // accumulator, and each following chunk one iteration ahead, so the (row-strided, ~1 us) global-load
+      // latency hides behind the main loop instead of serialising the epilogue.
+      const bool use_res = p.residual != nullptr && first_split && row_valid;
+      const float* res_row = nullptr;
+      if (use_res) res_row = p.residual + (p.res_mod > 0 ? (row % p.res_mod) : row) * p.ldr;
+      float4 rpre[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rpre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (use_res && n0 + egroup * 32 + 32 <= p.N && egroup < p.bn / 32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rpre[j] = *reinterpret_cast<const float4*>(res_row + n0 + egroup * 32 + 4 * j);
+      }
+
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kMaxBN;
@@ -260,6 +274,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       for (int c = egroup; c < p.bn / 32; c += kEpiWarps / 4) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c * 32, r);
+        float4 rcur[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rcur[j] = rpre[j];
+        {
+          const int cn = c + kEpiWarps / 4;
+          if (use_res && cn < p.bn / 32 && n0 + cn * 32 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rpre[j] = *reinterpret_cast<const float4*>(res_row + n0 + cn * 32 + 4 * j);
+          }
+        }
         tmem_ld_wait();
         const int col0 = n0 + c * 32;
         const int ncols = min(32, p.N - col0);
@@ -344,14 +368,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
           }
 
-          if (p.residual != nullptr && first_split) {
-            const long long rr = p.res_mod > 0 ? (row % p.res_mod) : row;
-            const float* rp = p.residual + rr * p.ldr + col0;
+          if (use_res) {
+            const float* rp = res_row + col0;
             if (full32) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 x = *reinterpret_cast<const float4*>(rp + j);
-                v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] += rcur[j].x; v[4 * j + 1] += rcur[j].y; v[4 * j + 2] += rcur[j].z; v[4 * j + 3] += rcur[j].w;
               }
             } else {
 #pragma unroll

@@ -113,23 +113,42 @@ def forward_encoder(sd, cfg, imgs):
     return layer_norm(x, sd, "norm", cfg["eps"])                                          # :146
 
 
-def exemplar_encoder(sd, boxes_one_shot):
+class _Round16STE(torch.autograd.Function):
+    """fp16 storage rounding with a straight-through gradient.  Test aid only: lets the oracle mimic
+    the 16-bit activation storage of the reference's fp16-autocast training (FSC_finetune_cross.py:286)
+    at chosen points, so gradients that are routed by max-pool arg-max / ReLU masks can be compared
+    against a reference that takes the same routing decisions."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.half().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def exemplar_encoder(sd, boxes_one_shot, round16=False):
     """decoder_proj1..4, models_mae_cross.py:47-71: conv3x3 -> InstanceNorm2d (no affine, eps 1e-5)
     -> ReLU -> MaxPool2d(2) x3, last stage AdaptiveAvgPool2d(1)."""
     y = boxes_one_shot
     for i in (1, 2, 3, 4):
         y = F.conv2d(y, sd[f"decoder_proj{i}.0.weight"], sd[f"decoder_proj{i}.0.bias"], padding=1)
+        if round16:
+            y = _Round16STE.apply(y)
         y = F.relu(F.instance_norm(y, eps=1e-5))
         y = F.max_pool2d(y, 2) if i < 4 else y.mean((2, 3), keepdim=True)
+        if round16 and i < 4:
+            y = _Round16STE.apply(y)
     return y.squeeze(-1).squeeze(-1)
 
 
-def forward_decoder(sd, cfg, latent, boxes, shot_num, taps=None):
+def forward_decoder(sd, cfg, latent, boxes, shot_num, taps=None, exemplar_round16=False):
     """models_mae_cross.py:150-199."""
     x = linear(latent, sd, "decoder_embed") + sd["decoder_pos_embed"]                     # :152-154
     N = latent.shape[0]
     if shot_num > 0:
-        ys = [exemplar_encoder(sd, boxes[:, s]) for s in range(shot_num)]                 # :157-171 (first shot_num boxes)
+        ys = [exemplar_encoder(sd, boxes[:, s], exemplar_round16) for s in range(shot_num)]                 # :157-171 (first shot_num boxes)
         y = torch.stack(ys, 0).transpose(0, 1)                                            # :174,177 -> [N, S, C]
     else:
         y = sd["shot_token"].repeat(N, 1).unsqueeze(0).transpose(0, 1)                    # :176-177 -> [N, 1, C]
@@ -152,13 +171,13 @@ def forward_decoder(sd, cfg, latent, boxes, shot_num, taps=None):
     return x.squeeze(-3)                                                                  # :197
 
 
-def forward(sd, cfg, imgs, boxes, shot_num, taps=None):
+def forward(sd, cfg, imgs, boxes, shot_num, taps=None, exemplar_round16=False):
     """models_mae_cross.py:201-207: encoder under no_grad, then decoder."""
     with torch.no_grad():
         latent = forward_encoder(sd, cfg, imgs)
     if taps is not None:
         taps["latent"] = latent
-    return forward_decoder(sd, cfg, latent, boxes, shot_num, taps)
+    return forward_decoder(sd, cfg, latent, boxes, shot_num, taps, exemplar_round16)
 
 
 def decoder_param_names(sd, shot_num):
