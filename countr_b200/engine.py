@@ -15,6 +15,7 @@ Reference correspondence: encoder_forward = SupervisedMAE.forward_encoder (model
 136-148); decoder_forward = forward_decoder (:150-199).
 """
 import math
+import weakref
 
 import torch
 
@@ -46,16 +47,20 @@ class WeightCache:
         self.cache = {}
 
     def _lookup(self, p, kind, shape, fill):
+        # keyed by id(p) but validated with a weak reference: ids (and device pointers) are recycled when a
+        # model is freed and another one is built, so identity must be checked, not assumed.
         key = (id(p), kind)
         ent = self.cache.get(key)
         ver = (p.data_ptr(), p._version)
-        if ent is None or ent[0] != ver or ent[1].device != p.device:
-            buf = ent[1] if (ent is not None and ent[1].device == p.device and ent[1].shape == torch.Size(shape)) else \
-                torch.empty(shape, dtype=F16, device=p.device)
+        if ent is None or ent[0]() is not p or ent[1] != ver or ent[2].device != p.device:
+            reuse = ent is not None and ent[2].device == p.device and ent[2].shape == torch.Size(shape)
+            buf = ent[2] if reuse else torch.empty(shape, dtype=F16, device=p.device)
             fill(p.detach(), buf)
-            ent = (ver, buf)
+            ent = (weakref.ref(p), ver, buf)
             self.cache[key] = ent
-        return ent[1]
+            if len(self.cache) > 4096:      # drop entries of dead parameters
+                self.cache = {k: e for k, e in self.cache.items() if e[0]() is not None}
+        return ent[2]
 
     def w16(self, p):
         """[N, K] row-major copy (B operand of y = x W^T)."""
