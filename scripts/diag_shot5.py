@@ -2,7 +2,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from oracle import countr_oracle as O, synth
-from tests.test_parity_gpu import build, rel
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from test_parity_gpu import build, rel
 from countr_b200.engine import engine
 dev = torch.device("cuda:0")
 m, sd, cfg = build("small", 1, dev); m.eval()
