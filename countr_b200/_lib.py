@@ -1,7 +1,7 @@
 """ctypes binding of libcountr_sm100.so (the C ABI declared in include/countr_b200.h).
 
 There is no fallback: if the shared library is missing or the device is not sm_100 the
-import-time / call-time checks raise.  Nothing here touches `oracle/`.
+import-time / call-time checks raise.  Nothing here touches the CPU test infrastructure.
 """
 import ctypes
 import os
