@@ -155,7 +155,8 @@ def run_ours(args):
     opt = torch.optim.AdamW(param_groups(model, 0.05), lr=1e-5, betas=(0.9, 0.95), fused=True, capturable=True)
     loss_scale = 4096.0
     eng = engine()
-    eng.grad_allreduce = (lambda arena: dist.all_reduce(arena, op=dist.ReduceOp.AVG)) if world > 1 else None
+    from countr_b200.dist import make_grad_allreduce
+    eng.grad_allreduce = make_grad_allreduce() if world > 1 else None
 
     # host inputs (pinned), a few distinct batches rotated over the steps
     g = torch.Generator().manual_seed(1234 + rank)

@@ -17,6 +17,7 @@ all-reduce); they are returned to autograd, which accumulates them into `.grad` 
 import torch
 
 from . import ops
+from .dist import build_grad_arena
 from .engine import F16, F32, _contig32
 
 
@@ -84,14 +85,10 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
 
     # ---- flat gradient arena
     names, params = m._decoder_params(shot_num)
-    total = sum((p.numel() + 3) // 4 * 4 for p in params)
-    arena = torch.empty(total, dtype=F32, device=dev)
+    arena, views = build_grad_arena(names, params, dev)
     ops.zero_(arena)
-    grads, off = {"__names__": {}}, 0
-    for n, p in zip(names, params):
-        grads[n] = arena[off:off + p.numel()].view(p.shape)
-        grads["__names__"][id(p)] = n
-        off += (p.numel() + 3) // 4 * 4
+    grads = {"__names__": {id(p): n for n, p in zip(names, params)}}
+    grads.update(views)
 
     def G(p):
         return grads[grads["__names__"][id(p)]]
