@@ -142,6 +142,36 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
 }
 
 // ---------------------------------------------------------------------------
+// thread-block clusters: rank, cluster-wide barrier, TMA multicast, multicast commit
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// One L2 read, delivered to the same CTA-relative smem offset (and mbarrier) of every CTA in cta_mask.
+__device__ __forceinline__ void tma_load_4d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                               int c3, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4, %5, %6}], [%2], %7;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at this CTA-relative offset in every CTA of cta_mask.
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ---------------------------------------------------------------------------
 template <uint32_t kCols>

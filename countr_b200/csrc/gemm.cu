@@ -39,7 +39,8 @@ struct GemmArgs {
   int a_mn, b_mn;
   int bf16;
   int split_k, k_per_split;
-  int m_tiles, n_tiles, total_tiles;
+  int m_tiles, n_tiles, total_tiles;   // total_tiles counts CLUSTER tiles (cs consecutive m tiles x one n tile)
+  int cs, m_groups;                    // cluster size (CTAs sharing the B tile via TMA multicast), ceil(m_tiles / cs)
   // conv mode
   int conv, H, W, cin_blocks, bx, by, tiles_x;   // conv: 0 none, 1 forward/dX implicit GEMM, 2 dW (pixels are K)
   int tiles_per_img;
@@ -62,10 +63,10 @@ struct TileCoord {
   int m, n, s, b1, b2;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int idx) {
+__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int idx, int rank) {
   TileCoord t;
-  t.m = idx % p.m_tiles;
-  idx /= p.m_tiles;
+  t.m = (idx % p.m_groups) * p.cs + rank;
+  idx /= p.m_groups;
   t.n = idx % p.n_tiles;
   idx /= p.n_tiles;
   t.s = idx % p.split_k;
@@ -109,7 +110,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tma_prefetch_desc(&tma_b);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], p.cs);     // every CTA of the cluster must have consumed the stage (multicast writes all of them)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -119,9 +120,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
   tc_fence_before();
-  __syncthreads();
+  if (p.cs > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers must be initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const int rank = p.cs > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / p.cs, num_clusters = gridDim.x / p.cs;
+  const uint16_t mc_mask = static_cast<uint16_t>((1u << p.cs) - 1u);
 
   const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * BK * 2;
 
@@ -130,8 +134,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+        const TileCoord t = decode_tile(p, tile, rank);
         const int k_begin = t.s * p.k_per_split;
         const int k_end = min(p.K, k_begin + p.k_per_split);
         const int nkb = (k_end - k_begin + BK - 1) / BK;
@@ -155,8 +159,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const int ky = t.b2 / 3, kx = t.b2 - ky * 3;
             tma_load_4d(sa, &tma_a, &full[stage], t.m * BM, px0, py0, b);
             tma_load_4d(sa + 8192, &tma_a, &full[stage], t.m * BM + 64, px0, py0, b);
-            for (int i = 0; i < p.bn / 64; ++i)
-              tma_load_4d(sb + i * 8192, &tma_b, &full[stage], t.n * p.bn + i * 64, px0 + kx - 1, py0 + ky - 1, b);
+            if (p.cs == 1) {
+              for (int i = 0; i < p.bn / 64; ++i)
+                tma_load_4d(sb + i * 8192, &tma_b, &full[stage], t.n * p.bn + i * 64, px0 + kx - 1, py0 + ky - 1, b);
+            } else {
+              const int per = p.bn / 64 / p.cs;
+              for (int i = rank * per; i < (rank + 1) * per; ++i)
+                tma_load_4d_mc(sb + i * 8192, &tma_b, &full[stage], t.n * p.bn + i * 64, px0 + kx - 1, py0 + ky - 1, b, mc_mask);
+            }
           } else if (p.conv) {
             const int tap = kb / p.cin_blocks;
             const int cb = kb - tap * p.cin_blocks;
@@ -170,10 +180,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           }
           if (p.conv == 2) {
           } else if (!p.b_mn) {
-            tma_load_4d(sb, &tma_b, &full[stage], k, t.n * p.bn, p.conv ? 0 : t.b2, p.conv ? 0 : t.b1);
-          } else {
+            if (p.cs == 1) {
+              tma_load_4d(sb, &tma_b, &full[stage], k, t.n * p.bn, p.conv ? 0 : t.b2, p.conv ? 0 : t.b1);
+            } else {
+              // this CTA fetches rows [rank*bn/cs, (rank+1)*bn/cs) of the shared B tile once and multicasts them
+              const int rows = p.bn / p.cs;
+              tma_load_4d_mc(sb + rank * rows * 128, &tma_b, &full[stage], k, t.n * p.bn + rank * rows, p.conv ? 0 : t.b2,
+                             p.conv ? 0 : t.b1, mc_mask);
+            }
+          } else if (p.cs == 1) {
             for (int i = 0; i < p.bn / 64; ++i)
               tma_load_4d(sb + i * 8192, &tma_b, &full[stage], t.n * p.bn + i * 64, k, t.b2, t.b1);
+          } else {
+            const int per = p.bn / 64 / p.cs;
+            for (int i = rank * per; i < (rank + 1) * per; ++i)
+              tma_load_4d_mc(sb + i * 8192, &tma_b, &full[stage], t.n * p.bn + i * 64, k, t.b2, t.b1, mc_mask);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -190,8 +211,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+        const TileCoord t = decode_tile(p, tile, rank);
         const int k_begin = t.s * p.k_per_split;
         const int k_end = min(p.K, k_begin + p.k_per_split);
         const int nkb = (k_end - k_begin + BK - 1) / BK;
@@ -214,7 +235,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int k = 0; k < BK / 16; ++k)
             umma_f16_ss(d_tmem, a_desc + static_cast<uint64_t>(a_step * k), b_desc + static_cast<uint64_t>(b_step * k),
                         idesc, (kb | k) != 0);
-          umma_commit(&empty[stage]);
+          if (p.cs > 1) umma_commit_mc(&empty[stage], mc_mask); else umma_commit(&empty[stage]);
           if (kb == nkb - 1) umma_commit(&tmem_full[acc]);
           if (++stage == kStages) {
             stage = 0;
@@ -234,8 +255,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int r_in_tile = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+      const TileCoord t = decode_tile(p, tile, rank);
       bool row_valid;
       long long row;        // logical row (for residual / aux addressing)
       long long c_off;      // element offset of (row, 0) inside C
@@ -437,7 +458,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (p.cs > 1) cluster_sync_all(); else __syncthreads();   // no peer may still signal this CTA's barriers after it exits
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -521,7 +542,15 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   COUNTR_REQUIRE(bn >= 32 && bn <= kMaxBN && bn % 32 == 0 && (!d->b_mn || bn % 64 == 0), "bad N tile %d", bn);
   p.bn = bn;
   p.n_tiles = (d->N + bn - 1) / bn;
-  p.total_tiles = p.m_tiles * p.n_tiles * p.split_k * nb1 * nb2;
+  // Cluster of `cs` CTAs on consecutive m tiles of the same n tile: the B tile is fetched from L2 once per
+  // cluster (each CTA loads 1/cs of it and multicasts).  The kernel is L2->SM bandwidth bound at 128 x bn
+  // tiles (85 FLOP/B), so this is worth ~1.4x on every large GEMM / conv.
+  int cs = d->cluster > 0 ? d->cluster : 2;
+  if (cs != 1 && cs != 2 && cs != 4) cs = 2;
+  while (cs > 1 && (p.m_tiles < cs || (d->b_mn || conv_dw ? (bn / 64) % cs != 0 : (bn % (8 * cs)) != 0))) cs >>= 1;
+  p.cs = cs;
+  p.m_groups = (p.m_tiles + cs - 1) / cs;
+  p.total_tiles = p.m_groups * p.n_tiles * p.split_k * nb1 * nb2;
 
   p.C = d->c; p.ldc = d->ldc; p.sc1 = d->sc1; p.sc2 = d->sc2;
   p.out_f32 = d->out_f32; p.atomic = d->atomic;
@@ -571,7 +600,7 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   } else if (!d->b_mn) {
     const uint64_t dims[4] = {(uint64_t)d->K, (uint64_t)d->N, (uint64_t)bnb2, (uint64_t)bnb1};
     const uint64_t str[4] = {1, (uint64_t)d->ldb, (uint64_t)(bnb2 > 1 ? d->sb2 : d->ldb), (uint64_t)(bnb1 > 1 ? d->sb1 : d->ldb)};
-    const uint32_t box[4] = {BK, (uint32_t)bn, 1, 1};
+    const uint32_t box[4] = {BK, (uint32_t)(bn / p.cs), 1, 1};
     rc = make_tmap_4d_16b(&tb, d->b, dims, str, box, TMAP_SW_128);
   } else {
     const uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->K, (uint64_t)bnb2, (uint64_t)bnb1};
@@ -586,8 +615,20 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
     COUNTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);
-  COUNTR_CHECK_CUDA(cudaGetLastError());
+  const int max_clusters = sms / p.cs;
+  const int clusters = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * p.cs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  COUNTR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel, ta, tb, p));
   return COUNTR_OK;
 }

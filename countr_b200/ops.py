@@ -35,7 +35,7 @@ def _count(n=1):
 
 def gemm(a, b, c, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, nb1=1, nb2=1,
          sa=(0, 0), sb=(0, 0), sc=(0, 0), bias=None, act=0, aux=None, ldaux=0, residual=None, ldr=0,
-         res_mod=0, alpha=1.0, atomic=False, split_k=1, bn=0, conv=None, gn_stats=None, conv_dw=None):
+         res_mod=0, alpha=1.0, atomic=False, split_k=1, bn=0, conv=None, gn_stats=None, conv_dw=None, cluster=0):
     """C = epilogue(alpha * A @ B^T); see countr_gemm_desc for the layout rules."""
     assert a.dtype in (F16, BF16) and b.dtype == a.dtype
     d = GemmDesc()
@@ -46,7 +46,7 @@ def gemm(a, b, c, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, nb1=1, nb2=
     d.M, d.N, d.K = M, N, K
     d.nb1, d.nb2 = nb1, nb2
     d.bf16 = _is_bf16(a)
-    d.bn, d.split_k = bn, split_k
+    d.bn, d.split_k, d.cluster = bn, split_k, cluster
     if conv is not None:
         d.conv_h, d.conv_w, d.conv_cin, d.conv_bx, d.conv_by = conv
     if conv_dw is not None:

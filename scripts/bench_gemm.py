@@ -22,28 +22,28 @@ def timeit(fn, reps=20):
     return e0.elapsed_time(e1) / reps * 1e3  # us
 
 
-def lin(name, m, n, k, mode, bn=0):
+def lin(name, m, n, k, mode, bn=0, cl=0):
     a = torch.randn(m, k, device=dev).half()
     w = torch.randn(n, k, device=dev).half() * 0.05
     bias = torch.zeros(n, device=dev)
     if mode == "f16":
         c = torch.empty(m, n, device=dev, dtype=torch.float16)
-        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, bn=bn)
+        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, bn=bn, cluster=cl)
     elif mode == "gelu":
         c = torch.empty(m, n, device=dev, dtype=torch.float16)
-        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, act=1, bn=bn)
+        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, act=1, bn=bn, cluster=cl)
     elif mode == "gelubwd":
         c = torch.empty(m, n, device=dev, dtype=torch.float16)
         aux = torch.randn(m, n, device=dev).half()
-        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, act=2, aux=aux, ldaux=n, bn=bn)
+        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, act=2, aux=aux, ldaux=n, bn=bn, cluster=cl)
     elif mode == "res":
         c = torch.zeros(m, n, device=dev)
-        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, residual=c, ldr=n, bn=bn)
+        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, residual=c, ldr=n, bn=bn, cluster=cl)
     elif mode == "f32":
         c = torch.zeros(m, n, device=dev)
-        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bn=bn)
+        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bn=bn, cluster=cl)
     us = timeit(f)
-    print(f"{name:28s} M={m:6d} N={n:5d} K={k:5d} {mode:8s} bn={bn:3d}: {us:8.1f} us  {2.0*m*n*k/us/1e6:7.1f} TFLOP/s")
+    print(f"{name:28s} M={m:6d} N={n:5d} K={k:5d} {mode:8s} bn={bn:3d} cl={cl}: {us:8.1f} us  {2.0*m*n*k/us/1e6:7.1f} TFLOP/s")
 
 
 def dw(name, m_tok, n_out, k_in, split):
@@ -77,29 +77,24 @@ def attn(name, H, dh):
 
 
 print(f"B={B}")
-lin("enc qkv", M, 2304, 768, "f16")
-lin("enc proj (+res)", M, 768, 768, "res")
-lin("enc proj (+res) bn=96", M, 768, 768, "res", 96)
-lin("enc proj (+res) bn=128", M, 768, 768, "res", 128)
-lin("enc proj (+res) bn=256", M, 768, 768, "res", 256)
-lin("enc fc1 (gelu)", M, 3072, 768, "gelu")
-lin("enc fc1 (gelu) bn=256", M, 3072, 768, "gelu", 256)
-lin("enc fc1 (gelu) bn=128", M, 3072, 768, "gelu", 128)
-lin("enc fc2 (+res)", M, 768, 3072, "res")
-lin("enc fc2 (+res) bn=128", M, 768, 3072, "res", 128)
-lin("enc qkv bn=256", M, 2304, 768, "f16", 256)
-lin("enc qkv bn=128", M, 2304, 768, "f16", 128)
-lin("fim qkv", M, 1536, 512, "f16")
-lin("fim proj (+res)", M, 512, 512, "res")
-lin("fim fc1 (gelu)", M, 2048, 512, "gelu")
-lin("fim fc2 (+res)", M, 512, 2048, "res")
-lin("fim fc2 dX (gelu bwd)", M, 2048, 512, "gelubwd")
-lin("fim fc1 dX (f32)", M, 512, 2048, "f32")
-lin("big square", 8192, 8192, 8192, "f16", 256)
-for sp in (1, 2, 4, 9):
-    dw("fim fc2 dW", M, 512, 2048, sp)
+lin("tiny", 128, 128, 64, "f16")
+lin("tiny2", 128, 128, 512, "f16")
+for cl in (1, 2, 4):
+    lin("enc qkv", M, 2304, 768, "f16", 0, cl)
+    lin("enc qkv bn256", M, 2304, 768, "f16", 256, cl)
+    lin("enc proj (+res)", M, 768, 768, "res", 0, cl)
+    lin("enc fc1 (gelu)", M, 3072, 768, "gelu", 0, cl)
+    lin("enc fc1 (gelu) bn256", M, 3072, 768, "gelu", 256, cl)
+    lin("enc fc2 (+res)", M, 768, 3072, "res", 0, cl)
+    lin("enc fc2 (+res) bn256", M, 768, 3072, "res", 256, cl)
+    lin("fim qkv", M, 1536, 512, "f16", 0, cl)
+    lin("fim proj (+res)", M, 512, 512, "res", 0, cl)
+    lin("fim fc1 (gelu)", M, 2048, 512, "gelu", 0, cl)
+    lin("fim fc2 (+res)", M, 512, 2048, "res", 0, cl)
+    lin("fim fc2 dX (gelu bwd)", M, 2048, 512, "gelubwd", 0, cl)
+    lin("big square", 8192, 8192, 8192, "f16", 256, cl)
+dw("fim fc2 dW", M, 512, 2048, 4)
 dw("fim proj dW", M, 512, 512, 9)
-dw("fim proj dW", M, 512, 512, 4)
 dw("fim qkv dW", M, 1536, 512, 3)
 conv("head0", 24, 512, 256)
 conv("head1", 48, 256, 256)
