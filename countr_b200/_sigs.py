@@ -24,7 +24,7 @@ SIGS = {
     "countr_colsum": [P, I, P, L, I, L, P],
     "countr_softmax_bwd_rows": [P, P, P, L, I, F, I, P],
     "countr_cross_attn_core_bwd": [P, P, P, P, P, P, P, P, I, I, I, I, I, F, I, I, P],
-    "countr_inorm_relu_pool_bwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, P],
+    "countr_inorm_relu_pool_bwd": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, P],
     "countr_exemplar_conv1_dw": [P, I, L, L, L, L, L, P, P, I, I, I, I, P],
     "countr_conv_dw_unpack": [P, P, I, I, P],
 }

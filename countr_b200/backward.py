@@ -206,7 +206,9 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
             d_pool = _conv_grads(d_raw, ex["pooled"][i - 1], convs[i], grads, wc, F16)
             raw = ex["raw"][i - 1]
             d_raw = torch.empty_like(raw)
-            ops.inorm_relu_pool_bwd(raw, ex["mean"][i - 1], ex["rstd"][i - 1], d_raw, 0, dpool16=d_pool, dbias=G(convs[i - 1].bias))
+            scratch = torch.empty(raw.shape[0], raw.shape[3], 2, dtype=F32, device=dev)
+            ops.inorm_relu_pool_bwd(raw, ex["mean"][i - 1], ex["rstd"][i - 1], d_raw, 0, dpool16=d_pool, dbias=G(convs[i - 1].bias),
+                                    scratch=scratch)
         ops.exemplar_conv1_dw(boxes, S, d_raw, G(convs[0].weight))
     if eng.grad_allreduce is not None:
         eng.grad_allreduce(arena)      # data-parallel mean of every decoder gradient in one collective

@@ -537,45 +537,128 @@ __global__ void __launch_bounds__(256) inorm_relu_pool_bwd_kernel(const uint16_t
 }
 
 // ------------------------------------------------------------------------------------------
+// pixel-parallel variant of the InstanceNorm+ReLU+MaxPool backward (mode 0) for large maps:
+// pass 1 accumulates A = sum dxhat, Bq = sum dxhat*xhat per (sample, channel) with atomics into
+// `ab` [N][C][2]; pass 2 writes d_raw.  grid = (C/64, N, pixel splits).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) inorm_pool_bwd_split_kernel(const uint16_t* __restrict__ raw, const float* __restrict__ mean_in,
+                                                                    const float* __restrict__ rstd_in,
+                                                                    const uint16_t* __restrict__ dpool16, float* __restrict__ ab,
+                                                                    uint16_t* __restrict__ d_raw, float* __restrict__ dbias, int H,
+                                                                    int W, int C, int ppb, int pass, int bf16) {
+  __shared__ float red[2][8][64];
+  const int n = blockIdx.y, c0 = blockIdx.x * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int HW = H * W, OW = W / 2, OH = H / 2;
+  const int ca = c0 + lane * 2;
+  const long long nc = static_cast<long long>(n) * C + ca;
+  const float ma = mean_in[nc], mb = mean_in[nc + 1], ra = rstd_in[nc], rb = rstd_in[nc + 1];
+  const uint16_t* xb = raw + static_cast<long long>(n) * HW * C + ca;
+  uint16_t* ob = d_raw + static_cast<long long>(n) * HW * C + ca;
+  const int p_end = min(OH * OW, (static_cast<int>(blockIdx.z) + 1) * ppb);
+  float mA0 = 0.f, mA1 = 0.f, mB0 = 0.f, mB1 = 0.f;
+  if (pass == 1) {
+    mA0 = ab[nc * 2] / HW; mB0 = ab[nc * 2 + 1] / HW;
+    mA1 = ab[nc * 2 + 2] / HW; mB1 = ab[nc * 2 + 3] / HW;
+  }
+  float A0 = 0.f, A1 = 0.f, B0 = 0.f, B1 = 0.f;   // pass 0: sums; pass 1: A0/A1 = bias-gradient partials
+  for (int p = blockIdx.z * ppb + warp; p < p_end; p += 8) {
+    const int oy = p / OW, ox = p % OW;
+    const long long o00 = (static_cast<long long>(2 * oy) * W + 2 * ox) * C;
+    const long long offs[4] = {o00, o00 + C, o00 + static_cast<long long>(W) * C, o00 + static_cast<long long>(W) * C + C};
+    float2 f[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f[k] = unpack2(*reinterpret_cast<const uint32_t*>(xb + offs[k]), bf16);
+    int ia = 0, ib = 0;   // arg-max in window scan order; first maximum wins (max_pool2d semantics)
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      if (f[k].x > f[ia].x) ia = k;
+      if (f[k].y > f[ib].y) ib = k;
+    }
+    const float2 d = unpack2(*reinterpret_cast<const uint32_t*>(dpool16 + (static_cast<long long>(n) * OH * OW + p) * C + ca), bf16);
+    if (pass == 0) {
+      float va = f[0].x, vb = f[0].y;
+#pragma unroll
+      for (int k = 1; k < 4; ++k) { va = k == ia ? f[k].x : va; vb = k == ib ? f[k].y : vb; }
+      const float xa = (va - ma) * ra, xbb = (vb - mb) * rb;
+      if (xa > 0.f) { A0 += d.x; B0 += d.x * xa; }
+      if (xbb > 0.f) { A1 += d.y; B1 += d.y * xbb; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float xa = (f[k].x - ma) * ra, xbb = (f[k].y - mb) * rb;
+        const float da = (k == ia && xa > 0.f) ? d.x : 0.f, db = (k == ib && xbb > 0.f) ? d.y : 0.f;
+        const float oa = ra * (da - mA0 - xa * mB0), obv = rb * (db - mA1 - xbb * mB1);
+        A0 += oa; A1 += obv;
+        *reinterpret_cast<uint32_t*>(ob + offs[k]) = pack2(oa, obv, bf16);
+      }
+    }
+  }
+  if (pass == 1 && dbias == nullptr) return;
+  red[0][warp][lane * 2] = A0; red[0][warp][lane * 2 + 1] = A1;
+  red[1][warp][lane * 2] = B0; red[1][warp][lane * 2 + 1] = B1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float a = 0.f, q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a += red[0][k][threadIdx.x]; q += red[1][k][threadIdx.x]; }
+    if (pass == 0) {
+      atomicAdd(ab + (static_cast<long long>(n) * C + c0 + threadIdx.x) * 2, a);
+      atomicAdd(ab + (static_cast<long long>(n) * C + c0 + threadIdx.x) * 2 + 1, q);
+    } else {
+      atomicAdd(dbias + c0 + threadIdx.x, a);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // decoder_proj1[0] weight gradient: dW[co][ci][ky][kx] += sum_{n,y,x} d_raw[n,y,x,co] * box[n,ci,y+ky-1,x+kx-1]
 // (Cin = 3 -> K = 27: a direct smem-tiled reduction, not a tensor-core shape)
-// block = 128 pixels of one sample; thread (co = tid % 64, kq = tid / 64) owns taps kq, kq+4, ...
+// block = 512 pixels of one sample in 4 sub-tiles of 128; smem holds the sub-tile transposed
+// ([tap][pixel] fp32, [co][pixel] fp16) so each thread (co = tid % 64, taps tid/64 + 4j) reads 4 pixels per LDS.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) exemplar_conv1_dw_kernel(const void* __restrict__ boxes, int dtype, long long sB, long long sK,
                                                                  long long sC, long long sH, long long sW,
                                                                  const uint16_t* __restrict__ d_raw, float* __restrict__ dw, int S,
                                                                  int HW, int bf16) {
-  constexpr int PX = 128;
-  __shared__ float s_in[PX][28];
-  __shared__ uint16_t s_d[PX][64 + 2];
+  constexpr int PX = 128, SUB = 4;
+  __shared__ __align__(16) float s_in[27][PX];
+  __shared__ __align__(16) uint16_t s_d[64][PX + 4];
   const int n = blockIdx.y;
   const int b = n / S, s = n % S;
-  const int p0 = blockIdx.x * PX;
   const int H = HW, W = HW;
-  for (int i = threadIdx.x; i < PX * 27; i += blockDim.x) {
-    const int px = i / 27, k = i % 27;
-    const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
-    const int pix = p0 + px;
-    const int yy = pix / W + ky - 1, xx = pix % W + kx - 1;
-    float v = 0.f;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = load_any(boxes, b * sB + s * sK + ci * sC + yy * sH + xx * sW, dtype);
-    s_in[px][k] = v;
-  }
-  for (int i = threadIdx.x; i < PX * 64; i += blockDim.x) {
-    const int px = i / 64, co = i % 64;
-    s_d[px][co] = d_raw[(static_cast<long long>(n) * H * W + p0 + px) * 64 + co];
-  }
-  __syncthreads();
   const int co = threadIdx.x & 63, kq = threadIdx.x >> 6;
   float acc[7];
 #pragma unroll
   for (int j = 0; j < 7; ++j) acc[j] = 0.f;
-  for (int px = 0; px < PX; ++px) {
-    const float d = bf16 ? __uint_as_float(static_cast<uint32_t>(s_d[px][co]) << 16) : __half2float(__ushort_as_half(s_d[px][co]));
+  for (int sub = 0; sub < SUB; ++sub) {
+    const int p0 = (blockIdx.x * SUB + sub) * PX;
+    __syncthreads();
+    for (int i = threadIdx.x; i < PX * 27; i += blockDim.x) {
+      const int px = i % PX, k = i / PX;
+      const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
+      const int pix = p0 + px;
+      const int yy = pix / W + ky - 1, xx = pix % W + kx - 1;
+      float v = 0.f;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = load_any(boxes, b * sB + s * sK + ci * sC + yy * sH + xx * sW, dtype);
+      s_in[k][px] = v;
+    }
+    for (int i = threadIdx.x; i < PX * 64; i += blockDim.x) {
+      const int c = i % 64, px = i / 64;
+      s_d[c][px] = d_raw[(static_cast<long long>(n) * H * W + p0 + px) * 64 + c];
+    }
+    __syncthreads();
+    for (int px = 0; px < PX; px += 4) {
+      const uint2 dv = *reinterpret_cast<const uint2*>(&s_d[co][px]);
+      const float2 d01 = unpack2(dv.x, bf16), d23 = unpack2(dv.y, bf16);
 #pragma unroll
-    for (int j = 0; j < 7; ++j) {
-      const int k = kq + 4 * j;
-      if (k < 27) acc[j] += d * s_in[px][k];
+      for (int j = 0; j < 7; ++j) {
+        const int k = kq + 4 * j;
+        if (k < 27) {
+          const float4 iv = *reinterpret_cast<const float4*>(&s_in[k][px]);
+          acc[j] += d01.x * iv.x + d01.y * iv.y + d23.x * iv.z + d23.y * iv.w;
+        }
+      }
     }
   }
 #pragma unroll
@@ -700,11 +783,26 @@ extern "C" int countr_cross_attn_core_bwd(const void* q16, const float* k32, con
 }
 
 extern "C" int countr_inorm_relu_pool_bwd(const void* raw, const float* mean, const float* rstd, const void* dpool16,
-                                          const float* dpool32, void* d_raw, float* dbias, int N, int H, int W, int C, int mode,
-                                          int bf16, countr_stream_t stream_) {
+                                          const float* dpool32, void* d_raw, float* dbias, float* scratch, int N, int H, int W,
+                                          int C, int mode, int bf16, countr_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(raw && mean && rstd && d_raw && (mode == 0 ? dpool16 != nullptr : dpool32 != nullptr), "null pointer");
   COUNTR_REQUIRE(C % 64 == 0 && (mode == 1 || (H % 2 == 0 && W % 2 == 0)), "bad shape");
+  if (mode == 0 && scratch != nullptr && H * W >= 256) {
+    const int OHW = H * W / 4, cblocks = C / 64;
+    int split = (2 * 148 + cblocks * N - 1) / (cblocks * N);
+    if (split > OHW / 16) split = OHW / 16;
+    if (split < 1) split = 1;
+    const int ppb = (OHW + split - 1) / split;
+    dim3 grid(cblocks, N, (OHW + ppb - 1) / ppb);
+    COUNTR_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * N * C, stream));
+    for (int pass = 0; pass < 2; ++pass)
+      inorm_pool_bwd_split_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(raw), mean, rstd,
+                                                            reinterpret_cast<const uint16_t*>(dpool16), scratch,
+                                                            reinterpret_cast<uint16_t*>(d_raw), dbias, H, W, C, ppb, pass, bf16);
+    COUNTR_CHECK_CUDA(cudaGetLastError());
+    return COUNTR_OK;
+  }
   dim3 grid(C / 64, N);
   inorm_relu_pool_bwd_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(raw), mean, rstd,
                                                        reinterpret_cast<const uint16_t*>(dpool16), dpool32,
@@ -716,8 +814,8 @@ extern "C" int countr_inorm_relu_pool_bwd(const void* raw, const float* mean, co
 extern "C" int countr_exemplar_conv1_dw(const void* boxes, int dtype, int64_t sB, int64_t sK, int64_t sC, int64_t sH, int64_t sW,
                                         const void* d_raw, float* dw, int B, int S, int HW, int bf16, countr_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  COUNTR_REQUIRE(boxes && d_raw && dw && (HW * HW) % 128 == 0, "bad arguments");
-  dim3 grid(HW * HW / 128, B * S);
+  COUNTR_REQUIRE(boxes && d_raw && dw && (HW * HW) % 512 == 0, "bad arguments");
+  dim3 grid(HW * HW / 512, B * S);
   exemplar_conv1_dw_kernel<<<grid, 256, 0, stream>>>(boxes, dtype, sB, sK, sC, sH, sW, reinterpret_cast<const uint16_t*>(d_raw), dw, S,
                                                      HW, bf16);
   COUNTR_CHECK_CUDA(cudaGetLastError());

@@ -263,44 +263,125 @@ __global__ void up2_f32_kernel(const float* __restrict__ x, void* __restrict__ y
 // direct fp32 FMA (27 MACs per output; not worth a tensor-core tile) -> NHWC 16-bit raw output.
 // replaces: decoder_proj1[0] (models_mae_cross.py:47-48,166); sample index n = b*S + s.
 // ------------------------------------------------------------------------------------------
+// block = 2 image rows (128 pixels) x 64 output channels; thread = 4 consecutive pixels x 8 channels, so every
+// weight vector read from smem (2 x LDS.128) feeds 32 FMAs.
 __global__ void __launch_bounds__(256) exemplar_conv1_kernel(const void* __restrict__ boxes, int dtype, long long sB,
                                                               long long sK, long long sC, long long sH, long long sW,
                                                               const float* __restrict__ w, const float* __restrict__ bias,
                                                               uint16_t* __restrict__ out, int S, int HW, int Cout, int bf16) {
-  __shared__ float sw[27 * 64];
+  __shared__ __align__(16) float sw[27 * 64];
   __shared__ float sbias[64];
+  __shared__ float s_in[3][4][64 + 4];   // rows y0-1 .. y0+2, columns -1 .. 64 (zero halo), +pad
+  const int n = blockIdx.y;
+  const int b = n / S, s = n % S;
+  const int y0 = blockIdx.x * 2;
+  const int H = HW, W = HW;
   for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
     const int co = i % Cout, k = i / Cout;  // k = ci*9 + tap
     sw[k * Cout + co] = w[co * 27 + k];
   }
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sbias[i] = bias[i];
+  for (int i = threadIdx.x; i < 3 * 4 * 66; i += blockDim.x) {
+    const int xx = i % 66 - 1, r = (i / 66) % 4, ci = i / (66 * 4);
+    const int yy = y0 + r - 1;
+    float v = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = load_any(boxes, b * sB + s * sK + ci * sC + yy * sH + xx * sW, dtype);
+    s_in[ci][r][xx + 1] = v;
+  }
   __syncthreads();
-  const int n = blockIdx.y;
-  const int b = n / S, s = n % S;
-  const int pix = blockIdx.x * 32 + (threadIdx.x >> 3);
-  const int cg = threadIdx.x & 7;  // 8 output channels
-  const int H = HW, W = HW;
-  const int py = pix / W, px = pix % W;
-  float in[27];
+  const int cg = threadIdx.x & 7;           // 8 output channels
+  const int pg = threadIdx.x >> 3;          // 4 consecutive pixels
+  const int ry = pg >> 4, x0 = (pg & 15) * 4;
+  float acc[4][8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[q][j] = sbias[cg * 8 + j];
 #pragma unroll
   for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+    for (int ky = 0; ky < 3; ++ky) {
+      float in[6];
+#pragma unroll
+      for (int t = 0; t < 6; ++t) in[t] = s_in[ci][ry + ky][x0 + t];
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int yy = py + ky - 1, xx = px + kx - 1;
-        float v = 0.f;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = load_any(boxes, b * sB + s * sK + ci * sC + yy * sH + xx * sW, dtype);
-        in[ci * 9 + ky * 3 + kx] = v;
+        const int k = ci * 9 + ky * 3 + kx;
+        const float4 w0 = *reinterpret_cast<const float4*>(&sw[k * 64 + cg * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&sw[k * 64 + cg * 8 + 4]);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[q][j] += in[q + kx] * wv[j];
       }
-  float acc[8];
+    }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = sbias[cg * 8 + j];
+  for (int q = 0; q < 4; ++q) {
+    const int pix = (y0 + ry) * W + x0 + q;
+    *reinterpret_cast<uint4*>(out + (static_cast<long long>(n) * H * W + pix) * 64 + cg * 8) = pack8(acc[q], bf16);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// InstanceNorm statistics, pixel-parallel: raw sums (sum x, sum x^2) per (sample, channel) -> atomics,
+// then a tiny finalize turns them into (mean, rstd) in place.  Used when one CTA per (sample, 64 ch)
+// would leave the GPU idle (stage 1: 24 samples x 1 channel block over 4096 pixels).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) inorm_stats_kernel(const uint16_t* __restrict__ x, float* __restrict__ s1,
+                                                           float* __restrict__ s2, int HW, int C, int ppb, int bf16) {
+  __shared__ float red[2][8][64];
+  const int n = blockIdx.y, c0 = blockIdx.x * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint16_t* xb = x + static_cast<long long>(n) * HW * C + c0 + lane * 2;
+  const int p_end = min(HW, (static_cast<int>(blockIdx.z) + 1) * ppb);
+  float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+  for (int p = blockIdx.z * ppb + warp; p < p_end; p += 8) {
+    const float2 f = unpack2(*reinterpret_cast<const uint32_t*>(xb + static_cast<long long>(p) * C), bf16);
+    a0 += f.x; a1 += f.y; q0 += f.x * f.x; q1 += f.y * f.y;
+  }
+  red[0][warp][lane * 2] = a0; red[0][warp][lane * 2 + 1] = a1;
+  red[1][warp][lane * 2] = q0; red[1][warp][lane * 2 + 1] = q1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float a = 0.f, q = 0.f;
 #pragma unroll
-  for (int k = 0; k < 27; ++k)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += in[k] * sw[k * Cout + cg * 8 + j];
-  *reinterpret_cast<uint4*>(out + (static_cast<long long>(n) * H * W + pix) * Cout + cg * 8) = pack8(acc, bf16);
+    for (int k = 0; k < 8; ++k) { a += red[0][k][threadIdx.x]; q += red[1][k][threadIdx.x]; }
+    atomicAdd(s1 + static_cast<long long>(n) * C + c0 + threadIdx.x, a);
+    atomicAdd(s2 + static_cast<long long>(n) * C + c0 + threadIdx.x, q);
+  }
+}
+__global__ void inorm_finalize_kernel(float* __restrict__ mean, float* __restrict__ rstd, int total, int HW, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float m = mean[i] / HW;
+  const float var = fmaxf(rstd[i] / HW - m * m, 0.f);
+  mean[i] = m;
+  rstd[i] = rsqrtf(var + eps);
+}
+// normalise + ReLU + MaxPool2d(2), pixel-parallel (reads the finalized mean / rstd)
+__global__ void __launch_bounds__(256) inorm_apply_pool_kernel(const uint16_t* __restrict__ x, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, uint16_t* __restrict__ y16,
+                                                                int H, int W, int C, int ppb, int bf16) {
+  const int n = blockIdx.y, c0 = blockIdx.x * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ca = c0 + lane * 2;
+  const float ma = mean[static_cast<long long>(n) * C + ca], mb = mean[static_cast<long long>(n) * C + ca + 1];
+  const float ra = rstd[static_cast<long long>(n) * C + ca], rb = rstd[static_cast<long long>(n) * C + ca + 1];
+  const int OH = H / 2, OW = W / 2;
+  const uint16_t* xb = x + static_cast<long long>(n) * H * W * C + ca;
+  uint16_t* yb = y16 + static_cast<long long>(n) * OH * OW * C + ca;
+  const int p_end = min(OH * OW, (static_cast<int>(blockIdx.z) + 1) * ppb);
+  for (int p = blockIdx.z * ppb + warp; p < p_end; p += 8) {
+    const int oy = p / OW, ox = p % OW;
+    const uint16_t* q = xb + (static_cast<long long>(2 * oy) * W + 2 * ox) * C;
+    const float2 f0 = unpack2(*reinterpret_cast<const uint32_t*>(q), bf16);
+    const float2 f1 = unpack2(*reinterpret_cast<const uint32_t*>(q + C), bf16);
+    const float2 f2 = unpack2(*reinterpret_cast<const uint32_t*>(q + static_cast<long long>(W) * C), bf16);
+    const float2 f3 = unpack2(*reinterpret_cast<const uint32_t*>(q + static_cast<long long>(W) * C + C), bf16);
+    const float va = fmaxf(fmaxf(f0.x, f1.x), fmaxf(f2.x, f3.x)), vb = fmaxf(fmaxf(f0.y, f1.y), fmaxf(f2.y, f3.y));
+    *reinterpret_cast<uint32_t*>(yb + static_cast<long long>(p) * C) = pack2(fmaxf((va - ma) * ra, 0.f), fmaxf((vb - mb) * rb, 0.f), bf16);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -549,8 +630,8 @@ extern "C" int countr_exemplar_conv1(const void* boxes, int dtype, int64_t sB, i
                                      countr_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(boxes && w && bias && out, "null pointer");
-  COUNTR_REQUIRE(Cout == 64 && HW % 32 == 0 && B > 0 && S > 0, "exemplar conv1 expects Cout=64 (got %d), side %% 32 == 0", Cout);
-  dim3 grid(HW * HW / 32, B * S);
+  COUNTR_REQUIRE(Cout == 64 && HW == 64 && B > 0 && S > 0, "exemplar conv1 expects Cout=64 and 64x64 crops (got %d, %d)", Cout, HW);
+  dim3 grid(HW / 2, B * S);
   exemplar_conv1_kernel<<<grid, 256, 0, stream>>>(boxes, dtype, sB, sK, sC, sH, sW, w, bias, reinterpret_cast<uint16_t*>(out), S, HW,
                                                   Cout, bf16);
   COUNTR_CHECK_CUDA(cudaGetLastError());
@@ -562,6 +643,25 @@ extern "C" int countr_inorm_relu_pool(const void* x, void* y16, float* y32, floa
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(x && (y16 || y32), "null pointer");
   COUNTR_REQUIRE(C % 64 == 0 && (mode == 1 || (H % 2 == 0 && W % 2 == 0 && y16)), "bad shape C=%d H=%d W=%d mode=%d", C, H, W, mode);
+  if (mode == 0 && mean != nullptr && rstd != nullptr && H * W >= 256) {
+    // pixel-parallel path: raw sums by atomics -> finalize -> apply (3 launches, each filling the GPU)
+    const int HW = H * W, cblocks = C / 64;
+    int split = (2 * 148 + cblocks * N - 1) / (cblocks * N);
+    if (split > HW / 64) split = HW / 64;
+    if (split < 1) split = 1;
+    const int ppb = (HW + split - 1) / split;
+    COUNTR_CHECK_CUDA(cudaMemsetAsync(mean, 0, sizeof(float) * N * C, stream));
+    COUNTR_CHECK_CUDA(cudaMemsetAsync(rstd, 0, sizeof(float) * N * C, stream));
+    inorm_stats_kernel<<<dim3(cblocks, N, (HW + ppb - 1) / ppb), 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(x), mean, rstd, HW,
+                                                                                 C, ppb, bf16);
+    inorm_finalize_kernel<<<(N * C + 255) / 256, 256, 0, stream>>>(mean, rstd, N * C, HW, eps);
+    const int OHW = HW / 4;
+    const int ppb2 = (OHW + split - 1) / split;
+    inorm_apply_pool_kernel<<<dim3(cblocks, N, (OHW + ppb2 - 1) / ppb2), 256, 0, stream>>>(
+        reinterpret_cast<const uint16_t*>(x), mean, rstd, reinterpret_cast<uint16_t*>(y16), H, W, C, ppb2, bf16);
+    COUNTR_CHECK_CUDA(cudaGetLastError());
+    return COUNTR_OK;
+  }
   dim3 grid(C / 64, N);
   inorm_relu_pool_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(x), reinterpret_cast<uint16_t*>(y16), y32, mean,
                                                    rstd, H, W, C, eps, mode, bf16);

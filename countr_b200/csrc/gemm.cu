@@ -542,11 +542,13 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   COUNTR_REQUIRE(bn >= 32 && bn <= kMaxBN && bn % 32 == 0 && (!d->b_mn || bn % 64 == 0), "bad N tile %d", bn);
   p.bn = bn;
   p.n_tiles = (d->N + bn - 1) / bn;
-  // Cluster of `cs` CTAs on consecutive m tiles of the same n tile: the B tile is fetched from L2 once per
-  // cluster (each CTA loads 1/cs of it and multicasts).  The kernel is L2->SM bandwidth bound at 128 x bn
-  // tiles (85 FLOP/B), so this is worth ~1.4x on every large GEMM / conv.
-  int cs = d->cluster > 0 ? d->cluster : 2;
-  if (cs != 1 && cs != 2 && cs != 4) cs = 2;
+  // Optional cluster of `cs` CTAs on consecutive m tiles of the same n tile: the B tile is fetched from L2 once
+  // per cluster (each CTA loads 1/cs of it and multicasts).  Measured on B200 (profiles/r1_bench_gemm_v4.log):
+  // no gain at cs=2 and a loss at cs=4 — the kernel is NOT L2->SM bound (the limiter at 128 x 256 tiles is
+  // shared-memory bandwidth: TMA fill + UMMA operand reads = 192 B/clk against 128 B/clk), so the default is
+  // cs = 1 and the path is kept for experiments (cta_group::2 is the real fix).
+  int cs = d->cluster > 0 ? d->cluster : 1;
+  if (cs != 1 && cs != 2 && cs != 4) cs = 1;
   while (cs > 1 && (p.m_tiles < cs || (d->b_mn || conv_dw ? (bn / 64) % cs != 0 : (bn % (8 * cs)) != 0))) cs >>= 1;
   p.cs = cs;
   p.m_groups = (p.m_tiles + cs - 1) / cs;

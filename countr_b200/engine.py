@@ -154,8 +154,8 @@ class Engine:
         for i, conv in enumerate(stages):
             n, hh, ww, cc = cur.shape
             pooled = get(f"ex_pool{i}", (n, hh // 2, ww // 2, cc), F16)
-            mean = get(f"ex_mean{i}", (n, cc), F32) if save is not None else None
-            rstd = get(f"ex_rstd{i}", (n, cc), F32) if save is not None else None
+            mean = get(f"ex_mean{i}", (n, cc), F32)       # always: enables the pixel-parallel statistics path
+            rstd = get(f"ex_rstd{i}", (n, cc), F32)
             ops.inorm_relu_pool(cur, 0, 1e-5, y16=pooled, mean=mean, rstd=rstd)
             cout = conv.weight.shape[0]
             nxt = get(f"ex_raw{i + 2}", (n, hh // 2, ww // 2, cout), F16)

@@ -188,7 +188,7 @@ def inorm_relu_pool(x16, mode, eps, y16=None, y32=None, mean=None, rstd=None):
     N, H, W, C = x16.shape
     check(lib().countr_inorm_relu_pool(_ptr(x16), _ptr(y16), _ptr(y32), _ptr(mean), _ptr(rstd), N, H, W, C, eps, mode,
                                        _is_bf16(x16), _stream()))
-    _count()
+    _count(3 if (mode == 0 and mean is not None and rstd is not None and H * W >= 256) else 1)
 
 
 def zero_(t):
@@ -238,11 +238,11 @@ def cross_attn_core_bwd(q16, k32, v32, probs, do16, dq16, dk32, dv32, B, L, S, D
     _count()
 
 
-def inorm_relu_pool_bwd(raw16, mean, rstd, d_raw16, mode, dpool16=None, dpool32=None, dbias=None):
+def inorm_relu_pool_bwd(raw16, mean, rstd, d_raw16, mode, dpool16=None, dpool32=None, dbias=None, scratch=None):
     N, H, W, C = raw16.shape
     check(lib().countr_inorm_relu_pool_bwd(_ptr(raw16), _ptr(mean), _ptr(rstd), _ptr(dpool16), _ptr(dpool32), _ptr(d_raw16),
-                                           _ptr(dbias), N, H, W, C, mode, _is_bf16(raw16), _stream()))
-    _count()
+                                           _ptr(dbias), _ptr(scratch), N, H, W, C, mode, _is_bf16(raw16), _stream()))
+    _count(3 if (scratch is not None and mode == 0 and H * W >= 256) else 1)
 
 
 def exemplar_conv1_dw(boxes, S, d_raw16, dw32):

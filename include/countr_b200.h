@@ -173,7 +173,8 @@ int countr_exemplar_conv1(const void* boxes, int dtype, int64_t sB, int64_t sK, 
                           const float* w, const float* bias, void* out, int B, int S, int HW, int Cout, int bf16,
                           countr_stream_t stream);
 /* InstanceNorm2d(eps, no affine) + ReLU + MaxPool2d(2) (mode 0 -> y16 [N][H/2][W/2][C]) or
- * AdaptiveAvgPool2d(1) (mode 1 -> y32 [N][C] and/or y16 [N][C]); mean/rstd [N][C] optional */
+ * AdaptiveAvgPool2d(1) (mode 1 -> y32 [N][C] and/or y16 [N][C]); mean/rstd [N][C] optional
+ * (when given, large maps take a pixel-parallel stats -> finalize -> apply path) */
 int countr_inorm_relu_pool(const void* x, void* y16, float* y32, float* mean, float* rstd, int N, int H, int W, int C,
                            float eps, int mode, int bf16, countr_stream_t stream);
 
@@ -206,10 +207,11 @@ int countr_cross_attn_core_bwd(const void* q16, const float* k32, const float* v
                                void* dq16, float* dk32, float* dv32, int B, int L, int S, int D, int dh, float scale,
                                int bf16, int kv_broadcast, countr_stream_t stream);
 /* backward of countr_inorm_relu_pool (InstanceNorm + ReLU + MaxPool2d(2) | avg-pool);
- * dbias [C] (optional) += sum d_raw = gradient of the preceding conv bias */
+ * dbias [C] (optional) += sum d_raw = gradient of the preceding conv bias;
+ * scratch (optional, [N][C][2] fp32) enables the pixel-parallel two-pass path for large maps */
 int countr_inorm_relu_pool_bwd(const void* raw, const float* mean, const float* rstd, const void* dpool16,
-                               const float* dpool32, void* d_raw, float* dbias, int N, int H, int W, int C, int mode,
-                               int bf16, countr_stream_t stream);
+                               const float* dpool32, void* d_raw, float* dbias, float* scratch, int N, int H, int W, int C,
+                               int mode, int bf16, countr_stream_t stream);
 /* decoder_proj1[0] weight gradient dw [64][3][3][3] += (direct reduction, K = 27) */
 int countr_exemplar_conv1_dw(const void* boxes, int dtype, int64_t sB, int64_t sK, int64_t sC, int64_t sH, int64_t sW,
                              const void* d_raw, float* dw, int B, int S, int HW, int bf16, countr_stream_t stream);

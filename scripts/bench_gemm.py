@@ -10,13 +10,20 @@ M = B * 576
 
 
 def timeit(fn, reps=20):
+    """GPU time per call: the calls are captured in a CUDA graph so host launch cost (ctypes + tensor-map
+    encode, ~15 us per GEMM call) does not bound the measurement."""
     for _ in range(3):
         fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    for _ in range(reps):
-        fn()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1e3  # us
@@ -79,7 +86,7 @@ def attn(name, H, dh):
 print(f"B={B}")
 lin("tiny", 128, 128, 64, "f16")
 lin("tiny2", 128, 128, 512, "f16")
-for cl in (1, 2, 4):
+for cl in (1, 2):
     lin("enc qkv", M, 2304, 768, "f16", 0, cl)
     lin("enc qkv bn256", M, 2304, 768, "f16", 256, cl)
     lin("enc proj (+res)", M, 768, 768, "res", 0, cl)
