@@ -89,7 +89,7 @@ def test_input_conventions(cuda):
         b = m(wide.to(cuda)[:, :, :, 64:448], boxes.to(cuda), 3)
         c = m(imgs.to(cuda).half(), boxes.to(cuda).half(), 3)
         d = m(imgs[1:2].to(cuda), boxes[1:2].to(cuda), 3)
-    assert torch.equal(a, b)
+    assert rel(b, a) < 1e-5      # same arithmetic; fp32 atomics in the InstanceNorm statistics reorder sums run to run
     assert c.dtype == torch.float16 and rel(c.float(), a) < 2e-3
     assert rel(d[0], a[1]) < 1e-5
     with pytest.raises(AssertionError):
