@@ -27,6 +27,10 @@ SIGS = {
     "countr_inorm_relu_pool_bwd": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, P],
     "countr_exemplar_conv1_dw": [P, I, L, L, L, L, L, P, P, I, I, I, I, P],
     "countr_conv_dw_unpack": [P, P, I, I, P],
+    "countr_gather_rows": [P, P, P, I, I, I, I, P],
+    "countr_mae_unshuffle": [P, P, P, P, P, I, I, I, I, P],
+    "countr_mae_loss": [P, P, I, L, L, L, L, P, P, I, I, I, I, I, I, P],
+    "countr_cast_scaled_f32_to_16": [P, P, P, L, I, P],
 }
 
 

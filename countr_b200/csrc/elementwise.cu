@@ -536,6 +536,97 @@ __global__ void __launch_bounds__(256) cross_attn_core_kernel(const uint16_t* __
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// MAE pre-training glue (models_mae_noct.py:110-198)
+// ------------------------------------------------------------------------------------------
+// dst[b][j][:] = src[b][idx[b][j]][:]   rows of row_bytes (multiple of 16) — random_masking's torch.gather
+// (:124) and, with the shuffle indices, its backward.
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, const long long* __restrict__ idx, uint4* __restrict__ dst,
+                                   int n_src, int n_dst, int vec_per_row, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = i % vec_per_row;
+  const long long r = i / vec_per_row;
+  const int j = r % n_dst;
+  const long long b = r / n_dst;
+  const long long s = idx[b * n_dst + j];
+  dst[i] = src[(b * n_src + s) * vec_per_row + v];
+}
+
+// decoder input of the MAE (:158-165): x[b][l] = (ids_restore[b][l] < Lk ? xk[b][ids_restore[b][l]] : mask_token) + pos[l]
+__global__ void mae_unshuffle_kernel(const float4* __restrict__ xk, const long long* __restrict__ ids_restore,
+                                     const float4* __restrict__ mask_token, const float4* __restrict__ pos, float4* __restrict__ out,
+                                     int L, int Lk, int vec_per_row, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = i % vec_per_row;
+  const long long r = i / vec_per_row;
+  const int l = r % L;
+  const long long b = r / L;
+  const long long s = ids_restore[b * L + l];
+  const float4 a = s < Lk ? xk[(b * Lk + s) * vec_per_row + v] : mask_token[v];
+  const float4 p = pos[static_cast<long long>(l) * vec_per_row + v];
+  out[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+}
+
+// Pixel-reconstruction loss (:177-198): target = patchify(imgs) (per patch: (py, px, c) order, optionally normalised
+// per patch with the unbiased variance), loss = mean over all patches of mean((pred - target)^2).
+// One warp per patch: accumulates the loss (atomic, fp32) and writes dpred = 2 (pred - target) / (N L P) (fp32).
+__global__ void __launch_bounds__(256) mae_loss_kernel(const float* __restrict__ pred, const void* __restrict__ img, int dtype,
+                                                        long long sb, long long sc, long long sh, long long sw,
+                                                        float* __restrict__ loss, float* __restrict__ dpred, int NL, int gw, int gh,
+                                                        int P, int C, int norm_pix) {
+  const int patch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (patch >= NL) return;
+  const int px = patch % gw, py = (patch / gw) % gh, b = patch / (gw * gh);
+  const int D = P * P * C;
+  float mean = 0.f, inv = 1.f;
+  if (norm_pix) {
+    float s = 0.f, q = 0.f;
+    for (int e = lane; e < D; e += 32) {
+      const int c = e % C, qx = (e / C) % P, qy = e / (C * P);
+      const float t = load_any(img, b * sb + c * sc + static_cast<long long>(py * P + qy) * sh + static_cast<long long>(px * P + qx) * sw, dtype);
+      s += t; q += t * t;
+    }
+    s = warp_sum(s); q = warp_sum(q);
+    mean = s / D;
+    const float var = fmaxf((q - s * mean) / (D - 1), 0.f);   // torch.var default: unbiased
+    inv = rsqrtf(var + 1e-6f);
+  }
+  const float gscale = 2.f / (static_cast<float>(NL) * D);
+  float acc = 0.f;
+  for (int e = lane; e < D; e += 32) {
+    const int c = e % C, qx = (e / C) % P, qy = e / (C * P);
+    float t = load_any(img, b * sb + c * sc + static_cast<long long>(py * P + qy) * sh + static_cast<long long>(px * P + qx) * sw, dtype);
+    t = (t - mean) * inv;
+    const float d = pred[static_cast<long long>(patch) * D + e] - t;
+    acc += d * d;
+    if (dpred) dpred[static_cast<long long>(patch) * D + e] = d * gscale;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) atomicAdd(loss, acc / (static_cast<float>(NL) * D));
+}
+
+// dst16[i] = 16-bit( src[i] * (*scale_ptr) ) : gradient recast with the (device-resident) upstream loss-scale
+__global__ void cast_scaled_kernel(const float* __restrict__ src, const float* __restrict__ scale_ptr, uint16_t* __restrict__ dst,
+                                   long long n, int bf16) {
+  const float scale = *scale_ptr;
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = *reinterpret_cast<const float4*>(src + i), b = *reinterpret_cast<const float4*>(src + i + 4);
+    uint4 o;
+    o.x = pack2(a.x * scale, a.y * scale, bf16);
+    o.y = pack2(a.z * scale, a.w * scale, bf16);
+    o.z = pack2(b.x * scale, b.y * scale, bf16);
+    o.w = pack2(b.z * scale, b.w * scale, bf16);
+    *reinterpret_cast<uint4*>(dst + i) = o;
+  } else {
+    for (long long j = i; j < n; ++j) dst[j] = static_cast<uint16_t>(pack2(src[j] * scale, 0.f, bf16) & 0xffffu);
+  }
+}
+
 }  // namespace
 }  // namespace countr
 
@@ -682,6 +773,52 @@ extern "C" int countr_cross_attn_core(const void* q16, const float* k32, const f
   cross_attn_core_kernel<<<blocks, 256, smem, stream>>>(reinterpret_cast<const uint16_t*>(q16), k32, v32,
                                                        reinterpret_cast<uint16_t*>(out16), probs, L, S, D, scale, tpb, bf16,
                                                        kv_broadcast ? 0ll : static_cast<long long>(S) * D);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_gather_rows(const void* src, const int64_t* idx, void* dst, int B, int n_src, int n_dst, int row_bytes,
+                                  countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(src && idx && dst && row_bytes % 16 == 0 && B > 0 && n_dst > 0, "bad arguments");
+  const int vpr = row_bytes / 16;
+  const long long total = static_cast<long long>(B) * n_dst * vpr;
+  gather_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(src), reinterpret_cast<const long long*>(idx), reinterpret_cast<uint4*>(dst), n_src, n_dst, vpr, total);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_mae_unshuffle(const float* xk, const int64_t* ids_restore, const float* mask_token, const float* pos, float* out,
+                                    int B, int L, int Lk, int D, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(xk && ids_restore && mask_token && pos && out && D % 4 == 0, "bad arguments");
+  const int vpr = D / 4;
+  const long long total = static_cast<long long>(B) * L * vpr;
+  mae_unshuffle_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(xk), reinterpret_cast<const long long*>(ids_restore), reinterpret_cast<const float4*>(mask_token),
+      reinterpret_cast<const float4*>(pos), reinterpret_cast<float4*>(out), L, Lk, vpr, total);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_mae_loss(const float* pred, const void* img, int dtype, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+                               float* loss, float* dpred, int B, int C, int H, int W, int P, int norm_pix, countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(pred && img && loss && H % P == 0 && W % P == 0 && dtype >= 0 && dtype <= 2, "bad arguments");
+  const int NL = B * (H / P) * (W / P);
+  COUNTR_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), stream));
+  mae_loss_kernel<<<(NL + 7) / 8, 256, 0, stream>>>(pred, img, dtype, sb, sc, sh, sw, loss, dpred, NL, W / P, H / P, P, C, norm_pix);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_cast_scaled_f32_to_16(const float* src, const float* scale_ptr, void* dst, int64_t n, int bf16,
+                                            countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(src && dst && scale_ptr && n > 0, "bad arguments");
+  const long long threads = (n + 7) / 8;
+  cast_scaled_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(src, scale_ptr, reinterpret_cast<uint16_t*>(dst), n, bf16);
   COUNTR_CHECK_CUDA(cudaGetLastError());
   return COUNTR_OK;
 }

@@ -256,3 +256,31 @@ def exemplar_conv1_dw(boxes, S, d_raw16, dw32):
 def conv_dw_unpack(src32, dst32, Cout, Cin):
     check(lib().countr_conv_dw_unpack(_ptr(src32), _ptr(dst32), Cout, Cin, _stream()))
     _count()
+
+
+def gather_rows(src, idx, dst):
+    """dst[b, j] = src[b, idx[b, j]] for [B, n, D] row tensors of any dtype (rows must be a multiple of 16 bytes)."""
+    B, n_src = src.shape[0], src.shape[1]
+    n_dst = idx.shape[1]
+    row_bytes = src.shape[2] * src.element_size()
+    check(lib().countr_gather_rows(_ptr(src), _ptr(idx), _ptr(dst), B, n_src, n_dst, row_bytes, _stream()))
+    _count()
+
+
+def mae_unshuffle(xk, ids_restore, mask_token, pos, out):
+    B, L, D = out.shape
+    check(lib().countr_mae_unshuffle(_ptr(xk), _ptr(ids_restore), _ptr(mask_token), _ptr(pos), _ptr(out), B, L, xk.shape[1], D, _stream()))
+    _count()
+
+
+def mae_loss(pred, imgs, loss, dpred, P, norm_pix):
+    B, C, H, W = imgs.shape
+    sb, sc, sh, sw = imgs.stride()
+    check(lib().countr_mae_loss(_ptr(pred), _ptr(imgs), _DTYPE_CODE[imgs.dtype], sb, sc, sh, sw, _ptr(loss), _ptr(dpred), B, C, H, W, P,
+                                int(bool(norm_pix)), _stream()))
+    _count()
+
+
+def cast16_scaled(src32, scale_tensor, dst16):
+    check(lib().countr_cast_scaled_f32_to_16(_ptr(src32), _ptr(scale_tensor), _ptr(dst16), src32.numel(), _is_bf16(dst16), _stream()))
+    _count()

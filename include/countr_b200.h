@@ -218,6 +218,24 @@ int countr_exemplar_conv1_dw(const void* boxes, int dtype, int64_t sB, int64_t s
 /* [Cout][9][Cin] (implicit-GEMM dW layout) -> Conv2d.weight.grad layout [Cout][Cin][3][3] */
 int countr_conv_dw_unpack(const float* src, float* dst, int Cout, int Cin, countr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * MAE pre-training glue (models_mae_noct.py).
+ * ------------------------------------------------------------------------------------------ */
+/* dst[b][j][:] = src[b][idx[b][j]][:]; rows of row_bytes (multiple of 16).  torch.gather of random_masking
+ * (models_mae_noct.py:124) and, with the shuffle indices, its backward. */
+int countr_gather_rows(const void* src, const int64_t* idx, void* dst, int B, int n_src, int n_dst, int row_bytes,
+                       countr_stream_t stream);
+/* MAE decoder input (:158-165): out[b][l] = (ids_restore[b][l] < Lk ? xk[b][ids_restore[b][l]] : mask_token) + pos[l] */
+int countr_mae_unshuffle(const float* xk, const int64_t* ids_restore, const float* mask_token, const float* pos, float* out,
+                         int B, int L, int Lk, int D, countr_stream_t stream);
+/* forward_loss (:177-198): loss = mean_patches mean((pred - patchify(img))^2) (optionally per-patch normalised
+ * targets); also writes dpred = d loss / d pred (fp32, optional) */
+int countr_mae_loss(const float* pred, const void* img, int dtype, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+                    float* loss, float* dpred, int B, int C, int H, int W, int P, int norm_pix, countr_stream_t stream);
+/* dst16 = 16-bit(src * *scale_ptr): the upstream gradient scalar stays on the device (no host sync) */
+int countr_cast_scaled_f32_to_16(const float* src, const float* scale_ptr, void* dst, int64_t n, int bf16,
+                                 countr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

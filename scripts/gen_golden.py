@@ -78,6 +78,9 @@ def import_reference():
     spec = importlib.util.spec_from_file_location("ref_models_mae_cross", os.path.join(REF, "models_mae_cross.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    spec2 = importlib.util.spec_from_file_location("ref_models_mae_noct", os.path.join(REF, "models_mae_noct.py"))
+    mod.noct = importlib.util.module_from_spec(spec2)
+    spec2.loader.exec_module(mod.noct)
     return mod
 
 
@@ -96,6 +99,42 @@ def build_ref_model(ref, cfg, sd):
     assert torch.equal(ref_sd["pos_embed"], sd["pos_embed"]) and torch.equal(ref_sd["decoder_pos_embed"], sd["decoder_pos_embed"])
     m.load_state_dict(sd, strict=True)
     return m
+
+
+NOCT_SMALL = dict(img_size=384, patch_size=16, embed_dim=256, depth=2, num_heads=4, decoder_embed_dim=512, decoder_depth=2,
+                  decoder_num_heads=16, mlp_ratio=4, eps=1e-6)
+
+
+def gen_noct(ref, out_dir):
+    """MAE pre-training model (BASELINE config 5 path): loss / pred / mask and every parameter-gradient norm."""
+    from functools import partial
+    from oracle import noct_oracle as NO
+    cfg = NOCT_SMALL
+    sd = NO.make_state_dict(cfg, seed=2)
+    out = {}
+    for norm_pix in (False, True):
+        m = ref.noct.MaskedAutoencoderViTNoCT(img_size=384, patch_size=16, embed_dim=cfg["embed_dim"], depth=cfg["depth"],
+                                              num_heads=cfg["num_heads"], decoder_embed_dim=512, decoder_depth=cfg["decoder_depth"],
+                                              decoder_num_heads=16, mlp_ratio=4, norm_layer=partial(nn.LayerNorm, eps=1e-6),
+                                              norm_pix_loss=norm_pix)
+        assert list(m.state_dict().keys()) == list(sd.keys())
+        m.load_state_dict(sd, strict=True)
+        m.train()
+        imgs, _ = synth.make_inputs(2, seed=91)
+        torch.manual_seed(123)                     # the reference draws its masking noise from the global RNG
+        loss, pred, mask = m(imgs, mask_ratio=0.5)
+        loss.backward()
+        tag = "np1" if norm_pix else "np0"
+        out[f"{tag}/loss"] = loss.detach().numpy()
+        out[f"{tag}/mask"] = mask.numpy()
+        out[f"{tag}/pred_head"] = pred.detach()[:, :4, :64].numpy()
+        out[f"{tag}/pred_rowsum"] = pred.detach().sum(-1).numpy()
+        for name, p in m.named_parameters():
+            if p.grad is not None:
+                out[f"{tag}/g/{name}/norm"] = p.grad.norm().numpy()
+                out[f"{tag}/g/{name}/head"] = p.grad.flatten()[:16].numpy()
+        print(f"noct norm_pix={norm_pix}: loss={loss.item():.6f} kept={int((mask == 0).sum())}")
+    np.savez_compressed(os.path.join(out_dir, "noct_small.npz"), **out)
 
 
 def pool8(x):
@@ -152,6 +191,7 @@ def main():
         print(f"small shot={shot}: loss={loss.item():.6f} sums={out.detach().sum((1,2)).tolist()}")
     np.savez_compressed(os.path.join(out_dir, "small_fwd.npz"), **fwd)
     np.savez_compressed(os.path.join(out_dir, "small_grads.npz"), **grads)
+    gen_noct(ref, out_dir)
     for f in sorted(os.listdir(out_dir)):
         print(f, os.path.getsize(os.path.join(out_dir, f)))
 

@@ -1,0 +1,82 @@
+"""GPU parity of the MAE pre-training model (models_mae_noct, BASELINE config 5 path) against the goldens the
+reference produced and against autograd through the CPU oracle, with the reference's masking noise injected."""
+import os
+from functools import partial
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import noct_oracle as NO
+from oracle import synth
+from test_oracle import NOCT_SMALL, noct_noise
+from test_parity_gpu import rel
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+LOSS_SCALE = 1024.0
+
+
+@pytest.mark.parametrize("norm_pix", [False, True])
+def test_noct_forward_backward(cuda, norm_pix):
+    import models_mae_noct as N
+    g = np.load(os.path.join(GOLD, "noct_small.npz"))
+    tag = "np1" if norm_pix else "np0"
+    cfg = NOCT_SMALL
+    sd = NO.make_state_dict(cfg, seed=2)
+    m = N.MaskedAutoencoderViTNoCT(img_size=384, patch_size=16, embed_dim=cfg["embed_dim"], depth=cfg["depth"],
+                                   num_heads=cfg["num_heads"], decoder_embed_dim=512, decoder_depth=cfg["decoder_depth"],
+                                   decoder_num_heads=16, mlp_ratio=4, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
+                                   norm_pix_loss=norm_pix)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd, strict=True)
+    m = m.to(cuda).train()
+    imgs, _ = synth.make_inputs(2, seed=91)
+    noise = noct_noise(2, 576)
+    m._noise_override = noise
+    loss, pred, mask = m(imgs.to(cuda), mask_ratio=0.5)
+    (loss * LOSS_SCALE).backward()
+    torch.cuda.synchronize()
+    e_loss = abs(loss.item() - float(g[f"{tag}/loss"])) / float(g[f"{tag}/loss"])
+    e_pred = rel(pred[:, :4, :64], g[f"{tag}/pred_head"])
+    assert torch.equal(mask.cpu(), torch.from_numpy(g[f"{tag}/mask"]))
+    # oracle autograd
+    train = [k for k in sd if k not in ("pos_embed", "decoder_pos_embed")]
+    for k in train:
+        sd[k] = sd[k].clone().requires_grad_(True)
+    rl, rp, _ = NO.forward(sd, cfg, imgs, 0.5, noise, norm_pix)
+    rl.backward()
+    num = den = 0.0
+    worst = (0.0, "")
+    params = dict(m.named_parameters())
+    assert sorted(k for k, p in params.items() if p.grad is not None) == sorted(train)
+    all_norm = torch.cat([sd[k].grad.flatten() for k in train]).norm().item()
+    for k in train:
+        got = (params[k].grad / LOSS_SCALE).double().cpu()
+        ref = sd[k].grad.double()
+        num += (got - ref).pow(2).sum().item()
+        den += ref.pow(2).sum().item()
+        e = (got - ref).norm().item() / (ref.norm().item() + 1e-4 * all_norm)
+        if e > worst[0]:
+            worst = (e, k)
+        gold = float(g[f"{tag}/g/{k}/norm"])
+        assert abs(ref.norm().item() - gold) <= 1e-3 * gold + 1e-9, k
+    total = (num / den) ** 0.5
+    print(f"\n[noct parity norm_pix={norm_pix}] loss rel={e_loss:.2e} pred relL2={e_pred:.2e} vs oracle pred relL2={rel(pred, rp):.2e} "
+          f"all-grads relL2={total:.3e} worst {worst[1]} {worst[0]:.3e}")
+    assert e_loss < 2e-3 and e_pred < 3e-3 and rel(pred, rp) < 3e-3
+    assert total < 1e-2 and worst[0] < 5e-2
+
+
+def test_noct_eval_and_masking_api(cuda):
+    import models_mae_noct as N
+    m = N.MaskedAutoencoderViTNoCT(embed_dim=256, depth=1, num_heads=4, decoder_depth=1).to(cuda).eval()
+    imgs = torch.rand(2, 3, 384, 384, device=cuda)
+    with torch.no_grad():
+        loss, pred, mask = m(imgs, mask_ratio=0.75)
+    assert pred.shape == (2, 576, 768) and mask.shape == (2, 576) and int(mask.sum()) == 2 * 432
+    assert torch.isfinite(loss)
+    x = torch.randn(2, 576, 256, device=cuda)
+    xm, mk, ids = m.random_masking(x, 0.5)
+    assert xm.shape == (2, 288, 256) and torch.equal(xm, torch.gather(x, 1, torch.argsort(ids, 1)[:, :288].unsqueeze(-1).repeat(1, 1, 256)))
+    assert torch.equal(m.unpatchify(m.patchify(imgs)), imgs)

@@ -75,3 +75,36 @@ def test_small_decoder_grads_match_reference(shot):
         ref_norm = float(g[f"s{shot}/{n}/norm"])
         assert abs(gr.norm().item() - ref_norm) <= 5e-4 * ref_norm + 1e-12, n
         assert rel(gr[:16], g[f"s{shot}/{n}/head"]) < 1e-3 or ref_norm < 1e-10, n
+
+
+# ------------------------------------------------------------------------------------------------
+# MAE pre-training model (models_mae_noct.py) — oracle vs reference-generated goldens
+# ------------------------------------------------------------------------------------------------
+NOCT_SMALL = dict(img_size=384, patch_size=16, embed_dim=256, depth=2, num_heads=4, decoder_embed_dim=512, decoder_depth=2,
+                  decoder_num_heads=16, mlp_ratio=4, eps=1e-6)
+
+
+def noct_noise(n, l):
+    torch.manual_seed(123)          # the reference's forward draws torch.rand(N, L) first (models_mae_noct.py:118)
+    return torch.rand(n, l)
+
+
+@pytest.mark.parametrize("norm_pix", [False, True])
+def test_noct_oracle_matches_reference(norm_pix):
+    from oracle import noct_oracle as NO
+    g = np.load(os.path.join(GOLD, "noct_small.npz"))
+    tag = "np1" if norm_pix else "np0"
+    sd = NO.make_state_dict(NOCT_SMALL, seed=2)
+    train = [k for k in sd if k not in ("pos_embed", "decoder_pos_embed")]
+    for k in train:
+        sd[k] = sd[k].clone().requires_grad_(True)
+    imgs, _ = synth.make_inputs(2, seed=91)
+    loss, pred, mask = NO.forward(sd, NOCT_SMALL, imgs, 0.5, noct_noise(2, 576), norm_pix)
+    loss.backward()
+    assert rel(loss, g[f"{tag}/loss"]) < 1e-5
+    assert torch.equal(mask, torch.from_numpy(g[f"{tag}/mask"]))
+    assert rel(pred[:, :4, :64], g[f"{tag}/pred_head"]) < 2e-5
+    assert rel(pred.sum(-1), g[f"{tag}/pred_rowsum"]) < 2e-4
+    for k in train:
+        ref_norm = float(g[f"{tag}/g/{k}/norm"])
+        assert abs(sd[k].grad.norm().item() - ref_norm) <= 1e-3 * ref_norm + 1e-9, k
