@@ -148,15 +148,15 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     _lib.require_device()
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))   # a stuck collective aborts instead of hanging the box
     B = PER_GPU_BATCH
     torch.manual_seed(0)
     model = models_mae_cross.mae_vit_base_patch16(norm_pix_loss=False).to(dev).train()
     opt = torch.optim.AdamW(param_groups(model, 0.05), lr=1e-5, betas=(0.9, 0.95), fused=True, capturable=True)
     loss_scale = 4096.0
     eng = engine()
-    from countr_b200.dist import make_grad_allreduce
-    eng.grad_allreduce = make_grad_allreduce() if world > 1 else None
+    eng.grad_allreduce = None      # the bench issues the all-reduce itself, between the two CUDA graphs of a step
 
     # host inputs (pinned), a few distinct batches rotated over the steps
     g = torch.Generator().manual_seed(1234 + rank)
@@ -183,19 +183,44 @@ def run_ours(args):
         d_gt.copy_(hb["gt"], non_blocking=True)
         d_mask.copy_(hb["mask"], non_blocking=True)
 
-    def step():
+    def step_fwd_bwd():
         out = model(d_imgs, d_boxes, SHOTS)                                   # models_mae_cross.SupervisedMAE.forward
         loss = ((out - d_gt) ** 2 * d_mask / (384 * 384)).sum() / B           # FSC_finetune_cross.py:290-295
         (loss * loss_scale).backward()
+        d_loss.copy_(loss.detach())
+
+    def step_update():
         grads = [p.grad for p in model.parameters() if p.grad is not None]
         torch._foreach_mul_(grads, 1.0 / loss_scale)
         opt.step()
-        d_loss.copy_(loss.detach())
+
+    state = {"aliased": None}
+
+    def allreduce_grads():
+        """Data-parallel gradient mean: ONE NCCL all-reduce over the flat arena (the .grad tensors are views of it)."""
+        if world == 1:
+            return
+        arena = eng.last_arena
+        grads = [p.grad for p in model.parameters() if p.grad is not None]
+        if state["aliased"] is None:
+            base = arena.untyped_storage().data_ptr()
+            state["aliased"] = all(g.untyped_storage().data_ptr() == base for g in grads)
+        if state["aliased"]:
+            dist.all_reduce(arena, op=dist.ReduceOp.AVG)
+        else:   # autograd cloned the views: reduce the clones (slower, still exact)
+            for g in grads:
+                dist.all_reduce(g, op=dist.ReduceOp.AVG)
+
+    def step():
+        step_fwd_bwd()
+        allreduce_grads()
+        step_update()
 
     upload(0)
     torch.cuda.synchronize()
-    # warm-up (eager) on a side stream, then capture the whole step in a CUDA graph
-    graph = None
+    # warm-up (eager) on a side stream, then capture the step in CUDA graphs.  The NCCL all-reduce is NOT captured:
+    # for N > 1 the step is two graphs (forward+backward | unscale+AdamW) with the collective enqueued between them.
+    graphs = None
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -208,23 +233,40 @@ def run_ours(args):
     if not args.no_graph:
         try:
             opt.zero_grad(set_to_none=True)
-            graph = torch.cuda.CUDAGraph()
             n0 = ops.LAUNCHES[0]
-            with torch.cuda.graph(graph):
-                step()
+            if world == 1:
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    step()
+                graphs = (g1,)
+            else:
+                g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    step_fwd_bwd()
+                with torch.cuda.graph(g2, pool=g1.pool()):
+                    step_update()
+                graphs = (g1, g2)
             launches_per_step = ops.LAUNCHES[0] - n0
         except Exception as e:  # pragma: no cover
-            if rank == 0:
-                print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
-            graph = None
+            print(f"[bench] rank {rank}: CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+            graphs = None
             torch.cuda.synchronize()
+    if world > 1:   # all ranks must agree on the mode
+        flag = torch.tensor([1 if graphs is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() == 0:
+            graphs = None
 
     def run_step():
-        if graph is not None:
-            graph.replay()
-        else:
+        if graphs is None:
             opt.zero_grad(set_to_none=True)
             step()
+        elif len(graphs) == 1:
+            graphs[0].replay()
+        else:
+            graphs[0].replay()
+            allreduce_grads()
+            graphs[1].replay()
 
     if launches_per_step is None:
         n0 = ops.LAUNCHES[0]
@@ -304,7 +346,7 @@ def run_ours(args):
         "config": {"workload": "FSC147 fine-tune: ViT-B/16, 384x384, 3 shots, batch 8 per GPU (BASELINE configs[1])",
                    "global_batch": imgs_per_step, "step": "encoder fwd (frozen) + decoder fwd/bwd + masked-MSE + AdamW"
                    + (" + NCCL grad all-reduce (avg)" if world > 1 else ""),
-                   "cuda_graph": graph is not None, "loss_scale": loss_scale,
+                   "cuda_graph": graphs is not None, "grad_arena_aliased": state["aliased"], "loss_scale": loss_scale,
                    "l2": "per-step working set (~1.5 GB of activations) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": round(e2e, 2), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / args.steps, 4)},

@@ -210,6 +210,7 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
             ops.inorm_relu_pool_bwd(raw, ex["mean"][i - 1], ex["rstd"][i - 1], d_raw, 0, dpool16=d_pool, dbias=G(convs[i - 1].bias),
                                     scratch=scratch)
         ops.exemplar_conv1_dw(boxes, S, d_raw, G(convs[0].weight))
+    eng.last_arena = arena             # trainers that all-reduce outside the autograd node pick the arena up here
     if eng.grad_allreduce is not None:
         eng.grad_allreduce(arena)      # data-parallel mean of every decoder gradient in one collective
     return grads

@@ -94,6 +94,7 @@ class Engine:
         # optional callable(arena): averages the flat fp32 gradient arena over the data-parallel ranks
         # (one NCCL all-reduce per step, set by the trainer / bench when WORLD_SIZE > 1)
         self.grad_allreduce = None
+        self.last_arena = None          # flat fp32 gradient arena of the most recent backward
 
     # ------------------------------------------------------------------ encoder
     def encoder_forward(self, m, imgs):

@@ -15,6 +15,13 @@ elif which == "qkv":
     a = torch.randn(m, k, device=dev).half(); w = torch.randn(n, k, device=dev).half() * 0.05
     c = torch.empty(m, n, device=dev, dtype=torch.float16); bias = torch.zeros(n, device=dev)
     f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias)
+elif which == "conv":
+    x16 = torch.randn(8, 192, 192, 256, device=dev).half()
+    w16 = torch.randn(256, 9 * 256, device=dev).half() * 0.02
+    y16 = torch.empty(8, 192, 192, 256, device=dev, dtype=torch.float16)
+    bias = torch.zeros(256, device=dev)
+    stats = torch.zeros(8, 8, 2, device=dev, dtype=torch.float64)
+    f = lambda: ops.conv3x3(x16, w16, y16, bias=bias, gn_stats=stats)
 elif which == "attn":
     qkv = torch.randn(8, 576, 3, 12, 64, device=dev).half()
     out = torch.empty(8, 576, 768, device=dev, dtype=torch.float16)
