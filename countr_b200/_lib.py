@@ -26,7 +26,7 @@ class GemmDesc(Structure):
         ("M", c_int32), ("N", c_int32), ("K", c_int32),
         ("nb1", c_int32), ("nb2", c_int32),
         ("bf16", c_int32),
-        ("bn", c_int32), ("split_k", c_int32), ("cluster", c_int32),
+        ("bn", c_int32), ("split_k", c_int32), ("cluster", c_int32), ("cta_pair", c_int32),
         ("conv_h", c_int32), ("conv_w", c_int32), ("conv_cin", c_int32), ("conv_bx", c_int32), ("conv_by", c_int32),
         ("conv_dw", c_int32), ("conv_batch", c_int32),
         ("c", c_void_p),

@@ -40,6 +40,7 @@ struct GemmArgs {
   int bf16;
   int split_k, k_per_split;
   int m_tiles, n_tiles, total_tiles;   // total_tiles counts CLUSTER tiles (cs consecutive m tiles x one n tile)
+  int pair;                            // 1: CTA pair (cta_group::2): 256 x bn tile over two SMs, 6 stages of 32 KB
   int cs, m_groups;                    // cluster size (CTAs sharing the B tile via TMA multicast), ceil(m_tiles / cs)
   // conv mode
   int conv, H, W, cin_blocks, bx, by, tiles_x;   // conv: 0 none, 1 forward/dX implicit GEMM, 2 dW (pixels are K)
@@ -95,12 +96,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 192 KB of operand stages: 4 x (A 16 KB + B 32 KB), or in pair mode 6 x (A 16 KB + half of B 16 KB)
+  const int nstages = p.pair ? 6 : kStages;
+  const uint32_t stage_bytes = p.pair ? 32768u : kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* full = bars;                      // [kStages]
-  uint64_t* empty = bars + kStages;           // [kStages]
-  uint64_t* tmem_full = bars + 2 * kStages;   // [2]
-  uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* full = bars;                 // [6]
+  uint64_t* empty = bars + 6;            // [6]
+  uint64_t* tmem_full = bars + 12;       // [2]
+  uint64_t* tmem_empty = bars + 14;      // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -108,17 +112,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < nstages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], p.cs);     // every CTA of the cluster must have consumed the stage (multicast writes all of them)
+      // multicast clusters: every CTA must have consumed the stage (one commit each); pair: ONE multicast commit
+      mbar_init(&empty[i], p.pair ? 1 : p.cs);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kEpiWarps);
+      mbar_init(&tmem_empty[i], p.pair ? 2 * kEpiWarps : kEpiWarps);   // pair: the leader waits for both CTAs' epilogues
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  if (warp == 1) {
+    if (p.pair) tmem_alloc_2cta<512>(tmem_ptr); else tmem_alloc<512>(tmem_ptr);
+  }
   tc_fence_before();
   if (p.cs > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers must be initialised before any multicast
   tc_fence_after();
@@ -127,7 +134,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int cluster_id = blockIdx.x / p.cs, num_clusters = gridDim.x / p.cs;
   const uint16_t mc_mask = static_cast<uint16_t>((1u << p.cs) - 1u);
 
-  const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * BK * 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.pair ? p.bn / 2 : p.bn) * BK * 2;   // B bytes landing in THIS CTA per stage
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
@@ -146,10 +153,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + kABytes;
-          mbar_arrive_expect_tx(&full[stage], kABytes + b_bytes);
           const int k = k_begin + kb * BK;
+          if (p.pair) {
+            // both CTAs fill their own stage; all bytes are credited to the LEADER's full barrier, which the
+            // leader's MMA thread waits on before issuing the cta_group::2 MMAs over both shared memories
+            const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (kABytes + b_bytes));
+            if (p.conv) {
+              const int tap = kb / p.cin_blocks;
+              const int cb = kb - tap * p.cin_blocks;
+              const int ky = tap / 3, kx = tap - ky * 3;
+              tma_load_4d_2sm(sa, &tma_a, full_leader, cb * BK, x0 + kx - 1, y0 + ky - 1, t.b1);
+            } else if (!p.a_mn) {
+              tma_load_4d_2sm(sa, &tma_a, full_leader, k, t.m * BM, t.b2, t.b1);
+            } else {
+              tma_load_4d_2sm(sa, &tma_a, full_leader, t.m * BM, k, t.b2, t.b1);
+              tma_load_4d_2sm(sa + 8192, &tma_a, full_leader, t.m * BM + 64, k, t.b2, t.b1);
+            }
+            tma_load_4d_2sm(sb, &tma_b, full_leader, k, t.n * p.bn + rank * (p.bn / 2), p.conv ? 0 : t.b2, p.conv ? 0 : t.b1);
+            if (++stage == nstages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
+          mbar_arrive_expect_tx(&full[stage], kABytes + b_bytes);
           if (p.conv == 2) {
             // dW: k-block = one bx x by (= 64) pixel tile of image b; A = dY (M = Cout), B = X shifted by the tap
             const int kbg = k / BK;
@@ -196,7 +226,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             for (int i = rank * per; i < (rank + 1) * per; ++i)
               tma_load_4d_mc(sb + i * 8192, &tma_b, &full[stage], t.n * p.bn + i * 64, k, t.b2, t.b1, mc_mask);
           }
-          if (++stage == kStages) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -205,8 +235,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(BM, p.bn, p.a_mn != 0, p.b_mn != 0, p.bf16 != 0);
+    if (lane == 0 && (!p.pair || rank == 0)) {   // pair mode: only the leader CTA issues MMAs
+      const uint32_t idesc = make_idesc_f16(p.pair ? 2 * BM : BM, p.bn, p.a_mn != 0, p.b_mn != 0, p.bf16 != 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -222,7 +252,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint32_t sb = sa + kABytes;
           // K-major : 8-row groups 1024 B apart; +32 B per 16-element k-step inside the swizzle atom
           // MN-major: 64-wide MN blocks 8192 B apart (LBO), 8-row k groups 1024 B apart (SBO);
@@ -231,13 +261,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const uint64_t b_desc = p.b_mn ? make_smem_desc_sw128(sb, 8192, 1024) : make_smem_desc_sw128(sb, 16, 1024);
           const uint32_t a_step = p.a_mn ? (2048u >> 4) : (32u >> 4);
           const uint32_t b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
+          if (p.pair) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_f16_ss(d_tmem, a_desc + static_cast<uint64_t>(a_step * k), b_desc + static_cast<uint64_t>(b_step * k),
-                        idesc, (kb | k) != 0);
-          if (p.cs > 1) umma_commit_mc(&empty[stage], mc_mask); else umma_commit(&empty[stage]);
-          if (kb == nkb - 1) umma_commit(&tmem_full[acc]);
-          if (++stage == kStages) {
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16_ss_2cta(d_tmem, a_desc + static_cast<uint64_t>(a_step * k), b_desc + static_cast<uint64_t>(b_step * k),
+                               idesc, (kb | k) != 0);
+            umma_commit_2cta_mc(&empty[stage], 3);                       // frees the stage in BOTH CTAs
+            if (kb == nkb - 1) umma_commit_2cta_mc(&tmem_full[acc], 3);  // wakes BOTH epilogues
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16_ss(d_tmem, a_desc + static_cast<uint64_t>(a_step * k), b_desc + static_cast<uint64_t>(b_step * k),
+                          idesc, (kb | k) != 0);
+            if (p.cs > 1) umma_commit_mc(&empty[stage], mc_mask); else umma_commit(&empty[stage]);
+            if (kb == nkb - 1) umma_commit(&tmem_full[acc]);
+          }
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -449,7 +488,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       // accumulator drained: hand the TMEM stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (p.pair && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));   // the leader owns the MMA
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -461,7 +503,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (p.cs > 1) cluster_sync_all(); else __syncthreads();   // no peer may still signal this CTA's barriers after it exits
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if (p.pair) tmem_dealloc_2cta<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -547,7 +589,10 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   // no gain at cs=2 and a loss at cs=4 — the kernel is NOT L2->SM bound (the limiter at 128 x 256 tiles is
   // shared-memory bandwidth: TMA fill + UMMA operand reads = 192 B/clk against 128 B/clk), so the default is
   // cs = 1 and the path is kept for experiments (cta_group::2 is the real fix).
-  int cs = d->cluster > 0 ? d->cluster : 1;
+  // CTA pair (cta_group::2): K-major B only; the pair computes a 256 x bn tile with half of B per SM.
+  const bool pair_ok = !d->b_mn && !conv_dw && p.m_tiles >= 2 && bn % 32 == 0;
+  p.pair = (d->cta_pair > 0 && pair_ok) ? 1 : 0;
+  int cs = p.pair ? 2 : (d->cluster > 0 ? d->cluster : 1);
   if (cs != 1 && cs != 2 && cs != 4) cs = 1;
   while (cs > 1 && (p.m_tiles < cs || (d->b_mn || conv_dw ? (bn / 64) % cs != 0 : (bn % (8 * cs)) != 0))) cs >>= 1;
   p.cs = cs;

@@ -35,7 +35,7 @@ def _count(n=1):
 
 def gemm(a, b, c, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, nb1=1, nb2=1,
          sa=(0, 0), sb=(0, 0), sc=(0, 0), bias=None, act=0, aux=None, ldaux=0, residual=None, ldr=0,
-         res_mod=0, alpha=1.0, atomic=False, split_k=1, bn=0, conv=None, gn_stats=None, conv_dw=None, cluster=0):
+         res_mod=0, alpha=1.0, atomic=False, split_k=1, bn=0, conv=None, gn_stats=None, conv_dw=None, cluster=0, pair=0):
     """C = epilogue(alpha * A @ B^T); see countr_gemm_desc for the layout rules."""
     assert a.dtype in (F16, BF16) and b.dtype == a.dtype
     d = GemmDesc()
@@ -46,7 +46,7 @@ def gemm(a, b, c, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, nb1=1, nb2=
     d.M, d.N, d.K = M, N, K
     d.nb1, d.nb2 = nb1, nb2
     d.bf16 = _is_bf16(a)
-    d.bn, d.split_k, d.cluster = bn, split_k, cluster
+    d.bn, d.split_k, d.cluster, d.cta_pair = bn, split_k, cluster, pair
     if conv is not None:
         d.conv_h, d.conv_w, d.conv_cin, d.conv_bx, d.conv_by = conv
     if conv_dw is not None:
@@ -80,14 +80,14 @@ def linear(x16, w16, out, bias=None, act=0, aux=None, residual=None, res_mod=0, 
                 ldr=residual.stride(0) if residual is not None else 0, res_mod=res_mod, alpha=alpha)
 
 
-def conv3x3(x16, w16, out, bias=None, gn_stats=None):
+def conv3x3(x16, w16, out, bias=None, gn_stats=None, pair=0):
     """NHWC implicit-GEMM conv: x16 [B,H,W,Cin], w16 [Cout, 9*Cin] (ky,kx,ci), out [B,H,W,Cout]."""
     B, H, W, Cin = x16.shape
     Cout = w16.shape[0]
     bx = next((t for t in (128, 64, 32, 16, 8) if W % t == 0), 8)
     by = 128 // bx
     return gemm(x16, w16, out, B * H * W, Cout, 9 * Cin, lda=Cin, ldb=w16.stride(0), ldc=Cout, nb1=B,
-                sa=(H * W * Cin, 0), sc=(H * W * Cout, 0), bias=bias, conv=(H, W, Cin, bx, by), gn_stats=gn_stats)
+                sa=(H * W * Cin, 0), sc=(H * W * Cout, 0), bias=bias, conv=(H, W, Cin, bx, by), gn_stats=gn_stats, pair=pair)
 
 
 def conv3x3_dw(dy16, x16, dw32, split_k=0):

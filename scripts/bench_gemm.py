@@ -29,28 +29,28 @@ def timeit(fn, reps=20):
     return e0.elapsed_time(e1) / reps * 1e3  # us
 
 
-def lin(name, m, n, k, mode, bn=0, cl=0):
+def lin(name, m, n, k, mode, bn=0, cl=0, pr=0):
     a = torch.randn(m, k, device=dev).half()
     w = torch.randn(n, k, device=dev).half() * 0.05
     bias = torch.zeros(n, device=dev)
     if mode == "f16":
         c = torch.empty(m, n, device=dev, dtype=torch.float16)
-        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, bn=bn, cluster=cl)
+        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, bn=bn, cluster=cl, pair=pr)
     elif mode == "gelu":
         c = torch.empty(m, n, device=dev, dtype=torch.float16)
-        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, act=1, bn=bn, cluster=cl)
+        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, act=1, bn=bn, cluster=cl, pair=pr)
     elif mode == "gelubwd":
         c = torch.empty(m, n, device=dev, dtype=torch.float16)
         aux = torch.randn(m, n, device=dev).half()
-        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, act=2, aux=aux, ldaux=n, bn=bn, cluster=cl)
+        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, act=2, aux=aux, ldaux=n, bn=bn, cluster=cl, pair=pr)
     elif mode == "res":
         c = torch.zeros(m, n, device=dev)
-        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, residual=c, ldr=n, bn=bn, cluster=cl)
+        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, residual=c, ldr=n, bn=bn, cluster=cl, pair=pr)
     elif mode == "f32":
         c = torch.zeros(m, n, device=dev)
-        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bn=bn, cluster=cl)
+        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bn=bn, cluster=cl, pair=pr)
     us = timeit(f)
-    print(f"{name:28s} M={m:6d} N={n:5d} K={k:5d} {mode:8s} bn={bn:3d} cl={cl}: {us:8.1f} us  {2.0*m*n*k/us/1e6:7.1f} TFLOP/s")
+    print(f"{name:28s} M={m:6d} N={n:5d} K={k:5d} {mode:8s} bn={bn:3d} cl={cl} pair={pr}: {us:8.1f} us  {2.0*m*n*k/us/1e6:7.1f} TFLOP/s")
 
 
 def dw(name, m_tok, n_out, k_in, split):
@@ -62,18 +62,18 @@ def dw(name, m_tok, n_out, k_in, split):
     print(f"{name:28s} dW [{n_out}x{k_in}] over {m_tok} split={split:2d}: {us:8.1f} us  {2.0*m_tok*n_out*k_in/us/1e6:7.1f} TFLOP/s")
 
 
-def conv(name, h, cin, cout):
+def conv(name, h, cin, cout, pr=0):
     x = torch.randn(B, h, h, cin, device=dev).half()
     w = torch.randn(cout, 9 * cin, device=dev).half() * 0.02
     y = torch.empty(B, h, h, cout, device=dev, dtype=torch.float16)
     bias = torch.zeros(cout, device=dev)
     stats = torch.zeros(B, cout // 32, 2, device=dev, dtype=torch.float64)
-    us = timeit(lambda: ops.conv3x3(x, w, y, bias=bias, gn_stats=stats))
+    us = timeit(lambda: ops.conv3x3(x, w, y, bias=bias, gn_stats=stats, pair=pr))
     fl = 2.0 * B * h * h * cout * 9 * cin
     dyv = torch.randn(B, h, h, cout, device=dev).half()
     dwp = torch.zeros(cout, 9 * cin, device=dev)
     us2 = timeit(lambda: ops.conv3x3_dw(dyv, x, dwp))
-    print(f"{name:28s} conv {h}x{h} {cin}->{cout}: fwd {us:8.1f} us {fl/us/1e6:7.1f} TF | dW {us2:8.1f} us {fl/us2/1e6:7.1f} TF")
+    print(f"{name:28s} pair={pr} conv {h}x{h} {cin}->{cout}: fwd {us:8.1f} us {fl/us/1e6:7.1f} TF | dW {us2:8.1f} us {fl/us2/1e6:7.1f} TF")
 
 
 def attn(name, H, dh):
@@ -84,28 +84,17 @@ def attn(name, H, dh):
 
 
 print(f"B={B}")
-lin("tiny", 128, 128, 64, "f16")
-lin("tiny2", 128, 128, 512, "f16")
-for cl in (1, 2):
-    lin("enc qkv", M, 2304, 768, "f16", 0, cl)
-    lin("enc qkv bn256", M, 2304, 768, "f16", 256, cl)
-    lin("enc proj (+res)", M, 768, 768, "res", 0, cl)
-    lin("enc fc1 (gelu)", M, 3072, 768, "gelu", 0, cl)
-    lin("enc fc1 (gelu) bn256", M, 3072, 768, "gelu", 256, cl)
-    lin("enc fc2 (+res)", M, 768, 3072, "res", 0, cl)
-    lin("enc fc2 (+res) bn256", M, 768, 3072, "res", 256, cl)
-    lin("fim qkv", M, 1536, 512, "f16", 0, cl)
-    lin("fim proj (+res)", M, 512, 512, "res", 0, cl)
-    lin("fim fc1 (gelu)", M, 2048, 512, "gelu", 0, cl)
-    lin("fim fc2 (+res)", M, 512, 2048, "res", 0, cl)
-    lin("fim fc2 dX (gelu bwd)", M, 2048, 512, "gelubwd", 0, cl)
-    lin("big square", 8192, 8192, 8192, "f16", 256, cl)
-dw("fim fc2 dW", M, 512, 2048, 4)
-dw("fim proj dW", M, 512, 512, 9)
-dw("fim qkv dW", M, 1536, 512, 3)
-conv("head0", 24, 512, 256)
-conv("head1", 48, 256, 256)
-conv("head2", 96, 256, 256)
-conv("head3", 192, 256, 256)
-attn("encoder", 12, 64)
-attn("fim", 16, 32)
+for pr in (0, 1):
+    lin("enc qkv", M, 2304, 768, "f16", 0, 0, pr)
+    lin("enc qkv bn256", M, 2304, 768, "f16", 256, 0, pr)
+    lin("enc proj (+res)", M, 768, 768, "res", 0, 0, pr)
+    lin("enc proj (+res) bn256", M, 768, 768, "res", 256, 0, pr)
+    lin("enc fc1 (gelu) bn256", M, 3072, 768, "gelu", 256, 0, pr)
+    lin("enc fc2 (+res)", M, 768, 3072, "res", 0, 0, pr)
+    lin("enc fc2 (+res) bn256", M, 768, 3072, "res", 256, 0, pr)
+    lin("fim qkv", M, 1536, 512, "f16", 0, 0, pr)
+    lin("fim fc2 (+res)", M, 512, 2048, "res", 0, 0, pr)
+    lin("big square", 8192, 8192, 8192, "f16", 256, 0, pr)
+    conv("head1", 48, 256, 256, pr)
+    conv("head2", 96, 256, 256, pr)
+    conv("head3", 192, 256, 256, pr)

@@ -335,3 +335,38 @@ def test_exemplar_stage1_and_inorm(cuda):
     torch.cuda.synchronize()
     refa = F.relu(F.instance_norm(r, eps=1e-5)).mean((2, 3))
     assert_close(y32, refa, 1e-5, "IN+relu+avgpool")
+
+
+# ------------------------------------------------------------------------------------------
+# cta_group::2 (two SMs per 256 x N tile)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,bn", [(256, 256, 64, 256), (256, 128, 128, 128), (512, 512, 512, 256), (4608, 768, 768, 0),
+                                      (4608, 2304, 768, 256), (1000, 520, 200, 0), (8192, 1024, 1024, 256)])
+def test_gemm_cta_pair(cuda, M, N, K, bn):
+    from countr_b200 import ops
+    a = _rand16((M, K), cuda, seed=71)
+    b = _rand16((N, K), cuda, seed=72)
+    bias = torch.randn(N, device=cuda)
+    c = torch.empty(M, N, device=cuda, dtype=torch.float32)
+    ops.gemm(a, b, c, M, N, K, lda=K, ldb=K, ldc=N, bn=bn, bias=bias, pair=1)
+    torch.cuda.synchronize()
+    assert_close(c, a.float() @ b.float().t() + bias, 2e-5, f"pair gemm {M}x{N}x{K} bn={bn}")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 24, 24, 512, 256), (2, 48, 48, 256, 256), (1, 96, 96, 256, 256), (3, 16, 16, 128, 256)])
+def test_conv3x3_cta_pair(cuda, B, H, W, Cin, Cout):
+    from countr_b200 import ops
+    x = _rand16((B, H, W, Cin), cuda, seed=73)
+    w = torch.randn(Cout, Cin, 3, 3, device=cuda) * 0.05
+    bias = torch.randn(Cout, device=cuda)
+    w16 = torch.empty(Cout, 9 * Cin, device=cuda, dtype=torch.float16)
+    ops.conv_weight_pack(w, w16, 0)
+    y = torch.empty(B, H, W, Cout, device=cuda, dtype=torch.float16)
+    stats = torch.zeros(B, Cout // 32, 2, device=cuda, dtype=torch.float64)
+    ops.conv3x3(x, w16, y, bias=bias, gn_stats=stats, pair=1)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), bias, padding=1).permute(0, 2, 3, 1)
+    assert_close(y.reshape(-1, Cout), ref.reshape(-1, Cout), 1.5e-3, f"pair conv {B}x{H}x{W} {Cin}->{Cout}")
+    rg = ref.reshape(B, H * W, Cout // 32, 32).double()
+    ref_stats = torch.stack([rg.sum((1, 3)), (rg * rg).sum((1, 3))], -1)
+    assert_close(stats.reshape(-1, 2), ref_stats.reshape(-1, 2), 1e-4, "gn stats (pair)")
