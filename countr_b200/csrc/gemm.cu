@@ -91,14 +91,17 @@ __device__ __forceinline__ float2 unpack_16b(uint32_t v, int bf16) {
   return __half22float2(h);
 }
 
+// kPair instantiates the cta_group::2 code path; kernels that contain cta_group::2 instructions must be launched
+// as clusters of two, so the single-CTA variant is a separate instantiation.
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // 192 KB of operand stages: 4 x (A 16 KB + B 32 KB), or in pair mode 6 x (A 16 KB + half of B 16 KB)
-  const int nstages = p.pair ? 6 : kStages;
-  const uint32_t stage_bytes = p.pair ? 32768u : kStageBytes;
+  const int nstages = kPair ? 6 : kStages;
+  const uint32_t stage_bytes = kPair ? 32768u : kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* full = bars;                 // [6]
   uint64_t* empty = bars + 6;            // [6]
@@ -115,16 +118,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     for (int i = 0; i < nstages; ++i) {
       mbar_init(&full[i], 1);
       // multicast clusters: every CTA must have consumed the stage (one commit each); pair: ONE multicast commit
-      mbar_init(&empty[i], p.pair ? 1 : p.cs);
+      mbar_init(&empty[i], kPair ? 1 : p.cs);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], p.pair ? 2 * kEpiWarps : kEpiWarps);   // pair: the leader waits for both CTAs' epilogues
+      mbar_init(&tmem_empty[i], kPair ? 2 * kEpiWarps : kEpiWarps);   // pair: the leader waits for both CTAs' epilogues
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    if (p.pair) tmem_alloc_2cta<512>(tmem_ptr); else tmem_alloc<512>(tmem_ptr);
+    if (kPair) tmem_alloc_2cta<512>(tmem_ptr); else tmem_alloc<512>(tmem_ptr);
   }
   tc_fence_before();
   if (p.cs > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers must be initialised before any multicast
@@ -134,7 +137,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int cluster_id = blockIdx.x / p.cs, num_clusters = gridDim.x / p.cs;
   const uint16_t mc_mask = static_cast<uint16_t>((1u << p.cs) - 1u);
 
-  const uint32_t b_bytes = static_cast<uint32_t>(p.pair ? p.bn / 2 : p.bn) * BK * 2;   // B bytes landing in THIS CTA per stage
+  const uint32_t b_bytes = static_cast<uint32_t>(kPair ? p.bn / 2 : p.bn) * BK * 2;   // B bytes landing in THIS CTA per stage
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
@@ -156,7 +159,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + kABytes;
           const int k = k_begin + kb * BK;
-          if (p.pair) {
+          if (kPair) {
             // both CTAs fill their own stage; all bytes are credited to the LEADER's full barrier, which the
             // leader's MMA thread waits on before issuing the cta_group::2 MMAs over both shared memories
             const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
@@ -235,8 +238,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0 && (!p.pair || rank == 0)) {   // pair mode: only the leader CTA issues MMAs
-      const uint32_t idesc = make_idesc_f16(p.pair ? 2 * BM : BM, p.bn, p.a_mn != 0, p.b_mn != 0, p.bf16 != 0);
+    if (lane == 0 && (!kPair || rank == 0)) {   // pair mode: only the leader CTA issues MMAs
+      const uint32_t idesc = make_idesc_f16(kPair ? 2 * BM : BM, p.bn, p.a_mn != 0, p.b_mn != 0, p.bf16 != 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -261,7 +264,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const uint64_t b_desc = p.b_mn ? make_smem_desc_sw128(sb, 8192, 1024) : make_smem_desc_sw128(sb, 16, 1024);
           const uint32_t a_step = p.a_mn ? (2048u >> 4) : (32u >> 4);
           const uint32_t b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
-          if (p.pair) {
+          if (kPair) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
               umma_f16_ss_2cta(d_tmem, a_desc + static_cast<uint64_t>(a_step * k), b_desc + static_cast<uint64_t>(b_step * k),
@@ -489,7 +492,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (p.pair && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));   // the leader owns the MMA
+        if (kPair && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));   // the leader owns the MMA
         else mbar_arrive(&tmem_empty[acc]);
       }
       if (++acc == 2) {
@@ -503,7 +506,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (p.cs > 1) cluster_sync_all(); else __syncthreads();   // no peer may still signal this CTA's barriers after it exits
   if (warp == 1) {
     tc_fence_after();
-    if (p.pair) tmem_dealloc_2cta<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
+    if (kPair) tmem_dealloc_2cta<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -659,7 +662,8 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    COUNTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    COUNTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    COUNTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   const int max_clusters = sms / p.cs;
@@ -676,6 +680,7 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  COUNTR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel, ta, tb, p));
+  if (p.pair) COUNTR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<true>, ta, tb, p));
+  else COUNTR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<false>, ta, tb, p));
   return COUNTR_OK;
 }
