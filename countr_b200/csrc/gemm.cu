@@ -594,7 +594,11 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   // cs = 1 and the path is kept for experiments (cta_group::2 is the real fix).
   // CTA pair (cta_group::2): K-major B only; the pair computes a 256 x bn tile with half of B per SM.
   const bool pair_ok = !d->b_mn && !conv_dw && p.m_tiles >= 2 && bn % 32 == 0;
-  p.pair = (d->cta_pair > 0 && pair_ok) ? 1 : 0;
+  // auto policy (cta_pair == 0): pairs for the big implicit-GEMM convolutions, where the larger operand reuse
+  // (32 KB instead of 48 KB of smem fill per k-block and SM) is worth +13 % (1.10 -> 1.24 PF/s on decode_head3);
+  // neutral on the mid-size Linear layers, which are latency- not throughput-bound (profiles/r1_bench_gemm_pair.log).
+  const bool pair_auto = conv && static_cast<long long>(p.m_tiles) * nb1 >= 128 && bn == 256;
+  p.pair = (pair_ok && (d->cta_pair > 0 || (d->cta_pair == 0 && pair_auto))) ? 1 : 0;
   int cs = p.pair ? 2 : (d->cluster > 0 ? d->cluster : 1);
   if (cs != 1 && cs != 2 && cs != 4) cs = 1;
   while (cs > 1 && (p.m_tiles < cs || (d->b_mn || conv_dw ? (bn / 64) % cs != 0 : (bn % (8 * cs)) != 0))) cs >>= 1;

@@ -74,7 +74,8 @@ typedef struct countr_gemm_desc {
   int32_t bn;      /* N tile: 0 = choose; else multiple of 32 (64 if b_mn), <= 256 */
   int32_t split_k; /* >= 1; > 1 requires atomic == 1 */
   int32_t cluster; /* CTAs per cluster sharing the B tile by TMA multicast: 0 = choose, else 1, 2 or 4 */
-  int32_t cta_pair; /* 1: tcgen05 cta_group::2 — two SMs compute one 256 x bn tile (K-major B only) */
+  int32_t cta_pair; /* tcgen05 cta_group::2 — two SMs compute one 256 x bn tile (K-major B only):
+                       0 = choose (on for large convolutions), 1 = on, -1 = off */
   /* conv mode */
   int32_t conv_h, conv_w, conv_cin, conv_bx, conv_by;
   int32_t conv_dw, conv_batch; /* conv_dw != 0: weight-gradient mode, see below */
