@@ -17,7 +17,7 @@ SIGS = {
     "countr_gn_relu_conv1x1": [P, P, P, P, P, P, P, I, I, I, I, F, I, P],
     "countr_upsample2x_f32": [P, P, I, I, I, I, P],
     "countr_exemplar_conv1": [P, I, L, L, L, L, L, P, P, P, I, I, I, I, I, P],
-    "countr_inorm_relu_pool": [P, P, P, P, P, I, I, I, I, F, I, I, P],
+    "countr_inorm_relu_pool": [P, P, P, P, P, P, I, I, I, I, F, I, I, P],
     "countr_upsample2x_bwd": [P, I, P, I, I, I, P],
     "countr_gn_relu_bwd_reduce": [P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, F, I, P],
     "countr_gn_bwd_apply": [P, P, P, P, P, P, P, I, I, I, I, F, I, P],

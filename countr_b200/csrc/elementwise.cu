@@ -328,8 +328,11 @@ __global__ void __launch_bounds__(256) exemplar_conv1_kernel(const void* __restr
 // then a tiny finalize turns them into (mean, rstd) in place.  Used when one CTA per (sample, 64 ch)
 // would leave the GPU idle (stage 1: 24 samples x 1 channel block over 4096 pixels).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) inorm_stats_kernel(const uint16_t* __restrict__ x, float* __restrict__ s1,
-                                                           float* __restrict__ s2, int HW, int C, int ppb, int bf16) {
+__global__ void __launch_bounds__(256) inorm_stats_kernel(const uint16_t* __restrict__ x, float* __restrict__ partial, int HW, int C,
+                                                           int N, int ppb, int bf16) {
+  // partial[z][n][c][2]: per pixel-split partial sums, reduced in fixed order by the finalize kernel
+  // (deterministic: no atomics — a 1e-7 wobble in these statistics is amplified ~1000x by the fp16
+  // rounding / ReLU / max-pool decisions of the following stages)
   __shared__ float red[2][8][64];
   const int n = blockIdx.y, c0 = blockIdx.x * 64;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -347,15 +350,22 @@ __global__ void __launch_bounds__(256) inorm_stats_kernel(const uint16_t* __rest
     float a = 0.f, q = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) { a += red[0][k][threadIdx.x]; q += red[1][k][threadIdx.x]; }
-    atomicAdd(s1 + static_cast<long long>(n) * C + c0 + threadIdx.x, a);
-    atomicAdd(s2 + static_cast<long long>(n) * C + c0 + threadIdx.x, q);
+    float* dst = partial + ((static_cast<long long>(blockIdx.z) * N + n) * C + c0 + threadIdx.x) * 2;
+    dst[0] = a;
+    dst[1] = q;
   }
 }
-__global__ void inorm_finalize_kernel(float* __restrict__ mean, float* __restrict__ rstd, int total, int HW, float eps) {
+__global__ void inorm_finalize_kernel(const float* __restrict__ partial, float* __restrict__ mean, float* __restrict__ rstd, int total,
+                                      int split, int HW, float eps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const float m = mean[i] / HW;
-  const float var = fmaxf(rstd[i] / HW - m * m, 0.f);
+  float a = 0.f, q = 0.f;
+  for (int z = 0; z < split; ++z) {
+    a += partial[(static_cast<long long>(z) * total + i) * 2];
+    q += partial[(static_cast<long long>(z) * total + i) * 2 + 1];
+  }
+  const float m = a / HW;
+  const float var = fmaxf(q / HW - m * m, 0.f);
   mean[i] = m;
   rstd[i] = rsqrtf(var + eps);
 }
@@ -729,23 +739,22 @@ extern "C" int countr_exemplar_conv1(const void* boxes, int dtype, int64_t sB, i
   return COUNTR_OK;
 }
 
-extern "C" int countr_inorm_relu_pool(const void* x, void* y16, float* y32, float* mean, float* rstd, int N, int H, int W, int C,
-                                      float eps, int mode, int bf16, countr_stream_t stream_) {
+extern "C" int countr_inorm_relu_pool(const void* x, void* y16, float* y32, float* mean, float* rstd, float* scratch, int N, int H,
+                                      int W, int C, float eps, int mode, int bf16, countr_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(x && (y16 || y32), "null pointer");
   COUNTR_REQUIRE(C % 64 == 0 && (mode == 1 || (H % 2 == 0 && W % 2 == 0 && y16)), "bad shape C=%d H=%d W=%d mode=%d", C, H, W, mode);
-  if (mode == 0 && mean != nullptr && rstd != nullptr && H * W >= 256) {
-    // pixel-parallel path: raw sums by atomics -> finalize -> apply (3 launches, each filling the GPU)
+  if (mode == 0 && mean != nullptr && rstd != nullptr && scratch != nullptr && H * W >= 256) {
+    // pixel-parallel path: per-split partial sums -> fixed-order finalize -> apply (3 launches, each filling the GPU)
     const int HW = H * W, cblocks = C / 64;
     int split = (2 * 148 + cblocks * N - 1) / (cblocks * N);
     if (split > HW / 64) split = HW / 64;
+    if (split > 32) split = 32;          // scratch holds at most 32 partials per (sample, channel)
     if (split < 1) split = 1;
     const int ppb = (HW + split - 1) / split;
-    COUNTR_CHECK_CUDA(cudaMemsetAsync(mean, 0, sizeof(float) * N * C, stream));
-    COUNTR_CHECK_CUDA(cudaMemsetAsync(rstd, 0, sizeof(float) * N * C, stream));
-    inorm_stats_kernel<<<dim3(cblocks, N, (HW + ppb - 1) / ppb), 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(x), mean, rstd, HW,
-                                                                                 C, ppb, bf16);
-    inorm_finalize_kernel<<<(N * C + 255) / 256, 256, 0, stream>>>(mean, rstd, N * C, HW, eps);
+    split = (HW + ppb - 1) / ppb;
+    inorm_stats_kernel<<<dim3(cblocks, N, split), 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(x), scratch, HW, C, N, ppb, bf16);
+    inorm_finalize_kernel<<<(N * C + 255) / 256, 256, 0, stream>>>(scratch, mean, rstd, N * C, split, HW, eps);
     const int OHW = HW / 4;
     const int ppb2 = (OHW + split - 1) / split;
     inorm_apply_pool_kernel<<<dim3(cblocks, N, (OHW + ppb2 - 1) / ppb2), 256, 0, stream>>>(

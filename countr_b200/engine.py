@@ -157,7 +157,8 @@ class Engine:
             pooled = get(f"ex_pool{i}", (n, hh // 2, ww // 2, cc), F16)
             mean = get(f"ex_mean{i}", (n, cc), F32)       # always: enables the pixel-parallel statistics path
             rstd = get(f"ex_rstd{i}", (n, cc), F32)
-            ops.inorm_relu_pool(cur, 0, 1e-5, y16=pooled, mean=mean, rstd=rstd)
+            scratch = ws.get("ex_scratch", (64 * n * cc,), F32, dev)   # per-split partial sums (deterministic reduction)
+            ops.inorm_relu_pool(cur, 0, 1e-5, y16=pooled, mean=mean, rstd=rstd, scratch=scratch)
             cout = conv.weight.shape[0]
             nxt = get(f"ex_raw{i + 2}", (n, hh // 2, ww // 2, cout), F16)
             ops.conv3x3(pooled, wc.conv16(conv.weight), nxt, bias=_contig32(conv.bias))

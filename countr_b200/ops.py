@@ -184,12 +184,13 @@ def exemplar_conv1(boxes, S, w, bias, out16):
     _count()
 
 
-def inorm_relu_pool(x16, mode, eps, y16=None, y32=None, mean=None, rstd=None):
+def inorm_relu_pool(x16, mode, eps, y16=None, y32=None, mean=None, rstd=None, scratch=None):
     N, H, W, C = x16.shape
-    check(lib().countr_inorm_relu_pool(_ptr(x16), _ptr(y16), _ptr(y32), _ptr(mean), _ptr(rstd), N, H, W, C, eps, mode,
+    split_path = mode == 0 and mean is not None and rstd is not None and scratch is not None and H * W >= 256
+    assert scratch is None or scratch.numel() >= 64 * N * C
+    check(lib().countr_inorm_relu_pool(_ptr(x16), _ptr(y16), _ptr(y32), _ptr(mean), _ptr(rstd), _ptr(scratch), N, H, W, C, eps, mode,
                                        _is_bf16(x16), _stream()))
-    _count(3 if (mode == 0 and mean is not None and rstd is not None and H * W >= 256) else 1)
-
+    _count(3 if split_path else 1)
 
 def zero_(t):
     check(lib().countr_memset_zero(_ptr(t), t.numel() * t.element_size(), _stream()))

@@ -176,9 +176,10 @@ int countr_exemplar_conv1(const void* boxes, int dtype, int64_t sB, int64_t sK, 
                           countr_stream_t stream);
 /* InstanceNorm2d(eps, no affine) + ReLU + MaxPool2d(2) (mode 0 -> y16 [N][H/2][W/2][C]) or
  * AdaptiveAvgPool2d(1) (mode 1 -> y32 [N][C] and/or y16 [N][C]); mean/rstd [N][C] optional
- * (when given, large maps take a pixel-parallel stats -> finalize -> apply path) */
-int countr_inorm_relu_pool(const void* x, void* y16, float* y32, float* mean, float* rstd, int N, int H, int W, int C,
-                           float eps, int mode, int bf16, countr_stream_t stream);
+ * (when mean, rstd and scratch [32][N][C][2] fp32 are given, large maps take a pixel-parallel, deterministic
+ * partial-sums -> finalize -> apply path) */
+int countr_inorm_relu_pool(const void* x, void* y16, float* y32, float* mean, float* rstd, float* scratch, int N, int H, int W,
+                           int C, float eps, int mode, int bf16, countr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Backward-only kernels of the fine-tune step (autograd call sites listed in SURVEY.md §2.3).

@@ -37,6 +37,11 @@ def assert_close(got, ref, rtol, what=""):
     assert err <= rtol * scale, f"{what}: {_describe(got, ref)}"
 
 
+def rel_close(a, b, tol=2e-3):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item() < tol
+
+
 def _rand16(shape, dev, dtype=torch.float16, seed=0, scale=1.0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     return (torch.randn(shape, generator=g) * scale).to(dtype).to(dev)
@@ -324,8 +329,12 @@ def test_exemplar_stage1_and_inorm(cuda):
     pooled = torch.empty(B * S, 32, 32, 64, device=cuda, dtype=torch.float16)
     mean = torch.empty(B * S, 64, device=cuda)
     rstd = torch.empty(B * S, 64, device=cuda)
-    ops.inorm_relu_pool(raw, 0, 1e-5, y16=pooled, mean=mean, rstd=rstd)
+    scratch = torch.empty(64 * B * S * 64, device=cuda)
+    ops.inorm_relu_pool(raw, 0, 1e-5, y16=pooled, mean=mean, rstd=rstd, scratch=scratch)      # pixel-parallel path
+    pooled1 = torch.empty_like(pooled)
+    ops.inorm_relu_pool(raw, 0, 1e-5, y16=pooled1)                                            # one CTA per (sample, 64 ch)
     torch.cuda.synchronize()
+    assert rel_close(pooled1, pooled)
     r = raw.float().permute(0, 3, 1, 2)
     refp = F.max_pool2d(F.relu(F.instance_norm(r, eps=1e-5)), 2)
     assert_close(pooled.permute(0, 3, 1, 2).reshape(B * S * 64, -1), refp.reshape(B * S * 64, -1), 1e-3, "IN+relu+maxpool")

@@ -89,11 +89,9 @@ def test_input_conventions(cuda):
         b = m(wide.to(cuda)[:, :, :, 64:448], boxes.to(cuda), 3)
         c = m(imgs.to(cuda).half(), boxes.to(cuda).half(), 3)
         d = m(imgs[1:2].to(cuda), boxes[1:2].to(cuda), 3)
-    # same arithmetic, but the InstanceNorm / GroupNorm statistics are accumulated with atomics whose order varies
-    # run to run; a 1e-7 wobble there flips a few fp16 roundings downstream
-    assert rel(b, a) < 2e-4
+    assert torch.equal(a, b)          # the forward pass is bit-reproducible (no order-dependent fp32 atomics)
     assert c.dtype == torch.float16 and rel(c.float(), a) < 2e-3
-    assert rel(d[0], a[1]) < 2e-4
+    assert rel(d[0], a[1]) < 1e-3     # other tile shapes / statistics splits at batch 1: same math, different rounding
     with pytest.raises(AssertionError):
         m(torch.rand(1, 3, 256, 256, device=cuda), boxes[:1].to(cuda), 3)   # timm PatchEmbed's size assert
 
