@@ -94,12 +94,17 @@ __global__ void up2_bwd_kernel(const void* __restrict__ dy, int dtype, float* __
 // S1 = sum dyh*gamma, S2 = sum dyh*gamma*xhat (double).
 // ------------------------------------------------------------------------------------------
 constexpr int kC = 256;
+// Per channel only two running sums are needed:
+//   MODE 0: R1 = sum dy, R2 = sum dy*xhat                     (dbeta = R1, dgamma = R2)
+//   MODE 1: with r = dmap * 1[y>0]:  R1 = sum r, R2 = sum r*xhat
+//           dbeta = w R1, dgamma = w R2, dw1 = gamma R2 + beta R1   (relu(y) = y where the mask is 1)
+// and the group sums follow at the end as S1 = sum_c gamma_c dbeta_c, S2 = sum_c gamma_c dgamma_c.
+template <int MODE>
 __global__ void __launch_bounds__(256) gn_relu_bwd_reduce_kernel(
     const uint16_t* __restrict__ raw, const double* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ beta, const uint16_t* __restrict__ d_next, const float* __restrict__ dmap,
     const float* __restrict__ w1, uint16_t* __restrict__ dyh, float* __restrict__ dgamma, float* __restrict__ dbeta,
-    float* __restrict__ dw1, float* __restrict__ db1, double* __restrict__ gsum, int H, int W, int G, float eps,
-    int mode, int bf16) {
+    float* __restrict__ dw1, float* __restrict__ db1, double* __restrict__ gsum, int H, int W, int G, float eps, int bf16) {
   __shared__ float s_mean[8], s_rstd[8];
   __shared__ float red[8][kC + 8];
   const int b = blockIdx.y;
@@ -124,28 +129,45 @@ __global__ void __launch_bounds__(256) gn_relu_bwd_reduce_kernel(
   for (int j = 0; j < 8; ++j) {
     gam[j] = gamma[c0 + j];
     bet[j] = beta[c0 + j];
-    wv[j] = mode == 1 ? w1[c0 + j] : 0.f;
+    wv[j] = MODE == 1 ? w1[c0 + j] : 0.f;
   }
-  float a_dg[8], a_db[8], a_dw[8];
+  float R1[8], R2[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) a_dg[j] = a_db[j] = a_dw[j] = 0.f;
-  float s1 = 0.f, s2 = 0.f, a_b1 = 0.f;
+  for (int j = 0; j < 8; ++j) R1[j] = R2[j] = 0.f;
+  float a_b1 = 0.f;
   const uint16_t* rb = raw + static_cast<long long>(b) * HW * kC + c0;
   uint16_t* ob = dyh + static_cast<long long>(b) * HW * kC + c0;
-  for (int pix = blockIdx.x * 8 + pl; pix < HW; pix += gridDim.x * 8) {
-    float x[8], dz[8];
-    unpack8(*reinterpret_cast<const uint4*>(rb + static_cast<long long>(pix) * kC), x, bf16);
-    if (mode == 1) {
-      const float dm = dmap[static_cast<long long>(b) * HW + pix];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dz[j] = dm * wv[j];
-      if (cv == 0) a_b1 += dm;
+  const int stride = gridDim.x * 8;
+  if (MODE == 1) {
+    // two pixels per iteration: two independent 16-byte loads in flight per thread (the loop is latency-bound)
+    for (int pix = blockIdx.x * 8 + pl; pix < HW; pix += 2 * stride) {
+      const int pix2 = pix + stride;
+      const bool has2 = pix2 < HW;
+      const uint4 u0 = *reinterpret_cast<const uint4*>(rb + static_cast<long long>(pix) * kC);
+      const uint4 u1 = has2 ? *reinterpret_cast<const uint4*>(rb + static_cast<long long>(pix2) * kC) : make_uint4(0, 0, 0, 0);
+      const float dm0 = dmap[static_cast<long long>(b) * HW + pix];
+      const float dm1 = has2 ? dmap[static_cast<long long>(b) * HW + pix2] : 0.f;
+      float x0[8], x1[8], d0[8], d1[8];
+      unpack8(u0, x0, bf16);
+      unpack8(u1, x1, bf16);
+      if (cv == 0) a_b1 += dm0 + dm1;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float y = (x[j] - mean) * rstd * gam[j] + bet[j];
-        a_dw[j] += dm * fmaxf(y, 0.f);
+        const float xh0 = (x0[j] - mean) * rstd, xh1 = (x1[j] - mean) * rstd;
+        const float r0 = fmaf(xh0, gam[j], bet[j]) > 0.f ? dm0 : 0.f;
+        const float r1 = fmaf(xh1, gam[j], bet[j]) > 0.f ? dm1 : 0.f;
+        R1[j] += r0 + r1;
+        R2[j] += r0 * xh0 + r1 * xh1;
+        d0[j] = r0 * wv[j];
+        d1[j] = r1 * wv[j];
       }
-    } else {
+      *reinterpret_cast<uint4*>(ob + static_cast<long long>(pix) * kC) = pack8(d0, bf16);
+      if (has2) *reinterpret_cast<uint4*>(ob + static_cast<long long>(pix2) * kC) = pack8(d1, bf16);
+    }
+  } else {
+    for (int pix = blockIdx.x * 8 + pl; pix < HW; pix += stride) {
+      float x[8], dz[8], dy[8];
+      unpack8(*reinterpret_cast<const uint4*>(rb + static_cast<long long>(pix) * kC), x, bf16);
       const int ix = pix % W, iy = pix / W;
       int ox[4], oy[4];
       float wx[4], wy[4];
@@ -167,26 +189,32 @@ __global__ void __launch_bounds__(256) gn_relu_bwd_reduce_kernel(
           for (int j = 0; j < 8; ++j) dz[j] += ww * t[j];
         }
       }
-    }
-    float dy[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (x[j] - mean) * rstd;
-      const float y = xh * gam[j] + bet[j];
-      dy[j] = y > 0.f ? dz[j] : 0.f;
-      a_dg[j] += dy[j] * xh;
-      a_db[j] += dy[j];
-      s1 += dy[j] * gam[j];
-      s2 += dy[j] * gam[j] * xh;
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (x[j] - mean) * rstd;
+        dy[j] = fmaf(xh, gam[j], bet[j]) > 0.f ? dz[j] : 0.f;
+        R1[j] += dy[j];
+        R2[j] += dy[j] * xh;
+      }
+      *reinterpret_cast<uint4*>(ob + static_cast<long long>(pix) * kC) = pack8(dy, bf16);
     }
-    *reinterpret_cast<uint4*>(ob + static_cast<long long>(pix) * kC) = pack8(dy, bf16);
+  }
+  float a_dg[8], a_db[8], a_dw[8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a_db[j] = MODE == 1 ? wv[j] * R1[j] : R1[j];
+    a_dg[j] = MODE == 1 ? wv[j] * R2[j] : R2[j];
+    a_dw[j] = gam[j] * R2[j] + bet[j] * R1[j];
+    s1 += gam[j] * a_db[j];
+    s2 += gam[j] * a_dg[j];
   }
   // group sums: 4 consecutive lanes share a group
   s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
   s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
   // cross-pixel-lane reductions through smem, one quantity at a time
   for (int q = 0; q < 4; ++q) {
-    if (q == 2 && mode != 1) continue;
+    if (q == 2 && MODE != 1) continue;
 #pragma unroll
     for (int j = 0; j < 8; ++j) red[pl][c0 + j] = q == 0 ? a_dg[j] : q == 1 ? a_db[j] : q == 2 ? a_dw[j] : 0.f;
     if (q == 3) {
@@ -203,7 +231,7 @@ __global__ void __launch_bounds__(256) gn_relu_bwd_reduce_kernel(
       // threadIdx.x = cv*8 + {0: s1, 1: s2, 2: db1}; one representative lane per group (cv % 4 == 0)
       const int cvv = threadIdx.x >> 3, which = threadIdx.x & 7;
       if ((cvv & 3) == 0 && which < 2) atomicAdd(gsum + (static_cast<long long>(b) * G + (cvv >> 2)) * 2 + which, static_cast<double>(v));
-      if (mode == 1 && cvv == 0 && which == 2) atomicAdd(db1, v);
+      if (MODE == 1 && cvv == 0 && which == 2) atomicAdd(db1, v);
     }
     __syncthreads();
   }
@@ -714,10 +742,14 @@ extern "C" int countr_gn_relu_bwd_reduce(const void* raw, const double* stats, c
   COUNTR_REQUIRE(mode == 0 || (dmap && w1 && dw1 && db1), "1x1-conv mode needs dmap, w1, dw1, db1");
   dim3 grid;
   gn_grid(H * W, B, &grid);
-  gn_relu_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(raw), stats, gamma, beta,
-                                                      reinterpret_cast<const uint16_t*>(d_next), dmap, w1,
-                                                      reinterpret_cast<uint16_t*>(dyh), dgamma, dbeta, dw1, db1, gsum, H, W, G, eps,
-                                                      mode, bf16);
+  if (mode == 0)
+    gn_relu_bwd_reduce_kernel<0><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(raw), stats, gamma, beta,
+                                                           reinterpret_cast<const uint16_t*>(d_next), dmap, w1,
+                                                           reinterpret_cast<uint16_t*>(dyh), dgamma, dbeta, dw1, db1, gsum, H, W, G, eps, bf16);
+  else
+    gn_relu_bwd_reduce_kernel<1><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(raw), stats, gamma, beta,
+                                                           reinterpret_cast<const uint16_t*>(d_next), dmap, w1,
+                                                           reinterpret_cast<uint16_t*>(dyh), dgamma, dbeta, dw1, db1, gsum, H, W, G, eps, bf16);
   COUNTR_CHECK_CUDA(cudaGetLastError());
   return COUNTR_OK;
 }

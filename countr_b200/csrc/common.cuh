@@ -376,4 +376,64 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return fmaf(x * 0.39894228040143267794f, g, 0.5f * (1.0f + copysignf(e, x)));
 }
 
+
+// ---------------------------------------------------------------------------
+// packed fp32x2 math (sm_100 FFMA2 / FMUL2 / FADD2): two lanes per instruction.  The GELU epilogues are
+// issue-bound (M x 4D erf evaluations per MLP), so halving the FMA instruction count matters.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long f2_pack(float2 v) {
+  return (static_cast<unsigned long long>(__float_as_uint(v.y)) << 32) | __float_as_uint(v.x);
+}
+__device__ __forceinline__ float2 f2_unpack(unsigned long long u) {
+  return make_float2(__uint_as_float(static_cast<uint32_t>(u)), __uint_as_float(static_cast<uint32_t>(u >> 32)));
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx_f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// two-lane version of erf_parts (same A&S 7.1.26 polynomial): e = erf(x/sqrt2) with the sign of x, g = exp(-x^2/2)
+__device__ __forceinline__ void erf_parts2(float2 x, float2& e, float2& g) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 z = mul2(ax, splat2(0.70710678118654752440f));
+  const float2 den = fma2(z, splat2(0.3275911f), splat2(1.0f));
+  const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  const float2 e2 = mul2(mul2(z, z), splat2(-1.44269504088896340736f));
+  g = make_float2(ex2_approx_f(e2.x), ex2_approx_f(e2.y));
+  float2 np = fma2(splat2(-1.061405429f), t, splat2(1.453152027f));   // negated polynomial
+  np = fma2(np, t, splat2(-1.421413741f));
+  np = fma2(np, t, splat2(0.284496736f));
+  np = fma2(np, t, splat2(-0.254829592f));
+  const float2 ea = fma2(mul2(np, t), g, splat2(1.0f));                // erf(|x|/sqrt2) >= 0
+  e = make_float2(__uint_as_float(__float_as_uint(ea.x) | (__float_as_uint(x.x) & 0x80000000u)),
+                  __uint_as_float(__float_as_uint(ea.y) | (__float_as_uint(x.y) & 0x80000000u)));
+}
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  float2 e, g;
+  erf_parts2(x, e, g);
+  const float2 hx = mul2(x, splat2(0.5f));
+  return fma2(hx, e, hx);
+}
+__device__ __forceinline__ float2 gelu_erf_grad2(float2 x) {
+  float2 e, g;
+  erf_parts2(x, e, g);
+  return fma2(mul2(x, splat2(0.39894228040143267794f)), g, fma2(e, splat2(0.5f), splat2(0.5f)));
+}
+
 }  // namespace countr

@@ -145,6 +145,10 @@ __global__ void __launch_bounds__(256) gn_relu_up2_kernel(const uint16_t* __rest
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            uint16_t* __restrict__ y, int H, int W, int C, int G, float eps,
                                                            int bf16) {
+  // thread = one INPUT pixel x 8 channels -> the 2x2 output block it is the centre of:
+  //   out[2i]   = .25 a[i-1] + .75 a[i],   out[2i+1] = .75 a[i] + .25 a[i+1]      (indices clamped)
+  // so the 3x3 input neighbourhood is normalised once (9 instead of 16 activations per 4 outputs) and
+  // blended separably.  The kernel is instruction-bound, not HBM-bound, hence the restructuring.
   extern __shared__ float sm_ab[];  // [2][C]
   float* sa = sm_ab;
   float* sb = sm_ab + C;
@@ -164,33 +168,57 @@ __global__ void __launch_bounds__(256) gn_relu_up2_kernel(const uint16_t* __rest
   }
   __syncthreads();
   const int vecs = C / 8;
-  const int OW = 2 * W, OH = 2 * H;
-  const long long total = static_cast<long long>(OH) * OW * vecs;
+  const int OW = 2 * W;
+  const long long total = static_cast<long long>(H) * W * vecs;
+  const uint16_t* xb0 = x + static_cast<long long>(b) * H * W * C;
+  uint16_t* yb0 = y + static_cast<long long>(b) * 4 * H * W * C;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int cv = idx % vecs;
-    const long long pix = idx / vecs;
-    const int ox = pix % OW, oy = pix / OW;
-    // source taps: even o=2i -> (i-1: .25, i: .75); odd o=2i+1 -> (i: .75, i+1: .25); indices clamped
-    const int ix = ox >> 1, iy = oy >> 1;
-    const int x0 = (ox & 1) ? ix : max(ix - 1, 0), x1 = (ox & 1) ? min(ix + 1, W - 1) : ix;
-    const int y0 = (oy & 1) ? iy : max(iy - 1, 0), y1 = (oy & 1) ? min(iy + 1, H - 1) : iy;
-    const float wx1 = (ox & 1) ? 0.25f : 0.75f, wy1 = (oy & 1) ? 0.25f : 0.75f;
-    const float wx0 = 1.f - wx1, wy0 = 1.f - wy1;
-    const uint16_t* xb = x + static_cast<long long>(b) * H * W * C + cv * 8;
-    float f00[8], f01[8], f10[8], f11[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(xb + (static_cast<long long>(y0) * W + x0) * C), f00, bf16);
-    unpack8(*reinterpret_cast<const uint4*>(xb + (static_cast<long long>(y0) * W + x1) * C), f01, bf16);
-    unpack8(*reinterpret_cast<const uint4*>(xb + (static_cast<long long>(y1) * W + x0) * C), f10, bf16);
-    unpack8(*reinterpret_cast<const uint4*>(xb + (static_cast<long long>(y1) * W + x1) * C), f11, bf16);
+    const int pix = static_cast<int>(idx / vecs);
+    const int ix = pix % W, iy = pix / W;
+    const int xs[3] = {max(ix - 1, 0), ix, min(ix + 1, W - 1)};
+    const int ys[3] = {max(iy - 1, 0), iy, min(iy + 1, H - 1)};
+    float av[8], bv[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float a = sa[cv * 8 + j], bb = sb[cv * 8 + j];
-      const float v00 = fmaxf(f00[j] * a + bb, 0.f), v01 = fmaxf(f01[j] * a + bb, 0.f);
-      const float v10 = fmaxf(f10[j] * a + bb, 0.f), v11 = fmaxf(f11[j] * a + bb, 0.f);
-      o[j] = wy0 * (wx0 * v00 + wx1 * v01) + wy1 * (wx0 * v10 + wx1 * v11);
+      av[j] = sa[cv * 8 + j];
+      bv[j] = sb[cv * 8 + j];
     }
-    *reinterpret_cast<uint4*>(y + ((static_cast<long long>(b) * OH + oy) * OW + ox) * C + cv * 8) = pack8(o, bf16);
+    uint4 raw[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) raw[r][c] = *reinterpret_cast<const uint4*>(xb0 + (static_cast<long long>(ys[r]) * W + xs[c]) * C + cv * 8);
+    float hl[3][8], hr[3][8];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float a0[8], a1[8], a2[8];
+      unpack8(raw[r][0], a0, bf16);
+      unpack8(raw[r][1], a1, bf16);
+      unpack8(raw[r][2], a2, bf16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v0 = fmaxf(fmaf(a0[j], av[j], bv[j]), 0.f), v1 = fmaxf(fmaf(a1[j], av[j], bv[j]), 0.f);
+        const float v2 = fmaxf(fmaf(a2[j], av[j], bv[j]), 0.f);
+        hl[r][j] = 0.25f * v0 + 0.75f * v1;
+        hr[r][j] = 0.75f * v1 + 0.25f * v2;
+      }
+    }
+    float o[8];
+    uint16_t* yo = yb0 + (static_cast<long long>(2 * iy) * OW + 2 * ix) * C + cv * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.25f * hl[0][j] + 0.75f * hl[1][j];
+    *reinterpret_cast<uint4*>(yo) = pack8(o, bf16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.25f * hr[0][j] + 0.75f * hr[1][j];
+    *reinterpret_cast<uint4*>(yo + C) = pack8(o, bf16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.75f * hl[1][j] + 0.25f * hl[2][j];
+    *reinterpret_cast<uint4*>(yo + static_cast<long long>(OW) * C) = pack8(o, bf16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.75f * hr[1][j] + 0.25f * hr[2][j];
+    *reinterpret_cast<uint4*>(yo + static_cast<long long>(OW) * C + C) = pack8(o, bf16);
   }
 }
 
@@ -222,17 +250,34 @@ __global__ void __launch_bounds__(256) gn_relu_dot_kernel(const uint16_t* __rest
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float b0 = bias[0];
-  for (int pix = blockIdx.x * 8 + warp; pix < HW; pix += gridDim.x * 8) {
-    const uint16_t* xp = x + (static_cast<long long>(b) * HW + pix) * C;
-    float acc = 0.f;
+  // one warp handles 4 pixels per iteration: 4 independent 16-byte loads in flight per lane (the kernel is
+  // latency-bound with one), and the four warp reductions interleave.
+  for (int pix0 = (blockIdx.x * 8 + warp) * 4; pix0 < HW; pix0 += gridDim.x * 8 * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c0 = lane * 8; c0 < C; c0 += 256) {
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(xp + c0), f, bf16);
+      uint4 v[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc += fmaxf(f[j] * sa[c0 + j] + sb[c0 + j], 0.f) * sw[c0 + j];
+      for (int u = 0; u < 4; ++u) {
+        const int pix = min(pix0 + u, HW - 1);
+        v[u] = *reinterpret_cast<const uint4*>(x + (static_cast<long long>(b) * HW + pix) * C + c0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v[u], f, bf16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[u] += fmaxf(fmaf(f[j], sa[c0 + j], sb[c0 + j]), 0.f) * sw[c0 + j];
+      }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) out[static_cast<long long>(b) * HW + pix] = acc + b0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+    }
+    if (lane < 4 && pix0 + lane < HW) {
+      const float r = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+      out[static_cast<long long>(b) * HW + pix0 + lane] = r + b0;
+    }
   }
 }
 
@@ -688,7 +733,7 @@ extern "C" int countr_gn_relu_upsample2x(const void* x, const double* stats, con
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(x && stats && gamma && beta && y, "null pointer");
   COUNTR_REQUIRE(C % 8 == 0 && C % G == 0 && C <= 4096, "bad channel count %d / groups %d", C, G);
-  const long long total = 4ll * H * W * (C / 8);
+  const long long total = 1ll * H * W * (C / 8);
   long long blocks = (total + 255) / 256;
   const long long cap = 148ll * 8 * 4;
   if (blocks * B > cap) blocks = (cap + B - 1) / B;
@@ -706,7 +751,7 @@ extern "C" int countr_gn_relu_conv1x1(const void* x, const double* stats, const 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(x && stats && gamma && beta && w && bias && out, "null pointer");
   COUNTR_REQUIRE(C % 8 == 0 && C % G == 0 && C <= 4096, "bad channel count %d / groups %d", C, G);
-  long long blocks = (HW + 7) / 8;
+  long long blocks = (HW + 31) / 32;
   const long long cap = 148ll * 8 * 2;
   if (blocks * B > cap) blocks = (cap + B - 1) / B;
   if (blocks < 1) blocks = 1;

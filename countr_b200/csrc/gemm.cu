@@ -409,7 +409,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               }
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            for (int j = 0; j < 32; j += 2) {
+              const float2 gq = gelu_erf2(make_float2(v[j], v[j + 1]));
+              v[j] = gq.x;
+              v[j + 1] = gq.y;
+            }
           } else if (p.act == 2) {
             const uint16_t* ap = reinterpret_cast<const uint16_t*>(p.aux) + row * p.ldaux + col0;
             if (full32) {
@@ -419,9 +423,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 const uint32_t w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  const float2 f = unpack_16b(w[q], p.bf16);
-                  v[j + 2 * q] *= gelu_erf_grad(f.x);
-                  v[j + 2 * q + 1] *= gelu_erf_grad(f.y);
+                  const float2 gq = gelu_erf_grad2(unpack_16b(w[q], p.bf16));
+                  v[j + 2 * q] *= gq.x;
+                  v[j + 2 * q + 1] *= gq.y;
                 }
               }
             } else {

@@ -84,17 +84,46 @@ def attn(name, H, dh):
 
 
 print(f"B={B}")
-for pr in (0, 1):
-    lin("enc qkv", M, 2304, 768, "f16", 0, 0, pr)
-    lin("enc qkv bn256", M, 2304, 768, "f16", 256, 0, pr)
-    lin("enc proj (+res)", M, 768, 768, "res", 0, 0, pr)
-    lin("enc proj (+res) bn256", M, 768, 768, "res", 256, 0, pr)
-    lin("enc fc1 (gelu) bn256", M, 3072, 768, "gelu", 256, 0, pr)
-    lin("enc fc2 (+res)", M, 768, 3072, "res", 0, 0, pr)
-    lin("enc fc2 (+res) bn256", M, 768, 3072, "res", 256, 0, pr)
-    lin("fim qkv", M, 1536, 512, "f16", 0, 0, pr)
-    lin("fim fc2 (+res)", M, 512, 2048, "res", 0, 0, pr)
-    lin("big square", 8192, 8192, 8192, "f16", 256, 0, pr)
-    conv("head1", 48, 256, 256, pr)
-    conv("head2", 96, 256, 256, pr)
-    conv("head3", 192, 256, 256, pr)
+lin("enc qkv", M, 2304, 768, "f16")
+lin("enc fc1 (gelu)", M, 3072, 768, "gelu")
+lin("enc fc2 (+res)", M, 768, 3072, "res")
+lin("fim fc1 (gelu)", M, 2048, 512, "gelu")
+lin("fim fc2 dX (gelu bwd)", M, 2048, 512, "gelubwd")
+
+
+def head_elementwise():
+    C, G = 256, 8
+    for h in (24, 48, 96):
+        x = torch.randn(B, h, h, C, device=dev).half()
+        stats = torch.stack([x.double().reshape(B, h * h, G, 32).sum((1, 3)), (x.double() ** 2).reshape(B, h * h, G, 32).sum((1, 3))], -1).contiguous()
+        gamma = torch.ones(C, device=dev); beta = torch.zeros(C, device=dev)
+        y = torch.empty(B, 2 * h, 2 * h, C, device=dev, dtype=torch.float16)
+        us = timeit(lambda: ops.gn_relu_upsample2x(x, stats, gamma, beta, y, G, 1e-5))
+        mb = (x.numel() + y.numel()) * 2 / 1e6
+        print(f"gn_relu_up2 {h}->{2*h}: {us:7.1f} us  {mb/us*1e3:7.1f} GB/s")
+    h = 192
+    x = torch.randn(B, h, h, C, device=dev).half()
+    stats = torch.stack([x.double().reshape(B, h * h, G, 32).sum((1, 3)), (x.double() ** 2).reshape(B, h * h, G, 32).sum((1, 3))], -1).contiguous()
+    gamma = torch.ones(C, device=dev); beta = torch.zeros(C, device=dev)
+    w = torch.randn(C, device=dev); bias = torch.zeros(1, device=dev)
+    d = torch.empty(B, h, h, device=dev)
+    us = timeit(lambda: ops.gn_relu_conv1x1(x, stats, gamma, beta, w, bias, d, G, 1e-5))
+    print(f"gn_relu_conv1x1 192: {us:7.1f} us  {x.numel()*2/1e6/us*1e3:7.1f} GB/s")
+    dyh = torch.empty_like(x); dg = torch.zeros(C, device=dev); db = torch.zeros(C, device=dev)
+    gsum = torch.zeros(B, G, 2, device=dev, dtype=torch.float64); dw1 = torch.zeros(C, device=dev); db1 = torch.zeros(1, device=dev)
+    dmap = torch.randn(B, h, h, device=dev)
+    us = timeit(lambda: ops.gn_relu_bwd_reduce(x, stats, gamma, beta, dyh, dg, db, gsum, G, 1e-5, dmap=dmap, w1=w, dw1=dw1, db1=db1))
+    print(f"gn_relu_bwd_reduce mode1 192: {us:7.1f} us  {2*x.numel()*2/1e6/us*1e3:7.1f} GB/s")
+    dbias = torch.zeros(C, device=dev)
+    us = timeit(lambda: ops.gn_bwd_apply(x, dyh, stats, gsum, gamma, dyh, dbias, G, 1e-5))
+    print(f"gn_bwd_apply 192: {us:7.1f} us  {3*x.numel()*2/1e6/us*1e3:7.1f} GB/s")
+    for hh in (96, 48):
+        xs = torch.randn(B, hh, hh, C, device=dev).half()
+        st = torch.stack([xs.double().reshape(B, hh * hh, G, 32).sum((1, 3)), (xs.double() ** 2).reshape(B, hh * hh, G, 32).sum((1, 3))], -1).contiguous()
+        dn = torch.randn(B, 2 * hh, 2 * hh, C, device=dev).half()
+        dy2 = torch.empty_like(xs)
+        us = timeit(lambda: ops.gn_relu_bwd_reduce(xs, st, gamma, beta, dy2, dg, db, gsum, G, 1e-5, d_next=dn))
+        print(f"gn_relu_bwd_reduce mode0 {hh}: {us:7.1f} us  {(2*xs.numel()+dn.numel())*2/1e6/us*1e3:7.1f} GB/s")
+
+
+head_elementwise()
