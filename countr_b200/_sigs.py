@@ -8,6 +8,7 @@ SIGS = {
     "countr_layernorm_fwd": [P, P, P, P, P, P, P, I, I, F, I, P],
     "countr_layernorm_bwd": [P, P, P, P, P, P, P, P, P, I, I, I, I, P],
     "countr_attention_fwd": [P, P, P, I, I, I, I, F, I, P],
+    "countr_attention_bwd": [P, P, P, P, P, I, I, I, I, F, I, P],
     "countr_cross_attn_core": [P, P, P, P, P, I, I, I, I, I, F, I, I, P],
     "countr_cast_f32_to_16": [P, P, L, F, I, P],
     "countr_cast_transpose_f32_to_16": [P, P, I, I, I, P],

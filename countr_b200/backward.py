@@ -32,11 +32,17 @@ def _dw_linear(dy16, x16, dw32):
              atomic=True, split_k=split)
 
 
-def attention_backward(qkv, lse, datt, B, L, H, dh, scale):
-    """qkv fp16 [B*L, 3*H*dh] (packed), lse fp32 [B,H,L], datt fp16 [B*L, H*dh] -> dqkv fp16 [B*L, 3*H*dh]."""
+def attention_backward(qkv, lse, datt, B, L, H, dh, scale, att=None, fused=True):
+    """qkv fp16 [B*L, 3*H*dh] (packed), lse fp32 [B,H,L], datt fp16 [B*L, H*dh] -> dqkv fp16 [B*L, 3*H*dh].
+    head_dim 32 (the FIM) runs the fused flash-style kernel (needs the forward output `att`); other head sizes use
+    batched tcgen05 GEMMs over materialised [B,H,L,L] scores plus a row softmax-backward."""
     dev = qkv.device
     D = H * dh
     row = 3 * D
+    if fused and att is not None and dh == 32 and L <= 640:
+        dqkv = torch.empty(B * L, row, dtype=F16, device=dev)
+        ops.attention_bwd(qkv, att, datt, lse, dqkv, B, L, H, dh, scale)
+        return dqkv
     flat = qkv.view(-1)
     q, k, v = flat, flat[D:], flat[2 * D:]
     s16 = torch.empty(B, H, L, L, dtype=F16, device=dev)
@@ -183,7 +189,7 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
         _dw_linear(g16, s["att"], G(sa.proj.weight))
         datt = torch.empty(M, Dd, dtype=F16, device=dev)
         ops.linear(g16, wc.w16_t(sa.proj.weight), datt)
-        dqkv = attention_backward(s["qkv"], s["lse"], datt, B, L, H, dhd, sa.scale)
+        dqkv = attention_backward(s["qkv"], s["lse"], datt, B, L, H, dhd, sa.scale, att=s["att"])
         ops.colsum(dqkv, G(sa.qkv.bias))
         _dw_linear(dqkv, s["h0"], G(sa.qkv.weight))
         ops.linear(dqkv, wc.w16_t(sa.qkv.weight), dh)

@@ -62,7 +62,7 @@ def vit_block_backward(wc, blk, s, g, g16, G):
     _dw_linear(g16, s["att"], G(blk.attn.proj.weight))
     datt = torch.empty(M, D, dtype=F16, device=dev)
     ops.linear(g16, wc.w16_t(blk.attn.proj.weight), datt)
-    dqkv = attention_backward(s["qkv"], s["lse"], datt, B, L, H, dhd, blk.attn.scale)
+    dqkv = attention_backward(s["qkv"], s["lse"], datt, B, L, H, dhd, blk.attn.scale, att=s["att"])
     ops.colsum(dqkv, G(blk.attn.qkv.bias))
     _dw_linear(dqkv, s["h1"], G(blk.attn.qkv.weight))
     ops.linear(dqkv, wc.w16_t(blk.attn.qkv.weight), dh)

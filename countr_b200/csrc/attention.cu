@@ -341,6 +341,248 @@ int launch_attention(const void* qkv, void* out, float* lse, int B, int L, int H
   return COUNTR_OK;
 }
 
+
+// ================================================================================================
+// Fused self-attention BACKWARD (flash-style) for head_dim 32 — the FIM self-attention of the fine-tune step.
+//
+//   P = exp(scale*Q K^T - lse),  dP = dO V^T,  dS = scale * P * (dP - delta),  delta = rowsum(dO * O)
+//   dV = P^T dO,   dK = dS^T Q,   dQ = dS K
+//
+// replaces: autograd of Attention.forward (models_crossvit.py:87-91): bmm / _softmax_backward_data / bmm's.
+// One CTA = one (batch, head): Q, K, V, dO of the whole head (L <= 640) stay in shared memory (160 KB, TMA,
+// SWIZZLE_64B), every accumulator stays in tensor memory: dV_j, dK_j (32 columns each), dQ_i for all query
+// blocks (5 x 32), S and dP (128 each) = 480 of 512 columns.  No [B,H,L,L] tensor ever reaches HBM (the
+// unfused path writes and re-reads four of them, 85 MB each at B=8).
+// Out-of-range rows are zero-filled by TMA and get lse = delta = 0, which makes every masked contribution
+// vanish without explicit masking.
+// ================================================================================================
+constexpr int kBwdThreads = 256;
+constexpr int kBwdMaxBlk = 5;
+
+struct AttnBwdArgs {
+  const uint16_t* dO;   // [B*L][H*dh]
+  const uint16_t* O;    // [B*L][H*dh]
+  const float* lse;     // [B][H][L]
+  uint16_t* dqkv;       // [B][L][3][H][dh]
+  int B, L, H;
+  float scale;
+  int bf16;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
+                     const AttnBwdArgs p) {
+  static_assert(DH == 32, "fused attention backward is built for head_dim 32");
+  constexpr uint32_t kBlkBytes = 128 * DH * 2;       // 8 KB: one 128-row block of Q / K / V / dO
+  constexpr uint32_t kTileBytes = 128 * 128 * 2;     // 32 KB: P or dS tile
+  constexpr uint32_t kOffQ = 0, kOffK = kBwdMaxBlk * kBlkBytes, kOffV = 2 * kBwdMaxBlk * kBlkBytes, kOffdO = 3 * kBwdMaxBlk * kBlkBytes;
+  constexpr uint32_t kOffP = 4 * kBwdMaxBlk * kBlkBytes, kOffdS = kOffP + kTileBytes, kOffBar = kOffdS + kTileBytes;
+  constexpr uint32_t tdV = 0, tdK = DH, tdQ = 2 * DH, tS = 256, tP = 384;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* bar_s = bar_load + 1;
+  uint64_t* bar_e = bar_load + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_load + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int r = quarter * 32 + lane;                 // row inside a 128-row block
+  const int h = blockIdx.x % p.H, b = blockIdx.x / p.H;
+  const int nblk = (p.L + 127) / 128;
+  const int D = p.H * DH;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_qkv);
+    tma_prefetch_desc(&tma_do);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_e, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_load, 4u * nblk * kBlkBytes);
+    for (int i = 0; i < nblk; ++i) {
+      tma_load_4d(smem + kOffQ + i * kBlkBytes, &tma_qkv, bar_load, 0, i * 128, h, b);
+      tma_load_4d(smem + kOffK + i * kBlkBytes, &tma_qkv, bar_load, 0, i * 128, p.H + h, b);
+      tma_load_4d(smem + kOffV + i * kBlkBytes, &tma_qkv, bar_load, 0, i * 128, 2 * p.H + h, b);
+      tma_load_4d(smem + kOffdO + i * kBlkBytes, &tma_do, bar_load, 0, i * 128, h, b);
+    }
+  }
+
+  // per-row constants of this thread's query row in every query block (overlaps the TMA loads)
+  const float sl2 = p.scale * 1.44269504088896340736f;
+  float lse2[kBwdMaxBlk], delta[kBwdMaxBlk];
+#pragma unroll
+  for (int i = 0; i < kBwdMaxBlk; ++i) {
+    lse2[i] = 0.f;
+    delta[i] = 0.f;
+    const int q = i * 128 + r;
+    if (i < nblk && q < p.L) {
+      lse2[i] = p.lse[(static_cast<long long>(b) * p.H + h) * p.L + q] * 1.44269504088896340736f;
+      const uint4* po = reinterpret_cast<const uint4*>(p.O + (static_cast<long long>(b) * p.L + q) * D + h * DH);
+      const uint4* pd = reinterpret_cast<const uint4*>(p.dO + (static_cast<long long>(b) * p.L + q) * D + h * DH);
+      float acc = 0.f;
+#pragma unroll
+      for (int v = 0; v < DH / 8; ++v) {
+        const uint4 a = po[v], c = pd[v];
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          float2 fa, fc;
+          if (p.bf16) {
+            fa = make_float2(__uint_as_float(aw[w] << 16), __uint_as_float(aw[w] & 0xffff0000u));
+            fc = make_float2(__uint_as_float(cw[w] << 16), __uint_as_float(cw[w] & 0xffff0000u));
+          } else {
+            fa = __half22float2(*reinterpret_cast<const __half2*>(&aw[w]));
+            fc = __half22float2(*reinterpret_cast<const __half2*>(&cw[w]));
+          }
+          acc += fa.x * fc.x + fa.y * fc.y;
+        }
+      }
+      delta[i] = acc;
+    }
+  }
+
+  const uint32_t idesc_s = make_idesc_f16(128, 128, false, false, p.bf16 != 0);
+  const uint32_t idesc_mm = make_idesc_f16(128, DH, true, true, p.bf16 != 0);   // A = P^T / dS^T (MN-major), B MN-major
+  const uint32_t idesc_km = make_idesc_f16(128, DH, false, true, p.bf16 != 0);  // A = dS (K-major), B MN-major
+  const uint32_t sP = smem_u32(smem + kOffP), sdS = smem_u32(smem + kOffdS);
+
+  int pair = 0;
+  for (int j = 0; j < nblk; ++j) {
+    for (int i = 0; i < nblk; ++i, ++pair) {
+      if (tid == 0) {
+        if (pair == 0) mbar_wait(bar_load, 0);
+        tc_fence_after();
+        const uint64_t dq = make_desc(smem_u32(smem + kOffQ + i * kBlkBytes), 16, 512, 4u);
+        const uint64_t dk = make_desc(smem_u32(smem + kOffK + j * kBlkBytes), 16, 512, 4u);
+        const uint64_t dd = make_desc(smem_u32(smem + kOffdO + i * kBlkBytes), 16, 512, 4u);
+        const uint64_t dv = make_desc(smem_u32(smem + kOffV + j * kBlkBytes), 16, 512, 4u);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_f16_ss(tmem_base + tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_f16_ss(tmem_base + tP, dd + 2 * k, dv + 2 * k, idesc_s, k != 0);
+        umma_commit(bar_s);
+      }
+      // S, dP of this pair are ready (=> the dV/dK/dQ MMAs of the previous pair have drained: P/dS tiles are free)
+      mbar_wait(bar_s, pair & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int gi = 0; gi < 2; ++gi) {
+        const int g = half * 2 + gi;
+        uint32_t rs[32], rp[32];
+        tmem_ld_32x32b_x32(t_lane + tS + g * 32, rs);
+        tmem_ld_32x32b_x32(t_lane + tP + g * 32, rp);
+        tmem_ld_wait();
+        float pv[32], dsv[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          pv[c] = ex2_approx(fmaf(__uint_as_float(rs[c]), sl2, -lse2[i]));
+          dsv[c] = pv[c] * (__uint_as_float(rp[c]) - delta[i]) * p.scale;
+        }
+        const uint32_t row_off = (g >> 1) * (128 * 128) + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o, o2;
+          o.x = pack2(pv[8 * q + 0], pv[8 * q + 1], p.bf16);
+          o.y = pack2(pv[8 * q + 2], pv[8 * q + 3], p.bf16);
+          o.z = pack2(pv[8 * q + 4], pv[8 * q + 5], p.bf16);
+          o.w = pack2(pv[8 * q + 6], pv[8 * q + 7], p.bf16);
+          o2.x = pack2(dsv[8 * q + 0], dsv[8 * q + 1], p.bf16);
+          o2.y = pack2(dsv[8 * q + 2], dsv[8 * q + 3], p.bf16);
+          o2.z = pack2(dsv[8 * q + 4], dsv[8 * q + 5], p.bf16);
+          o2.w = pack2(dsv[8 * q + 6], dsv[8 * q + 7], p.bf16);
+          const uint32_t off = row_off + ((((g & 1) * 4 + q) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(smem + kOffP + off) = o;
+          *reinterpret_cast<uint4*>(smem + kOffdS + off) = o2;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(smem + kOffQ + i * kBlkBytes), adO = smem_u32(smem + kOffdO + i * kBlkBytes);
+        const uint32_t aK = smem_u32(smem + kOffK + j * kBlkBytes);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // 16 query rows (dV, dK) / 16 keys (dQ) per step
+          const uint64_t p_mn = make_desc(sP + ks * 2048, 16384, 1024, 2u);
+          const uint64_t ds_mn = make_desc(sdS + ks * 2048, 16384, 1024, 2u);
+          const uint64_t ds_k = make_desc(sdS + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024, 2u);
+          umma_f16_ss(tmem_base + tdV, p_mn, make_desc(adO + ks * 1024, 16, 512, 4u), idesc_mm, (i | ks) != 0);
+          umma_f16_ss(tmem_base + tdK, ds_mn, make_desc(aQ + ks * 1024, 16, 512, 4u), idesc_mm, (i | ks) != 0);
+          umma_f16_ss(tmem_base + tdQ + i * DH, ds_k, make_desc(aK + ks * 1024, 16, 512, 4u), idesc_km, (j | ks) != 0);
+        }
+        if (i == nblk - 1) umma_commit(bar_e);
+      }
+    }
+    // dV_j, dK_j complete: thread (key row r, column half) writes its 16 columns of each
+    mbar_wait(bar_e, j & 1);
+    tc_fence_after();
+    {
+      const int key = j * 128 + r;
+      uint32_t rv[16], rk[16];
+      tmem_ld_32x32b_x16(t_lane + tdV + half * 16, rv);
+      tmem_ld_32x32b_x16(t_lane + tdK + half * 16, rk);
+      tmem_ld_wait();
+      if (key < p.L) {
+        uint16_t* base = p.dqkv + (static_cast<long long>(b) * p.L + key) * (3 * D) + h * DH + half * 16;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint4 ov, ok;
+          ov.x = pack2(__uint_as_float(rv[8 * q + 0]), __uint_as_float(rv[8 * q + 1]), p.bf16);
+          ov.y = pack2(__uint_as_float(rv[8 * q + 2]), __uint_as_float(rv[8 * q + 3]), p.bf16);
+          ov.z = pack2(__uint_as_float(rv[8 * q + 4]), __uint_as_float(rv[8 * q + 5]), p.bf16);
+          ov.w = pack2(__uint_as_float(rv[8 * q + 6]), __uint_as_float(rv[8 * q + 7]), p.bf16);
+          ok.x = pack2(__uint_as_float(rk[8 * q + 0]), __uint_as_float(rk[8 * q + 1]), p.bf16);
+          ok.y = pack2(__uint_as_float(rk[8 * q + 2]), __uint_as_float(rk[8 * q + 3]), p.bf16);
+          ok.z = pack2(__uint_as_float(rk[8 * q + 4]), __uint_as_float(rk[8 * q + 5]), p.bf16);
+          ok.w = pack2(__uint_as_float(rk[8 * q + 6]), __uint_as_float(rk[8 * q + 7]), p.bf16);
+          *reinterpret_cast<uint4*>(base + 2 * D + 8 * q) = ov;   // V slot
+          *reinterpret_cast<uint4*>(base + D + 8 * q) = ok;       // K slot
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();   // dV/dK TMEM columns are overwritten by the next key block
+  }
+  // dQ of every query block (the bar_e commit of the last key block covered all MMAs)
+  for (int i = 0; i < nblk; ++i) {
+    const int q = i * 128 + r;
+    uint32_t rq[16];
+    tmem_ld_32x32b_x16(t_lane + tdQ + i * DH + half * 16, rq);
+    tmem_ld_wait();
+    if (q < p.L) {
+      uint16_t* base = p.dqkv + (static_cast<long long>(b) * p.L + q) * (3 * D) + h * DH + half * 16;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint4 o;
+        o.x = pack2(__uint_as_float(rq[8 * c + 0]), __uint_as_float(rq[8 * c + 1]), p.bf16);
+        o.y = pack2(__uint_as_float(rq[8 * c + 2]), __uint_as_float(rq[8 * c + 3]), p.bf16);
+        o.z = pack2(__uint_as_float(rq[8 * c + 4]), __uint_as_float(rq[8 * c + 5]), p.bf16);
+        o.w = pack2(__uint_as_float(rq[8 * c + 6]), __uint_as_float(rq[8 * c + 7]), p.bf16);
+        *reinterpret_cast<uint4*>(base + 8 * c) = o;              // Q slot
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace
 }  // namespace countr
 
@@ -353,4 +595,46 @@ extern "C" int countr_attention_fwd(const void* qkv, void* out, float* lse, int 
   if (dh == 64) return launch_attention<64>(qkv, out, lse, B, L, H, scale, bf16, stream);
   if (dh == 32) return launch_attention<32>(qkv, out, lse, B, L, H, scale, bf16, stream);
   return set_error(COUNTR_ERR_UNSUPPORTED, "attention head_dim %d not supported (32 or 64)", dh);
+}
+
+extern "C" int countr_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int L, int H,
+                                    int dh, float scale, int bf16, countr_stream_t stream_) {
+  using namespace countr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(qkv && out && dout && lse && dqkv, "null pointer");
+  COUNTR_REQUIRE(dh == 32, "fused attention backward supports head_dim 32 (got %d)", dh);
+  COUNTR_REQUIRE(L >= 1 && L <= 128 * kBwdMaxBlk, "fused attention backward supports L <= %d (got %d)", 128 * kBwdMaxBlk, L);
+  const int D = H * dh;
+  CUtensorMap tq, td;
+  {
+    const uint64_t dims[4] = {(uint64_t)dh, (uint64_t)L, (uint64_t)(3 * H), (uint64_t)B};
+    const uint64_t str[4] = {1, (uint64_t)(3 * D), (uint64_t)dh, (uint64_t)L * 3 * D};
+    const uint32_t box[4] = {(uint32_t)dh, 128, 1, 1};
+    int rc = make_tmap_4d_16b(&tq, qkv, dims, str, box, TMAP_SW_64);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)dh, (uint64_t)L, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[4] = {1, (uint64_t)D, (uint64_t)dh, (uint64_t)L * D};
+    const uint32_t box[4] = {(uint32_t)dh, 128, 1, 1};
+    int rc = make_tmap_4d_16b(&td, dout, dims, str, box, TMAP_SW_64);
+    if (rc) return rc;
+  }
+  constexpr uint32_t smem_bytes = 4 * kBwdMaxBlk * (128 * 32 * 2) + 2 * (128 * 128 * 2) + 64 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    COUNTR_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set = true;
+  }
+  AttnBwdArgs a;
+  a.dO = reinterpret_cast<const uint16_t*>(dout);
+  a.O = reinterpret_cast<const uint16_t*>(out);
+  a.lse = lse;
+  a.dqkv = reinterpret_cast<uint16_t*>(dqkv);
+  a.B = B; a.L = L; a.H = H;
+  a.scale = scale;
+  a.bf16 = bf16;
+  attention_bwd_kernel<32><<<B * H, kBwdThreads, smem_bytes, stream>>>(tq, td, a);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
 }

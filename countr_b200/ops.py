@@ -124,6 +124,12 @@ def attention_fwd(qkv16, out16, B, L, H, dh, scale, lse=None):
     _count()
 
 
+def attention_bwd(qkv16, out16, dout16, lse, dqkv16, B, L, H, dh, scale):
+    check(lib().countr_attention_bwd(_ptr(qkv16), _ptr(out16), _ptr(dout16), _ptr(lse), _ptr(dqkv16), B, L, H, dh, scale,
+                                     _is_bf16(qkv16), _stream()))
+    _count()
+
+
 def cross_attn_core(q16, k32, v32, out16, B, L, S, D, dh, scale, probs=None, kv_broadcast=False):
     check(lib().countr_cross_attn_core(_ptr(q16), _ptr(k32), _ptr(v32), _ptr(out16), _ptr(probs), B, L, S, D, dh, scale,
                                        _is_bf16(q16), int(kv_broadcast), _stream()))

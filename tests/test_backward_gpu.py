@@ -92,23 +92,24 @@ def test_colsum_and_softmax_bwd(cuda):
     assert_close(dp_io, sr.grad * 0.5, 2e-3, "softmax bwd")
 
 
-def test_attention_backward(cuda):
+@pytest.mark.parametrize("B,L,H,dh,fused", [(2, 576, 16, 32, True), (2, 576, 16, 32, False), (1, 200, 3, 32, True), (1, 640, 2, 32, True),
+                                             (1, 288, 4, 64, False)])
+def test_attention_backward(cuda, B, L, H, dh, fused):
     from countr_b200 import ops
     from countr_b200.backward import attention_backward
-    B, L, H, dh = 2, 576, 16, 32
     qkv = _rand16((B, L, 3, H, dh), cuda, seed=30)
     datt = _rand16((B * L, H * dh), cuda, seed=31)
     out = torch.empty(B, L, H * dh, device=cuda, dtype=torch.float16)
     lse = torch.empty(B, H, L, device=cuda)
     scale = dh ** -0.5
     ops.attention_fwd(qkv, out, B, L, H, dh, scale, lse=lse)
-    dqkv = attention_backward(qkv.view(B * L, -1), lse, datt, B, L, H, dh, scale)
+    dqkv = attention_backward(qkv.view(B * L, -1), lse, datt, B, L, H, dh, scale, att=out.view(B * L, -1), fused=fused)
     x = qkv.float().requires_grad_(True)
     q, k, v = [x[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
     o = ((q @ k.transpose(-1, -2) * scale).softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B * L, H * dh)
     o.backward(datt.float())
     torch.cuda.synchronize()
-    assert_close(dqkv, x.grad.reshape(B * L, -1), 4e-3, "attention bwd")
+    assert_close(dqkv, x.grad.reshape(B * L, -1), 4e-3, f"attention bwd fused={fused} {B},{L},{H},{dh}")
 
 
 @pytest.mark.parametrize("S,bcast", [(3, False), (1, False), (5, False), (1, True)])
