@@ -164,18 +164,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             // leader's MMA thread waits on before issuing the cta_group::2 MMAs over both shared memories
             const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
             if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (kABytes + b_bytes));
-            if (p.conv) {
-              const int tap = kb / p.cin_blocks;
-              const int cb = kb - tap * p.cin_blocks;
-              const int ky = tap / 3, kx = tap - ky * 3;
-              tma_load_4d_2sm(sa, &tma_a, full_leader, cb * BK, x0 + kx - 1, y0 + ky - 1, t.b1);
-            } else if (!p.a_mn) {
-              tma_load_4d_2sm(sa, &tma_a, full_leader, k, t.m * BM, t.b2, t.b1);
+            const int nbox = p.bn / 128;   // 64-wide MN boxes of B held by EACH CTA (MN-major B only)
+            if (p.conv == 2) {
+              // weight gradient: A = this CTA's 128 output channels of dY, B = its half of the input channels
+              const int kbg = k / BK;
+              const int bimg = kbg / p.tiles_per_img;
+              const int rr = kbg - bimg * p.tiles_per_img;
+              const int px0 = (rr % p.tiles_x) * p.bx, py0 = (rr / p.tiles_x) * p.by;
+              const int ky = t.b2 / 3, kx = t.b2 - ky * 3;
+              tma_load_4d_2sm(sa, &tma_a, full_leader, t.m * BM, px0, py0, bimg);
+              tma_load_4d_2sm(sa + 8192, &tma_a, full_leader, t.m * BM + 64, px0, py0, bimg);
+              for (int i = 0; i < nbox; ++i)
+                tma_load_4d_2sm(sb + i * 8192, &tma_b, full_leader, t.n * p.bn + (rank * nbox + i) * 64, px0 + kx - 1, py0 + ky - 1, bimg);
             } else {
-              tma_load_4d_2sm(sa, &tma_a, full_leader, t.m * BM, k, t.b2, t.b1);
-              tma_load_4d_2sm(sa + 8192, &tma_a, full_leader, t.m * BM + 64, k, t.b2, t.b1);
+              if (p.conv) {
+                const int tap = kb / p.cin_blocks;
+                const int cb = kb - tap * p.cin_blocks;
+                const int ky = tap / 3, kx = tap - ky * 3;
+                tma_load_4d_2sm(sa, &tma_a, full_leader, cb * BK, x0 + kx - 1, y0 + ky - 1, t.b1);
+              } else if (!p.a_mn) {
+                tma_load_4d_2sm(sa, &tma_a, full_leader, k, t.m * BM, t.b2, t.b1);
+              } else {
+                tma_load_4d_2sm(sa, &tma_a, full_leader, t.m * BM, k, t.b2, t.b1);
+                tma_load_4d_2sm(sa + 8192, &tma_a, full_leader, t.m * BM + 64, k, t.b2, t.b1);
+              }
+              if (!p.b_mn) {
+                tma_load_4d_2sm(sb, &tma_b, full_leader, k, t.n * p.bn + rank * (p.bn / 2), p.conv ? 0 : t.b2, p.conv ? 0 : t.b1);
+              } else {
+                for (int i = 0; i < nbox; ++i)
+                  tma_load_4d_2sm(sb + i * 8192, &tma_b, full_leader, t.n * p.bn + (rank * nbox + i) * 64, k, t.b2, t.b1);
+              }
             }
-            tma_load_4d_2sm(sb, &tma_b, full_leader, k, t.n * p.bn + rank * (p.bn / 2), p.conv ? 0 : t.b2, p.conv ? 0 : t.b1);
             if (++stage == nstages) {
               stage = 0;
               phase ^= 1;
@@ -597,11 +616,12 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   // shared-memory bandwidth: TMA fill + UMMA operand reads = 192 B/clk against 128 B/clk), so the default is
   // cs = 1 and the path is kept for experiments (cta_group::2 is the real fix).
   // CTA pair (cta_group::2): K-major B only; the pair computes a 256 x bn tile with half of B per SM.
-  const bool pair_ok = !d->b_mn && !conv_dw && p.m_tiles >= 2 && bn % 32 == 0;
+  const bool pair_ok = p.m_tiles >= 2 && ((d->b_mn || conv_dw) ? (bn % 128 == 0) : (bn % 32 == 0));
   // auto policy (cta_pair == 0): pairs for the big implicit-GEMM convolutions, where the larger operand reuse
   // (32 KB instead of 48 KB of smem fill per k-block and SM) is worth +13 % (1.10 -> 1.24 PF/s on decode_head3);
   // neutral on the mid-size Linear layers, which are latency- not throughput-bound (profiles/r1_bench_gemm_pair.log).
-  const bool pair_auto = conv && static_cast<long long>(p.m_tiles) * nb1 >= 128 && bn == 256;
+  const bool pair_auto = bn == 256 && ((conv && static_cast<long long>(p.m_tiles) * nb1 >= 128) ||
+                                       (conv_dw && p.m_tiles % 2 == 0 && d->K >= 64 * 64));
   p.pair = (pair_ok && (d->cta_pair > 0 || (d->cta_pair == 0 && pair_auto))) ? 1 : 0;
   int cs = p.pair ? 2 : (d->cluster > 0 ? d->cluster : 1);
   if (cs != 1 && cs != 2 && cs != 4) cs = 1;

@@ -90,7 +90,7 @@ def conv3x3(x16, w16, out, bias=None, gn_stats=None, pair=0):
                 sa=(H * W * Cin, 0), sc=(H * W * Cout, 0), bias=bias, conv=(H, W, Cin, bx, by), gn_stats=gn_stats, pair=pair)
 
 
-def conv3x3_dw(dy16, x16, dw32, split_k=0):
+def conv3x3_dw(dy16, x16, dw32, split_k=0, pair=0):
     """dw32 [Cout, 9*Cin] fp32 (tap-major, PRE-ZEROED or accumulating) += dY^T (*) X over all pixels."""
     B, H, W, Cout = dy16.shape
     Cin = x16.shape[-1]
@@ -102,7 +102,7 @@ def conv3x3_dw(dy16, x16, dw32, split_k=0):
         out_tiles = 9 * ((Cout + 127) // 128) * ((Cin + 255) // 256)
         split_k = max(1, min(kblocks, 148 // out_tiles))
     return gemm(dy16, x16, dw32, Cout, Cin, kblocks * 64, lda=Cout, ldb=Cin, ldc=9 * Cin, a_mn=True, b_mn=True, nb2=9,
-                sc=(0, Cin), atomic=True, split_k=split_k, conv_dw=(H, W, bx, by, B))
+                sc=(0, Cin), atomic=True, split_k=split_k, conv_dw=(H, W, bx, by, B), pair=pair)
 
 
 def layernorm_fwd(x, gamma, beta, eps, y16=None, y32=None, mean=None, rstd=None):

@@ -84,46 +84,22 @@ def attn(name, H, dh):
 
 
 print(f"B={B}")
-lin("enc qkv", M, 2304, 768, "f16")
-lin("enc fc1 (gelu)", M, 3072, 768, "gelu")
-lin("enc fc2 (+res)", M, 768, 3072, "res")
-lin("fim fc1 (gelu)", M, 2048, 512, "gelu")
-lin("fim fc2 dX (gelu bwd)", M, 2048, 512, "gelubwd")
-
-
-def head_elementwise():
-    C, G = 256, 8
-    for h in (24, 48, 96):
-        x = torch.randn(B, h, h, C, device=dev).half()
-        stats = torch.stack([x.double().reshape(B, h * h, G, 32).sum((1, 3)), (x.double() ** 2).reshape(B, h * h, G, 32).sum((1, 3))], -1).contiguous()
-        gamma = torch.ones(C, device=dev); beta = torch.zeros(C, device=dev)
-        y = torch.empty(B, 2 * h, 2 * h, C, device=dev, dtype=torch.float16)
-        us = timeit(lambda: ops.gn_relu_upsample2x(x, stats, gamma, beta, y, G, 1e-5))
-        mb = (x.numel() + y.numel()) * 2 / 1e6
-        print(f"gn_relu_up2 {h}->{2*h}: {us:7.1f} us  {mb/us*1e3:7.1f} GB/s")
-    h = 192
-    x = torch.randn(B, h, h, C, device=dev).half()
-    stats = torch.stack([x.double().reshape(B, h * h, G, 32).sum((1, 3)), (x.double() ** 2).reshape(B, h * h, G, 32).sum((1, 3))], -1).contiguous()
-    gamma = torch.ones(C, device=dev); beta = torch.zeros(C, device=dev)
-    w = torch.randn(C, device=dev); bias = torch.zeros(1, device=dev)
-    d = torch.empty(B, h, h, device=dev)
-    us = timeit(lambda: ops.gn_relu_conv1x1(x, stats, gamma, beta, w, bias, d, G, 1e-5))
-    print(f"gn_relu_conv1x1 192: {us:7.1f} us  {x.numel()*2/1e6/us*1e3:7.1f} GB/s")
-    dyh = torch.empty_like(x); dg = torch.zeros(C, device=dev); db = torch.zeros(C, device=dev)
-    gsum = torch.zeros(B, G, 2, device=dev, dtype=torch.float64); dw1 = torch.zeros(C, device=dev); db1 = torch.zeros(1, device=dev)
-    dmap = torch.randn(B, h, h, device=dev)
-    us = timeit(lambda: ops.gn_relu_bwd_reduce(x, stats, gamma, beta, dyh, dg, db, gsum, G, 1e-5, dmap=dmap, w1=w, dw1=dw1, db1=db1))
-    print(f"gn_relu_bwd_reduce mode1 192: {us:7.1f} us  {2*x.numel()*2/1e6/us*1e3:7.1f} GB/s")
-    dbias = torch.zeros(C, device=dev)
-    us = timeit(lambda: ops.gn_bwd_apply(x, dyh, stats, gsum, gamma, dyh, dbias, G, 1e-5))
-    print(f"gn_bwd_apply 192: {us:7.1f} us  {3*x.numel()*2/1e6/us*1e3:7.1f} GB/s")
-    for hh in (96, 48):
-        xs = torch.randn(B, hh, hh, C, device=dev).half()
-        st = torch.stack([xs.double().reshape(B, hh * hh, G, 32).sum((1, 3)), (xs.double() ** 2).reshape(B, hh * hh, G, 32).sum((1, 3))], -1).contiguous()
-        dn = torch.randn(B, 2 * hh, 2 * hh, C, device=dev).half()
-        dy2 = torch.empty_like(xs)
-        us = timeit(lambda: ops.gn_relu_bwd_reduce(xs, st, gamma, beta, dy2, dg, db, gsum, G, 1e-5, d_next=dn))
-        print(f"gn_relu_bwd_reduce mode0 {hh}: {us:7.1f} us  {(2*xs.numel()+dn.numel())*2/1e6/us*1e3:7.1f} GB/s")
-
-
-head_elementwise()
+def dwp(name, m_tok, n_out, k_in, split, pr):
+    dy = torch.randn(m_tok, n_out, device=dev).half()
+    x = torch.randn(m_tok, k_in, device=dev).half()
+    c = torch.zeros(n_out, k_in, device=dev)
+    f = lambda: ops.gemm(dy, x, c, n_out, k_in, m_tok, lda=n_out, ldb=k_in, ldc=k_in, a_mn=True, b_mn=True, atomic=True, split_k=split, bn=256, pair=pr)
+    us = timeit(f)
+    print(f"{name:28s} dW [{n_out}x{k_in}] over {m_tok} split={split:2d} pair={pr}: {us:8.1f} us  {2.0*m_tok*n_out*k_in/us/1e6:7.1f} TFLOP/s")
+for pr in (-1, 1):
+    dwp("fim fc2 dW", M, 512, 2048, 4, pr)
+    dwp("fim fc1 dW", M, 2048, 512, 4, pr)
+    dwp("fim qkv dW", M, 1536, 512, 6, pr)
+    dwp("fim proj dW", M, 512, 512, 16, pr)
+    for h, cin in ((24, 512), (48, 256), (96, 256), (192, 256)):
+        x = torch.randn(B, h, h, cin, device=dev).half()
+        dyv = torch.randn(B, h, h, 256, device=dev).half()
+        dwq = torch.zeros(256, 9 * cin, device=dev)
+        us2 = timeit(lambda: ops.conv3x3_dw(dyv, x, dwq, pair=pr))
+        fl = 2.0 * B * h * h * 256 * 9 * cin
+        print(f"conv dW {h}x{h} {cin}->256 pair={pr}: {us2:8.1f} us {fl/us2/1e6:7.1f} TF")

@@ -379,3 +379,26 @@ def test_conv3x3_cta_pair(cuda, B, H, W, Cin, Cout):
     rg = ref.reshape(B, H * W, Cout // 32, 32).double()
     ref_stats = torch.stack([rg.sum((1, 3)), (rg * rg).sum((1, 3))], -1)
     assert_close(stats.reshape(-1, 2), ref_stats.reshape(-1, 2), 1e-4, "gn stats (pair)")
+
+
+@pytest.mark.parametrize("pair", [1, -1])
+def test_conv_dw_and_linear_dw_cta_pair(cuda, pair):
+    from countr_b200 import ops
+    for (B, H, W, Cin, Cout) in [(2, 24, 24, 512, 256), (2, 48, 48, 256, 256), (3, 16, 16, 128, 256)]:
+        x = _rand16((B, H, W, Cin), cuda, seed=81)
+        dy = _rand16((B, H, W, Cout), cuda, seed=82)
+        w = torch.zeros(Cout, Cin, 3, 3, device=cuda, requires_grad=True)
+        F.conv2d(x.float().permute(0, 3, 1, 2), w, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+        dwp = torch.zeros(Cout, 9 * Cin, device=cuda)
+        ops.conv3x3_dw(dy, x, dwp, pair=pair)
+        dw = torch.empty(Cout, Cin, 3, 3, device=cuda)
+        ops.conv_dw_unpack(dwp, dw, Cout, Cin)
+        torch.cuda.synchronize()
+        assert_close(dw.reshape(Cout, -1), w.grad.reshape(Cout, -1), 1e-4, f"conv dW pair={pair} {B}x{H}x{W} {Cin}->{Cout}")
+    M, N, K = 512, 2048, 4608          # Linear dW = dY^T X, both operands MN-major
+    a = _rand16((K, M), cuda, seed=83)
+    b = _rand16((K, N), cuda, seed=84)
+    c = torch.zeros(M, N, device=cuda, dtype=torch.float32)
+    ops.gemm(a, b, c, M, N, K, lda=M, ldb=N, ldc=N, a_mn=True, b_mn=True, atomic=True, split_k=4, bn=256, pair=pair)
+    torch.cuda.synchronize()
+    assert_close(c, a.float().t() @ b.float(), 3e-5, f"linear dW pair={pair}")
