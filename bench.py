@@ -30,6 +30,16 @@ PER_GPU_BATCH = 8
 SHOTS = 3
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+    `ncu --set full` capture of the same launch (profiles/r1_conv_h3_ncu_summary.json); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_conv_h3_ncu_summary.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -355,7 +365,7 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel (decode_head3 conv3x3 implicit GEMM, M=%d N=256 K=2304)" % (B * 192 * 192),
                      "achieved": round(k_tflops, 1), "peak": peaks.get("bf16_tflops"), "unit": "TFLOP/s",
                      "frac": round(k_tflops / peaks.get("bf16_tflops"), 4), "peak_source": peak_src + " bf16_tflops (burst: kernel timed alone)",
-                     "ms_per_launch": round(k_ms, 4), "traffic": None,
+                     "ms_per_launch": round(k_ms, 4), "traffic": ncu_traffic(), "algorithmic_bytes": 2 * (2 * B * 192 * 192 * 256) + 2 * 256 * 2304,
                      "whole_step": {"achieved": round(step_tflops, 1), "peak": peaks.get("bf16_tflops_sustained"),
                                     "frac": round(step_tflops / peaks.get("bf16_tflops_sustained"), 4),
                                     "gflop_per_image": GFLOP_PER_IMG_FINETUNE}},
