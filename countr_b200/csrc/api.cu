@@ -1,6 +1,7 @@
 // countr_b200 — C-ABI plumbing: error reporting, version, device probe, tensor-map encode.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -71,6 +72,15 @@ int make_tmap_4d_16b(CUtensorMap* out, const void* base, const uint64_t dims[4],
                      (unsigned long long)dims[3], (unsigned long long)strides[1], (unsigned long long)strides[2],
                      (unsigned long long)strides[3], box[0], box[1], box[2], box[3]);
   return COUNTR_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("COUNTR_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 int num_sms() {

@@ -113,6 +113,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   const int q0 = qt * BQ;
   const int nchunks = (p.L + KC - 1) / KC;
 
+  pdl_trigger();
   if (tid == 0) {
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_kv);
@@ -129,6 +130,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+  pdl_wait();   // qkv is the previous kernel's output
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_q, SM::kQBytes);
@@ -336,8 +338,7 @@ int launch_attention(const void* qkv, void* out, float* lse, int B, int L, int H
   p.bf16 = bf16;
   p.q_tiles = (L + BQ - 1) / BQ;
   const int grid = B * H * p.q_tiles;
-  attention_fwd_kernel<DH><<<grid, kThreads, SM::kTotal, stream>>>(tq, tkv, p);
-  COUNTR_CHECK_CUDA(cudaGetLastError());
+  COUNTR_CHECK_CUDA(launch_pdl(attention_fwd_kernel<DH>, dim3(grid), dim3(kThreads), SM::kTotal, stream, tq, tkv, p));
   return COUNTR_OK;
 }
 
@@ -394,6 +395,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
   const int nblk = (p.L + 127) / 128;
   const int D = p.H * DH;
 
+  pdl_trigger();
   if (tid == 0) {
     tma_prefetch_desc(&tma_qkv);
     tma_prefetch_desc(&tma_do);
@@ -408,6 +410,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+  pdl_wait();   // qkv / out / dout come from earlier kernels
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_load, 4u * nblk * kBlkBytes);
@@ -634,7 +637,6 @@ extern "C" int countr_attention_bwd(const void* qkv, const void* out, const void
   a.B = B; a.L = L; a.H = H;
   a.scale = scale;
   a.bf16 = bf16;
-  attention_bwd_kernel<32><<<B * H, kBwdThreads, smem_bytes, stream>>>(tq, td, a);
-  COUNTR_CHECK_CUDA(cudaGetLastError());
+  COUNTR_CHECK_CUDA(launch_pdl(attention_bwd_kernel<32>, dim3(B * H), dim3(kBwdThreads), smem_bytes, stream, tq, td, a));
   return COUNTR_OK;
 }

@@ -296,6 +296,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x,
                                                       int N, long long ld, int rows_per_block) {
   // thread = 2 columns; blockDim.x = 128 threads along N, blockDim.y = 2 row lanes
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  pdl_trigger();
+  pdl_wait();
   if (c >= N) return;
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
   const long long r1 = min(R, r0 + rows_per_block);
@@ -777,8 +779,7 @@ extern "C" int countr_colsum(const void* x, int dtype, float* out, int64_t R, in
   if (row_blocks < 1) row_blocks = 1;
   const int rpb = static_cast<int>((R + row_blocks - 1) / row_blocks);
   dim3 grid(col_blocks, static_cast<unsigned>((R + rpb - 1) / rpb)), block(128, 2);
-  colsum_kernel<<<grid, block, 0, stream>>>(x, dtype, out, R, N, ld, rpb);
-  COUNTR_CHECK_CUDA(cudaGetLastError());
+  COUNTR_CHECK_CUDA(launch_pdl(colsum_kernel, grid, block, 0, stream, x, dtype, out, static_cast<long long>(R), N, static_cast<long long>(ld), rpb));
   return COUNTR_OK;
 }
 

@@ -112,6 +112,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_trigger();   // the next kernel may start its prologue as soon as SMs drain
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -136,6 +137,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int rank = p.cs > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const int cluster_id = blockIdx.x / p.cs, num_clusters = gridDim.x / p.cs;
   const uint16_t mc_mask = static_cast<uint16_t>((1u << p.cs) - 1u);
+  pdl_wait();      // operands, residual, aux ... are produced by earlier kernels
 
   const uint32_t b_bytes = static_cast<uint32_t>(kPair ? p.bn / 2 : p.bn) * BK * 2;   // B bytes landing in THIS CTA per stage
 
@@ -701,13 +703,15 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   if (p.pair) COUNTR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<true>, ta, tb, p));
   else COUNTR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<false>, ta, tb, p));
   return COUNTR_OK;

@@ -30,6 +30,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                              int bf16) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
+  pdl_wait();
   if (warp >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp) * D);
   float4 v[NV];
@@ -80,6 +82,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                              int rows_per_warp, int bf16) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
+  pdl_wait();
   float4 dg[NV], db[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -160,7 +164,7 @@ extern "C" int countr_layernorm_fwd(const float* x, const float* gamma, const fl
   uint16_t* y = reinterpret_cast<uint16_t*>(y16);
 #define LN_CASE(NV)                                                                                             \
   case NV:                                                                                                      \
-    layernorm_fwd_kernel<NV><<<blocks, 256, 0, stream>>>(x, gamma, beta, y, y32, mean, rstd, rows, D, eps, bf16); \
+    COUNTR_CHECK_CUDA(launch_pdl(layernorm_fwd_kernel<NV>, dim3(blocks), dim3(256), 0, stream, x, gamma, beta, y, y32, mean, rstd, rows, D, eps, bf16)); \
     break;
   switch (D / 128) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(8) LN_CASE(10) LN_CASE(12)
@@ -188,8 +192,8 @@ extern "C" int countr_layernorm_bwd(const float* dy, const float* x, const float
   const int blocks = (warps + 7) / 8;
 #define LN_CASE(NV)                                                                                       \
   case NV:                                                                                                \
-    layernorm_bwd_kernel<NV><<<blocks, 256, 0, stream>>>(dy, x, gamma, mean, rstd, dx, reinterpret_cast<uint16_t*>(dx16), \
-                                                         dgamma, dbeta, rows, D, accumulate, rpw, bf16);  \
+    COUNTR_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel<NV>, dim3(blocks), dim3(256), 0, stream, dy, x, gamma, mean, rstd, dx,  \
+                                 reinterpret_cast<uint16_t*>(dx16), dgamma, dbeta, rows, D, accumulate, rpw, bf16)); \
     break;
   switch (D / 128) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(8) LN_CASE(10) LN_CASE(12)
