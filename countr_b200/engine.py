@@ -45,13 +45,19 @@ class WeightCache:
 
     def __init__(self):
         self.cache = {}
+        self.ext = {}          # id(p) -> counter bumped by trainers that update parameters with their own kernels
+
+    def bump(self, params):
+        """Mark parameters as modified outside torch (torch's version counter did not move)."""
+        for p in params:
+            self.ext[id(p)] = self.ext.get(id(p), 0) + 1
 
     def _lookup(self, p, kind, shape, fill):
         # keyed by id(p) but validated with a weak reference: ids (and device pointers) are recycled when a
         # model is freed and another one is built, so identity must be checked, not assumed.
         key = (id(p), kind)
         ent = self.cache.get(key)
-        ver = (p.data_ptr(), p._version)
+        ver = (p.data_ptr(), p._version, self.ext.get(id(p), 0))
         if ent is None or ent[0]() is not p or ent[1] != ver or ent[2].device != p.device:
             reuse = ent is not None and ent[2].device == p.device and ent[2].shape == torch.Size(shape)
             buf = ent[2] if reuse else torch.empty(shape, dtype=F16, device=p.device)

@@ -245,6 +245,22 @@ int countr_mae_loss(const float* pred, const void* img, int dtype, int64_t sb, i
 int countr_cast_scaled_f32_to_16(const float* src, const float* scale_ptr, void* dst, int64_t n, int bf16,
                                  countr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Script-side pieces of the fine-tune step as single kernels (used by countr_b200.train.FineTuner).
+ * ------------------------------------------------------------------------------------------ */
+/* FSC_finetune_cross.py:290-295: loss = sum((out-gt)^2 * mask / (H*W)) / B  (mask [H][W] broadcast over the batch);
+ * dout (optional, fp32 [B][H][W]) = d(loss * grad_scale)/d out */
+int countr_masked_mse(const void* out, int out_dtype, const float* gt, const float* mask, float* loss, float* dout, int B,
+                      int H, int W, float grad_scale, countr_stream_t stream);
+/* unscale + torch.optim.AdamW (decoupled weight decay, bias correction) over every tensor of a flat arena in one
+ * launch.  tensors: device array of {float* param; int64 grad_off; int64 moment_off; int64 numel; float weight_decay;
+ * int pad} (40 bytes);
+ * chunks: device array of {int tensor, int chunk_of_1024}; step: device fp32 counter (incremented here, so the call
+ * is CUDA-graph replayable). */
+int countr_adamw_step(const void* tensors, const void* chunks, int num_chunks, const float* grad, float* exp_avg,
+                      float* exp_avg_sq, float* step, float lr, float beta1, float beta2, float eps, float inv_scale,
+                      countr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

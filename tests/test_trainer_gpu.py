@@ -1,0 +1,72 @@
+"""FineTuner (fused loss + flat-arena AdamW) against the reference loop's pieces: the same model stepped with
+autograd + torch.optim.AdamW (the script's optimizer, FSC_finetune_cross.py:235) must move every parameter the same way."""
+import copy
+import ctypes
+
+import pytest
+import torch
+
+from oracle import synth
+from test_parity_gpu import build
+
+pytestmark = pytest.mark.gpu
+
+
+def test_masked_mse_and_adamw_kernels(cuda):
+    from countr_b200 import ops
+    from countr_b200._lib import check, lib
+    B, H, W = 3, 96, 96
+    out = torch.randn(B, H, W, device=cuda, requires_grad=True)
+    gt = torch.rand(B, H, W, device=cuda)
+    mask = (torch.rand(H, W, device=cuda) < 0.8).float()
+    ref = ((out - gt) ** 2 * mask / (H * W)).sum() / B
+    (ref * 7.0).backward()
+    loss = torch.zeros((), device=cuda)
+    dout = torch.empty(B, H, W, device=cuda)
+    check(lib().countr_masked_mse(ctypes.c_void_p(out.data_ptr()), 0, ctypes.c_void_p(gt.data_ptr()), ctypes.c_void_p(mask.data_ptr()),
+                                  ctypes.c_void_p(loss.data_ptr()), ctypes.c_void_p(dout.data_ptr()), B, H, W, 7.0, ops._stream()))
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item()) + 1e-7
+    assert torch.allclose(dout, out.grad, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("shots", [[3, 3, 3], [3, 0, 2]])
+def test_finetuner_matches_autograd_plus_torch_adamw(cuda, shots):
+    from countr_b200.train import FineTuner
+    m1, sd, cfg = build("small", 1, cuda)
+    m2 = copy.deepcopy(m1)
+    m1.train(); m2.train()
+    scale = 1024.0
+    decay, no_decay = [], []
+    for n, p in m1.named_parameters():
+        if p.requires_grad:
+            (no_decay if (p.ndim == 1 or n.endswith(".bias")) else decay).append(p)
+    opt = torch.optim.AdamW([{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": 0.05}], lr=1e-3, betas=(0.9, 0.95))
+    tuner = FineTuner(m2, lr=1e-3, weight_decay=0.05, betas=(0.9, 0.95), loss_scale=scale)
+    start = {n: p.detach().clone() for n, p in m1.named_parameters()}
+    for it, shot in enumerate(shots):
+        imgs, boxes = synth.make_inputs(2, seed=100 + it)
+        gt, mask = synth.make_targets(2, seed=200 + it)
+        imgs, boxes, gt, mask = imgs.to(cuda), boxes.to(cuda), gt.to(cuda), mask.to(cuda)
+        bx = boxes if shot else torch.empty(2, 0, device=cuda)
+        out = m1(imgs, bx, shot)
+        loss1 = ((out - gt) ** 2 * mask / (384 * 384)).sum() / 2
+        opt.zero_grad(set_to_none=True)
+        (loss1 * scale).backward()
+        torch._foreach_mul_([p.grad for p in m1.parameters() if p.grad is not None], 1.0 / scale)
+        opt.step()
+        loss2 = tuner.step(imgs, bx, gt, mask, shot)
+        torch.cuda.synchronize()
+        assert abs(loss1.item() - loss2.item()) < 1e-4 * abs(loss1.item())
+    p2 = dict(m2.named_parameters())
+    worst = 0.0
+    for n, p in m1.named_parameters():
+        d1 = (p.detach() - start[n]).double()
+        d2 = (p2[n].detach() - start[n]).double()
+        if d1.norm() == 0:
+            assert d2.norm() == 0, n          # frozen encoder / unused parameters do not move
+            continue
+        e = ((d1 - d2).norm() / d1.norm()).item()
+        worst = max(worst, e)
+        assert e < 5e-2, (n, e)
+    print(f"\n[finetuner] worst relative difference of a parameter update vs autograd+torch.optim.AdamW: {worst:.3e}")
