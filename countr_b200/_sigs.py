@@ -33,7 +33,7 @@ SIGS = {
     "countr_mae_loss": [P, P, I, L, L, L, L, P, P, I, I, I, I, I, I, P],
     "countr_cast_scaled_f32_to_16": [P, P, P, L, I, P],
     "countr_masked_mse": [P, I, P, P, P, P, I, I, I, F, P],
-    "countr_adamw_step": [P, P, I, P, P, P, P, F, F, F, F, F, P],
+    "countr_adamw_step": [P, I, P, I, P, P, P, P, F, F, F, F, F, P],
 }
 
 

@@ -47,10 +47,13 @@ struct AdamTensor {
   long long moment_off;  // offset of its Adam moments inside the (all-parameter) moment arenas
   long long numel;
   float weight_decay;
-  int pad;
+  int step_idx;          // index of this parameter's own step counter (torch.optim keeps one per parameter)
 };
 
-__global__ void adam_step_inc_kernel(float* __restrict__ step) { *step += 1.f; }
+__global__ void adam_step_inc_kernel(const AdamTensor* __restrict__ tensors, int n, float* __restrict__ steps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) steps[tensors[i].step_idx] += 1.f;
+}
 
 // one block = 1024 consecutive elements of one tensor (chunk table built by the host once)
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamTensor* __restrict__ tensors, const int2* __restrict__ chunks,
@@ -59,7 +62,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamTensor* __restrict
                                                      float beta1, float beta2, float eps, float inv_scale) {
   const int2 ch = chunks[blockIdx.x];
   const AdamTensor t = tensors[ch.x];
-  const float step = *step_ptr;
+  const float step = step_ptr[t.step_idx];
   const float bc1 = 1.f - powf(beta1, step), bc2 = 1.f - powf(beta2, step);
   const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
   const long long base = static_cast<long long>(ch.y) * 1024;
@@ -100,12 +103,12 @@ extern "C" int countr_masked_mse(const void* out, int out_dtype, const float* gt
   return COUNTR_OK;
 }
 
-extern "C" int countr_adamw_step(const void* tensors, const void* chunks, int num_chunks, const float* grad, float* exp_avg,
-                                 float* exp_avg_sq, float* step, float lr, float beta1, float beta2, float eps, float inv_scale,
-                                 countr_stream_t stream_) {
+extern "C" int countr_adamw_step(const void* tensors, int num_tensors, const void* chunks, int num_chunks, const float* grad,
+                                 float* exp_avg, float* exp_avg_sq, float* step, float lr, float beta1, float beta2, float eps,
+                                 float inv_scale, countr_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(tensors && chunks && grad && exp_avg && exp_avg_sq && step && num_chunks > 0, "bad arguments");
-  adam_step_inc_kernel<<<1, 1, 0, stream>>>(step);
+  adam_step_inc_kernel<<<(num_tensors + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const AdamTensor*>(tensors), num_tensors, step);
   adamw_kernel<<<num_chunks, 256, 0, stream>>>(reinterpret_cast<const AdamTensor*>(tensors), reinterpret_cast<const int2*>(chunks), grad,
                                                exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, inv_scale);
   COUNTR_CHECK_CUDA(cudaGetLastError());

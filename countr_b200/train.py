@@ -31,7 +31,6 @@ class FineTuner:
         self.dev = next(model.parameters()).device
         self._opt = {}                      # per shot-mode (shot_num > 0 / == 0): the parameter set differs
         self.loss = torch.zeros((), dtype=F32, device=self.dev)
-        self.step_count = torch.zeros((), dtype=F32, device=self.dev)
 
     def _optimizer_tables(self, shot_num):
         key = shot_num > 0
@@ -49,13 +48,15 @@ class FineTuner:
             self.exp_avg_sq = torch.zeros_like(arena)
             base = arena.data_ptr()
             self._moment_index = {n: (views[n].data_ptr() - base) // 4 for n in all_names}
+            self._step_index = {n: i for i, n in enumerate(all_names)}
+            self.step_count = torch.zeros(len(all_names), dtype=F32, device=self.dev)   # one counter per parameter, like torch.optim
         g_arena, g_views = build_grad_arena(names, params, self.dev)
         base = g_arena.data_ptr()
-        rec = np.zeros(len(names), dtype=np.dtype([("param", "<u8"), ("goff", "<i8"), ("moff", "<i8"), ("numel", "<i8"), ("wd", "<f4"), ("pad", "<i4")]))
+        rec = np.zeros(len(names), dtype=np.dtype([("param", "<u8"), ("goff", "<i8"), ("moff", "<i8"), ("numel", "<i8"), ("wd", "<f4"), ("step_idx", "<i4")]))
         chunks = []
         for i, (n, p) in enumerate(zip(names, params)):
             rec[i] = (p.data_ptr(), (g_views[n].data_ptr() - base) // 4, self._moment_index[n], p.numel(),
-                      0.0 if (p.ndim == 1 or n.endswith(".bias")) else self.wd, 0)     # timm add_weight_decay
+                      0.0 if (p.ndim == 1 or n.endswith(".bias")) else self.wd, self._step_index[n])     # timm add_weight_decay
             chunks += [(i, c) for c in range((p.numel() + 1023) // 1024)]
         t = dict(names=names, params=params, tensors=torch.from_numpy(rec.view(np.uint8).copy()).to(self.dev),
                  chunks=torch.tensor(chunks, dtype=torch.int32, device=self.dev), n_chunks=len(chunks))
@@ -79,7 +80,7 @@ class FineTuner:
         if self.allreduce is not None:
             self.allreduce(arena)
         t = self._optimizer_tables(shot_num)
-        check(lib().countr_adamw_step(ctypes.c_void_p(t["tensors"].data_ptr()), ctypes.c_void_p(t["chunks"].data_ptr()), t["n_chunks"],
+        check(lib().countr_adamw_step(ctypes.c_void_p(t["tensors"].data_ptr()), len(t["names"]), ctypes.c_void_p(t["chunks"].data_ptr()), t["n_chunks"],
                                       ctypes.c_void_p(arena.data_ptr()), ctypes.c_void_p(self.exp_avg.data_ptr()),
                                       ctypes.c_void_p(self.exp_avg_sq.data_ptr()), ctypes.c_void_p(self.step_count.data_ptr()),
                                       self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.loss_scale, ops._stream()))

@@ -254,12 +254,12 @@ int countr_masked_mse(const void* out, int out_dtype, const float* gt, const flo
                       int H, int W, float grad_scale, countr_stream_t stream);
 /* unscale + torch.optim.AdamW (decoupled weight decay, bias correction) over every tensor of a flat arena in one
  * launch.  tensors: device array of {float* param; int64 grad_off; int64 moment_off; int64 numel; float weight_decay;
- * int pad} (40 bytes);
- * chunks: device array of {int tensor, int chunk_of_1024}; step: device fp32 counter (incremented here, so the call
- * is CUDA-graph replayable). */
-int countr_adamw_step(const void* tensors, const void* chunks, int num_chunks, const float* grad, float* exp_avg,
-                      float* exp_avg_sq, float* step, float lr, float beta1, float beta2, float eps, float inv_scale,
-                      countr_stream_t stream);
+ * int step_idx} (40 bytes);
+ * chunks: device array of {int tensor, int chunk_of_1024}; step: device fp32 per-parameter step counters (incremented
+ * here for the participating tensors, so the call is CUDA-graph replayable). */
+int countr_adamw_step(const void* tensors, int num_tensors, const void* chunks, int num_chunks, const float* grad,
+                      float* exp_avg, float* exp_avg_sq, float* step, float lr, float beta1, float beta2, float eps,
+                      float inv_scale, countr_stream_t stream);
 
 #ifdef __cplusplus
 }
