@@ -64,7 +64,8 @@ class FineTuner:
         return t
 
     @torch.no_grad()
-    def step(self, imgs, boxes, gt_density, mask, shot_num):
+    def forward_backward(self, imgs, boxes, gt_density, mask, shot_num):
+        """Forward, loss and backward; leaves the (scaled) gradients in `self.arena`.  Returns the loss (device scalar)."""
         m, eng = self.model, engine()
         B = imgs.shape[0]
         _, lat16 = eng.encoder_forward(m, imgs)
@@ -75,15 +76,26 @@ class FineTuner:
                                       ctypes.c_void_p(mask.data_ptr()), ctypes.c_void_p(self.loss.data_ptr()),
                                       ctypes.c_void_p(dout.data_ptr()), B, out.shape[1], out.shape[2], self.loss_scale, ops._stream()))
         ops._count()
-        grads = decoder_backward(eng, m, save, boxes, dout)
-        arena = eng.last_arena
-        if self.allreduce is not None:
-            self.allreduce(arena)
-        t = self._optimizer_tables(shot_num)
-        check(lib().countr_adamw_step(ctypes.c_void_p(t["tensors"].data_ptr()), len(t["names"]), ctypes.c_void_p(t["chunks"].data_ptr()), t["n_chunks"],
-                                      ctypes.c_void_p(arena.data_ptr()), ctypes.c_void_p(self.exp_avg.data_ptr()),
+        decoder_backward(eng, m, save, boxes, dout)
+        self.arena = eng.last_arena
+        self._shot = shot_num
+        return self.loss
+
+    @torch.no_grad()
+    def update(self):
+        """Unscale + AdamW on the arena left by forward_backward (all-reduce it first when data-parallel)."""
+        eng = engine()
+        t = self._optimizer_tables(self._shot)
+        check(lib().countr_adamw_step(ctypes.c_void_p(t["tensors"].data_ptr()), len(t["names"]), ctypes.c_void_p(t["chunks"].data_ptr()),
+                                      t["n_chunks"], ctypes.c_void_p(self.arena.data_ptr()), ctypes.c_void_p(self.exp_avg.data_ptr()),
                                       ctypes.c_void_p(self.exp_avg_sq.data_ptr()), ctypes.c_void_p(self.step_count.data_ptr()),
                                       self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.loss_scale, ops._stream()))
         ops._count(2)
         eng.wc.bump(t["params"])      # parameters changed behind torch's back: refresh their fp16 copies next step
-        return self.loss
+
+    def step(self, imgs, boxes, gt_density, mask, shot_num):
+        loss = self.forward_backward(imgs, boxes, gt_density, mask, shot_num)
+        if self.allreduce is not None:
+            self.allreduce(self.arena)
+        self.update()
+        return loss

@@ -61,6 +61,8 @@ def test_finetuner_matches_autograd_plus_torch_adamw(cuda, shots):
     p2 = dict(m2.named_parameters())
     worst = 0.0
     for n, p in m1.named_parameters():
+        if n.endswith(".attn.wk.bias") or (n.startswith("decoder_proj") and n.endswith(".bias")):
+            continue      # exactly-zero true gradient (softmax shift / InstanceNorm mean removal): Adam amplifies pure noise
         d1 = (p.detach() - start[n]).double()
         d2 = (p2[n].detach() - start[n]).double()
         if d1.norm() == 0:
