@@ -194,7 +194,7 @@ def run_ours(args):
         d_mask.copy_(hb["mask"], non_blocking=True)
 
     from countr_b200.train import FineTuner
-    tuner = None if args.script_loop else FineTuner(model, lr=1e-5, weight_decay=0.05, betas=(0.9, 0.95), loss_scale=loss_scale)
+    tuner = FineTuner(model, lr=1e-5, weight_decay=0.05, betas=(0.9, 0.95), loss_scale=loss_scale) if args.fused_step else None
     state = {"aliased": None}
 
     # --- a step in two halves, so that for N > 1 the gradient all-reduce sits BETWEEN two CUDA graphs
@@ -404,8 +404,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--script-loop", action="store_true",
-                    help="drive the step like the unmodified reference script (autograd + torch.optim.AdamW) instead of countr_b200.train.FineTuner")
+    ap.add_argument("--fused-step", action="store_true",
+                    help="drive the step with countr_b200.train.FineTuner (fused loss kernel + flat-arena AdamW kernel) instead of the "
+                         "reference script's loop (model() -> loss.backward() -> torch.optim.AdamW), which is the default because it is "
+                         "the drop-in API; both run the same forward/backward kernels and measure within 1.5 % of each other")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
