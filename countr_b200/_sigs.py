@@ -34,6 +34,7 @@ SIGS = {
     "countr_cast_scaled_f32_to_16": [P, P, P, L, I, P],
     "countr_masked_mse": [P, I, P, P, P, P, I, I, I, F, P],
     "countr_adamw_step": [P, I, P, I, P, P, P, P, F, F, F, F, F, P],
+    "countr_window_blend": [P, I, P, I, I, I, I, P, P],
 }
 
 

@@ -682,6 +682,31 @@ __global__ void cast_scaled_kernel(const float* __restrict__ src, const float* _
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Sliding-window blend of the evaluation path (demo.py:124-160, FSC_test_cross(few-shot).py:322-349):
+// windows of width Wwin at x = starts[i] are visited left to right; a column already covered by an earlier
+// window takes the average of the running map and the new window, a new column takes the window's value.
+// One thread per output pixel replays that recurrence over the (few) windows that cover its column.
+// ------------------------------------------------------------------------------------------
+__global__ void window_blend_kernel(const void* __restrict__ outs, int dtype, const int* __restrict__ starts, int nw, int H, int Wwin,
+                                    int W, float* __restrict__ density) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(H) * W) return;
+  const int x = idx % W, y = idx / W;
+  float v = 0.f;
+  bool covered = false;
+  for (int i = 0; i < nw; ++i) {
+    const int s = starts[i];
+    if (x >= s && x < s + Wwin) {
+      const float o = load_any(outs, (static_cast<long long>(i) * H + y) * Wwin + (x - s), dtype);
+      v = covered ? 0.5f * v + 0.5f * o : o;
+      covered = true;
+    }
+  }
+  density[idx] = v;
+}
+
 }  // namespace
 }  // namespace countr
 
@@ -873,6 +898,16 @@ extern "C" int countr_cast_scaled_f32_to_16(const float* src, const float* scale
   COUNTR_REQUIRE(src && dst && scale_ptr && n > 0, "bad arguments");
   const long long threads = (n + 7) / 8;
   cast_scaled_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(src, scale_ptr, reinterpret_cast<uint16_t*>(dst), n, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_window_blend(const void* outs, int dtype, const int32_t* starts, int nw, int H, int Wwin, int W, float* density,
+                                   countr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(outs && starts && density && nw > 0 && dtype >= 0 && dtype <= 2, "bad arguments");
+  const long long total = static_cast<long long>(H) * W;
+  window_blend_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(outs, dtype, starts, nw, H, Wwin, W, density);
   COUNTR_CHECK_CUDA(cudaGetLastError());
   return COUNTR_OK;
 }

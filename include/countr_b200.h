@@ -261,6 +261,12 @@ int countr_adamw_step(const void* tensors, int num_tensors, const void* chunks, 
                       float* exp_avg, float* exp_avg_sq, float* step, float lr, float beta1, float beta2, float eps,
                       float inv_scale, countr_stream_t stream);
 
+/* Sliding-window evaluation blend (demo.py:124-160; FSC_test_cross(few-shot).py:322-349): outs [nw][H][Wwin] are the
+ * density maps of the windows at columns starts[i] (visited left to right); density [H][W] receives the running
+ * average the reference's loop produces (overlap -> (old + new) / 2, new columns -> new). */
+int countr_window_blend(const void* outs, int dtype, const int32_t* starts, int nw, int H, int Wwin, int W, float* density,
+                        countr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,9 @@ CONFIGS = {
     "base": dict(img_size=384, patch_size=16, embed_dim=768, depth=12, num_heads=12, decoder_embed_dim=512,
                  decoder_depth=2, decoder_num_heads=16, mlp_ratio=4, eps=1e-6),
     # a shallow, narrow encoder with the real decoder: quick enough for many CPU parity cases
+    # ViT-L/16 geometry (embed 1024, 16 heads of 64; models_mae_cross.py:218-223) with a 4-block FIM (:232-237), shallow
+    "large_fim4": dict(img_size=384, patch_size=16, embed_dim=1024, depth=2, num_heads=16, decoder_embed_dim=512,
+                       decoder_depth=4, decoder_num_heads=16, mlp_ratio=4, eps=1e-6),
     "small": dict(img_size=384, patch_size=16, embed_dim=256, depth=2, num_heads=4, decoder_embed_dim=512,
                   decoder_depth=2, decoder_num_heads=16, mlp_ratio=4, eps=1e-6),
 }

@@ -109,3 +109,16 @@ def test_submodules_standalone(cuda):
     out = blk(x.to(cuda), y.to(cuda))
     ref = O.fim_block(x, y, sd, "b", 16, 1e-5)
     assert rel(out, ref) < 2e-3
+
+
+def test_large_width_and_deeper_fim_variant(cuda):
+    """Kernel templates generalise over (D, heads, FIM depth): ViT-L width with a 4-block FIM."""
+    m, sd, cfg = build("large_fim4", 3, cuda)
+    m.eval()
+    imgs, boxes = synth.make_inputs(1, seed=9)
+    with torch.no_grad():
+        out = m(imgs.to(cuda), boxes.to(cuda), 2)
+        ref = O.forward(sd, cfg, imgs, boxes, 2)
+    e = rel(out, ref)
+    print(f"\n[parity large_fim4] relL2={e:.3e}")
+    assert e < MAP_TOL
