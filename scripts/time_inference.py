@@ -28,4 +28,4 @@ for B, shot in ((128, 0), (8, 3), (1, 3)):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
     gf = 179.48 if shot == 0 else 180.89
-    print(f"inference B={B} shots={shot}: {ms:.3f} ms -> {B / ms * 1e3:.1f} img/s  ({B / ms * gf / 1e3:.1f} TFLOP/s algorithmic)")
+    print(f"inference B={B} shots={shot}: {ms:.3f} ms -> {B / ms * 1e3:.1f} img/s  ({B / ms * gf:.1f} TFLOP/s algorithmic)")
