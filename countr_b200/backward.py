@@ -82,6 +82,24 @@ def _conv_grads(d_raw, inp, conv, grads, wc, dx_dtype):
     return d_in
 
 
+def _exemplar_backward(m, sv, boxes, S, dy32, grads, wc, G):
+    """decoder_proj1..4 backward (models_mae_cross.py:157-177 reversed) given dL/dy [B*S, C]."""
+    dev = dy32.device
+    ex = sv["exemplar"]
+    convs = [m.decoder_proj1[0], m.decoder_proj2[0], m.decoder_proj3[0], m.decoder_proj4[0]]
+    raw4 = ex["raw"][3]
+    d_raw = torch.empty_like(raw4)
+    ops.inorm_relu_pool_bwd(raw4, ex["mean"][3], ex["rstd"][3], d_raw, 1, dpool32=dy32, dbias=G(convs[3].bias))
+    for i in (3, 2, 1):
+        d_pool = _conv_grads(d_raw, ex["pooled"][i - 1], convs[i], grads, wc, F16)
+        raw = ex["raw"][i - 1]
+        d_raw = torch.empty_like(raw)
+        scratch = torch.empty(raw.shape[0], raw.shape[3], 2, dtype=F32, device=dev)
+        ops.inorm_relu_pool_bwd(raw, ex["mean"][i - 1], ex["rstd"][i - 1], d_raw, 0, dpool16=d_pool, dbias=G(convs[i - 1].bias),
+                                scratch=scratch)
+    ops.exemplar_conv1_dw(boxes, S, d_raw, G(convs[0].weight))
+
+
 def decoder_backward(eng, m, sv, boxes, grad_out):
     dev = grad_out.device
     wc = eng.wc
@@ -141,7 +159,9 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
         dy32 = torch.empty(ny, Dd, dtype=F32, device=dev)
         ops.zero_(dy32)
     dh = torch.empty(M, Dd, dtype=F32, device=dev)
-    for blk, s in zip(reversed(list(m.decoder_blocks)), reversed(sv["blocks"])):
+    side = None
+    n_blocks = len(sv["blocks"])
+    for bi, (blk, s) in enumerate(zip(reversed(list(m.decoder_blocks)), reversed(sv["blocks"]))):
         H = blk.selfattn.num_heads
         dhd = Dd // H
         hid = blk.mlp.fc1.weight.shape[0]
@@ -181,6 +201,16 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
         _dw_linear(dv16, y16, G(ca.wv.weight))
         ops.linear(dk16, wc.w16_t(ca.wk.weight), dy32, residual=dy32)
         ops.linear(dv16, wc.w16_t(ca.wv.weight), dy32, residual=dy32)
+        if bi == n_blocks - 1 and shot_num > 0:
+            # dL/dy is complete: the exemplar-CNN backward (~45 tiny launches) runs on the side stream while this
+            # stream finishes block 0's self-attention backward and decoder_embed
+            if eng.overlap_exemplar:
+                side = eng.side_stream(dev)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    _exemplar_backward(m, sv, boxes, S, dy32, grads, wc, G)
+            else:
+                _exemplar_backward(m, sv, boxes, S, dy32, grads, wc, G)
         ops.layernorm_bwd(dh, s["x1"], _contig32(blk.norm1.weight), s["mean1"], s["rstd1"], g, G(blk.norm1.weight),
                           G(blk.norm1.bias), accumulate=True, dx16=g16)
         # --- self attention: x1 = x0 + proj(attn(qkv(LN0 x0)))
@@ -201,21 +231,8 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
     ops.colsum(g, G(de.bias))
     _dw_linear(g16, sv["lat16"], G(de.weight))
 
-    # ---- exemplar CNN (models_mae_cross.py:157-177 reversed)
-    if shot_num > 0:
-        ex = sv["exemplar"]
-        convs = [m.decoder_proj1[0], m.decoder_proj2[0], m.decoder_proj3[0], m.decoder_proj4[0]]
-        raw4 = ex["raw"][3]
-        d_raw = torch.empty_like(raw4)
-        ops.inorm_relu_pool_bwd(raw4, ex["mean"][3], ex["rstd"][3], d_raw, 1, dpool32=dy32, dbias=G(convs[3].bias))
-        for i in (3, 2, 1):
-            d_pool = _conv_grads(d_raw, ex["pooled"][i - 1], convs[i], grads, wc, F16)
-            raw = ex["raw"][i - 1]
-            d_raw = torch.empty_like(raw)
-            scratch = torch.empty(raw.shape[0], raw.shape[3], 2, dtype=F32, device=dev)
-            ops.inorm_relu_pool_bwd(raw, ex["mean"][i - 1], ex["rstd"][i - 1], d_raw, 0, dpool16=d_pool, dbias=G(convs[i - 1].bias),
-                                    scratch=scratch)
-        ops.exemplar_conv1_dw(boxes, S, d_raw, G(convs[0].weight))
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)     # join the exemplar-CNN backward
     eng.last_arena = arena             # trainers that all-reduce outside the autograd node pick the arena up here
     if eng.grad_allreduce is not None:
         eng.grad_allreduce(arena)      # data-parallel mean of every decoder gradient in one collective

@@ -101,6 +101,8 @@ class Engine:
         # (one NCCL all-reduce per step, set by the trainer / bench when WORLD_SIZE > 1)
         self.grad_allreduce = None
         self.last_arena = None          # flat fp32 gradient arena of the most recent backward
+        self._side = {}                 # per-device side stream: the exemplar CNN runs concurrently with the encoder
+        self.overlap_exemplar = True
 
     # ------------------------------------------------------------------ encoder
     def encoder_forward(self, m, imgs):
@@ -143,6 +145,23 @@ class Engine:
         return lat32, lat16
 
     # ------------------------------------------------------------------ exemplar encoder
+    def side_stream(self, dev):
+        key = str(dev)
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(device=dev)
+        return self._side[key]
+
+    def exemplar_async(self, m, boxes, S, train):
+        """Start decoder_proj1..4 on the side stream (it only depends on the boxes): ~45 tiny latency-bound
+        launches that would otherwise sit on the critical path overlap the encoder instead.  The consumer calls
+        `current_stream().wait_stream(side_stream)` before touching the result (decoder_forward does)."""
+        side = self.side_stream(boxes.device)
+        side.wait_stream(torch.cuda.current_stream())
+        saved = {} if train else None
+        with torch.cuda.stream(side):
+            y32, y16 = self.exemplar_forward(m, boxes, S, saved)
+        return dict(y32=y32, y16=y16, saved=None if saved is None else saved["exemplar"], side=side)
+
     def exemplar_forward(self, m, boxes, S, save):
         """decoder_proj1..4 on the first S boxes of every image -> y32 [B*S, C], y16 [B*S, C]."""
         dev = boxes.device
@@ -182,7 +201,7 @@ class Engine:
         return y32, y16
 
     # ------------------------------------------------------------------ decoder
-    def decoder_forward(self, m, lat16, boxes, shot_num, B, out_dtype, save=None):
+    def decoder_forward(self, m, lat16, boxes, shot_num, B, out_dtype, save=None, pre=None):
         """lat16: fp16 [B*L, D] encoder output.  Returns the density map [B, 2^4*h, 2^4*w]."""
         dev = lat16.device
         ws, wc = self.ws, self.wc
@@ -201,7 +220,13 @@ class Engine:
         if shot_num > 0:
             assert boxes.dim() == 5 and boxes.shape[1] >= shot_num, "boxes must be [N, K>=shot_num, 3, 64, 64]"
             S = shot_num
-            y32, y16 = self.exemplar_forward(m, boxes, S, save)
+            if pre is not None:       # computed concurrently on the side stream (exemplar_async)
+                y32, y16 = pre["y32"], pre["y16"]
+                if train:
+                    save["exemplar"] = pre["saved"]
+                torch.cuda.current_stream().wait_stream(pre["side"])
+            else:
+                y32, y16 = self.exemplar_forward(m, boxes, S, save)
             kv_broadcast = False
         else:
             S = 1

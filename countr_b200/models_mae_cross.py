@@ -25,9 +25,9 @@ class _DecoderFn(torch.autograd.Function):
     """forward_decoder as a single autograd node over the decoder parameters."""
 
     @staticmethod
-    def forward(ctx, model, lat16, boxes, shot_num, B, out_dtype, names, *params):
+    def forward(ctx, model, lat16, boxes, shot_num, B, out_dtype, names, pre, *params):
         save = {}
-        out = engine().decoder_forward(model, lat16, boxes, shot_num, B, out_dtype, save=save)
+        out = engine().decoder_forward(model, lat16, boxes, shot_num, B, out_dtype, save=save, pre=pre)
         ctx.model, ctx.saved, ctx.names, ctx.boxes = model, save, names, boxes
         return out
 
@@ -36,7 +36,7 @@ class _DecoderFn(torch.autograd.Function):
         from .backward import decoder_backward
         grads = decoder_backward(engine(), ctx.model, ctx.saved, ctx.boxes, grad_out)
         ctx.saved = None
-        return (None, None, None, None, None, None, None) + tuple(grads.get(n) for n in ctx.names)
+        return (None, None, None, None, None, None, None, None) + tuple(grads.get(n) for n in ctx.names)
 
 
 class SupervisedMAE(nn.Module):
@@ -133,13 +133,15 @@ class SupervisedMAE(nn.Module):
             params.append(p)
         return names, params
 
-    def _decode(self, lat16, y_, shot_num, B, out_dtype):
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.decoder_embed.parameters())
-        if need_grad:
+    def _needs_grad(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.decoder_embed.parameters())
+
+    def _decode(self, lat16, y_, shot_num, B, out_dtype, pre=None):
+        if self._needs_grad():
             names, params = self._decoder_params(shot_num)
-            return _DecoderFn.apply(self, lat16, y_, shot_num, B, out_dtype, tuple(names), *params)
+            return _DecoderFn.apply(self, lat16, y_, shot_num, B, out_dtype, tuple(names), pre, *params)
         with torch.no_grad():
-            return engine().decoder_forward(self, lat16, y_, shot_num, B, out_dtype)
+            return engine().decoder_forward(self, lat16, y_, shot_num, B, out_dtype, pre=pre)
 
     def forward_decoder(self, x, y_, shot_num=3):
         """x: encoder output [N, L, D]; y_: boxes [N, K, 3, 64, 64] or an empty tensor (:150-199)."""
@@ -153,9 +155,17 @@ class SupervisedMAE(nn.Module):
 
     def forward(self, imgs, boxes, shot_num):
         """-> density map [N, H, W]; count = map.sum() / 60 (models_mae_cross.py:201-207)."""
+        self._check(imgs)
+        eng = engine()
+        pre = None
+        if shot_num > 0 and eng.overlap_exemplar:
+            assert boxes.dim() == 5 and boxes.shape[1] >= shot_num, "boxes must be [N, K>=shot_num, 3, 64, 64]"
+            train = self._needs_grad()
+            with torch.no_grad():
+                pre = eng.exemplar_async(self, boxes, shot_num, train=train)   # overlaps the encoder
         _, lat16 = self._encode(imgs)
         out_dtype = imgs.dtype if imgs.dtype in (F32, F16, torch.bfloat16) else F32
-        return self._decode(lat16, boxes, shot_num, imgs.shape[0], out_dtype)
+        return self._decode(lat16, boxes, shot_num, imgs.shape[0], out_dtype, pre)
 
 
 def mae_vit_base_patch16_dec512d8b(**kwargs):

@@ -68,9 +68,10 @@ class FineTuner:
         """Forward, loss and backward; leaves the (scaled) gradients in `self.arena`.  Returns the loss (device scalar)."""
         m, eng = self.model, engine()
         B = imgs.shape[0]
+        pre = eng.exemplar_async(m, boxes, shot_num, train=True) if (shot_num > 0 and eng.overlap_exemplar) else None
         _, lat16 = eng.encoder_forward(m, imgs)
         save = {}
-        out = eng.decoder_forward(m, lat16, boxes, shot_num, B, F32, save=save)
+        out = eng.decoder_forward(m, lat16, boxes, shot_num, B, F32, save=save, pre=pre)
         dout = torch.empty_like(out)
         check(lib().countr_masked_mse(ctypes.c_void_p(out.data_ptr()), _DTYPE_CODE[out.dtype], ctypes.c_void_p(gt_density.data_ptr()),
                                       ctypes.c_void_p(mask.data_ptr()), ctypes.c_void_p(self.loss.data_ptr()),
