@@ -146,8 +146,11 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
     g = torch.empty(M, Dd, dtype=F32, device=dev)       # gradient of the fp32 residual stream
     g16 = torch.empty(M, Dd, dtype=F16, device=dev)
     dn = m.decoder_norm
+    blocks_rev = list(reversed(list(m.decoder_blocks)))
+    # every LayerNorm backward also emits the column sums of the residual gradient it produces = the bias gradient of the
+    # Linear that consumes it next (fc2 of the block below, the two attention projections, decoder_embed)
     ops.layernorm_bwd(d_next.view(M, Dd), sv["x_final"], _contig32(dn.weight), sv["meanf"], sv["rstdf"], g, G(dn.weight),
-                      G(dn.bias), accumulate=False, dx16=g16)
+                      G(dn.bias), accumulate=False, dx16=g16, dx_colsum=G(blocks_rev[0].mlp.fc2.bias))
 
     # ---- FIM blocks (models_crossvit.py:152-156 reversed)
     y16 = sv["y16"]
@@ -161,12 +164,11 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
     dh = torch.empty(M, Dd, dtype=F32, device=dev)
     side = None
     n_blocks = len(sv["blocks"])
-    for bi, (blk, s) in enumerate(zip(reversed(list(m.decoder_blocks)), reversed(sv["blocks"]))):
+    for bi, (blk, s) in enumerate(zip(blocks_rev, reversed(sv["blocks"]))):
         H = blk.selfattn.num_heads
         dhd = Dd // H
         hid = blk.mlp.fc1.weight.shape[0]
         # --- MLP: x3 = x2 + fc2(gelu(fc1(LN2 x2)))
-        ops.colsum(g, G(blk.mlp.fc2.bias))
         _dw_linear(g16, s["u"], G(blk.mlp.fc2.weight))
         dpre = torch.empty(M, hid, dtype=F16, device=dev)
         ops.linear(g16, wc.w16_t(blk.mlp.fc2.weight), dpre, act=2, aux=s["pre"])
@@ -174,10 +176,9 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
         _dw_linear(dpre, s["h2"], G(blk.mlp.fc1.weight))
         ops.linear(dpre, wc.w16_t(blk.mlp.fc1.weight), dh)
         ops.layernorm_bwd(dh, s["x2"], _contig32(blk.norm2.weight), s["mean2"], s["rstd2"], g, G(blk.norm2.weight),
-                          G(blk.norm2.bias), accumulate=True, dx16=g16)
+                          G(blk.norm2.bias), accumulate=True, dx16=g16, dx_colsum=G(blk.attn.proj.bias))
         # --- cross attention: x2 = x1 + proj(core(wq(LN1 x1), wk(y), wv(y)))
         ca = blk.attn
-        ops.colsum(g, G(ca.proj.bias))
         _dw_linear(g16, s["c16"], G(ca.proj.weight))
         dc = torch.empty(M, Dd, dtype=F16, device=dev)
         ops.linear(g16, wc.w16_t(ca.proj.weight), dc)
@@ -212,10 +213,9 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
             else:
                 _exemplar_backward(m, sv, boxes, S, dy32, grads, wc, G)
         ops.layernorm_bwd(dh, s["x1"], _contig32(blk.norm1.weight), s["mean1"], s["rstd1"], g, G(blk.norm1.weight),
-                          G(blk.norm1.bias), accumulate=True, dx16=g16)
+                          G(blk.norm1.bias), accumulate=True, dx16=g16, dx_colsum=G(blk.selfattn.proj.bias))
         # --- self attention: x1 = x0 + proj(attn(qkv(LN0 x0)))
         sa = blk.selfattn
-        ops.colsum(g, G(sa.proj.bias))
         _dw_linear(g16, s["att"], G(sa.proj.weight))
         datt = torch.empty(M, Dd, dtype=F16, device=dev)
         ops.linear(g16, wc.w16_t(sa.proj.weight), datt)
@@ -223,12 +223,12 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
         ops.colsum(dqkv, G(sa.qkv.bias))
         _dw_linear(dqkv, s["h0"], G(sa.qkv.weight))
         ops.linear(dqkv, wc.w16_t(sa.qkv.weight), dh)
+        nxt_bias = blocks_rev[bi + 1].mlp.fc2.bias if bi + 1 < n_blocks else m.decoder_embed.bias
         ops.layernorm_bwd(dh, s["x0"], _contig32(blk.norm0.weight), s["mean0"], s["rstd0"], g, G(blk.norm0.weight),
-                          G(blk.norm0.bias), accumulate=True, dx16=g16)
+                          G(blk.norm0.bias), accumulate=True, dx16=g16, dx_colsum=G(nxt_bias))
 
     # ---- decoder_embed: weight / bias only (its input is the frozen encoder's output)
     de = m.decoder_embed
-    ops.colsum(g, G(de.bias))
     _dw_linear(g16, sv["lat16"], G(de.weight))
 
     if side is not None:

@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(256) cross_attn_core_bwd_kernel(
     float adk[kMaxShots][2], adv[kMaxShots][2];
 #pragma unroll
     for (int s = 0; s < kMaxShots; ++s) adk[s][0] = adk[s][1] = adv[s][0] = adv[s][1] = 0.f;
+#pragma unroll 8
     for (int t = 0; t < kTokPerBlock; ++t) {
       const long long tok = tok0 + t;
       const float2 q = unpack2(*reinterpret_cast<const uint32_t*>(q16 + tok * D + c), bf16);

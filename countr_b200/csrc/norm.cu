@@ -78,15 +78,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                              const float* __restrict__ mean_in,
                                                              const float* __restrict__ rstd_in, float* __restrict__ dx,
                                                              uint16_t* __restrict__ dx16, float* __restrict__ dgamma,
-                                                             float* __restrict__ dbeta, int rows, int D, int accumulate,
-                                                             int rows_per_warp, int bf16) {
+                                                             float* __restrict__ dbeta, float* __restrict__ dx_colsum, int rows,
+                                                             int D, int accumulate, int rows_per_warp, int bf16) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   pdl_trigger();
   pdl_wait();
-  float4 dg[NV], db[NV];
+  float4 dg[NV], db[NV], dxs[NV];   // dxs: column sums of the OUTPUT dx = bias gradient of the next Linear in the chain
 #pragma unroll
-  for (int i = 0; i < NV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) dg[i] = db[i] = dxs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   for (int rr = 0; rr < rows_per_warp; ++rr) {
     const int row = warp * rows_per_warp + rr;
@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
       }
       dxr[lane + 32 * i] = o;
+      dxs[i].x += o.x; dxs[i].y += o.y; dxs[i].z += o.z; dxs[i].w += o.w;
       if (dx16) {
         uint2 h;
         h.x = pack2(o.x, o.y, bf16);
@@ -129,12 +130,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   // block-level reduction of dgamma/dbeta over the 8 warps, then one atomic per column per block
   __shared__ float4 red[8][32];
   const int w = threadIdx.x >> 5;
-  if (dgamma == nullptr) return;
+  if (dgamma == nullptr && dx_colsum == nullptr) return;
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < 3; ++pass) {
+    if (pass < 2 && dgamma == nullptr) continue;
+    if (pass == 2 && dx_colsum == nullptr) continue;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      red[w][lane] = pass == 0 ? dg[i] : db[i];
+      red[w][lane] = pass == 0 ? dg[i] : pass == 1 ? db[i] : dxs[i];
       __syncthreads();
       if (w == 0) {
         float4 a = red[0][lane];
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         for (int k = 1; k < 8; ++k) {
           a.x += red[k][lane].x; a.y += red[k][lane].y; a.z += red[k][lane].z; a.w += red[k][lane].w;
         }
-        float* dst = (pass == 0 ? dgamma : dbeta) + (lane + 32 * i) * 4;
+        float* dst = (pass == 0 ? dgamma : pass == 1 ? dbeta : dx_colsum) + (lane + 32 * i) * 4;
         atomicAdd(dst, a.x); atomicAdd(dst + 1, a.y); atomicAdd(dst + 2, a.z); atomicAdd(dst + 3, a.w);
       }
       __syncthreads();
@@ -177,8 +180,8 @@ extern "C" int countr_layernorm_fwd(const float* x, const float* gamma, const fl
 }
 
 extern "C" int countr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
-                                    const float* rstd, float* dx, void* dx16, float* dgamma, float* dbeta, int rows,
-                                    int D, int accumulate, int bf16, countr_stream_t stream_) {
+                                    const float* rstd, float* dx, void* dx16, float* dgamma, float* dbeta, float* dx_colsum,
+                                    int rows, int D, int accumulate, int bf16, countr_stream_t stream_) {
   using namespace countr;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(dy && x && gamma && mean && rstd && dx, "null pointer");
@@ -193,7 +196,7 @@ extern "C" int countr_layernorm_bwd(const float* dy, const float* x, const float
 #define LN_CASE(NV)                                                                                       \
   case NV:                                                                                                \
     COUNTR_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel<NV>, dim3(blocks), dim3(256), 0, stream, dy, x, gamma, mean, rstd, dx,  \
-                                 reinterpret_cast<uint16_t*>(dx16), dgamma, dbeta, rows, D, accumulate, rpw, bf16)); \
+                                 reinterpret_cast<uint16_t*>(dx16), dgamma, dbeta, dx_colsum, rows, D, accumulate, rpw, bf16)); \
     break;
   switch (D / 128) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(8) LN_CASE(10) LN_CASE(12)

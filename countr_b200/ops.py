@@ -112,10 +112,11 @@ def layernorm_fwd(x, gamma, beta, eps, y16=None, y32=None, mean=None, rstd=None)
     _count()
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma=None, dbeta=None, accumulate=False, dx16=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma=None, dbeta=None, accumulate=False, dx16=None, dx_colsum=None):
     rows, D = x.shape
     check(lib().countr_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dx16), _ptr(dgamma),
-                                     _ptr(dbeta), rows, D, int(accumulate), _is_bf16(dx16) if dx16 is not None else 0, _stream()))
+                                     _ptr(dbeta), _ptr(dx_colsum), rows, D, int(accumulate), _is_bf16(dx16) if dx16 is not None else 0,
+                                     _stream()))
     _count()
 
 

@@ -109,10 +109,11 @@ int countr_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
                          float* mean, float* rstd, int rows, int D, float eps, int bf16,
                          countr_stream_t stream);
 /* dx (+)= LN'(dy); dx16 (optional) = 16-bit copy of the updated dx (next GEMM's operand);
- * dgamma/dbeta (optional, pre-zeroed or carrying earlier contributions) += */
+ * dgamma/dbeta (optional, pre-zeroed or carrying earlier contributions) +=;
+ * dx_colsum [D] (optional) += column sums of the updated dx = bias gradient of the next Linear up the chain */
 int countr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
-                         const float* rstd, float* dx, void* dx16, float* dgamma, float* dbeta, int rows, int D,
-                         int accumulate, int bf16, countr_stream_t stream);
+                         const float* rstd, float* dx, void* dx16, float* dgamma, float* dbeta, float* dx_colsum, int rows,
+                         int D, int accumulate, int bf16, countr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused multi-head self-attention forward: softmax(scale * Q K^T) V, flash-style on tcgen05.

@@ -218,9 +218,11 @@ def test_layernorm(cuda, rows, D):
     dx = torch.ones(rows, D, device=cuda)
     dg = torch.zeros(D, device=cuda)
     db = torch.zeros(D, device=cuda)
-    ops.layernorm_bwd(dy, x, g, mean, rstd, dx, dg, db, accumulate=True)
+    cs = torch.zeros(D, device=cuda)
+    ops.layernorm_bwd(dy, x, g, mean, rstd, dx, dg, db, accumulate=True, dx_colsum=cs)
     torch.cuda.synchronize()
     assert_close(dx, xr.grad + 1.0, 2e-5, "ln dx (accumulated)")
+    assert_close(cs[None], dx.sum(0)[None], 1e-4, "ln dx column sums")
     assert_close(dg[None], gr.grad[None], 1e-4, "ln dgamma")
     assert_close(db[None], br.grad[None], 1e-4, "ln dbeta")
 
