@@ -103,3 +103,28 @@ def make_targets(B, seed=4321, img_size=384):
     gt = torch.rand(B, img_size, img_size, generator=g) * 0.5
     mask = (torch.rand(img_size, img_size, generator=g) < 0.8).float()   # np.random.binomial(1, .8) stand-in
     return gt, mask
+
+
+# ---- the fine-tune loss-curve case (tests/golden/small_curve.npz) ----
+CURVE = dict(steps=16, lr=2e-5, weight_decay=0.05, betas=(0.9, 0.95), batch=2, shots=[3, 3, 0, 2, 3, 1, 3, 3, 0, 3, 3, 2, 3, 3, 3, 3])
+
+
+def curve_batches():
+    """Two fixed batches visited alternately, so the loss moves a long way in few steps."""
+    out = []
+    for i in range(2):
+        imgs, boxes = make_inputs(CURVE["batch"], seed=500 + i)
+        gt, mask = make_targets(CURVE["batch"], seed=600 + i)
+        out.append((imgs, boxes, gt, mask))
+    return out
+
+
+def weight_decay_groups(named_params, weight_decay):
+    """timm.optim.optim_factory.add_weight_decay as FSC_finetune_cross.py:234 calls it: trainable 1-D tensors and
+    biases get no decay."""
+    decay, no_decay = [], []
+    for n, p in named_params:
+        if not p.requires_grad:
+            continue
+        (no_decay if (p.ndim == 1 or n.endswith(".bias")) else decay).append(p)
+    return [{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": weight_decay}]

@@ -137,6 +137,34 @@ def gen_noct(ref, out_dir):
     np.savez_compressed(os.path.join(out_dir, "noct_small.npz"), **out)
 
 
+def gen_curve(ref, out_dir):
+    """The reference model stepped the way FSC_finetune_cross.py:234-315 steps it (fp32 here: no autocast on CPU):
+    per-step loss, and where a few parameters end up."""
+    cfg = synth.CONFIGS["small"]
+    sd = synth.make_state_dict(cfg, seed=1)
+    m = build_ref_model(ref, cfg, sd).train()
+    opt = torch.optim.AdamW(synth.weight_decay_groups(m.named_parameters(), synth.CURVE["weight_decay"]), lr=synth.CURVE["lr"], betas=synth.CURVE["betas"])
+    batches = synth.curve_batches()
+    losses, counts = [], []
+    opt.zero_grad()
+    for it in range(synth.CURVE["steps"]):
+        imgs, boxes, gt, mask = batches[it % 2]
+        shot = synth.CURVE["shots"][it]
+        out = m(imgs, boxes[:, :shot] if shot else torch.empty(synth.CURVE["batch"], 0), shot)
+        loss = O.finetune_loss(out, gt, mask)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        losses.append(loss.item())
+        counts.append((out.detach().sum((1, 2)) / 60).numpy())
+        print(f"curve step {it} shot={shot}: loss={loss.item():.6f}")
+    res = {"loss": np.array(losses, np.float64), "count": np.stack(counts)}
+    for name, p in m.named_parameters():
+        if p.requires_grad:
+            res[f"final/{name}/delta_norm"] = (p.detach() - sd[name]).norm().numpy()
+    np.savez_compressed(os.path.join(out_dir, "small_curve.npz"), **res)
+
+
 def pool8(x):
     return torch.nn.functional.avg_pool2d(x[:, None], 8)[:, 0]
 
@@ -147,6 +175,8 @@ def main():
     ref = import_reference()
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if "--curve-only" in sys.argv:
+        return gen_curve(ref, out_dir)
 
     # ---- C1: base model, one image, 3 exemplars, eval, fp32 (demo.py path) ----
     cfg = synth.CONFIGS["base"]
@@ -192,6 +222,7 @@ def main():
     np.savez_compressed(os.path.join(out_dir, "small_fwd.npz"), **fwd)
     np.savez_compressed(os.path.join(out_dir, "small_grads.npz"), **grads)
     gen_noct(ref, out_dir)
+    gen_curve(ref, out_dir)
     for f in sorted(os.listdir(out_dir)):
         print(f, os.path.getsize(os.path.join(out_dir, f)))
 

@@ -77,6 +77,40 @@ def test_small_decoder_grads_match_reference(shot):
         assert rel(gr[:16], g[f"s{shot}/{n}/head"]) < 1e-3 or ref_norm < 1e-10, n
 
 
+def test_finetune_loss_curve_tracks_reference():
+    """north_star: "training loss curves track the reference step-for-step".  The oracle stepped with torch.optim.AdamW the
+    way FSC_finetune_cross.py:234-315 steps the reference reproduces the reference's own 16-step curve."""
+    g = np.load(os.path.join(GOLD, "small_curve.npz"))
+    cfg = synth.CONFIGS["small"]
+    sd = synth.make_state_dict(cfg, seed=1)
+    start = {k: v.clone() for k, v in sd.items()}
+    # few-shot steps leave shot_token without a gradient and zero-shot steps leave the exemplar CNN without one: AdamW
+    # skips a parameter whose .grad is None (no decay, no moment update), so the optimizer holds the union
+    names = sorted(set(O.decoder_param_names(sd, 3)) | set(O.decoder_param_names(sd, 0)))
+    for n in names:
+        sd[n] = sd[n].clone().requires_grad_(True)
+    C = synth.CURVE
+    opt = torch.optim.AdamW(synth.weight_decay_groups([(n, sd[n]) for n in names], C["weight_decay"]), lr=C["lr"], betas=C["betas"])
+    batches = synth.curve_batches()
+    devs = []
+    for it in range(C["steps"]):
+        imgs, boxes, gt, mask = batches[it % 2]
+        shot = C["shots"][it]
+        out = O.forward(sd, cfg, imgs, boxes[:, :shot] if shot else torch.empty(C["batch"], 0), shot)
+        loss = O.finetune_loss(out, gt, mask)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        devs.append(abs(loss.item() - g["loss"][it]) / g["loss"][it])
+        assert rel(out.detach().sum((1, 2)) / 60, g["count"][it]) < 2e-3
+    print("\n[curve] oracle vs reference, relative loss deviation per step:", " ".join(f"{d:.1e}" for d in devs))
+    assert max(devs) < 2e-4
+    for n in names:
+        d = (sd[n].detach() - start[n]).norm().item()
+        ref = float(g[f"final/{n}/delta_norm"])
+        assert abs(d - ref) <= 2e-3 * ref + 1e-9, (n, d, ref)
+
+
 # ------------------------------------------------------------------------------------------------
 # MAE pre-training model (models_mae_noct.py) — oracle vs reference-generated goldens
 # ------------------------------------------------------------------------------------------------
