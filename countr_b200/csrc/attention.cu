@@ -6,25 +6,32 @@
 // transpose/reshape) for both the ViT encoder blocks (dh=64, H=12) and the FIM self-attention
 // (dh=32, H=16).  The [B,H,L,L] score tensor the reference materialises never leaves the SM.
 //
-// One CTA (8 warps) = one (batch, head, 128-query tile).  K/V are streamed in 128-key chunks by
-// TMA straight out of the packed qkv GEMM output [B][L][3][H][dh] (no permute / copy):
-//   S  = Q K_c^T        tcgen05.mma  (A,B K-major in smem)      -> TMEM columns [64,192)
-//   P  = exp2(S*c - m)  thread == row, online max/sum in fp32   -> smem (fp16, SWIZZLE_128B)
-//   O += P V_c          tcgen05.mma  (B = V chunk, MN-major)    -> TMEM columns [0,dh)
-// Two CTAs are co-resident per SM (80 KB smem, 256 TMEM columns each) so one CTA's softmax
-// (MUFU-bound: 128x576 exp2 per tile) overlaps the other's MMA/TMA.
+// Persistent, warp-specialised kernel: one CTA per SM walks work items = (batch, head, PAIR of 128-query tiles).
+// K/V are streamed in 128-key chunks by TMA straight out of the packed qkv GEMM output [B][L][3][H][dh] (no
+// permute / copy) through a 3-stage ring that both tiles share and that runs on into the next work item:
+//   S_t = Q_t K_c^T      tcgen05.mma  (A,B K-major in smem)      -> TMEM columns [128 + 128 t, +128)
+//   P_t = exp2(S*c - m)  thread == row, S row held in registers, online max/sum in fp32 (lazy rescale)
+//                                                                 -> smem (16-bit, SWIZZLE_128B)
+//   O_t += P_t V_c       tcgen05.mma  (B = V chunk, MN-major)    -> TMEM columns [64 t, +dh)
+// Measured (profiles/r1_attention_fwd.md): the kernel is bound by the softmax warps — MUFU.EX2 at 16/clk/SM and the
+// TMEM read path at 64 B/clk/SM are each ~1024 clk per 128x128 tile — not by the tensor pipe (14 % busy).
 #include "../../include/countr_b200.h"
 #include "common.cuh"
 #include "tma.h"
 
+#include <type_traits>
+
 namespace countr {
 namespace {
 
-constexpr int BQ = 128;   // query rows per CTA
+constexpr int BQ = 128;   // query rows per tile (one tcgen05.mma M)
 constexpr int KC = 128;   // keys per chunk
-constexpr int kThreads = 256;
-constexpr uint32_t kTmemCols = 256;
-constexpr uint32_t kTmemS = 64;  // S starts at this column; O occupies [0, dh)
+constexpr int kStages = 3;                 // K / V chunk ring
+constexpr int kSoftmaxWarps = 8;           // 4 per query tile: thread == query row
+constexpr int kMmaWarp = 8, kTmaWarp = 9;
+constexpr int kThreads = 32 * (kSoftmaxWarps + 2);
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemS = 128;           // S of tile t at columns [128 + 128 t, +128); O of tile t at [64 t, +dh)
 
 template <int DH>
 struct AttnSmem {
@@ -32,13 +39,12 @@ struct AttnSmem {
   static constexpr uint32_t kQBytes = BQ * kRowBytes;
   static constexpr uint32_t kKBytes = KC * kRowBytes;
   static constexpr uint32_t kPBytes = BQ * KC * 2;            // 2 column blocks of [128 x 128 B]
-  static constexpr uint32_t kOffQ = 0;
-  static constexpr uint32_t kOffK = kQBytes;
-  static constexpr uint32_t kOffV = kOffK + kKBytes;
-  static constexpr uint32_t kOffP = kOffV + kKBytes;
-  static constexpr uint32_t kOffBar = kOffP + kPBytes;
-  static constexpr uint32_t kOffXchg = kOffBar + 64;                 // [2][BQ] floats: row max / row sum exchange
-  static constexpr uint32_t kTotal = kOffXchg + 2 * BQ * 4 + 1024;
+  static constexpr uint32_t kOffQ = 0;                        // [2 buffers][2 query tiles]
+  static constexpr uint32_t kOffK = 4 * kQBytes;              // [kStages]
+  static constexpr uint32_t kOffV = kOffK + kStages * kKBytes;
+  static constexpr uint32_t kOffP = kOffV + kStages * kKBytes;   // [2]
+  static constexpr uint32_t kOffBar = kOffP + 2 * kPBytes;
+  static constexpr uint32_t kTotal = kOffBar + 256 + 1024;
 };
 
 // shared-memory matrix descriptor with explicit swizzle mode (2 = 128B, 4 = 64B)
@@ -67,8 +73,12 @@ struct AttnArgs {
   int B, L, H;
   float scale_log2;  // scale * log2(e)
   int bf16;
-  int q_tiles;
+  int q_pairs;     // pairs of 128-query tiles per (batch, head)
 };
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -76,243 +86,333 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// 8 warps: warp w owns TMEM lane quarter (w & 3) — i.e. query rows 32*(w&3) .. +31 — and the column half
-// (w >> 2) of every 128-key chunk.  The two threads that share a row exchange their partial row maximum /
-// row sum through shared memory.  Twice the warps per SM of a thread-per-row design: the softmax is
-// latency-bound (MUFU + dependent FMAs), so it needs the extra warps to keep the issue slots busy.
-template <int DH>
-__global__ void __launch_bounds__(kThreads, 2)
+// One CTA per SM = one (batch, head, PAIR of 128-query tiles), warp-specialised:
+//   warps 0-3 / 4-7  softmax of tile 0 / tile 1, thread == query row (TMEM lane), no cross-thread reductions
+//   warp 8           tcgen05.mma issue (one lane)
+//   warp 9           TMA producer (one lane): Q tiles once, K / V chunks through a 3-stage ring shared by both tiles
+// Per tile and chunk:  S = Q K_c^T (TMEM) -> softmax warps pull their row of S into registers and hand the S
+// columns straight back (the MMA warp issues S of the NEXT chunk while the exponentials of this one are computed)
+// -> P (16-bit, swizzled smem) -> O += P V_c (TMEM).  The two tiles ping-pong on the tensor core and share every
+// K / V byte.  The running maximum is only moved when it would grow by more than 2^8 (lazy rescale), so O is
+// almost never read back from TMEM.
+template <int DH, bool kBf16>
+__global__ void __launch_bounds__(kThreads, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
                      const AttnArgs p) {
   using SM = AttnSmem<DH>;
   constexpr uint32_t kLayout = DH == 64 ? 2u : 4u;            // SWIZZLE_128B : SWIZZLE_64B
   constexpr uint32_t kSboK = DH == 64 ? 1024u : 512u;         // 8 rows of the K-major tiles
   constexpr uint32_t kVStep = 16 * SM::kRowBytes;             // 16 key rows per k-step of P.V
-  constexpr int kOHalf = DH / 2;                              // O columns rescaled / written per thread
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem + SM::kOffQ;
-  uint8_t* sK = smem + SM::kOffK;
-  uint8_t* sV = smem + SM::kOffV;
-  uint8_t* sP = smem + SM::kOffP;
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
-  uint64_t* bar_k = bar_q + 1;
-  uint64_t* bar_v = bar_q + 2;
-  uint64_t* bar_s = bar_q + 3;
-  uint64_t* bar_o = bar_q + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_q + 5);
-  float* xchg = reinterpret_cast<float*>(smem + SM::kOffXchg);   // [2][BQ]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
+  uint64_t* q_full = bars;                 // [2]  Q tiles of work item i are in buffer i & 1
+  uint64_t* q_empty = q_full + 2;          // [2]
+  uint64_t* k_full = q_empty + 2;          // [kStages]
+  uint64_t* k_empty = k_full + kStages;
+  uint64_t* v_full = k_empty + kStages;
+  uint64_t* v_empty = v_full + kStages;
+  uint64_t* s_full = v_empty + kStages;    // [2]  S of tile t is in TMEM
+  uint64_t* s_free = s_full + 2;           // [2]  the softmax warps hold S in registers
+  uint64_t* p_full = s_free + 2;           // [2]  P of tile t is in smem (and O rescaled)
+  uint64_t* p_free = p_full + 2;           // [2]  P.V of tile t has completed
+  uint64_t* o_full = p_free + 2;           // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  const int quarter = warp & 3, half = warp >> 2;
-  const int qt = blockIdx.x % p.q_tiles;
-  const int h = (blockIdx.x / p.q_tiles) % p.H;
-  const int b = blockIdx.x / (p.q_tiles * p.H);
-  const int q0 = qt * BQ;
+  const int warp = tid >> 5, lane = tid & 31;
   const int nchunks = (p.L + KC - 1) / KC;
+  const int BH = p.B * p.H;
+  const int nitems = BH * p.q_pairs;
+  // Work item -> (batch*head, pair of query tiles).  Items are ordered full pairs first, so the ragged last pair of every
+  // head (one tile of 64 rows at L = 576) lands at the end of each CTA's list.
+  auto item_bh = [&](int item) { return item % BH; };
+  auto item_qp = [&](int item) { return item / BH; };
+  auto item_ntiles = [&](int item) { return ((2 * item_qp(item) + 1) * BQ < p.L) ? 2 : 1; };
 
   pdl_trigger();
   if (tid == 0) {
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_kv);
-    mbar_init(bar_q, 1);
-    mbar_init(bar_k, 1);
-    mbar_init(bar_v, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_o, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(q_full + s, 1);
+      mbar_init(q_empty + s, 1);
+    }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(k_full + s, 1);
+      mbar_init(k_empty + s, 1);
+      mbar_init(v_full + s, 1);
+      mbar_init(v_empty + s, 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(s_full + t, 1);
+      mbar_init(s_free + t, 4);      // one arrival per softmax warp of the tile
+      mbar_init(p_full + t, 4);
+      mbar_init(p_free + t, 1);
+      mbar_init(o_full + t, 1);
+    }
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc<kTmemCols>(tmem_ptr);
+  if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
   pdl_wait();   // qkv is the previous kernel's output
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, SM::kQBytes);
-    tma_load_4d(sQ, &tma_q, bar_q, 0, q0, h, b);
-    mbar_arrive_expect_tx(bar_k, SM::kKBytes);
-    tma_load_4d(sK, &tma_kv, bar_k, 0, 0, p.H + h, b);
-  }
-
-  const uint32_t idesc_s = make_idesc_f16(BQ, KC, false, false, p.bf16 != 0);
-  const uint32_t idesc_o = make_idesc_f16(BQ, DH, false, true, p.bf16 != 0);
-
-  float m_run = -INFINITY;  // running max (log2 domain, already scaled) — identical in both threads of a row
-  float l_run = 0.f;        // running sum over this thread's columns
-  const int row = quarter * 32 + (tid & 31);
-
-  for (int c = 0; c < nchunks; ++c) {
-    const int valid = min(KC, p.L - c * KC);          // keys in this chunk
-    const int groups = (valid + 31) / 32;             // 32-column groups that hold any valid key
-    if (tid == 0) {
-      if (c == 0) mbar_wait(bar_q, 0);
-      mbar_wait(bar_k, c & 1);
-      tc_fence_after();
-      const uint64_t a_desc = make_desc(smem_u32(sQ), 16, kSboK, kLayout);
-      const uint64_t b_desc = make_desc(smem_u32(sK), 16, kSboK, kLayout);
-#pragma unroll
-      for (int k = 0; k < DH / 16; ++k)
-        umma_f16_ss(tmem_base + kTmemS, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k),
-                    idesc_s, k != 0);
-      umma_commit(bar_s);
-    }
-    // S_c ready  (=> every earlier MMA, in particular P.V of chunk c-1, has completed:
-    // the K and V buffers and the P tile are free again)
-    mbar_wait(bar_s, c & 1);
-    tc_fence_after();
-    if (tid == 0) {
-      mbar_arrive_expect_tx(bar_v, SM::kKBytes);
-      tma_load_4d(sV, &tma_kv, bar_v, 0, c * KC, 2 * p.H + h, b);
-      if (c + 1 < nchunks) {
-        mbar_arrive_expect_tx(bar_k, SM::kKBytes);
-        tma_load_4d(sK, &tma_kv, bar_k, 0, (c + 1) * KC, p.H + h, b);
-      }
-    }
-
-    // ---- pass 1: maximum over this thread's 64 columns, then over the row ----
-    float mx = -INFINITY;
-#pragma unroll
-    for (int gi = 0; gi < 2; ++gi) {
-      const int g = half * 2 + gi;
-      if (g < groups) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_lane + kTmemS + g * 32, r);
-        tmem_ld_wait();
-        const int lim = valid - g * 32;
-        if (lim >= 32) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < lim) mx = fmaxf(mx, __uint_as_float(r[j]));
+  if (warp == kTmaWarp) {
+    if (lane == 0) {
+      auto load_q = [&](int item, int i) {      // i = index of the item in this CTA's list
+        const int buf = i & 1;
+        if (i >= 2) mbar_wait(q_empty + buf, ((i >> 1) - 1) & 1);
+        const int nt = item_ntiles(item), bh = item_bh(item), qp = item_qp(item);
+        mbar_arrive_expect_tx(q_full + buf, nt * SM::kQBytes);
+        for (int t = 0; t < nt; ++t)
+          tma_load_4d(smem + SM::kOffQ + (buf * 2 + t) * SM::kQBytes, &tma_q, q_full + buf, 0, (2 * qp + t) * BQ, bh % p.H,
+                      bh / p.H);
+      };
+      int j = 0, i = 0;                         // j: running chunk index over all items (K / V ring position)
+      if (static_cast<int>(blockIdx.x) < nitems) load_q(blockIdx.x, 0);
+      const int q_prefetch_chunk = min(2, nchunks - 1);
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++i) {
+        const int bh = item_bh(item), h = bh % p.H, b = bh / p.H;
+        for (int c = 0; c < nchunks; ++c, ++j) {
+          const int s = j % kStages;
+          const uint32_t ph = static_cast<uint32_t>(j / kStages) & 1u;
+          if (j >= kStages) mbar_wait(k_empty + s, ph ^ 1u);
+          mbar_arrive_expect_tx(k_full + s, SM::kKBytes);
+          tma_load_4d(smem + SM::kOffK + s * SM::kKBytes, &tma_kv, k_full + s, 0, c * KC, p.H + h, b);
+          if (j >= kStages) mbar_wait(v_empty + s, ph ^ 1u);
+          mbar_arrive_expect_tx(v_full + s, SM::kKBytes);
+          tma_load_4d(smem + SM::kOffV + s * SM::kKBytes, &tma_kv, v_full + s, 0, c * KC, 2 * p.H + h, b);
+          // the next item's Q tiles, once the ring has moved past the previous item (whose Q buffer this reuses)
+          if (c == q_prefetch_chunk && item + static_cast<int>(gridDim.x) < nitems) load_q(item + gridDim.x, i + 1);
         }
       }
     }
-    xchg[half * BQ + row] = mx;
-    __syncthreads();
-    mx = fmaxf(mx, xchg[(half ^ 1) * BQ + row]);
-    const float m_new = fmaxf(m_run, mx * p.scale_log2);
-    const float corr = ex2_approx(m_run - m_new);  // 0 on the first chunk (m_run = -inf)
-    m_run = m_new;
-
-    // ---- pass 2: P = exp2(S*c - m), partial row sum, fp16 P tile into swizzled smem ----
-    float lsum = 0.f;
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(BQ, KC, false, false, kBf16);
+      const uint32_t idesc_o = make_idesc_f16(BQ, DH, false, true, kBf16);
+      const uint32_t sQ = smem_u32(smem + SM::kOffQ), sK = smem_u32(smem + SM::kOffK);
+      const uint32_t sV = smem_u32(smem + SM::kOffV), sP = smem_u32(smem + SM::kOffP);
+      int n_s[2] = {0, 0};                      // S tiles issued so far per query tile (phase bookkeeping)
+      int n_p[2] = {0, 0};                      // P.V products issued so far per query tile
+      // S_t = Q_t K^T for every tile of item (index i in this CTA's list), chunk c; js = ring position of the chunk
+      auto issue_s = [&](int item, int i, int c, int js) {
+        const int buf = i & 1, nt = item_ntiles(item), s = js % kStages;
+        if (c == 0) mbar_wait(q_full + buf, (i >> 1) & 1);
+        mbar_wait(k_full + s, static_cast<uint32_t>(js / kStages) & 1u);
+        for (int t = 0; t < nt; ++t) {
+          if (n_s[t] > 0) mbar_wait(s_free + t, (n_s[t] - 1) & 1);   // the softmax warps hold the previous S_t in registers
+          tc_fence_after();
+          const uint64_t a_desc = make_desc(sQ + (buf * 2 + t) * SM::kQBytes, 16, kSboK, kLayout);
+          const uint64_t b_desc = make_desc(sK + s * SM::kKBytes, 16, kSboK, kLayout);
 #pragma unroll
-    for (int gi = 0; gi < 2; ++gi) {
-      const int g = half * 2 + gi;
-      if (g < groups) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_lane + kTmemS + g * 32, r);
-        tmem_ld_wait();
-        const int lim = valid - g * 32;
-        float pv[32];
-        if (lim >= 32) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            pv[j] = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -m_new));
-            lsum += pv[j];
+          for (int k = 0; k < DH / 16; ++k)
+            umma_f16_ss(tmem_base + kTmemS + t * KC, a_desc + static_cast<uint64_t>(2 * k),
+                        b_desc + static_cast<uint64_t>(2 * k), idesc_s, k != 0);
+          umma_commit(s_full + t);
+          ++n_s[t];
+        }
+        umma_commit(k_empty + s);
+        if (c == nchunks - 1) umma_commit(q_empty + buf);
+      };
+      int j = 0, i = 0;
+      if (static_cast<int>(blockIdx.x) < nitems) issue_s(blockIdx.x, 0, 0, 0);
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++i) {
+        const int nt = item_ntiles(item);
+        for (int c = 0; c < nchunks; ++c, ++j) {
+          // run one chunk ahead with S — into the next work item at the end of this one
+          if (c + 1 < nchunks) issue_s(item, i, c + 1, j + 1);
+          else if (item + static_cast<int>(gridDim.x) < nitems) issue_s(item + gridDim.x, i + 1, 0, j + 1);
+          const int s = j % kStages;
+          const int valid = min(KC, p.L - c * KC);
+          const int ksteps = ((valid + 31) / 32) * 2;   // 16 keys per k-step, whole 32-key groups
+          mbar_wait(v_full + s, static_cast<uint32_t>(j / kStages) & 1u);
+          for (int t = 0; t < nt; ++t) {
+            mbar_wait(p_full + t, n_p[t] & 1);
+            tc_fence_after();
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t a_desc = make_desc(sP + t * SM::kPBytes + (k >> 2) * (BQ * 128) + (k & 3) * 32, 16, 1024, 2u);
+              const uint64_t b_desc = make_desc(sV + s * SM::kKBytes + k * kVStep, 16, kSboK, kLayout);
+              umma_f16_ss(tmem_base + t * 64, a_desc, b_desc, idesc_o, (c | k) != 0);
+            }
+            umma_commit(p_free + t);
+            if (c == nchunks - 1) umma_commit(o_full + t);
+            ++n_p[t];
           }
-        } else {
+          umma_commit(v_empty + s);
+        }
+      }
+    }
+  } else {
+    const int t = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t t_s = t_lane + kTmemS + t * KC, t_o = t_lane + t * 64;
+    // 16-byte chunk j of this row's 128-byte line sits at chunk (j ^ (row & 7)) (SWIZZLE_128B): one base + an XOR immediate
+    const uint32_t prow = smem_u32(smem + SM::kOffP + t * SM::kPBytes + (row >> 3) * 1024 + (row & 7) * 128) | ((row & 7) << 4);
+    int n_c = 0;    // chunks of tile t seen so far (phase of s_full / s_free / p_full / p_free)
+    int n_o = 0;    // items of tile t finished so far (phase of o_full)
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      if (t >= item_ntiles(item)) continue;
+      const int bh = item_bh(item), h = bh % p.H, b = bh / p.H;
+      const int q0 = (2 * item_qp(item) + t) * BQ;
+      if (q0 + quarter * 32 >= p.L) {
+        // all 32 rows of this warp are past the end of the sequence: keep the barrier protocol in step, do no work
+        for (int c = 0; c < nchunks; ++c, ++n_c) {
+          mbar_wait(s_full + t, n_c & 1);
+          if (lane == 0) mbar_arrive(s_free + t);
+          if (lane == 0) mbar_arrive(p_full + t);
+          mbar_wait(p_free + t, n_c & 1);
+        }
+        ++n_o;
+        continue;
+      }
+      float m_run = -INFINITY;  // running max (log2 domain, already scaled)
+      float l_run = 0.f;
+      // One 128-key chunk of this thread's row per iteration (whole 32-key groups are read; keys past the end of the
+      // sequence are masked to -inf).
+      for (int c = 0; c < nchunks; ++c) {
+        constexpr bool kFull = false;
+        const int valid = min(KC, p.L - c * KC);          // keys in this chunk
+        const int groups = (valid + 31) / 32;             // 32-column groups that hold any valid key
+        mbar_wait(s_full + t, n_c & 1);
+        tc_fence_after();
+        // ---- the whole row of S into registers; the S columns go straight back to the MMA warp ----
+        uint32_t r[4][32];
+        tmem_ld_32x32b_x32(t_s, r[0]);
+        if (kFull || groups > 1) tmem_ld_32x32b_x32(t_s + 32, r[1]);
+        if (kFull || groups > 2) tmem_ld_32x32b_x32(t_s + 64, r[2]);
+        if (kFull || groups > 3) tmem_ld_32x32b_x32(t_s + 96, r[3]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free + t);
+        if (!kFull) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float e = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -m_new));
-            pv[j] = (j < lim) ? e : 0.f;
-            lsum += pv[j];
+          for (int g = 0; g < 4; ++g) {
+            const int lim = valid - g * 32;
+            if (lim > 0 && lim < 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j >= lim) r[g][j] = 0xff800000u;  // -inf
+            }
           }
         }
-        // group g covers key columns [32g, 32g+32) = 16-byte chunks (g&1)*4 .. +3 of column block g>>1
-        uint8_t* prow = sP + (g >> 1) * (BQ * 128) + (row >> 3) * 1024 + (row & 7) * 128;
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o;
-          o.x = pack2(pv[8 * q + 0], pv[8 * q + 1], p.bf16);
-          o.y = pack2(pv[8 * q + 2], pv[8 * q + 3], p.bf16);
-          o.z = pack2(pv[8 * q + 4], pv[8 * q + 5], p.bf16);
-          o.w = pack2(pv[8 * q + 6], pv[8 * q + 7], p.bf16);
-          const int chunk16 = (g & 1) * 4 + q;
-          *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (row & 7)) << 4)) = o;
+        for (int g = 0; g < 4; ++g)
+          if (kFull || g < groups) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              mx4[0] = fmaxf(mx4[0], fmaxf(__uint_as_float(r[g][j + 0]), __uint_as_float(r[g][j + 1])));
+              mx4[1] = fmaxf(mx4[1], fmaxf(__uint_as_float(r[g][j + 2]), __uint_as_float(r[g][j + 3])));
+              mx4[2] = fmaxf(mx4[2], fmaxf(__uint_as_float(r[g][j + 4]), __uint_as_float(r[g][j + 5])));
+              mx4[3] = fmaxf(mx4[3], fmaxf(__uint_as_float(r[g][j + 6]), __uint_as_float(r[g][j + 7])));
+            }
+          }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        // Lazy rescale: the running maximum only moves when it would grow by more than 2^8 — until then
+        // P = exp2(s - m_run) stays below 256 (fine in the 16-bit P tile and in the fp32 sums) and O needs no correction.
+        const float m_cand = fmaxf(m_run, mx * p.scale_log2);
+        float corr = 1.f;
+        if (m_cand - m_run > 8.f) {    // also taken on the first chunk (m_run = -inf): corr = 0
+          corr = ex2_approx(m_run - m_cand);
+          m_run = m_cand;
+        }
+        bool rescaled = false;
+        if (n_c > 0) {
+          mbar_wait(p_free + t, (n_c - 1) & 1);   // the previous P.V of this tile is done: the P tile and O are ours again
+          tc_fence_after();
+          if (c > 0 && __any_sync(0xffffffffu, corr != 1.f)) {
+            rescaled = true;
+#pragma unroll
+            for (int d0 = 0; d0 < DH; d0 += 16) {
+              uint32_t o[16];
+              tmem_ld_32x32b_x16(t_o + d0, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * corr);
+              tmem_st_32x32b_x16(t_o + d0, o);
+            }
+          }
+        }
+        // ---- P = exp2(S*c - m) (packed FFMA2 / FADD2), row sum, 16-bit P row into swizzled smem ----
+        const float2 sc2 = splat2(p.scale_log2), nm2 = splat2(-m_run);
+        float2 ls2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (kFull || g < groups) {
+            // group g covers key columns [32g, 32g+32) = 16-byte chunks (g&1)*4 .. +3 of column block g>>1
+            const uint32_t pblk = prow + (g >> 1) * (BQ * 128);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t w[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 x = fma2(make_float2(__uint_as_float(r[g][8 * q + 2 * j]), __uint_as_float(r[g][8 * q + 2 * j + 1])), sc2, nm2);
+                const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                ls2[j & 1] = add2(ls2[j & 1], e);
+                w[j] = pack2(e.x, e.y, kBf16);
+              }
+              st_shared_v4(pblk ^ (((g & 1) * 4 + q) << 4), make_uint4(w[0], w[1], w[2], w[3]));
+            }
+          }
+        l_run = l_run * corr + ((ls2[0].x + ls2[0].y) + (ls2[1].x + ls2[1].y));
+        if (rescaled) tmem_st_wait();
+        fence_proxy_async_smem();  // P row (generic-proxy stores) -> visible to the tensor core
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full + t);
+        ++n_c;
+      }
+
+      // ---- epilogue: O / l -> 16 bit, one dh-wide row segment per thread ----
+      mbar_wait(o_full + t, n_o & 1);
+      ++n_o;
+      tc_fence_after();
+      const float inv_l = 1.f / l_run;
+      const int q = q0 + row;
+      uint16_t* orow = p.out + (static_cast<long long>(b) * p.L + q) * (p.H * DH) + h * DH;
+#pragma unroll
+      for (int d0 = 0; d0 < DH; d0 += 16) {
+        uint32_t o[16];
+        tmem_ld_32x32b_x16(t_o + d0, o);
+        tmem_ld_wait();
+        if (q < p.L) {
+          uint4 o0, o1;
+          o0.x = pack2(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l, kBf16);
+          o0.y = pack2(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l, kBf16);
+          o0.z = pack2(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l, kBf16);
+          o0.w = pack2(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l, kBf16);
+          o1.x = pack2(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l, kBf16);
+          o1.y = pack2(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l, kBf16);
+          o1.z = pack2(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l, kBf16);
+          o1.w = pack2(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l, kBf16);
+          *reinterpret_cast<uint4*>(orow + d0) = o0;
+          *reinterpret_cast<uint4*>(orow + d0 + 8) = o1;
         }
       }
-    }
-    l_run = l_run * corr + lsum;
-
-    // ---- rescale this thread's half of the running output (TMEM) when the maximum moved ----
-    if (c > 0) {
-#pragma unroll
-      for (int d0 = 0; d0 < kOHalf; d0 += 16) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(t_lane + half * kOHalf + d0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * corr);
-        tmem_st_32x32b_x16(t_lane + half * kOHalf + d0, r);
-      }
-      tmem_st_wait();
-    }
-
-    fence_proxy_async_smem();  // P tile (generic-proxy stores) -> visible to the tensor core
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      mbar_wait(bar_v, c & 1);
-      tc_fence_after();
-      const int ksteps = groups * 2;
-      for (int k = 0; k < ksteps; ++k) {
-        const uint64_t a_desc = make_desc(smem_u32(sP) + (k >> 2) * (BQ * 128) + (k & 3) * 32, 16, 1024, 2u);
-        const uint64_t b_desc = make_desc(smem_u32(sV) + k * kVStep, 16, kSboK, kLayout);
-        umma_f16_ss(tmem_base, a_desc, b_desc, idesc_o, (c | k) != 0);
-      }
-      if (c == nchunks - 1) umma_commit(bar_o);
+      if (p.lse != nullptr && q < p.L)
+        p.lse[(static_cast<long long>(b) * p.H + h) * p.L + q] = (m_run + log2f(l_run)) * 0.69314718055994531f;
+      // O_t must not be overwritten by the next item's first P.V before every warp of the tile has read it: that P.V
+      // waits for p_full, which this warp only arrives on after these loads (program order + the fence below)
+      tc_fence_before();
     }
   }
-
-  // ---- epilogue: O / l -> 16-bit; each thread writes its half of the dh-wide row segment ----
-  xchg[half * BQ + row] = l_run;
-  __syncthreads();
-  const float l_tot = l_run + xchg[(half ^ 1) * BQ + row];
-  mbar_wait(bar_o, 0);
-  tc_fence_after();
-  const float inv_l = 1.f / l_tot;
-  const int q = q0 + row;
-  uint16_t* orow = p.out + (static_cast<long long>(b) * p.L + q) * (p.H * DH) + h * DH + half * kOHalf;
-#pragma unroll
-  for (int d0 = 0; d0 < kOHalf; d0 += 16) {
-    uint32_t r[16];
-    tmem_ld_32x32b_x16(t_lane + half * kOHalf + d0, r);
-    tmem_ld_wait();
-    if (q < p.L) {
-      uint4 o0, o1;
-      o0.x = pack2(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l, p.bf16);
-      o0.y = pack2(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l, p.bf16);
-      o0.z = pack2(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l, p.bf16);
-      o0.w = pack2(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l, p.bf16);
-      o1.x = pack2(__uint_as_float(r[8]) * inv_l, __uint_as_float(r[9]) * inv_l, p.bf16);
-      o1.y = pack2(__uint_as_float(r[10]) * inv_l, __uint_as_float(r[11]) * inv_l, p.bf16);
-      o1.z = pack2(__uint_as_float(r[12]) * inv_l, __uint_as_float(r[13]) * inv_l, p.bf16);
-      o1.w = pack2(__uint_as_float(r[14]) * inv_l, __uint_as_float(r[15]) * inv_l, p.bf16);
-      *reinterpret_cast<uint4*>(orow + d0) = o0;
-      *reinterpret_cast<uint4*>(orow + d0 + 8) = o1;
-    }
-  }
-  if (p.lse != nullptr && q < p.L && half == 0)
-    p.lse[(static_cast<long long>(b) * p.H + h) * p.L + q] = (m_run + log2f(l_tot)) * 0.69314718055994531f;
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
-template <int DH>
+template <int DH, bool kBf16>
 int launch_attention(const void* qkv, void* out, float* lse, int B, int L, int H, float scale, int bf16,
                      cudaStream_t stream) {
   using SM = AttnSmem<DH>;
@@ -327,7 +427,7 @@ int launch_attention(const void* qkv, void* out, float* lse, int B, int L, int H
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    COUNTR_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+    COUNTR_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<DH, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
     attr_set = true;
   }
   AttnArgs p;
@@ -336,9 +436,9 @@ int launch_attention(const void* qkv, void* out, float* lse, int B, int L, int H
   p.B = B; p.L = L; p.H = H;
   p.scale_log2 = scale * 1.44269504088896340736f;
   p.bf16 = bf16;
-  p.q_tiles = (L + BQ - 1) / BQ;
-  const int grid = B * H * p.q_tiles;
-  COUNTR_CHECK_CUDA(launch_pdl(attention_fwd_kernel<DH>, dim3(grid), dim3(kThreads), SM::kTotal, stream, tq, tkv, p));
+  p.q_pairs = ((L + BQ - 1) / BQ + 1) / 2;
+  const int grid = std::min(B * H * p.q_pairs, num_sms());   // persistent: one CTA per SM walks the work items
+  COUNTR_CHECK_CUDA(launch_pdl(attention_fwd_kernel<DH, kBf16>, dim3(grid), dim3(kThreads), SM::kTotal, stream, tq, tkv, p));
   return COUNTR_OK;
 }
 
@@ -595,8 +695,10 @@ extern "C" int countr_attention_fwd(const void* qkv, void* out, float* lse, int 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(qkv && out, "null pointer");
   COUNTR_REQUIRE(B > 0 && L > 0 && H > 0, "bad shape B=%d L=%d H=%d", B, L, H);
-  if (dh == 64) return launch_attention<64>(qkv, out, lse, B, L, H, scale, bf16, stream);
-  if (dh == 32) return launch_attention<32>(qkv, out, lse, B, L, H, scale, bf16, stream);
+  if (dh == 64) return bf16 ? launch_attention<64, true>(qkv, out, lse, B, L, H, scale, bf16, stream)
+                            : launch_attention<64, false>(qkv, out, lse, B, L, H, scale, bf16, stream);
+  if (dh == 32) return bf16 ? launch_attention<32, true>(qkv, out, lse, B, L, H, scale, bf16, stream)
+                            : launch_attention<32, false>(qkv, out, lse, B, L, H, scale, bf16, stream);
   return set_error(COUNTR_ERR_UNSUPPORTED, "attention head_dim %d not supported (32 or 64)", dh);
 }
 

@@ -122,6 +122,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
+#pragma unroll 1   // left alone, nvcc unrolls the poll 64x at every wait site (hundreds of KB of dead code per kernel)
   for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
     asm volatile(
         "{\n\t"
@@ -422,6 +423,11 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
   unsigned long long d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
   return f2_unpack(d);
 }
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }

@@ -246,6 +246,28 @@ def test_attention_fwd(cuda, B, L, H, dh):
     assert_close(lse.reshape(-1, L), torch.logsumexp(s, -1).reshape(-1, L), 1e-4, "lse")
 
 
+def test_attention_fwd_growing_scores(cuda):
+    """Scores that keep growing along the key axis: the running maximum moves in every 128-key chunk, by more and by less
+    than the lazy-rescale threshold (2^8), for some rows and not for others."""
+    from countr_b200 import ops
+    B, L, H, dh = 1, 576, 2, 64
+    qkv = _rand16((B, L, 3, H, dh), cuda, seed=21, scale=1.0).float()
+    ramp = torch.linspace(0.2, 6.0, L, device=cuda)[None, :, None, None]
+    qkv[:, :, 1] *= ramp                                   # |k| grows 30x from the first to the last key
+    qkv[:, ::3, 0] *= 0.05                                 # every third query barely moves its maximum
+    qkv = qkv.half()
+    out = torch.empty(B, L, H * dh, device=cuda, dtype=torch.float16)
+    lse = torch.empty(B, H, L, device=cuda)
+    scale = dh ** -0.5
+    ops.attention_fwd(qkv, out, B, L, H, dh, scale, lse=lse)
+    torch.cuda.synchronize()
+    q, k, v = [qkv[:, :, i].float().permute(0, 2, 1, 3) for i in range(3)]
+    s = (q @ k.transpose(-1, -2)) * scale
+    ref = (s.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B, L, H * dh)
+    assert_close(out.reshape(-1, H * dh), ref.reshape(-1, H * dh), 2e-3, "attention, growing scores")
+    assert_close(lse.reshape(-1, L), torch.logsumexp(s, -1).reshape(-1, L), 1e-4, "lse, growing scores")
+
+
 def test_cross_attn_core(cuda):
     from countr_b200 import ops
     B, L, D, dh = 2, 576, 512, 32
