@@ -369,9 +369,13 @@ __global__ void __launch_bounds__(256) cross_attn_core_bwd_kernel(
   float* spr = sds + kTokPerBlock * Hh * S;  // [tokens][Hh][S]
   const int tok0 = blockIdx.x * kTokPerBlock;
   const int b = tok0 / L;
+  // channel-permuted K/V (ch = lane*16 + j -> j*32 + lane inside each 512-channel chunk): conflict-free warp reads,
+  // see cross_attn_core_kernel in elementwise.cu
   for (int i = threadIdx.x; i < S * D; i += blockDim.x) {
-    sk[i] = k32[b * kv_bstride + i];
-    sv[i] = v32[b * kv_bstride + i];
+    const int s = i / D, ch = i - s * D;
+    const int pi = s * D + (ch & ~511) + ((ch & 15) << 5) + ((ch & 511) >> 4);
+    sk[pi] = k32[b * kv_bstride + i];
+    sv[pi] = v32[b * kv_bstride + i];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(256) cross_attn_core_bwd_kernel(
         if (s < S) {
           float d = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) d += dO[j] * sv[s * D + ch + j];
+          for (int j = 0; j < 16; ++j) d += dO[j] * sv[s * D + c0 + j * 32 + lane];
           d += __shfl_xor_sync(0xffffffffu, d, 1);
           pr[s] = probs[(tok * Hh + hh) * S + s];
           dpv[s] = d;
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(256) cross_attn_core_bwd_kernel(
             spr[(t * Hh + hh) * S + s] = pr[s];
           }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) dq[j] += ds * sk[s * D + ch + j];
+          for (int j = 0; j < 16; ++j) dq[j] += ds * sk[s * D + c0 + j * 32 + lane];
         }
       }
       float a[8], c[8];

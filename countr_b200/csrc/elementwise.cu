@@ -531,9 +531,14 @@ __global__ void __launch_bounds__(256) cross_attn_core_kernel(const uint16_t* __
   const int b = tok0 / L;
   float* sk = skv;
   float* sv = skv + S * D;
+  // K/V are stored channel-permuted inside every 512-channel chunk: channel ch = lane*16 + j lives at j*32 + lane, so the
+  // 32 lanes of a warp (16 contiguous channels each) read 32 consecutive floats for a fixed j — the natural [s][ch]
+  // layout makes every such read a 16-way bank conflict.
   for (int i = threadIdx.x; i < S * D; i += blockDim.x) {
-    sk[i] = k32[b * kv_bstride + i];
-    sv[i] = v32[b * kv_bstride + i];
+    const int s = i / D, ch = i - s * D;
+    const int pi = s * D + (ch & ~511) + ((ch & 15) << 5) + ((ch & 511) >> 4);
+    sk[pi] = k32[b * kv_bstride + i];
+    sv[pi] = v32[b * kv_bstride + i];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -559,7 +564,7 @@ __global__ void __launch_bounds__(256) cross_attn_core_kernel(const uint16_t* __
         if (s < S) {
           float d = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) d += q[j] * sk[s * D + ch + j];
+          for (int j = 0; j < 16; ++j) d += q[j] * sk[s * D + c0 + j * 32 + lane];
           d += __shfl_xor_sync(0xffffffffu, d, 1);
           sc[s] = d * scale;
           mx = fmaxf(mx, sc[s]);
@@ -579,7 +584,7 @@ __global__ void __launch_bounds__(256) cross_attn_core_kernel(const uint16_t* __
           const float pr = sc[s] * inv;
           if (probs && (lane & 1) == 0) probs[(tok * Hh + (ch >> 5)) * S + s] = pr;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] += pr * sv[s * D + ch + j];
+          for (int j = 0; j < 16; ++j) o[j] += pr * sv[s * D + c0 + j * 32 + lane];
         }
       }
       float a[8], c[8];

@@ -4,8 +4,14 @@
 //                 fp16 tiles in SWIZZLE_128B shared memory
 //   warp 1      : TMEM allocator + MMA issuer (one lane) — tcgen05.mma kind::f16, M=128, N=bn,
 //                 fp32 accumulators double-buffered in tensor memory (2 x 256 columns)
-//   warps 2..5  : epilogue — tcgen05.ld the accumulator (thread == row), apply
-//                 alpha/bias/GELU/GELU'/residual/GroupNorm statistics, store fp16 or fp32
+//   warps 2..9  : epilogue — tcgen05.ld the accumulator (thread == row), transpose each 32x32 chunk through
+//                 swizzled shared memory so that 8 lanes cover 128 contiguous bytes of ONE output row, then
+//                 alpha/bias/GELU/GELU'/residual/GroupNorm statistics and coalesced fp16 / fp32 stores
+//
+// Both single-thread roles run their loops WARP-UNIFORMLY and only predicate the issue itself with elect.sync:
+// inside an `if (lane == 0)` region ptxas cannot keep descriptors / coordinates in uniform registers and wraps
+// every UTMALDG / UTCHMMA in an ELECT + R2UR.BROADCAST loop (~130-190 clk per instruction, measured with
+// scripts/trace_gemm.py: the MMA thread then needs 730 clk per 64-wide k-block, twice the tensor-pipe time).
 //
 // Conv mode re-uses the whole pipeline: the A tile of k-block (tap, cin-block) is the TMA box of
 // the NHWC activation shifted by the tap offset; the TMA unit zero-fills the halo, so there is no
@@ -19,6 +25,26 @@
 
 namespace countr {
 
+// Optional in-kernel timeline (clock64 stamps of one CTA's producer / MMA / epilogue roles) for scripts/trace_gemm.py.
+// Compiled only into the -DCOUNTR_TRACE build (make trace); the product library carries none of it.
+#ifdef COUNTR_TRACE
+__device__ long long* g_trace = nullptr;
+__device__ int g_trace_cta = 0;
+__device__ int g_dbg = 0;   // experiment knobs: 1 = skip the C stores, 2 = skip the residual loads
+#define DBG_INIT const int dbg_ = g_dbg
+#define DBG(bit) (dbg_ & (bit))
+#define TR_INIT long long* const tr_ = (g_trace != nullptr && static_cast<int>(blockIdx.x) == g_trace_cta) ? g_trace : nullptr
+#define TR(slot)                                                     \
+  do {                                                               \
+    if (tr_ != nullptr && (threadIdx.x & 31) == 0 && (slot) < 2048) tr_[(slot)] = clock64();    \
+  } while (0)
+#else
+#define DBG_INIT do {} while (0)
+#define DBG(bit) 0
+#define TR_INIT do {} while (0)
+#define TR(slot) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int BM = 128;
@@ -28,9 +54,10 @@ constexpr int kMaxBN = 256;
 constexpr uint32_t kABytes = BM * BK * 2;       // 16 KB
 constexpr uint32_t kBBytes = kMaxBN * BK * 2;   // 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kEpiWarps = 8;                     // 2 per TMEM lane quarter: they split the 32-column chunks
 constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr uint32_t kStageBufBytes = 32 * 32 * 4;  // per epilogue warp: one 32 x 32 fp32 chunk, XOR-swizzled (transpose staging)
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * kStageBufBytes;
 
 struct GemmArgs {
   int M, N, K;
@@ -109,10 +136,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   uint64_t* tmem_empty = bars + 14;      // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
   pdl_trigger();   // the next kernel may start its prologue as soon as SMs drain
+  TR_INIT;
+  DBG_INIT;
+  if (threadIdx.x == 0) TR(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -134,33 +164,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (p.cs > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers must be initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) TR(1);
   const int rank = p.cs > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const int cluster_id = blockIdx.x / p.cs, num_clusters = gridDim.x / p.cs;
   const uint16_t mc_mask = static_cast<uint16_t>((1u << p.cs) - 1u);
   pdl_wait();      // operands, residual, aux ... are produced by earlier kernels
+  if (threadIdx.x == 0) TR(2);
 
   const uint32_t b_bytes = static_cast<uint32_t>(kPair ? p.bn / 2 : p.bn) * BK * 2;   // B bytes landing in THIS CTA per stage
 
   if (warp == 0) {
-    // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
-        const TileCoord t = decode_tile(p, tile, rank);
-        const int k_begin = t.s * p.k_per_split;
-        const int k_end = min(p.K, k_begin + p.k_per_split);
-        const int nkb = (k_end - k_begin + BK - 1) / BK;
-        int x0 = 0, y0 = 0;
-        if (p.conv == 1) {
-          x0 = (t.m % p.tiles_x) * p.bx;
-          y0 = (t.m / p.tiles_x) * p.by;
-        }
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * stage_bytes;
-          uint8_t* sb = sa + kABytes;
-          const int k = k_begin + kb * BK;
+    // ------------------------------- TMA producer (whole warp in the loop, one elected lane issues) -------------------------------
+    int stage = 0;
+    uint32_t phase = 0;
+    int trk = 0;
+    for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+      const TileCoord t = decode_tile(p, tile, rank);
+      const int k_begin = t.s * p.k_per_split;
+      const int k_end = min(p.K, k_begin + p.k_per_split);
+      const int nkb = (k_end - k_begin + BK - 1) / BK;
+      int x0 = 0, y0 = 0;
+      if (p.conv == 1) {
+        x0 = (t.m % p.tiles_x) * p.bx;
+        y0 = (t.m / p.tiles_x) * p.by;
+      }
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        TR(16 + trk); ++trk;
+        uint8_t* sa = smem + stage * stage_bytes;
+        uint8_t* sb = sa + kABytes;
+        const int k = k_begin + kb * BK;
+        if (elect_one()) {
           if (kPair) {
             // both CTAs fill their own stage; all bytes are credited to the LEADER's full barrier, which the
             // leader's MMA thread waits on before issuing the cta_group::2 MMAs over both shared memories
@@ -197,74 +231,78 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                   tma_load_4d_2sm(sb + i * 8192, &tma_b, full_leader, t.n * p.bn + (rank * nbox + i) * 64, k, t.b2, t.b1);
               }
             }
-            if (++stage == nstages) {
-              stage = 0;
-              phase ^= 1;
-            }
-            continue;
-          }
-          mbar_arrive_expect_tx(&full[stage], kABytes + b_bytes);
-          if (p.conv == 2) {
-            // dW: k-block = one bx x by (= 64) pixel tile of image b; A = dY (M = Cout), B = X shifted by the tap
-            const int kbg = k / BK;
-            const int b = kbg / p.tiles_per_img;
-            const int r = kbg - b * p.tiles_per_img;
-            const int px0 = (r % p.tiles_x) * p.bx, py0 = (r / p.tiles_x) * p.by;
-            const int ky = t.b2 / 3, kx = t.b2 - ky * 3;
-            tma_load_4d(sa, &tma_a, &full[stage], t.m * BM, px0, py0, b);
-            tma_load_4d(sa + 8192, &tma_a, &full[stage], t.m * BM + 64, px0, py0, b);
-            if (p.cs == 1) {
-              for (int i = 0; i < p.bn / 64; ++i)
-                tma_load_4d(sb + i * 8192, &tma_b, &full[stage], t.n * p.bn + i * 64, px0 + kx - 1, py0 + ky - 1, b);
-            } else {
-              const int per = p.bn / 64 / p.cs;
-              for (int i = rank * per; i < (rank + 1) * per; ++i)
-                tma_load_4d_mc(sb + i * 8192, &tma_b, &full[stage], t.n * p.bn + i * 64, px0 + kx - 1, py0 + ky - 1, b, mc_mask);
-            }
-          } else if (p.conv) {
-            const int tap = kb / p.cin_blocks;
-            const int cb = kb - tap * p.cin_blocks;
-            const int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_4d(sa, &tma_a, &full[stage], cb * BK, x0 + kx - 1, y0 + ky - 1, t.b1);
-          } else if (!p.a_mn) {
-            tma_load_4d(sa, &tma_a, &full[stage], k, t.m * BM, t.b2, t.b1);
           } else {
-            tma_load_4d(sa, &tma_a, &full[stage], t.m * BM, k, t.b2, t.b1);
-            tma_load_4d(sa + 8192, &tma_a, &full[stage], t.m * BM + 64, k, t.b2, t.b1);
-          }
-          if (p.conv == 2) {
-          } else if (!p.b_mn) {
-            if (p.cs == 1) {
-              tma_load_4d(sb, &tma_b, &full[stage], k, t.n * p.bn, p.conv ? 0 : t.b2, p.conv ? 0 : t.b1);
+            mbar_arrive_expect_tx(&full[stage], kABytes + b_bytes);
+            if (p.conv == 2) {
+              // dW: k-block = one bx x by (= 64) pixel tile of image b; A = dY (M = Cout), B = X shifted by the tap
+              const int kbg = k / BK;
+              const int b = kbg / p.tiles_per_img;
+              const int r = kbg - b * p.tiles_per_img;
+              const int px0 = (r % p.tiles_x) * p.bx, py0 = (r / p.tiles_x) * p.by;
+              const int ky = t.b2 / 3, kx = t.b2 - ky * 3;
+              tma_load_4d(sa, &tma_a, &full[stage], t.m * BM, px0, py0, b);
+              tma_load_4d(sa + 8192, &tma_a, &full[stage], t.m * BM + 64, px0, py0, b);
+              if (p.cs == 1) {
+                for (int i = 0; i < p.bn / 64; ++i)
+                  tma_load_4d(sb + i * 8192, &tma_b, &full[stage], t.n * p.bn + i * 64, px0 + kx - 1, py0 + ky - 1, b);
+              } else {
+                const int per = p.bn / 64 / p.cs;
+                for (int i = rank * per; i < (rank + 1) * per; ++i)
+                  tma_load_4d_mc(sb + i * 8192, &tma_b, &full[stage], t.n * p.bn + i * 64, px0 + kx - 1, py0 + ky - 1, b, mc_mask);
+              }
             } else {
-              // this CTA fetches rows [rank*bn/cs, (rank+1)*bn/cs) of the shared B tile once and multicasts them
-              const int rows = p.bn / p.cs;
-              tma_load_4d_mc(sb + rank * rows * 128, &tma_b, &full[stage], k, t.n * p.bn + rank * rows, p.conv ? 0 : t.b2,
-                             p.conv ? 0 : t.b1, mc_mask);
+              if (p.conv) {
+                const int tap = kb / p.cin_blocks;
+                const int cb = kb - tap * p.cin_blocks;
+                const int ky = tap / 3, kx = tap - ky * 3;
+                tma_load_4d(sa, &tma_a, &full[stage], cb * BK, x0 + kx - 1, y0 + ky - 1, t.b1);
+              } else if (!p.a_mn) {
+                tma_load_4d(sa, &tma_a, &full[stage], k, t.m * BM, t.b2, t.b1);
+              } else {
+                tma_load_4d(sa, &tma_a, &full[stage], t.m * BM, k, t.b2, t.b1);
+                tma_load_4d(sa + 8192, &tma_a, &full[stage], t.m * BM + 64, k, t.b2, t.b1);
+              }
+              if (!p.b_mn) {
+                if (p.cs == 1) {
+                  tma_load_4d(sb, &tma_b, &full[stage], k, t.n * p.bn, p.conv ? 0 : t.b2, p.conv ? 0 : t.b1);
+                } else {
+                  // this CTA fetches rows [rank*bn/cs, (rank+1)*bn/cs) of the shared B tile once and multicasts them
+                  const int rows = p.bn / p.cs;
+                  tma_load_4d_mc(sb + rank * rows * 128, &tma_b, &full[stage], k, t.n * p.bn + rank * rows, p.conv ? 0 : t.b2,
+                                 p.conv ? 0 : t.b1, mc_mask);
+                }
+              } else if (p.cs == 1) {
+                for (int i = 0; i < p.bn / 64; ++i)
+                  tma_load_4d(sb + i * 8192, &tma_b, &full[stage], t.n * p.bn + i * 64, k, t.b2, t.b1);
+              } else {
+                const int per = p.bn / 64 / p.cs;
+                for (int i = rank * per; i < (rank + 1) * per; ++i)
+                  tma_load_4d_mc(sb + i * 8192, &tma_b, &full[stage], t.n * p.bn + i * 64, k, t.b2, t.b1, mc_mask);
+              }
             }
-          } else if (p.cs == 1) {
-            for (int i = 0; i < p.bn / 64; ++i)
-              tma_load_4d(sb + i * 8192, &tma_b, &full[stage], t.n * p.bn + i * 64, k, t.b2, t.b1);
-          } else {
-            const int per = p.bn / 64 / p.cs;
-            for (int i = rank * per; i < (rank + 1) * per; ++i)
-              tma_load_4d_mc(sb + i * 8192, &tma_b, &full[stage], t.n * p.bn + i * 64, k, t.b2, t.b1, mc_mask);
           }
-          if (++stage == nstages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        TR(256 + trk - 1);
+        if (++stage == nstages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0 && (!kPair || rank == 0)) {   // pair mode: only the leader CTA issues MMAs
+    // ------------------------------- MMA issuer (whole warp in the loop, one elected lane issues) -------------------------------
+    if (!kPair || rank == 0) {   // pair mode: only the leader CTA issues MMAs
       const uint32_t idesc = make_idesc_f16(kPair ? 2 * BM : BM, p.bn, p.a_mn != 0, p.b_mn != 0, p.bf16 != 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int trk = 0;
+      // K-major : 8-row groups 1024 B apart; +32 B per 16-element k-step inside the swizzle atom
+      // MN-major: 64-wide MN blocks 8192 B apart (LBO), 8-row k groups 1024 B apart (SBO); +2048 B per 16-row k-step
+      const uint32_t a_step = p.a_mn ? (2048u >> 4) : (32u >> 4);
+      const uint32_t b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
       for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
         const TileCoord t = decode_tile(p, tile, rank);
         const int k_begin = t.s * p.k_per_split;
@@ -275,31 +313,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const uint32_t d_tmem = tmem_base + acc * kMaxBN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[stage], phase);
+          TR(512 + trk); ++trk;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint32_t sb = sa + kABytes;
-          // K-major : 8-row groups 1024 B apart; +32 B per 16-element k-step inside the swizzle atom
-          // MN-major: 64-wide MN blocks 8192 B apart (LBO), 8-row k groups 1024 B apart (SBO);
-          //           +2048 B per 16-row k-step
           const uint64_t a_desc = p.a_mn ? make_smem_desc_sw128(sa, 8192, 1024) : make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t b_desc = p.b_mn ? make_smem_desc_sw128(sb, 8192, 1024) : make_smem_desc_sw128(sb, 16, 1024);
-          const uint32_t a_step = p.a_mn ? (2048u >> 4) : (32u >> 4);
-          const uint32_t b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
-          if (kPair) {
+          if (elect_one()) {
+            if (kPair) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_f16_ss_2cta(d_tmem, a_desc + static_cast<uint64_t>(a_step * k), b_desc + static_cast<uint64_t>(b_step * k),
-                               idesc, (kb | k) != 0);
-            umma_commit_2cta_mc(&empty[stage], 3);                       // frees the stage in BOTH CTAs
-            if (kb == nkb - 1) umma_commit_2cta_mc(&tmem_full[acc], 3);  // wakes BOTH epilogues
-          } else {
+              for (int k = 0; k < BK / 16; ++k)
+                umma_f16_ss_2cta(d_tmem, a_desc + static_cast<uint64_t>(a_step * k), b_desc + static_cast<uint64_t>(b_step * k),
+                                 idesc, (kb | k) != 0);
+              umma_commit_2cta_mc(&empty[stage], 3);                       // frees the stage in BOTH CTAs
+              if (kb == nkb - 1) umma_commit_2cta_mc(&tmem_full[acc], 3);  // wakes BOTH epilogues
+            } else {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_f16_ss(d_tmem, a_desc + static_cast<uint64_t>(a_step * k), b_desc + static_cast<uint64_t>(b_step * k),
-                          idesc, (kb | k) != 0);
-            if (p.cs > 1) umma_commit_mc(&empty[stage], mc_mask); else umma_commit(&empty[stage]);
-            if (kb == nkb - 1) umma_commit(&tmem_full[acc]);
+              for (int k = 0; k < BK / 16; ++k)
+                umma_f16_ss(d_tmem, a_desc + static_cast<uint64_t>(a_step * k), b_desc + static_cast<uint64_t>(b_step * k),
+                            idesc, (kb | k) != 0);
+              if (p.cs > 1) umma_commit_mc(&empty[stage], mc_mask); else umma_commit(&empty[stage]);
+              if (kb == nkb - 1) umma_commit(&tmem_full[acc]);
+            }
           }
+          __syncwarp();
+          TR(768 + trk - 1);
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
@@ -313,93 +351,230 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
   } else {
     // ------------------------------- epilogue -------------------------------
+    // TMEM hands every thread one accumulator ROW (lane == row).  Storing from that mapping makes each warp store
+    // touch 32 different cache lines (32 LSU wavefronts per instruction; measured 8-18 k clk per 128 x bn tile), so every
+    // 32 x 32 chunk is transposed through shared memory: written row-per-lane with the 16-byte column chunk XOR-swizzled
+    // by (row & 7), read back as {row = 4*it + lane/8, 4 columns = lane%8} — 8 lanes cover 128 contiguous bytes of one
+    // output row, a warp instruction touches 4 lines.  All elementwise work happens in the coalesced mapping.
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
     const int egroup = (warp - 2) >> 2;  // which share of the column chunks this warp drains
-    const int r_in_tile = quarter * 32 + lane;
+    const uint32_t stg = smem_u32(smem + kStages * kStageBytes + 256) + (warp - 2) * kStageBufBytes;   // shared-space address
+    const int rr = lane >> 3, c4 = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int trt = 0;
     for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
       const TileCoord t = decode_tile(p, tile, rank);
-      bool row_valid;
-      long long row;        // logical row (for residual / aux addressing)
-      long long c_off;      // element offset of (row, 0) inside C
-      if (p.conv == 1) {
-        const int x = (t.m % p.tiles_x) * p.bx + r_in_tile % p.bx;
-        const int y = (t.m / p.tiles_x) * p.by + r_in_tile / p.bx;
-        row_valid = (x < p.W) && (y < p.H);
-        row = static_cast<long long>(y) * p.W + x;
-        c_off = t.b1 * p.sc1 + row * p.ldc;
-      } else {
-        row = static_cast<long long>(t.m) * BM + r_in_tile;
-        row_valid = row < p.M;
-        c_off = t.b1 * p.sc1 + t.b2 * p.sc2 + row * p.ldc;
+      // rows handled by this lane in the coalesced mapping: r_in_tile = quarter*32 + 4*it + rr, it = 0..7
+      int rowi[8];            // logical row (residual / aux addressing); c_off = cbase + rowi * ldc
+      uint32_t vmask = 0;
+      const long long cbase = p.conv == 1 ? t.b1 * p.sc1 : t.b1 * p.sc1 + t.b2 * p.sc2;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r_in_tile = quarter * 32 + it * 4 + rr;
+        bool ok;
+        if (p.conv == 1) {
+          const int x = (t.m % p.tiles_x) * p.bx + r_in_tile % p.bx;
+          const int y = (t.m / p.tiles_x) * p.by + r_in_tile / p.bx;
+          ok = (x < p.W) && (y < p.H);
+          rowi[it] = y * p.W + x;
+        } else {
+          rowi[it] = t.m * BM + r_in_tile;
+          ok = rowi[it] < p.M;
+        }
+        if (ok) vmask |= 1u << it;
       }
+      const bool all_valid = __all_sync(0xffffffffu, vmask == 0xffu);
       const int n0 = t.n * p.bn;
       const bool first_split = (t.s == 0);
+      const int nchunks = p.bn / 32;
 
       // The residual does not depend on the MMA: fetch this warp's first chunk of it BEFORE waiting for the
-      // accumulator, and each following chunk one iteration ahead, so the (row-strided, ~1 us) global-load
-      // latency hides behind the main loop instead of serialising the epilogue.
-      const bool use_res = p.residual != nullptr && first_split && row_valid;
-      const float* res_row = nullptr;
-      if (use_res) res_row = p.residual + (p.res_mod > 0 ? (row % p.res_mod) : row) * p.ldr;
+      // accumulator, and each following chunk one iteration ahead, so the global-load latency hides behind the
+      // main loop / the staging round trip instead of serialising the epilogue.
+      const bool use_res = p.residual != nullptr && first_split;
       float4 rpre[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) rpre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (use_res && n0 + egroup * 32 + 32 <= p.N && egroup < p.bn / 32) {
+      for (int it = 0; it < 8; ++it) rpre[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto fetch_res = [&](int c) {
+        const int col = n0 + c * 32 + c4 * 4;
+        if (use_res && c < nchunks && col + 4 <= p.N && !DBG(2)) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) rpre[j] = *reinterpret_cast<const float4*>(res_row + n0 + egroup * 32 + 4 * j);
-      }
+          for (int it = 0; it < 8; ++it)
+            if ((vmask >> it) & 1u) {
+              const long long rrow = p.res_mod > 0 ? (rowi[it] % p.res_mod) : rowi[it];
+              rpre[it] = *reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + col);
+            }
+        }
+      };
+      fetch_res(egroup);
 
       mbar_wait(&tmem_full[acc], acc_phase);
+      if (warp == 2) TR(1024 + 2 * trt);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kMaxBN;
 
-      for (int c = egroup; c < p.bn / 32; c += kEpiWarps / 4) {
+      int trc = 0;
+      for (int c = egroup; c < nchunks; c += kEpiWarps / 4) {
+        const int col0 = n0 + c * 32;           // first column of the chunk
+        const int col = col0 + c4 * 4;          // this lane's 4 columns
+        const int ncols = min(32, p.N - col0);  // valid columns of the chunk (<= 0: nothing)
+        const int nmine = min(4, p.N - col);    // valid columns of this lane
+        const bool full4 = nmine == 4;
+        const bool fast = ncols == 32 && all_valid;
+        const bool use_bias = p.bias != nullptr && first_split;
+        // issued before the TMEM read so its L2 latency hides behind the read and the transpose
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fast && use_bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
         uint32_t r[32];
+        if (warp == 2 && trt == 0) TR(1200 + 4 * trc);
         tmem_ld_32x32b_x32(t_row + c * 32, r);
-        float4 rcur[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) rcur[j] = rpre[j];
-        {
-          const int cn = c + kEpiWarps / 4;
-          if (use_res && cn < p.bn / 32 && n0 + cn * 32 + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rpre[j] = *reinterpret_cast<const float4*>(res_row + n0 + cn * 32 + 4 * j);
-          }
-        }
         tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        const int ncols = min(32, p.N - col0);
-        float v[32];
+        if (warp == 2 && trt == 0) TR(1201 + 4 * trc);
+        // transpose: lane == row  ->  8 lanes per row
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + ((j ^ (lane & 7)) << 4)), "r"(r[4 * j]),
+                       "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                       : "memory");
+        __syncwarp();
+        float4 v[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rw = it * 4 + rr;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(v[it].x), "=f"(v[it].y), "=f"(v[it].z), "=f"(v[it].w)
+                       : "r"(stg + rw * 128 + ((c4 ^ (rw & 7)) << 4))
+                       : "memory");
+        }
+        __syncwarp();   // the next chunk overwrites the staging buffer
+        if (warp == 2 && trt == 0) TR(1202 + 4 * trc);
 
-        const bool full32 = (ncols == 32);
-        if (p.bias != nullptr && first_split && ncols > 0) {
-          if (full32) {
+
+        if (fast) {
+          // ---------------- fast path: full 32 x 32 chunk.  Every mode test is hoisted out of the row loops
+          // (the modes are kernel-uniform), so each row costs one address IMAD plus the loads / stores themselves.
+          if (p.alpha != 1.0f) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+            for (int it = 0; it < 8; ++it) { v[it].x *= p.alpha; v[it].y *= p.alpha; v[it].z *= p.alpha; v[it].w *= p.alpha; }
+          }
+          if (use_bias) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) { v[it].x += bb.x; v[it].y += bb.y; v[it].z += bb.z; v[it].w += bb.w; }
+          }
+          if (p.gn_stats != nullptr) {
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              s1 += (v[it].x + v[it].y) + (v[it].z + v[it].w);
+              s2 += (v[it].x * v[it].x + v[it].y * v[it].y) + (v[it].z * v[it].z + v[it].w * v[it].w);
+            }
+            s1 = warp_sum(s1);
+            s2 = warp_sum(s2);
+            if (lane == 0) {
+              double* st = p.gn_stats + (static_cast<long long>(t.b1) * (p.N / 32) + col0 / 32) * 2;
+              atomicAdd(st, static_cast<double>(s1));
+              atomicAdd(st + 1, static_cast<double>(s2));
+            }
+          }
+          if (p.act == 1) {
+            if (p.aux != nullptr) {
+              uint16_t* ab = reinterpret_cast<uint16_t*>(p.aux) + col;
+              if (p.bf16) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                  *reinterpret_cast<uint2*>(ab + static_cast<long long>(rowi[it]) * p.ldaux) =
+                      make_uint2(pack_16b(v[it].x, v[it].y, 1), pack_16b(v[it].z, v[it].w, 1));
+              } else {
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                  *reinterpret_cast<uint2*>(ab + static_cast<long long>(rowi[it]) * p.ldaux) =
+                      make_uint2(pack_16b(v[it].x, v[it].y, 0), pack_16b(v[it].z, v[it].w, 0));
+              }
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const float2 g0 = gelu_erf2(make_float2(v[it].x, v[it].y)), g1 = gelu_erf2(make_float2(v[it].z, v[it].w));
+              v[it] = make_float4(g0.x, g0.y, g1.x, g1.y);
+            }
+          } else if (p.act == 2) {
+            const uint16_t* ab = reinterpret_cast<const uint16_t*>(p.aux) + col;
+            uint2 a[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) a[it] = *reinterpret_cast<const uint2*>(ab + static_cast<long long>(rowi[it]) * p.ldaux);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const float2 g0 = gelu_erf_grad2(unpack_16b(a[it].x, p.bf16)), g1 = gelu_erf_grad2(unpack_16b(a[it].y, p.bf16));
+              v[it].x *= g0.x; v[it].y *= g0.y; v[it].z *= g1.x; v[it].w *= g1.y;
+            }
+          }
+          if (use_res) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) { v[it].x += rpre[it].x; v[it].y += rpre[it].y; v[it].z += rpre[it].z; v[it].w += rpre[it].w; }
+          }
+          // next chunk's residual: issued BEFORE this chunk's stores (its registers are free now; behind the stores the
+          // loads would first wait for the store queue to drain) — it lands during the stores, the next TMEM read and transpose
+          fetch_res(c + kEpiWarps / 4);
+          if (DBG(1)) {
+          } else if (p.out_f32) {
+            float* cb = reinterpret_cast<float*>(p.C) + cbase + col;
+            if (p.atomic) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cb + static_cast<long long>(rowi[it]) * p.ldc),
+                             "f"(v[it].x), "f"(v[it].y), "f"(v[it].z), "f"(v[it].w)
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(cb + static_cast<long long>(rowi[it]) * p.ldc) = v[it];
             }
           } else {
+            uint16_t* cb = reinterpret_cast<uint16_t*>(p.C) + cbase + col;
+            if (p.bf16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
+              for (int it = 0; it < 8; ++it)
+                *reinterpret_cast<uint2*>(cb + static_cast<long long>(rowi[it]) * p.ldc) =
+                    make_uint2(pack_16b(v[it].x, v[it].y, 1), pack_16b(v[it].z, v[it].w, 1));
+            } else {
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                *reinterpret_cast<uint2*>(cb + static_cast<long long>(rowi[it]) * p.ldc) =
+                    make_uint2(pack_16b(v[it].x, v[it].y, 0), pack_16b(v[it].z, v[it].w, 0));
+            }
+          }
+          if (warp == 2 && trt == 0) TR(1203 + 4 * trc);
+          ++trc;
+          continue;
+        }
+        // ---------------- generic path: row / column tails
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          v[it].x *= p.alpha; v[it].y *= p.alpha; v[it].z *= p.alpha; v[it].w *= p.alpha;
+        }
+        if (p.bias != nullptr && first_split && nmine > 0) {
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (full4) {
+            bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          } else {
+            bb.x = __ldg(p.bias + col);
+            if (nmine > 1) bb.y = __ldg(p.bias + col + 1);
+            if (nmine > 2) bb.z = __ldg(p.bias + col + 2);
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            v[it].x += bb.x; v[it].y += bb.y; v[it].z += bb.z; v[it].w += bb.w;
           }
         }
 
         if (p.gn_stats != nullptr) {
-          // GroupNorm statistics of this 32-channel group over the 32 pixels of this warp.
+          // GroupNorm statistics of this 32-channel group over the 32 pixels of this warp (N % 32 == 0 in this mode).
           float s1 = 0.f, s2 = 0.f;
-          if (row_valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              s1 += v[j];
-              s2 += v[j] * v[j];
+          for (int it = 0; it < 8; ++it)
+            if ((vmask >> it) & 1u) {
+              s1 += (v[it].x + v[it].y) + (v[it].z + v[it].w);
+              s2 += (v[it].x * v[it].x + v[it].y * v[it].y) + (v[it].z * v[it].z + v[it].w * v[it].w);
             }
-          }
           s1 = warp_sum(s1);
           s2 = warp_sum(s2);
           if (lane == 0 && ncols > 0) {
@@ -409,111 +584,81 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           }
         }
 
-        if (row_valid && ncols > 0) {
-          if (p.act == 1) {
-            if (p.aux != nullptr) {
-              uint16_t* ap = reinterpret_cast<uint16_t*>(p.aux) + row * p.ldaux + col0;
-              if (full32) {
+        if (nmine > 0) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  uint4 o;
-                  o.x = pack_16b(v[j], v[j + 1], p.bf16);
-                  o.y = pack_16b(v[j + 2], v[j + 3], p.bf16);
-                  o.z = pack_16b(v[j + 4], v[j + 5], p.bf16);
-                  o.w = pack_16b(v[j + 6], v[j + 7], p.bf16);
-                  *reinterpret_cast<uint4*>(ap + j) = o;
+          for (int it = 0; it < 8; ++it) {
+            if (!((vmask >> it) & 1u)) continue;
+            float4 o = v[it];
+            if (p.act == 1) {
+              if (p.aux != nullptr) {
+                uint16_t* ap = reinterpret_cast<uint16_t*>(p.aux) + static_cast<long long>(rowi[it]) * p.ldaux + col;
+                if (full4) {
+                  *reinterpret_cast<uint2*>(ap) = make_uint2(pack_16b(o.x, o.y, p.bf16), pack_16b(o.z, o.w, p.bf16));
+                } else {
+                  const float e[4] = {o.x, o.y, o.z, o.w};
+                  for (int j = 0; j < nmine; ++j) ap[j] = static_cast<uint16_t>(pack_16b(e[j], 0.f, p.bf16) & 0xffffu);
                 }
+              }
+              const float2 g0 = gelu_erf2(make_float2(o.x, o.y)), g1 = gelu_erf2(make_float2(o.z, o.w));
+              o = make_float4(g0.x, g0.y, g1.x, g1.y);
+            } else if (p.act == 2) {
+              const uint16_t* ap = reinterpret_cast<const uint16_t*>(p.aux) + static_cast<long long>(rowi[it]) * p.ldaux + col;
+              if (full4) {
+                const uint2 a = *reinterpret_cast<const uint2*>(ap);
+                const float2 g0 = gelu_erf_grad2(unpack_16b(a.x, p.bf16)), g1 = gelu_erf_grad2(unpack_16b(a.y, p.bf16));
+                o.x *= g0.x; o.y *= g0.y; o.z *= g1.x; o.w *= g1.y;
               } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < ncols) ap[j] = static_cast<uint16_t>(pack_16b(v[j], 0.f, p.bf16) & 0xffffu);
+                float e[4] = {o.x, o.y, o.z, o.w};
+                for (int j = 0; j < nmine; ++j) e[j] *= gelu_erf_grad(unpack_16b(ap[j], p.bf16).x);
+                o = make_float4(e[0], e[1], e[2], e[3]);
               }
             }
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float2 gq = gelu_erf2(make_float2(v[j], v[j + 1]));
-              v[j] = gq.x;
-              v[j + 1] = gq.y;
-            }
-          } else if (p.act == 2) {
-            const uint16_t* ap = reinterpret_cast<const uint16_t*>(p.aux) + row * p.ldaux + col0;
-            if (full32) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 a = *reinterpret_cast<const uint4*>(ap + j);
-                const uint32_t w[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float2 gq = gelu_erf_grad2(unpack_16b(w[q], p.bf16));
-                  v[j + 2 * q] *= gq.x;
-                  v[j + 2 * q + 1] *= gq.y;
-                }
+            if (use_res) {
+              if (full4) {
+                o.x += rpre[it].x; o.y += rpre[it].y; o.z += rpre[it].z; o.w += rpre[it].w;
+              } else {
+                const long long rrow = p.res_mod > 0 ? (rowi[it] % p.res_mod) : rowi[it];
+                const float* rp = p.residual + rrow * p.ldr + col;
+                o.x += rp[0];
+                if (nmine > 1) o.y += rp[1];
+                if (nmine > 2) o.z += rp[2];
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) v[j] *= gelu_erf_grad(unpack_16b(ap[j], p.bf16).x);
             }
-          }
-
-          if (use_res) {
-            const float* rp = res_row + col0;
-            if (full32) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                v[4 * j] += rcur[j].x; v[4 * j + 1] += rcur[j].y; v[4 * j + 2] += rcur[j].z; v[4 * j + 3] += rcur[j].w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) v[j] += rp[j];
-            }
-          }
-
-          if (p.out_f32) {
-            float* cp = reinterpret_cast<float*>(p.C) + c_off + col0;
-            if (p.atomic) {
-              if (full32) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + j), "f"(v[j]), "f"(v[j + 1]),
-                               "f"(v[j + 2]), "f"(v[j + 3])
+            const long long c_off = cbase + static_cast<long long>(rowi[it]) * p.ldc + col;
+            if (p.out_f32) {
+              float* cp = reinterpret_cast<float*>(p.C) + c_off;
+              if (p.atomic) {
+                if (full4) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
                                : "memory");
+                } else {
+                  const float e[4] = {o.x, o.y, o.z, o.w};
+                  for (int j = 0; j < nmine; ++j) atomicAdd(cp + j, e[j]);
+                }
+              } else if (full4) {
+                *reinterpret_cast<float4*>(cp) = o;
               } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < ncols) atomicAdd(cp + j, v[j]);
-              }
-            } else if (full32) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) cp[j] = v[j];
-            }
-          } else {
-            uint16_t* cp = reinterpret_cast<uint16_t*>(p.C) + c_off + col0;
-            if (full32) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 o;
-                o.x = pack_16b(v[j], v[j + 1], p.bf16);
-                o.y = pack_16b(v[j + 2], v[j + 3], p.bf16);
-                o.z = pack_16b(v[j + 4], v[j + 5], p.bf16);
-                o.w = pack_16b(v[j + 6], v[j + 7], p.bf16);
-                *reinterpret_cast<uint4*>(cp + j) = o;
+                const float e[4] = {o.x, o.y, o.z, o.w};
+                for (int j = 0; j < nmine; ++j) cp[j] = e[j];
               }
             } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) cp[j] = static_cast<uint16_t>(pack_16b(v[j], 0.f, p.bf16) & 0xffffu);
+              uint16_t* cp = reinterpret_cast<uint16_t*>(p.C) + c_off;
+              if (full4) {
+                *reinterpret_cast<uint2*>(cp) = make_uint2(pack_16b(o.x, o.y, p.bf16), pack_16b(o.z, o.w, p.bf16));
+              } else {
+                const float e[4] = {o.x, o.y, o.z, o.w};
+                for (int j = 0; j < nmine; ++j) cp[j] = static_cast<uint16_t>(pack_16b(e[j], 0.f, p.bf16) & 0xffffu);
+              }
             }
           }
         }
+        if (warp == 2 && trt == 0) TR(1203 + 4 * trc);
+        ++trc;
+        fetch_res(c + kEpiWarps / 4);   // lands while the next chunk is read from TMEM and transposed
       }
       // accumulator drained: hand the TMEM stage back to the MMA warp
+      if (warp == 2) TR(1025 + 2 * trt);
+      ++trt;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -529,6 +674,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
   tc_fence_before();
   if (p.cs > 1) cluster_sync_all(); else __syncthreads();   // no peer may still signal this CTA's barriers after it exits
+  if (threadIdx.x == 0) TR(3);
   if (warp == 1) {
     tc_fence_after();
     if (kPair) tmem_dealloc_2cta<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
@@ -560,6 +706,19 @@ int pick_bn(int m_tiles, int N, int other, int b_mn, int sms) {
 }  // namespace
 
 }  // namespace countr
+
+#ifdef COUNTR_TRACE
+extern "C" int countr_debug_set_knobs(int knobs) {
+  COUNTR_CHECK_CUDA(cudaMemcpyToSymbol(countr::g_dbg, &knobs, sizeof(knobs)));
+  return 0;
+}
+extern "C" int countr_debug_set_trace(void* buf, int cta) {
+  long long* pbuf = reinterpret_cast<long long*>(buf);
+  COUNTR_CHECK_CUDA(cudaMemcpyToSymbol(countr::g_trace, &pbuf, sizeof(pbuf)));
+  COUNTR_CHECK_CUDA(cudaMemcpyToSymbol(countr::g_trace_cta, &cta, sizeof(cta)));
+  return 0;
+}
+#endif
 
 extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   using namespace countr;
@@ -704,14 +863,14 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = p.cs;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = p.cs;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 2;
+  cfg.numAttrs = p.cs > 1 ? 2 : 1;   // plain (non-cluster) launch path for single-CTA tiles
   if (p.pair) COUNTR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<true>, ta, tb, p));
   else COUNTR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<false>, ta, tb, p));
   return COUNTR_OK;

@@ -160,7 +160,28 @@ class Engine:
         saved = {} if train else None
         with torch.cuda.stream(side):
             y32, y16 = self.exemplar_forward(m, boxes, S, saved)
-        return dict(y32=y32, y16=y16, saved=None if saved is None else saved["exemplar"], side=side)
+            kv = self.kv_project(m, y16, train)     # wk(y), wv(y) of every FIM block: they only depend on y
+        return dict(y32=y32, y16=y16, kv=kv, saved=None if saved is None else saved["exemplar"], side=side)
+
+    def kv_project(self, m, y16, train):
+        """k = wk(y), v = wv(y) of every CrossAttentionBlock (models_crossvit.py:115-116).  y is the same for all blocks
+        (models_mae_cross.py:180-181) and does not depend on the image tokens, so these tiny (M = B*S rows) latency-bound
+        GEMMs are taken off the critical path: they run right behind the exemplar CNN on the side stream."""
+        dev = y16.device
+        ny = y16.shape[0]
+        out = []
+        for i, blk in enumerate(m.decoder_blocks):
+            Dd = blk.attn.wk.weight.shape[0]
+            if train:
+                k32 = torch.empty(ny, Dd, dtype=F32, device=dev)
+                v32 = torch.empty(ny, Dd, dtype=F32, device=dev)
+            else:
+                k32 = self.ws.get(f"dec_k{i}", (ny, Dd), F32, dev)
+                v32 = self.ws.get(f"dec_v{i}", (ny, Dd), F32, dev)
+            ops.linear(y16, self.wc.w16(blk.attn.wk.weight), k32, bias=_contig32(blk.attn.wk.bias))
+            ops.linear(y16, self.wc.w16(blk.attn.wv.weight), v32, bias=_contig32(blk.attn.wv.bias))
+            out.append((k32, v32))
+        return out
 
     def exemplar_forward(self, m, boxes, S, save):
         """decoder_proj1..4 on the first S boxes of every image -> y32 [B*S, C], y16 [B*S, C]."""
@@ -221,21 +242,22 @@ class Engine:
             assert boxes.dim() == 5 and boxes.shape[1] >= shot_num, "boxes must be [N, K>=shot_num, 3, 64, 64]"
             S = shot_num
             if pre is not None:       # computed concurrently on the side stream (exemplar_async)
-                y32, y16 = pre["y32"], pre["y16"]
+                y32, y16, kvs = pre["y32"], pre["y16"], pre["kv"]
                 if train:
                     save["exemplar"] = pre["saved"]
                 torch.cuda.current_stream().wait_stream(pre["side"])
             else:
                 y32, y16 = self.exemplar_forward(m, boxes, S, save)
+                kvs = self.kv_project(m, y16, train)
             kv_broadcast = False
         else:
             S = 1
             y16 = wc.v16(m.shot_token).reshape(1, Dd)     # same token for every image (models_mae_cross.py:176)
+            kvs = self.kv_project(m, y16, train)
             kv_broadcast = True
-        ny = y16.shape[0]
 
         blocks_saved = []
-        for blk in m.decoder_blocks:
+        for bi, blk in enumerate(m.decoder_blocks):
             H = blk.selfattn.num_heads
             dh = Dd // H
             hid = blk.mlp.fc1.weight.shape[0]
@@ -259,10 +281,7 @@ class Engine:
             ops.layernorm_fwd(x1, _contig32(blk.norm1.weight), _contig32(blk.norm1.bias), blk.norm1.eps, y16=h1, mean=mean1, rstd=rstd1)
             q16 = get("dec_q", (M, Dd), F16)
             ops.linear(h1, wc.w16(blk.attn.wq.weight), q16, bias=_contig32(blk.attn.wq.bias))
-            k32 = get("dec_k", (ny, Dd), F32)
-            v32 = get("dec_v", (ny, Dd), F32)
-            ops.linear(y16, wc.w16(blk.attn.wk.weight), k32, bias=_contig32(blk.attn.wk.bias))
-            ops.linear(y16, wc.w16(blk.attn.wv.weight), v32, bias=_contig32(blk.attn.wv.bias))
+            k32, v32 = kvs[bi]
             c16 = get("dec_c", (M, Dd), F16)
             probs = get("dec_probs", (M, H, S), F32) if train else None
             ops.cross_attn_core(q16, k32, v32, c16, B, L, S, Dd, dh, blk.attn.scale, probs=probs, kv_broadcast=kv_broadcast)

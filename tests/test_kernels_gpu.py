@@ -341,6 +341,7 @@ def test_gn_relu_upsample(cuda, B, H, W):
 def test_exemplar_stage1_and_inorm(cuda):
     from countr_b200 import ops
     B, K, S = 2, 3, 2
+    torch.manual_seed(341)     # fp16 outputs against a 1e-3 max-scaled bound: keep the draw fixed
     boxes = torch.rand(B, K, 3, 64, 64, device=cuda)
     w = torch.randn(64, 3, 3, 3, device=cuda) * 0.2
     bias = torch.randn(64, device=cuda) * 0.1
