@@ -164,22 +164,45 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
     dh = torch.empty(M, Dd, dtype=F32, device=dev)
     side = None
     n_blocks = len(sv["blocks"])
+    # Weight / bias gradients are leaves of the backward graph: the chain LayerNorm' -> dX GEMM -> attention' -> ... never
+    # reads them.  They run on the side stream (one fork per producer, one join at the end), so the latency-bound
+    # dX chain on the main stream is not serialised behind ~45 dW GEMMs and column sums.
+    main = torch.cuda.current_stream()
+    wstream = eng.side_stream(dev) if eng.overlap_dw else None
+    keep = []           # tensors the side stream reads: kept alive until the join (the allocator recycles by stream order)
+
+    def off(fn, *tensors):
+        if wstream is None:
+            fn()
+            return
+        keep.extend(tensors)
+        wstream.wait_stream(main)
+        with torch.cuda.stream(wstream):
+            fn()
+
+    def new_g16():
+        # the 16-bit residual gradient is read by side-stream dW GEMMs: a fresh buffer per LayerNorm backward
+        return torch.empty(M, Dd, dtype=F16, device=dev) if wstream is not None else g16
     for bi, (blk, s) in enumerate(zip(blocks_rev, reversed(sv["blocks"]))):
         H = blk.selfattn.num_heads
         dhd = Dd // H
         hid = blk.mlp.fc1.weight.shape[0]
         # --- MLP: x3 = x2 + fc2(gelu(fc1(LN2 x2)))
-        _dw_linear(g16, s["u"], G(blk.mlp.fc2.weight))
+        off(lambda g16=g16: _dw_linear(g16, s["u"], G(blk.mlp.fc2.weight)), g16)
         dpre = torch.empty(M, hid, dtype=F16, device=dev)
         ops.linear(g16, wc.w16_t(blk.mlp.fc2.weight), dpre, act=2, aux=s["pre"])
-        ops.colsum(dpre, G(blk.mlp.fc1.bias))
-        _dw_linear(dpre, s["h2"], G(blk.mlp.fc1.weight))
+
+        def _fc1_grads(dpre=dpre):
+            ops.colsum(dpre, G(blk.mlp.fc1.bias))
+            _dw_linear(dpre, s["h2"], G(blk.mlp.fc1.weight))
+        off(_fc1_grads, dpre)
         ops.linear(dpre, wc.w16_t(blk.mlp.fc1.weight), dh)
+        g16 = new_g16()
         ops.layernorm_bwd(dh, s["x2"], _contig32(blk.norm2.weight), s["mean2"], s["rstd2"], g, G(blk.norm2.weight),
                           G(blk.norm2.bias), accumulate=True, dx16=g16, dx_colsum=G(blk.attn.proj.bias))
         # --- cross attention: x2 = x1 + proj(core(wq(LN1 x1), wk(y), wv(y)))
         ca = blk.attn
-        _dw_linear(g16, s["c16"], G(ca.proj.weight))
+        off(lambda g16=g16: _dw_linear(g16, s["c16"], G(ca.proj.weight)), g16)
         dc = torch.empty(M, Dd, dtype=F16, device=dev)
         ops.linear(g16, wc.w16_t(ca.proj.weight), dc)
         dq = torch.empty(M, Dd, dtype=F16, device=dev)
@@ -189,19 +212,25 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
         ops.zero_(dv32)
         ops.cross_attn_core_bwd(s["q16"], s["k32"], s["v32"], s["probs"], dc, dq, dk32, dv32, B, L, S, Dd, dhd, ca.scale,
                                 kv_broadcast=kvb)
-        ops.colsum(dq, G(ca.wq.bias))
-        _dw_linear(dq, s["h1"], G(ca.wq.weight))
+        def _wq_grads(dq=dq):
+            ops.colsum(dq, G(ca.wq.bias))
+            _dw_linear(dq, s["h1"], G(ca.wq.weight))
+        off(_wq_grads, dq)
         ops.linear(dq, wc.w16_t(ca.wq.weight), dh)
-        dk16 = torch.empty(ny, Dd, dtype=F16, device=dev)
-        dv16 = torch.empty(ny, Dd, dtype=F16, device=dev)
-        ops.cast16(dk32, dk16)
-        ops.cast16(dv32, dv16)
-        ops.colsum(dk32, G(ca.wk.bias))
-        ops.colsum(dv32, G(ca.wv.bias))
-        _dw_linear(dk16, y16, G(ca.wk.weight))
-        _dw_linear(dv16, y16, G(ca.wv.weight))
-        ops.linear(dk16, wc.w16_t(ca.wk.weight), dy32, residual=dy32)
-        ops.linear(dv16, wc.w16_t(ca.wv.weight), dy32, residual=dy32)
+        def _kv_grads(dk32=dk32, dv32=dv32):
+            # everything downstream of dK / dV only feeds the exemplar branch (dL/dy), never the token stream
+            dk16 = torch.empty(ny, Dd, dtype=F16, device=dev)
+            dv16 = torch.empty(ny, Dd, dtype=F16, device=dev)
+            keep.extend((dk16, dv16))
+            ops.cast16(dk32, dk16)
+            ops.cast16(dv32, dv16)
+            ops.colsum(dk32, G(ca.wk.bias))
+            ops.colsum(dv32, G(ca.wv.bias))
+            _dw_linear(dk16, y16, G(ca.wk.weight))
+            _dw_linear(dv16, y16, G(ca.wv.weight))
+            ops.linear(dk16, wc.w16_t(ca.wk.weight), dy32, residual=dy32)
+            ops.linear(dv16, wc.w16_t(ca.wv.weight), dy32, residual=dy32)
+        off(_kv_grads, dk32, dv32)
         if bi == n_blocks - 1 and shot_num > 0:
             # dL/dy is complete: the exemplar-CNN backward (~45 tiny launches) runs on the side stream while this
             # stream finishes block 0's self-attention backward and decoder_embed
@@ -211,19 +240,26 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
                 with torch.cuda.stream(side):
                     _exemplar_backward(m, sv, boxes, S, dy32, grads, wc, G)
             else:
+                if wstream is not None:
+                    main.wait_stream(wstream)      # dL/dy is accumulated on the side stream
                 _exemplar_backward(m, sv, boxes, S, dy32, grads, wc, G)
+        g16 = new_g16()
         ops.layernorm_bwd(dh, s["x1"], _contig32(blk.norm1.weight), s["mean1"], s["rstd1"], g, G(blk.norm1.weight),
                           G(blk.norm1.bias), accumulate=True, dx16=g16, dx_colsum=G(blk.selfattn.proj.bias))
         # --- self attention: x1 = x0 + proj(attn(qkv(LN0 x0)))
         sa = blk.selfattn
-        _dw_linear(g16, s["att"], G(sa.proj.weight))
+        off(lambda g16=g16: _dw_linear(g16, s["att"], G(sa.proj.weight)), g16)
         datt = torch.empty(M, Dd, dtype=F16, device=dev)
         ops.linear(g16, wc.w16_t(sa.proj.weight), datt)
         dqkv = attention_backward(s["qkv"], s["lse"], datt, B, L, H, dhd, sa.scale, att=s["att"])
-        ops.colsum(dqkv, G(sa.qkv.bias))
-        _dw_linear(dqkv, s["h0"], G(sa.qkv.weight))
+
+        def _qkv_grads(dqkv=dqkv):
+            ops.colsum(dqkv, G(sa.qkv.bias))
+            _dw_linear(dqkv, s["h0"], G(sa.qkv.weight))
+        off(_qkv_grads, dqkv)
         ops.linear(dqkv, wc.w16_t(sa.qkv.weight), dh)
         nxt_bias = blocks_rev[bi + 1].mlp.fc2.bias if bi + 1 < n_blocks else m.decoder_embed.bias
+        g16 = new_g16()
         ops.layernorm_bwd(dh, s["x0"], _contig32(blk.norm0.weight), s["mean0"], s["rstd0"], g, G(blk.norm0.weight),
                           G(blk.norm0.bias), accumulate=True, dx16=g16, dx_colsum=G(nxt_bias))
 
@@ -231,8 +267,9 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
     de = m.decoder_embed
     _dw_linear(g16, sv["lat16"], G(de.weight))
 
-    if side is not None:
-        torch.cuda.current_stream().wait_stream(side)     # join the exemplar-CNN backward
+    if side is not None or wstream is not None:
+        torch.cuda.current_stream().wait_stream(eng.side_stream(dev))     # join the exemplar-CNN backward and the dW work
+    keep.clear()
     eng.last_arena = arena             # trainers that all-reduce outside the autograd node pick the arena up here
     if eng.grad_allreduce is not None:
         eng.grad_allreduce(arena)      # data-parallel mean of every decoder gradient in one collective

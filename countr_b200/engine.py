@@ -103,6 +103,7 @@ class Engine:
         self.last_arena = None          # flat fp32 gradient arena of the most recent backward
         self._side = {}                 # per-device side stream: the exemplar CNN runs concurrently with the encoder
         self.overlap_exemplar = True
+        self.overlap_dw = True          # FIM weight / bias gradients on the side stream (backward.py)
 
     # ------------------------------------------------------------------ encoder
     def encoder_forward(self, m, imgs):
