@@ -121,7 +121,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp-uniform for the compiler
   const int nchunks = (p.L + KC - 1) / KC;
   const int BH = p.B * p.H;
   const int nitems = BH * p.q_pairs;
@@ -161,16 +161,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();   // qkv is the previous kernel's output
 
+  // Both single-thread roles (TMA producer, MMA issuer) run their loops with the WHOLE warp and predicate only the
+  // issue itself with elect.sync: inside an `if (lane == 0)` region ptxas cannot prove descriptors / coordinates
+  // warp-uniform and wraps every UTMALDG / UTCHMMA / UTCBAR in an ELECT + R2UR loop (~100 clk per instruction).
   if (warp == kTmaWarp) {
-    if (lane == 0) {
+    {
       auto load_q = [&](int item, int i) {      // i = index of the item in this CTA's list
         const int buf = i & 1;
         if (i >= 2) mbar_wait(q_empty + buf, ((i >> 1) - 1) & 1);
         const int nt = item_ntiles(item), bh = item_bh(item), qp = item_qp(item);
-        mbar_arrive_expect_tx(q_full + buf, nt * SM::kQBytes);
-        for (int t = 0; t < nt; ++t)
-          tma_load_4d(smem + SM::kOffQ + (buf * 2 + t) * SM::kQBytes, &tma_q, q_full + buf, 0, (2 * qp + t) * BQ, bh % p.H,
-                      bh / p.H);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(q_full + buf, nt * SM::kQBytes);
+          for (int t = 0; t < nt; ++t)
+            tma_load_4d(smem + SM::kOffQ + (buf * 2 + t) * SM::kQBytes, &tma_q, q_full + buf, 0, (2 * qp + t) * BQ, bh % p.H,
+                        bh / p.H);
+        }
+        __syncwarp();
       };
       int j = 0, i = 0;                         // j: running chunk index over all items (K / V ring position)
       if (static_cast<int>(blockIdx.x) < nitems) load_q(blockIdx.x, 0);
@@ -181,18 +187,24 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           const int s = j % kStages;
           const uint32_t ph = static_cast<uint32_t>(j / kStages) & 1u;
           if (j >= kStages) mbar_wait(k_empty + s, ph ^ 1u);
-          mbar_arrive_expect_tx(k_full + s, SM::kKBytes);
-          tma_load_4d(smem + SM::kOffK + s * SM::kKBytes, &tma_kv, k_full + s, 0, c * KC, p.H + h, b);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(k_full + s, SM::kKBytes);
+            tma_load_4d(smem + SM::kOffK + s * SM::kKBytes, &tma_kv, k_full + s, 0, c * KC, p.H + h, b);
+          }
+          __syncwarp();
           if (j >= kStages) mbar_wait(v_empty + s, ph ^ 1u);
-          mbar_arrive_expect_tx(v_full + s, SM::kKBytes);
-          tma_load_4d(smem + SM::kOffV + s * SM::kKBytes, &tma_kv, v_full + s, 0, c * KC, 2 * p.H + h, b);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(v_full + s, SM::kKBytes);
+            tma_load_4d(smem + SM::kOffV + s * SM::kKBytes, &tma_kv, v_full + s, 0, c * KC, 2 * p.H + h, b);
+          }
+          __syncwarp();
           // the next item's Q tiles, once the ring has moved past the previous item (whose Q buffer this reuses)
           if (c == q_prefetch_chunk && item + static_cast<int>(gridDim.x) < nitems) load_q(item + gridDim.x, i + 1);
         }
       }
     }
   } else if (warp == kMmaWarp) {
-    if (lane == 0) {
+    {
       const uint32_t idesc_s = make_idesc_f16(BQ, KC, false, false, kBf16);
       const uint32_t idesc_o = make_idesc_f16(BQ, DH, false, true, kBf16);
       const uint32_t sQ = smem_u32(smem + SM::kOffQ), sK = smem_u32(smem + SM::kOffK);
@@ -209,15 +221,20 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           tc_fence_after();
           const uint64_t a_desc = make_desc(sQ + (buf * 2 + t) * SM::kQBytes, 16, kSboK, kLayout);
           const uint64_t b_desc = make_desc(sK + s * SM::kKBytes, 16, kSboK, kLayout);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k)
-            umma_f16_ss(tmem_base + kTmemS + t * KC, a_desc + static_cast<uint64_t>(2 * k),
-                        b_desc + static_cast<uint64_t>(2 * k), idesc_s, k != 0);
-          umma_commit(s_full + t);
+            for (int k = 0; k < DH / 16; ++k)
+              umma_f16_ss(tmem_base + kTmemS + t * KC, a_desc + static_cast<uint64_t>(2 * k),
+                          b_desc + static_cast<uint64_t>(2 * k), idesc_s, k != 0);
+            umma_commit(s_full + t);
+            if (t == nt - 1) {
+              umma_commit(k_empty + s);
+              if (c == nchunks - 1) umma_commit(q_empty + buf);
+            }
+          }
+          __syncwarp();
           ++n_s[t];
         }
-        umma_commit(k_empty + s);
-        if (c == nchunks - 1) umma_commit(q_empty + buf);
       };
       int j = 0, i = 0;
       if (static_cast<int>(blockIdx.x) < nitems) issue_s(blockIdx.x, 0, 0, 0);
@@ -234,16 +251,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           for (int t = 0; t < nt; ++t) {
             mbar_wait(p_full + t, n_p[t] & 1);
             tc_fence_after();
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t a_desc = make_desc(sP + t * SM::kPBytes + (k >> 2) * (BQ * 128) + (k & 3) * 32, 16, 1024, 2u);
-              const uint64_t b_desc = make_desc(sV + s * SM::kKBytes + k * kVStep, 16, kSboK, kLayout);
-              umma_f16_ss(tmem_base + t * 64, a_desc, b_desc, idesc_o, (c | k) != 0);
+            if (elect_one()) {
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t a_desc = make_desc(sP + t * SM::kPBytes + (k >> 2) * (BQ * 128) + (k & 3) * 32, 16, 1024, 2u);
+                const uint64_t b_desc = make_desc(sV + s * SM::kKBytes + k * kVStep, 16, kSboK, kLayout);
+                umma_f16_ss(tmem_base + t * 64, a_desc, b_desc, idesc_o, (c | k) != 0);
+              }
+              umma_commit(p_free + t);
+              if (c == nchunks - 1) umma_commit(o_full + t);
+              if (t == nt - 1) umma_commit(v_empty + s);
             }
-            umma_commit(p_free + t);
-            if (c == nchunks - 1) umma_commit(o_full + t);
+            __syncwarp();
             ++n_p[t];
           }
-          umma_commit(v_empty + s);
         }
       }
     }
@@ -488,7 +508,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
   uint64_t* bar_e = bar_load + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_load + 3);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp: uniform for the compiler
   const int quarter = warp & 3, half = warp >> 2;
   const int r = quarter * 32 + lane;                 // row inside a 128-row block
   const int h = blockIdx.x % p.H, b = blockIdx.x / p.H;
@@ -512,14 +532,18 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
   const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
   pdl_wait();   // qkv / out / dout come from earlier kernels
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_load, 4u * nblk * kBlkBytes);
-    for (int i = 0; i < nblk; ++i) {
-      tma_load_4d(smem + kOffQ + i * kBlkBytes, &tma_qkv, bar_load, 0, i * 128, h, b);
-      tma_load_4d(smem + kOffK + i * kBlkBytes, &tma_qkv, bar_load, 0, i * 128, p.H + h, b);
-      tma_load_4d(smem + kOffV + i * kBlkBytes, &tma_qkv, bar_load, 0, i * 128, 2 * p.H + h, b);
-      tma_load_4d(smem + kOffdO + i * kBlkBytes, &tma_do, bar_load, 0, i * 128, h, b);
+  // warp 0 issues every TMA / MMA: whole-warp control flow, elect.sync around the issue (see attention_fwd_kernel)
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar_load, 4u * nblk * kBlkBytes);
+      for (int i = 0; i < nblk; ++i) {
+        tma_load_4d(smem + kOffQ + i * kBlkBytes, &tma_qkv, bar_load, 0, i * 128, h, b);
+        tma_load_4d(smem + kOffK + i * kBlkBytes, &tma_qkv, bar_load, 0, i * 128, p.H + h, b);
+        tma_load_4d(smem + kOffV + i * kBlkBytes, &tma_qkv, bar_load, 0, i * 128, 2 * p.H + h, b);
+        tma_load_4d(smem + kOffdO + i * kBlkBytes, &tma_do, bar_load, 0, i * 128, h, b);
+      }
     }
+    __syncwarp();
   }
 
   // per-row constants of this thread's query row in every query block (overlaps the TMA loads)
@@ -564,18 +588,21 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
   int pair = 0;
   for (int j = 0; j < nblk; ++j) {
     for (int i = 0; i < nblk; ++i, ++pair) {
-      if (tid == 0) {
+      if (warp == 0) {
         if (pair == 0) mbar_wait(bar_load, 0);
         tc_fence_after();
         const uint64_t dq = make_desc(smem_u32(smem + kOffQ + i * kBlkBytes), 16, 512, 4u);
         const uint64_t dk = make_desc(smem_u32(smem + kOffK + j * kBlkBytes), 16, 512, 4u);
         const uint64_t dd = make_desc(smem_u32(smem + kOffdO + i * kBlkBytes), 16, 512, 4u);
         const uint64_t dv = make_desc(smem_u32(smem + kOffV + j * kBlkBytes), 16, 512, 4u);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_f16_ss(tmem_base + tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+          for (int k = 0; k < DH / 16; ++k) umma_f16_ss(tmem_base + tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_f16_ss(tmem_base + tP, dd + 2 * k, dv + 2 * k, idesc_s, k != 0);
-        umma_commit(bar_s);
+          for (int k = 0; k < DH / 16; ++k) umma_f16_ss(tmem_base + tP, dd + 2 * k, dv + 2 * k, idesc_s, k != 0);
+          umma_commit(bar_s);
+        }
+        __syncwarp();
       }
       // S, dP of this pair are ready (=> the dV/dK/dQ MMAs of the previous pair have drained: P/dS tiles are free)
       mbar_wait(bar_s, pair & 1);
@@ -613,20 +640,23 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
       fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after();
         const uint32_t aQ = smem_u32(smem + kOffQ + i * kBlkBytes), adO = smem_u32(smem + kOffdO + i * kBlkBytes);
         const uint32_t aK = smem_u32(smem + kOffK + j * kBlkBytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {   // 16 query rows (dV, dK) / 16 keys (dQ) per step
-          const uint64_t p_mn = make_desc(sP + ks * 2048, 16384, 1024, 2u);
-          const uint64_t ds_mn = make_desc(sdS + ks * 2048, 16384, 1024, 2u);
-          const uint64_t ds_k = make_desc(sdS + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024, 2u);
-          umma_f16_ss(tmem_base + tdV, p_mn, make_desc(adO + ks * 1024, 16, 512, 4u), idesc_mm, (i | ks) != 0);
-          umma_f16_ss(tmem_base + tdK, ds_mn, make_desc(aQ + ks * 1024, 16, 512, 4u), idesc_mm, (i | ks) != 0);
-          umma_f16_ss(tmem_base + tdQ + i * DH, ds_k, make_desc(aK + ks * 1024, 16, 512, 4u), idesc_km, (j | ks) != 0);
+          for (int ks = 0; ks < 8; ++ks) {   // 16 query rows (dV, dK) / 16 keys (dQ) per step
+            const uint64_t p_mn = make_desc(sP + ks * 2048, 16384, 1024, 2u);
+            const uint64_t ds_mn = make_desc(sdS + ks * 2048, 16384, 1024, 2u);
+            const uint64_t ds_k = make_desc(sdS + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024, 2u);
+            umma_f16_ss(tmem_base + tdV, p_mn, make_desc(adO + ks * 1024, 16, 512, 4u), idesc_mm, (i | ks) != 0);
+            umma_f16_ss(tmem_base + tdK, ds_mn, make_desc(aQ + ks * 1024, 16, 512, 4u), idesc_mm, (i | ks) != 0);
+            umma_f16_ss(tmem_base + tdQ + i * DH, ds_k, make_desc(aK + ks * 1024, 16, 512, 4u), idesc_km, (j | ks) != 0);
+          }
+          if (i == nblk - 1) umma_commit(bar_e);
         }
-        if (i == nblk - 1) umma_commit(bar_e);
+        __syncwarp();
       }
     }
     // dV_j, dK_j complete: thread (key row r, column half) writes its 16 columns of each
