@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(256) gn_relu_bwd_reduce_kernel(
     const uint16_t* __restrict__ raw, const double* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ beta, const uint16_t* __restrict__ d_next, const float* __restrict__ dmap,
     const float* __restrict__ w1, uint16_t* __restrict__ dyh, float* __restrict__ dgamma, float* __restrict__ dbeta,
-    float* __restrict__ dw1, float* __restrict__ db1, double* __restrict__ gsum, int H, int W, int G, float eps, int bf16) {
+    float* __restrict__ dw1, float* __restrict__ db1, double* __restrict__ gsum, int H, int W, int G, float eps, int bf16,
+    int R) {
   __shared__ float s_mean[8], s_rstd[8];
   __shared__ float red[8][kC + 8];
   const int b = blockIdx.y;
@@ -165,38 +166,55 @@ __global__ void __launch_bounds__(256) gn_relu_bwd_reduce_kernel(
       if (has2) *reinterpret_cast<uint4*>(ob + static_cast<long long>(pix2) * kC) = pack8(d1, bf16);
     }
   } else {
-    for (int pix = blockIdx.x * 8 + pl; pix < HW; pix += stride) {
-      float x[8], dz[8], dy[8];
-      unpack8(*reinterpret_cast<const uint4*>(rb + static_cast<long long>(pix) * kC), x, bf16);
-      const int ix = pix % W, iy = pix / W;
-      int ox[4], oy[4];
-      float wx[4], wy[4];
+    // Row-walking gather of the up-sample adjoint: the block owns 8 pixel columns x R rows (blockIdx.x = strip * x-tiles +
+    // x-tile) and walks down the rows.  The horizontally blended hi-res rows 2iy-1 .. 2iy+2 live in registers and the last
+    // two are re-used by the next row, so every step fetches 2 x 4 hi-res vectors instead of 4 x 4 and the rows a strip
+    // shares stay in L1 (the pixel-per-iteration loop re-read each d_next element 4x through L2: 1.4 TB/s at 96^2).
+    const int nxt = (W + 7) >> 3;
+    const int xt = blockIdx.x % nxt, strip = blockIdx.x / nxt;
+    const int ix = xt * 8 + pl;
+    const int y0 = strip * R, y1 = min(H, y0 + R);
+    if (ix < W) {
+      int ox[4];
+      float wx[4];
       up2_adjoint_taps(ix, W, ox, wx);
-      up2_adjoint_taps(iy, H, oy, wy);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dz[j] = 0.f;
       const uint16_t* nb = d_next + static_cast<long long>(b) * 4 * HW * kC + c0;
+      auto hrow = [&](int oy, float (&h)[8]) {
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        if (wy[a] == 0.f) continue;
+        for (int j = 0; j < 8; ++j) h[j] = 0.f;
+        const uint16_t* rp = nb + static_cast<long long>(oy) * (2 * W) * kC;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (wx[c] == 0.f) continue;
           float t[8];
-          unpack8(*reinterpret_cast<const uint4*>(nb + (static_cast<long long>(oy[a]) * (2 * W) + ox[c]) * kC), t, bf16);
-          const float ww = wy[a] * wx[c];
+          unpack8(*reinterpret_cast<const uint4*>(rp + static_cast<long long>(ox[c]) * kC), t, bf16);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dz[j] += ww * t[j];
+          for (int j = 0; j < 8; ++j) h[j] = fmaf(wx[c], t[j], h[j]);
         }
-      }
+      };
+      float h0[8], h1[8], h2[8], h3[8];
+      hrow(max(2 * y0 - 1, 0), h0);
+      hrow(2 * y0, h1);
+      for (int iy = y0; iy < y1; ++iy) {
+        hrow(2 * iy + 1, h2);
+        hrow(min(2 * iy + 2, 2 * H - 1), h3);
+        const float w0 = iy >= 1 ? 0.25f : 0.f, w1y = iy == 0 ? 1.f : 0.75f;
+        const float w2 = iy == H - 1 ? 1.f : 0.75f, w3 = iy <= H - 2 ? 0.25f : 0.f;
+        const int pix = iy * W + ix;
+        float x[8], dy[8];
+        unpack8(*reinterpret_cast<const uint4*>(rb + static_cast<long long>(pix) * kC), x, bf16);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (x[j] - mean) * rstd;
-        dy[j] = fmaf(xh, gam[j], bet[j]) > 0.f ? dz[j] : 0.f;
-        R1[j] += dy[j];
-        R2[j] += dy[j] * xh;
+        for (int j = 0; j < 8; ++j) {
+          const float dz = w0 * h0[j] + w1y * h1[j] + w2 * h2[j] + w3 * h3[j];
+          const float xh = (x[j] - mean) * rstd;
+          dy[j] = fmaf(xh, gam[j], bet[j]) > 0.f ? dz : 0.f;
+          R1[j] += dy[j];
+          R2[j] += dy[j] * xh;
+          h0[j] = h2[j];
+          h1[j] = h3[j];
+        }
+        *reinterpret_cast<uint4*>(ob + static_cast<long long>(pix) * kC) = pack8(dy, bf16);
       }
-      *reinterpret_cast<uint4*>(ob + static_cast<long long>(pix) * kC) = pack8(dy, bf16);
     }
   }
   float a_dg[8], a_db[8], a_dw[8];
@@ -749,14 +767,20 @@ extern "C" int countr_gn_relu_bwd_reduce(const void* raw, const double* stats, c
   COUNTR_REQUIRE(mode == 0 || (dmap && w1 && dw1 && db1), "1x1-conv mode needs dmap, w1, dw1, db1");
   dim3 grid;
   gn_grid(H * W, B, &grid);
-  if (mode == 0)
-    gn_relu_bwd_reduce_kernel<0><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(raw), stats, gamma, beta,
-                                                           reinterpret_cast<const uint16_t*>(d_next), dmap, w1,
-                                                           reinterpret_cast<uint16_t*>(dyh), dgamma, dbeta, dw1, db1, gsum, H, W, G, eps, bf16);
-  else
+  if (mode == 0) {
+    // strips of 8 columns x R rows; keep >= ~4 blocks per SM in flight
+    const int nxt = (W + 7) / 8;
+    int R = 8;
+    while (R > 2 && static_cast<long long>(nxt) * ((H + R - 1) / R) * B < 4 * 148) R >>= 1;
+    dim3 grid0(nxt * ((H + R - 1) / R), B);
+    gn_relu_bwd_reduce_kernel<0><<<grid0, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(raw), stats, gamma, beta,
+                                                            reinterpret_cast<const uint16_t*>(d_next), dmap, w1,
+                                                            reinterpret_cast<uint16_t*>(dyh), dgamma, dbeta, dw1, db1, gsum, H, W, G, eps, bf16, R);
+  } else {
     gn_relu_bwd_reduce_kernel<1><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(raw), stats, gamma, beta,
                                                            reinterpret_cast<const uint16_t*>(d_next), dmap, w1,
-                                                           reinterpret_cast<uint16_t*>(dyh), dgamma, dbeta, dw1, db1, gsum, H, W, G, eps, bf16);
+                                                           reinterpret_cast<uint16_t*>(dyh), dgamma, dbeta, dw1, db1, gsum, H, W, G, eps, bf16, 0);
+  }
   COUNTR_CHECK_CUDA(cudaGetLastError());
   return COUNTR_OK;
 }

@@ -67,6 +67,7 @@ struct GemmArgs {
   int bf16;
   int split_k, k_per_split;
   int m_tiles, n_tiles, total_tiles;   // total_tiles counts CLUSTER tiles (cs consecutive m tiles x one n tile)
+  int epi64;                           // 1: 16-bit outputs drain 64 columns per round (COUNTR_EPI64=0 turns it off for A/B runs)
   int pair;                            // 1: CTA pair (cta_group::2): 256 x bn tile over two SMs, 6 stages of 32 KB
   int cs, m_groups;                    // cluster size (CTAs sharing the B tile via TMA multicast), ceil(m_tiles / cs)
   // conv mode
@@ -168,7 +169,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int rank = p.cs > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const int cluster_id = blockIdx.x / p.cs, num_clusters = gridDim.x / p.cs;
   const uint16_t mc_mask = static_cast<uint16_t>((1u << p.cs) - 1u);
-  pdl_wait();      // operands, residual, aux ... are produced by earlier kernels
+  // pdl_wait() (griddepcontrol.wait: the predecessor grid has completed, its writes are visible) is issued per role,
+  // right before the role's first access to global memory, so tile decoding / row bookkeeping (a handful of integer
+  // divisions, ~0.5 us) also overlaps the predecessor's tail.  The MMA warp never touches global memory.
   if (threadIdx.x == 0) TR(2);
 
   const uint32_t b_bytes = static_cast<uint32_t>(kPair ? p.bn / 2 : p.bn) * BK * 2;   // B bytes landing in THIS CTA per stage
@@ -188,6 +191,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         x0 = (t.m % p.tiles_x) * p.bx;
         y0 = (t.m / p.tiles_x) * p.by;
       }
+      if (tile == cluster_id) pdl_wait();   // first tile: the operands come from earlier kernels
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         TR(16 + trk); ++trk;
@@ -407,6 +411,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
         }
       };
+      if (tile == cluster_id) pdl_wait();   // first tile: residual / bias / aux come from earlier kernels, C may still be read by them
       fetch_res(egroup);
 
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -414,6 +419,106 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kMaxBN;
 
+      // ---------------- 16-bit output, whole tile valid: 64 columns per round.  Bias / GELU / GroupNorm statistics are
+      // applied in the TMEM mapping (lane == row), the row is packed to 16 bit BEFORE the transpose — 128 bytes per
+      // row: half the staging traffic of the fp32 path, and each read-back instruction (8 lanes x 16 B per row, 4 rows)
+      // stores four complete 128-byte lines.
+      if (p.epi64 && !p.out_f32 && p.aux == nullptr && p.residual == nullptr && !p.atomic && (p.bn & 63) == 0 && all_valid &&
+          n0 + p.bn <= p.N) {
+        const bool use_bias = p.bias != nullptr && first_split;
+        uint16_t* cb = reinterpret_cast<uint16_t*>(p.C) + cbase + c4 * 8;
+        int trc = 0;
+        for (int c2 = egroup; c2 < p.bn / 64; c2 += kEpiWarps / 4) {
+          const int col0 = n0 + c2 * 64;
+          if (warp == 2 && trt == 0) TR(1200 + 4 * trc);
+          // bias of the first 32 columns: issued before the TMEM read (same address in every lane); the second half is
+          // fetched while the first is being processed
+          float4 bq[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (use_bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+          }
+          uint32_t r[2][32];
+          tmem_ld_32x32b_x32(t_row + c2 * 64, r[0]);
+          tmem_ld_32x32b_x32(t_row + c2 * 64 + 32, r[1]);
+          tmem_ld_wait();
+          if (warp == 2 && trt == 0) TR(1201 + 4 * trc);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j] = fmaf(__uint_as_float(r[hf][4 * j]), p.alpha, bq[j].x);
+              v[4 * j + 1] = fmaf(__uint_as_float(r[hf][4 * j + 1]), p.alpha, bq[j].y);
+              v[4 * j + 2] = fmaf(__uint_as_float(r[hf][4 * j + 2]), p.alpha, bq[j].z);
+              v[4 * j + 3] = fmaf(__uint_as_float(r[hf][4 * j + 3]), p.alpha, bq[j].w);
+            }
+            if (hf == 0 && use_bias) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 32 + 4 * j));
+            }
+            if (p.gn_stats != nullptr) {
+              float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                s1 += v[j];
+                s2 = fmaf(v[j], v[j], s2);
+              }
+              s1 = warp_sum(s1);
+              s2 = warp_sum(s2);
+              if (lane == 0) {
+                double* st = p.gn_stats + (static_cast<long long>(t.b1) * (p.N / 32) + (col0 + hf * 32) / 32) * 2;
+                atomicAdd(st, static_cast<double>(s1));
+                atomicAdd(st + 1, static_cast<double>(s2));
+              }
+            }
+            if (p.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const float2 gq = gelu_erf2(make_float2(v[j], v[j + 1]));
+                v[j] = gq.x;
+                v[j + 1] = gq.y;
+              }
+            }
+            // this lane's row: 16-byte chunk q of the 128-byte row goes to chunk q ^ (lane & 7)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t w0, w1, w2, w3;
+              if (p.bf16) {
+                w0 = pack_16b(v[8 * q], v[8 * q + 1], 1); w1 = pack_16b(v[8 * q + 2], v[8 * q + 3], 1);
+                w2 = pack_16b(v[8 * q + 4], v[8 * q + 5], 1); w3 = pack_16b(v[8 * q + 6], v[8 * q + 7], 1);
+              } else {
+                w0 = pack_16b(v[8 * q], v[8 * q + 1], 0); w1 = pack_16b(v[8 * q + 2], v[8 * q + 3], 0);
+                w2 = pack_16b(v[8 * q + 4], v[8 * q + 5], 0); w3 = pack_16b(v[8 * q + 6], v[8 * q + 7], 0);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + (((hf * 4 + q) ^ (lane & 7)) << 4)),
+                           "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                           : "memory");
+            }
+          }
+          __syncwarp();
+          if (warp == 2 && trt == 0) TR(1202 + 4 * trc);
+          uint4 o[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rw = it * 4 + rr;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(o[it].x), "=r"(o[it].y), "=r"(o[it].z), "=r"(o[it].w)
+                         : "r"(stg + rw * 128 + ((c4 ^ (rw & 7)) << 4))
+                         : "memory");
+          }
+          __syncwarp();   // the next round overwrites the staging buffer
+          if (!DBG(1)) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) *reinterpret_cast<uint4*>(cb + static_cast<long long>(rowi[it]) * p.ldc + col0) = o[it];
+          }
+          if (warp == 2 && trt == 0) TR(1203 + 4 * trc);
+          ++trc;
+        }
+      } else
+      {
       int trc = 0;
       for (int c = egroup; c < nchunks; c += kEpiWarps / 4) {
         const int col0 = n0 + c * 32;           // first column of the chunk
@@ -656,6 +761,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         ++trc;
         fetch_res(c + kEpiWarps / 4);   // lands while the next chunk is read from TMEM and transposed
       }
+      }
       // accumulator drained: hand the TMEM stage back to the MMA warp
       if (warp == 2) TR(1025 + 2 * trt);
       ++trt;
@@ -798,6 +904,14 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   p.act = d->act; p.aux = d->aux; p.ldaux = d->ldaux;
   p.residual = d->residual; p.ldr = d->ldr; p.res_mod = d->res_mod;
   p.gn_stats = d->gn_stats;
+  {
+    static int epi64 = -1;
+    if (epi64 < 0) {
+      const char* e = getenv("COUNTR_EPI64");
+      epi64 = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    p.epi64 = epi64;
+  }
   COUNTR_REQUIRE(d->act != 2 || d->aux != nullptr, "act=2 needs aux");
   COUNTR_REQUIRE(d->ldc > 0, "ldc must be positive");
   COUNTR_REQUIRE(d->bias == nullptr || (reinterpret_cast<uintptr_t>(d->bias) & 15u) == 0, "bias must be 16-byte aligned");

@@ -18,7 +18,10 @@ def run(name, m, n, k, mode, bn=0, pair=0, cluster=0, cta=0, show=14):
     a = torch.randn(m, k, device=dev).half()
     w = torch.randn(n, k, device=dev).half() * 0.05
     bias = torch.zeros(n, device=dev)
-    if mode == "res":
+    if mode == "gelu":
+        c = torch.empty(m, n, device=dev, dtype=torch.float16)
+        f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, act=1, bn=bn, pair=pair, cluster=cluster)
+    elif mode == "res":
         c = torch.zeros(m, n, device=dev)
         f = lambda: ops.gemm(a, w, c, m, n, k, lda=k, ldb=k, ldc=n, bias=bias, residual=c, ldr=n, bn=bn, pair=pair, cluster=cluster)
     else:
@@ -57,7 +60,5 @@ def run(name, m, n, k, mode, bn=0, pair=0, cluster=0, cta=0, show=14):
 
 for knobs in (0,):
     lib.countr_debug_set_knobs(knobs)
-    print(f"===== knobs={knobs} (1: no C stores, 2: no residual loads)")
-    run("enc proj", 4608, 768, 768, "res", cta=0)
-    run("enc fc2", 4608, 768, 3072, "res", cta=0)
-    run("enc qkv", 4608, 2304, 768, "f16", cta=0)
+    run("enc fc1 gelu", 4608, 3072, 768, "gelu", cta=0)
+    run("enc fc1 plain", 4608, 3072, 768, "f16", cta=0)
