@@ -10,8 +10,9 @@ Weak scaling: the per-GPU batch is fixed.
 
   value : images/sec with the step's inputs already resident in HBM (device-timed, CUDA events)
   e2e   : the same step driven through the public API with HOST (pinned) inputs: H2D of images,
-          exemplar boxes, density target and loss mask inside the timed region, and a D2H read of
-          the loss every step
+          exemplar boxes, density target and loss mask inside the timed region (prefetched on a copy
+          stream while the previous step computes, as an input pipeline does), and a D2H read of the
+          loss every step
   --impl reference : the reference's own algorithm (oracle/ port of models_mae_cross.py, fp32,
           torch CPU kernels, all host cores) on a bounded sample of the same workload.
 """
@@ -324,12 +325,42 @@ def run_ours(args):
     sampler.start()
     # (1) inputs resident in HBM
     ms_dev = timed(lambda i: run_step(), args.steps)
-    # (2) end to end: H2D of every input + D2H of the loss, every step
+    # (2) end to end: H2D of every step's inputs (pinned host -> device) + D2H of the loss, every step, all inside the timed
+    # region.  The loop is the usual prefetching input pipeline: while step i computes, the copy stream uploads the inputs of
+    # step i+1 into a staging set; the step starts with a device-to-device move of the staged inputs into the buffers the
+    # CUDA graph reads (20 MB, ~6 us).  Exactly `steps` uploads happen in the timed region; the first one is not hidden.
+    copy_stream = torch.cuda.Stream()
+    staging = [dict(imgs=torch.empty_like(d_imgs), boxes=torch.empty_like(d_boxes), gt=torch.empty_like(d_gt),
+                    mask=torch.empty_like(d_mask)) for _ in range(2)]
+    ev_up = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+
+    def stage_upload(i):
+        hb, st = host[i % n_host], staging[i % 2]
+        with torch.cuda.stream(copy_stream):
+            for k in ("imgs", "boxes", "gt", "mask"):
+                st[k].copy_(hb[k], non_blocking=True)
+            ev_up[i % 2].record(copy_stream)
+
+    e2e_state = {"n": args.steps}
+
     def e2e_step(i):
-        upload(i)
+        main = torch.cuda.current_stream()
+        if i == 0:
+            stage_upload(0)
+        st = staging[i % 2]
+        main.wait_event(ev_up[i % 2])
+        d_imgs.copy_(st["imgs"], non_blocking=True)
+        d_boxes.copy_(st["boxes"], non_blocking=True)
+        d_gt.copy_(st["gt"], non_blocking=True)
+        d_mask.copy_(st["mask"], non_blocking=True)
+        ev_free[i % 2].record(main)
+        if i + 1 < e2e_state["n"]:
+            copy_stream.wait_event(ev_free[(i + 1) % 2])   # (recorded two steps ago) the set being overwritten was consumed
+            stage_upload(i + 1)
         run_step()
         h_loss.copy_(d_loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()     # the script reads loss.item() every step (FSC_finetune_cross.py:306)
+        main.synchronize()     # the script reads loss.item() every step (FSC_finetune_cross.py:306)
     ms_e2e = timed(e2e_step, args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -375,7 +406,7 @@ def run_ours(args):
                    "loss_scale": loss_scale,
                    "l2": "per-step working set (~1.5 GB of activations) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": round(e2e, 2), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                "ms_per_step": round(ms_e2e / args.steps, 4)},
+                "ms_per_step": round(ms_e2e / args.steps, 4), "h2d": "prefetched on a copy stream during the previous step"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel (decode_head3 conv3x3 implicit GEMM, M=%d N=256 K=2304)" % (B * 192 * 192),

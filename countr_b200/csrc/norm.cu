@@ -34,13 +34,20 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   pdl_wait();
   if (warp >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp) * D);
-  float4 v[NV];
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  float4 v[NV], gm[NV], bt[NV];
   float s = 0.f;
 #pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+  // gamma / beta are fetched together with the row (not after the two reductions): one exposed memory latency, not two
+#pragma unroll
   for (int i = 0; i < NV; ++i) {
-    v[i] = xr[lane + 32 * i];
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    gm[i] = __ldg(g4 + lane + 32 * i);
+    bt[i] = __ldg(b4 + lane + 32 * i);
   }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   const float mean = warp_sum(s) / D;
   float q = 0.f;
 #pragma unroll
@@ -53,11 +60,9 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
     if (mean_out) mean_out[warp] = mean;
     if (rstd_out) rstd_out[warp] = rstd;
   }
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const float4 g = __ldg(g4 + lane + 32 * i), b = __ldg(b4 + lane + 32 * i);
+    const float4 g = gm[i], b = bt[i];
     const float o0 = (v[i].x - mean) * rstd * g.x + b.x, o1 = (v[i].y - mean) * rstd * g.y + b.y;
     const float o2 = (v[i].z - mean) * rstd * g.z + b.z, o3 = (v[i].w - mean) * rstd * g.w + b.w;
     if (y16) {
@@ -188,7 +193,7 @@ extern "C" int countr_layernorm_bwd(const float* dy, const float* x, const float
   COUNTR_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "dgamma/dbeta must both be given or both NULL");
   COUNTR_REQUIRE(rows > 0 && D % 128 == 0 && D <= 1536, "LayerNorm width %d unsupported", D);
   // one wave of 8-warp blocks: fewer blocks = fewer same-address dgamma/dbeta atomics
-  const int target_warps = 148 * 8;
+  const int target_warps = 148 * 16;   // two 8-warp blocks per SM: the per-row load -> reduce -> store chain is latency-bound
   int rpw = (rows + target_warps - 1) / target_warps;
   if (rpw < 1) rpw = 1;
   const int warps = (rows + rpw - 1) / rpw;
