@@ -33,9 +33,9 @@ SHOTS = 3
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
-    `ncu --set full` capture of the same launch (profiles/r1_conv_h3_ncu_summary.json); None if absent."""
+    `ncu --set full` capture of the same launch (profiles/r1_conv_h3_ncu_summary_v2.json); None if absent."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_conv_h3_ncu_summary.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1_conv_h3_ncu_summary_v2.json")) as f:
             return json.load(f).get("dram_bytes_per_launch")
     except Exception:
         return None
