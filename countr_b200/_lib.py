@@ -8,7 +8,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcountr_sm100.so")
+# COUNTR_B200_LIB points at an alternative build of the same ABI (A/B runs of two kernel versions on one box)
+LIB_PATH = os.environ.get("COUNTR_B200_LIB") or os.path.join(_HERE, "lib", "libcountr_sm100.so")
 
 
 class CountrError(RuntimeError):

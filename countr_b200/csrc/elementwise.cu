@@ -339,6 +339,44 @@ __global__ void __launch_bounds__(256) gn_relu_dot_kernel(const uint16_t* __rest
   const float b0 = bias[0];
   // one warp handles 4 pixels per iteration: 4 independent 16-byte loads in flight per lane (the kernel is
   // latency-bound with one), and the four warp reductions interleave.
+  if (C == 256) {
+    // the lane's 8 channels never change: scale / shift / 1x1 weight live in registers (the generic loop below re-reads
+    // them from shared memory with an 8-way bank conflict for every pixel group)
+    const int c0 = lane * 8;
+    float av[8], bv[8], wv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      av[j] = sa[c0 + j];
+      bv[j] = sb[c0 + j];
+      wv[j] = sw[c0 + j];
+    }
+    const uint16_t* xb = x + static_cast<long long>(b) * HW * C + c0;
+    for (int pix0 = (blockIdx.x * 8 + warp) * 4; pix0 < HW; pix0 += gridDim.x * 8 * 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(min(pix0 + u, HW - 1)) * C);
+      float acc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v[u], f, bf16);
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a = fmaf(fmaxf(fmaf(f[j], av[j], bv[j]), 0.f), wv[j], a);
+        acc[u] = a;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+      }
+      if (lane < 4 && pix0 + lane < HW) {
+        const float r = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+        out[static_cast<long long>(b) * HW + pix0 + lane] = r + b0;
+      }
+    }
+    return;
+  }
   for (int pix0 = (blockIdx.x * 8 + warp) * 4; pix0 < HW; pix0 += gridDim.x * 8 * 4) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c0 = lane * 8; c0 < C; c0 += 256) {
