@@ -140,30 +140,34 @@ __global__ void __launch_bounds__(256) gn_relu_bwd_reduce_kernel(
   uint16_t* ob = dyh + static_cast<long long>(b) * HW * kC + c0;
   const int stride = gridDim.x * 8;
   if (MODE == 1) {
-    // two pixels per iteration: two independent 16-byte loads in flight per thread (the loop is latency-bound)
-    for (int pix = blockIdx.x * 8 + pl; pix < HW; pix += 2 * stride) {
-      const int pix2 = pix + stride;
-      const bool has2 = pix2 < HW;
-      const uint4 u0 = *reinterpret_cast<const uint4*>(rb + static_cast<long long>(pix) * kC);
-      const uint4 u1 = has2 ? *reinterpret_cast<const uint4*>(rb + static_cast<long long>(pix2) * kC) : make_uint4(0, 0, 0, 0);
-      const float dm0 = dmap[static_cast<long long>(b) * HW + pix];
-      const float dm1 = has2 ? dmap[static_cast<long long>(b) * HW + pix2] : 0.f;
-      float x0[8], x1[8], d0[8], d1[8];
-      unpack8(u0, x0, bf16);
-      unpack8(u1, x1, bf16);
-      if (cv == 0) a_b1 += dm0 + dm1;
+    // four pixels per iteration: four independent 16-byte loads in flight per thread (the loop is latency-bound)
+    for (int pix = blockIdx.x * 8 + pl; pix < HW; pix += 4 * stride) {
+      uint4 u[4];
+      float dm[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh0 = (x0[j] - mean) * rstd, xh1 = (x1[j] - mean) * rstd;
-        const float r0 = fmaf(xh0, gam[j], bet[j]) > 0.f ? dm0 : 0.f;
-        const float r1 = fmaf(xh1, gam[j], bet[j]) > 0.f ? dm1 : 0.f;
-        R1[j] += r0 + r1;
-        R2[j] += r0 * xh0 + r1 * xh1;
-        d0[j] = r0 * wv[j];
-        d1[j] = r1 * wv[j];
+      for (int k = 0; k < 4; ++k) {
+        const int pk = pix + k * stride;
+        const bool has = pk < HW;
+        u[k] = has ? *reinterpret_cast<const uint4*>(rb + static_cast<long long>(pk) * kC) : make_uint4(0, 0, 0, 0);
+        dm[k] = has ? dmap[static_cast<long long>(b) * HW + pk] : 0.f;
       }
-      *reinterpret_cast<uint4*>(ob + static_cast<long long>(pix) * kC) = pack8(d0, bf16);
-      if (has2) *reinterpret_cast<uint4*>(ob + static_cast<long long>(pix2) * kC) = pack8(d1, bf16);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int pk = pix + k * stride;
+        if (pk >= HW) break;
+        float x[8], d[8];
+        unpack8(u[k], x, bf16);
+        if (cv == 0) a_b1 += dm[k];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (x[j] - mean) * rstd;
+          const float r = fmaf(xh, gam[j], bet[j]) > 0.f ? dm[k] : 0.f;
+          R1[j] += r;
+          R2[j] = fmaf(r, xh, R2[j]);
+          d[j] = r * wv[j];
+        }
+        *reinterpret_cast<uint4*>(ob + static_cast<long long>(pk) * kC) = pack8(d, bf16);
+      }
     }
   } else {
     // Row-walking gather of the up-sample adjoint: the block owns 8 pixel columns x R rows (blockIdx.x = strip * x-tiles +

@@ -93,17 +93,51 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 #pragma unroll
   for (int i = 0; i < NV; ++i) dg[i] = db[i] = dxs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  // software pipeline over the rows of this warp: the loads of row r+1 are in flight while row r is reduced and stored
+  // (the per-row chain load -> two warp reductions -> store was fully exposed: 19 us per launch for 47 MB)
+  const int row0 = warp * rows_per_warp;
+  float4 xn[NV], dn[NV];
+  float mean_n = 0.f, rstd_n = 0.f;
+  if (row0 < rows) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row0) * D);
+    const float4* dr = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row0) * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      xn[i] = xr[lane + 32 * i];
+      dn[i] = dr[lane + 32 * i];
+    }
+    mean_n = mean_in[row0];
+    rstd_n = rstd_in[row0];
+  }
+  float4 gm[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) gm[i] = __ldg(g4 + lane + 32 * i);
   for (int rr = 0; rr < rows_per_warp; ++rr) {
-    const int row = warp * rows_per_warp + rr;
+    const int row = row0 + rr;
     if (row >= rows) break;
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
-    const float4* dr = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * D);
+    const float mean = mean_n, rstd = rstd_n;
+    float4 xc[NV], dc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      xc[i] = xn[i];
+      dc[i] = dn[i];
+    }
+    if (rr + 1 < rows_per_warp && row + 1 < rows) {
+      const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row + 1) * D);
+      const float4* dr = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row + 1) * D);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        xn[i] = xr[lane + 32 * i];
+        dn[i] = dr[lane + 32 * i];
+      }
+      mean_n = mean_in[row + 1];
+      rstd_n = rstd_in[row + 1];
+    }
     float4 xh[NV], gy[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float4 xv = xr[lane + 32 * i], dv = dr[lane + 32 * i], g = __ldg(g4 + lane + 32 * i);
+      const float4 xv = xc[i], dv = dc[i], g = gm[i];
       xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
       gy[i] = make_float4(dv.x * g.x, dv.y * g.y, dv.z * g.z, dv.w * g.w);
       s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
