@@ -22,6 +22,17 @@
 #include <type_traits>
 
 namespace countr {
+
+// optional clock64 timeline of CTA 0 (softmax warp 0 of tile 0 and the MMA warp) for scripts/trace_attn.py; -DCOUNTR_TRACE only
+#ifdef COUNTR_TRACE
+__device__ long long* g_attn_trace = nullptr;
+#define ATR_INIT long long* const atr_ = (g_attn_trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) ? g_attn_trace : nullptr
+#define ATR(slot) do { if (atr_ != nullptr && (slot) < 4096) atr_[(slot)] = clock64(); } while (0)
+#else
+#define ATR_INIT do {} while (0)
+#define ATR(slot) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int BQ = 128;   // query rows per tile (one tcgen05.mma M)
@@ -86,6 +97,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// (An FMA-pipe cubic exp2 for a share of the exponentials — the FlashAttention-4 trick — was measured: 24.6 -> 23.2 us with
+// one pair in four, slower with more; the softmax warps are issue- and hand-off-bound rather than MUFU-bound, see
+// profiles/README.md.  Not kept: it costs exactness against the backward's recomputed probabilities.)
+
 // One CTA per SM = one (batch, head, PAIR of 128-query tiles), warp-specialised:
 //   warps 0-3 / 4-7  softmax of tile 0 / tile 1, thread == query row (TMEM lane), no cross-thread reductions
 //   warp 8           tcgen05.mma issue (one lane)
@@ -132,6 +147,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   auto item_ntiles = [&](int item) { return ((2 * item_qp(item) + 1) * BQ < p.L) ? 2 : 1; };
 
   pdl_trigger();
+  ATR_INIT;
+  if (tid == 0) ATR(0);
   if (tid == 0) {
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_kv);
@@ -242,14 +259,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         const int nt = item_ntiles(item);
         for (int c = 0; c < nchunks; ++c, ++j) {
           // run one chunk ahead with S — into the next work item at the end of this one
+          ATR(1024 + 8 * j);
           if (c + 1 < nchunks) issue_s(item, i, c + 1, j + 1);
           else if (item + static_cast<int>(gridDim.x) < nitems) issue_s(item + gridDim.x, i + 1, 0, j + 1);
+          ATR(1025 + 8 * j);
           const int s = j % kStages;
           const int valid = min(KC, p.L - c * KC);
           const int ksteps = ((valid + 31) / 32) * 2;   // 16 keys per k-step, whole 32-key groups
           mbar_wait(v_full + s, static_cast<uint32_t>(j / kStages) & 1u);
           for (int t = 0; t < nt; ++t) {
             mbar_wait(p_full + t, n_p[t] & 1);
+            ATR(1026 + 8 * j + 2 * t);
             tc_fence_after();
             if (elect_one()) {
               for (int k = 0; k < ksteps; ++k) {
@@ -262,6 +282,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
               if (t == nt - 1) umma_commit(v_empty + s);
             }
             __syncwarp();
+            ATR(1027 + 8 * j + 2 * t);
             ++n_p[t];
           }
         }
@@ -299,7 +320,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         constexpr bool kFull = false;
         const int valid = min(KC, p.L - c * KC);          // keys in this chunk
         const int groups = (valid + 31) / 32;             // 32-column groups that hold any valid key
+        if (warp == 0) ATR(16 + 8 * n_c);
         mbar_wait(s_full + t, n_c & 1);
+        if (warp == 0) ATR(17 + 8 * n_c);
         tc_fence_after();
         // ---- the whole row of S into registers; the S columns go straight back to the MMA warp ----
         uint32_t r[4][32];
@@ -311,6 +334,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_free + t);
+        if (warp == 0) ATR(18 + 8 * n_c);
         if (!kFull) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -344,6 +368,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           m_run = m_cand;
         }
         bool rescaled = false;
+        if (warp == 0) ATR(19 + 8 * n_c);
         if (n_c > 0) {
           mbar_wait(p_free + t, (n_c - 1) & 1);   // the previous P.V of this tile is done: the P tile and O are ours again
           tc_fence_after();
@@ -360,6 +385,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
             }
           }
         }
+        if (warp == 0) ATR(20 + 8 * n_c);
         // ---- P = exp2(S*c - m) (packed FFMA2 / FADD2), row sum, 16-bit P row into swizzled smem ----
         const float2 sc2 = splat2(p.scale_log2), nm2 = splat2(-m_run);
         float2 ls2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
@@ -387,6 +413,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full + t);
+        if (warp == 0) ATR(21 + 8 * n_c);
         ++n_c;
       }
 
@@ -718,6 +745,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
 
 }  // namespace
 }  // namespace countr
+
+#ifdef COUNTR_TRACE
+extern "C" int countr_debug_set_attn_trace(void* buf) {
+  long long* pbuf = reinterpret_cast<long long*>(buf);
+  COUNTR_CHECK_CUDA(cudaMemcpyToSymbol(countr::g_attn_trace, &pbuf, sizeof(pbuf)));
+  return 0;
+}
+#endif
 
 extern "C" int countr_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int dh, float scale,
                                     int bf16, countr_stream_t stream_) {
