@@ -1,0 +1,46 @@
+"""GPU input pipeline, first piece: ground-truth density maps from dot annotations.
+
+`density_from_dots` reproduces, for a whole batch on the device, what the reference's dataset transforms compute per image
+on the host with numpy + scipy (util/FSC147.py:262-273 for training without augmentation, :326-331 for validation): scatter
+a 1 per annotated point on the resized canvas, crop the 384-wide window, `ndimage.gaussian_filter`, multiply by 60.
+There is no CPU fallback: the kernels live in libcountr_sm100.so (csrc/data.cu).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import check, lib
+
+
+def gaussian_half_kernel(sigma, radius=None, truncate=4.0):
+    """The float64 weights scipy.ndimage uses (_gaussian_kernel1d, order 0), centre first: w[k] is the tap at distance k."""
+    sigma = float(sigma)
+    if radius is None:
+        radius = int(truncate * sigma + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    phi = phi / phi.sum()
+    return phi[radius:].copy(), radius
+
+
+def density_from_dots(dots, counts, out_hw=(384, 384), scale=(1.0, 1.0), canvas_hw=None, origin=(0, 0), sigma=1.0, radius=None,
+                      gain=60.0):
+    """dots: float64 [B, n_max, 2] (x, y) on the device, counts: int32 [B]; scale = (scale_factor_h, scale_factor_w);
+    canvas_hw = (new_H, new_W) of the resized image (defaults to out_hw); origin = (y0, x0) of the kept window.
+    Training (FSC147.py:262-273): sigma=1 (radius 4); validation (:326-331): sigma=4, radius=7.  Returns fp32 [B, H, W]."""
+    assert dots.is_cuda and dots.dtype == torch.float64 and dots.dim() == 3 and dots.shape[-1] == 2 and dots.is_contiguous()
+    assert counts.is_cuda and counts.dtype == torch.int32 and counts.shape == (dots.shape[0],)
+    B, n_max, _ = dots.shape
+    H, W = out_hw
+    ch, cw = canvas_hw if canvas_hw is not None else out_hw
+    w, r = gaussian_half_kernel(sigma, radius)
+    wd = torch.from_numpy(w).to(dots.device)
+    tmp = torch.empty(B, H, W, dtype=torch.float32, device=dots.device)
+    out = torch.empty(B, H, W, dtype=torch.float32, device=dots.device)
+    check(lib().countr_density_from_dots(ctypes.c_void_p(dots.data_ptr()), ctypes.c_void_p(counts.data_ptr()), B, n_max,
+                                         float(scale[0]), float(scale[1]), int(ch), int(cw), int(origin[0]), int(origin[1]), H, W,
+                                         ctypes.c_void_p(wd.data_ptr()), r, float(gain), ctypes.c_void_p(tmp.data_ptr()),
+                                         ctypes.c_void_p(out.data_ptr()), ops._stream()))
+    return out

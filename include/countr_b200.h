@@ -268,6 +268,16 @@ int countr_adamw_step(const void* tensors, int num_tensors, const void* chunks, 
 int countr_window_blend(const void* outs, int dtype, const int32_t* starts, int nw, int H, int Wwin, int W, float* density,
                         countr_stream_t stream);
 
+/* Ground-truth density-map synthesis on the GPU (util/FSC147.py:262-273 ResizeTrainImage no-augmentation
+ * path, :326-331 ResizeValImage): dots [B][n_max][2] (x, y; float64 as the annotation files hold them), counts [B];
+ * a 1 is written at (min(canvas_h-1, int(y*scale_h)), min(canvas_w-1, int(x*scale_w))) of the resized canvas, the H x W
+ * window at (y0, x0) is kept, filtered with scipy.ndimage.gaussian_filter's arithmetic (separable, axis 0 then axis 1,
+ * double accumulation, 'reflect' boundary; weights[0..radius] = the normalised float64 half kernel, centre first) and
+ * multiplied by gain (60).  tmp, out: [B][H][W] fp32. */
+int countr_density_from_dots(const double* dots, const int32_t* counts, int B, int n_max, double scale_h, double scale_w,
+                             int canvas_h, int canvas_w, int y0, int x0, int H, int W, const double* weights, int radius,
+                             float gain, float* tmp, float* out, countr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

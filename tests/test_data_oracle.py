@@ -1,0 +1,78 @@
+"""Density-map synthesis: the CPU oracle against its committed fixture, the kernel-weight helper against
+scipy's own, and (GPU) the CUDA kernels against the oracle — bit for bit, it is the same double-precision arithmetic."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import data_oracle as D
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "density_synth.npz")
+
+
+def test_oracle_matches_fixture():
+    g = np.load(GOLD)
+    H, W = (int(v) for v in g["hw"])
+    v = D.val_density(g["dots"], H, W)
+    assert v.dtype == np.float32 and v.shape == (384, 384)
+    assert np.array_equal(v[:48, :48], g["val_crop"]) and np.array_equal(v[-8:, -8:], g["val_corner"])
+    assert abs(v.astype(np.float64).sum() - float(g["val_sum"])) < 1e-6
+    new_H, new_W, start = (int(x) for x in g["train_meta"])
+    t = D.train_density(g["dots"], H, W, new_H, new_W, start)
+    assert np.array_equal(t[100:148, 200:248], g["train_crop"])
+    assert abs(t.astype(np.float64).sum() - float(g["train_sum"])) < 1e-6
+    # one coincident pair and the 60x gain: the count is recovered as sum / 60 (FSC_finetune_cross.py:299)
+    assert abs(v.sum() / 60 - (len(g["dots"]) - 1)) < 1e-3
+
+
+def test_half_kernel_is_scipys():
+    from scipy.ndimage import _filters
+    from countr_b200.data import gaussian_half_kernel
+    for sigma, radius in ((1.0, None), (4.0, 7), (2.5, None)):
+        w, r = gaussian_half_kernel(sigma, radius)
+        ref = _filters._gaussian_kernel1d(sigma, 0, r)
+        assert np.array_equal(w, ref[r:]) and np.array_equal(ref[:r][::-1], ref[r + 1:])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["val", "train"])
+def test_density_kernels_match_oracle(cuda, mode):
+    from countr_b200.data import density_from_dots
+    rng = np.random.default_rng(11)
+    sizes = [(480, 640), (333, 1000), (384, 384), (700, 400)]
+    B = len(sizes)
+    n = [61, 0, 300, 17]
+    n_max = max(n)
+    dots = np.zeros((B, n_max, 2))
+    outs, refs = [], []
+    for b, (H, W) in enumerate(sizes):
+        d = rng.random((n[b], 2)) * np.array([W, H])
+        if n[b] > 3:
+            d[1] = d[0]
+            d[2] = [W - 1e-9, H - 1e-9]
+        dots[b, :n[b]] = d
+    for b, (H, W) in enumerate(sizes):     # scale / canvas / window differ per image: one call per image, as the dataset does
+        dd = torch.from_numpy(dots[b:b + 1]).to(cuda).contiguous()
+        cc = torch.tensor([n[b]], dtype=torch.int32, device=cuda)
+        if mode == "val":
+            ref = D.val_density(dots[b, :n[b]], H, W)
+            got = density_from_dots(dd, cc, scale=(384.0 / H, 384.0 / W), sigma=4.0, radius=7)
+        else:
+            new_H, new_W = 384, max(384, 16 * int(W * 384 / H / 16))
+            start = (new_W - 384) // 3
+            ref = D.train_density(dots[b, :n[b]], H, W, new_H, new_W, start)
+            got = density_from_dots(dd, cc, scale=(float(new_H) / H, float(new_W) / W), canvas_hw=(new_H, new_W), origin=(0, start),
+                                    sigma=1.0)
+        torch.cuda.synchronize()
+        got = got[0].cpu().numpy()
+        assert got.shape == ref.shape
+        diff = np.abs(got.astype(np.float64) - ref.astype(np.float64)).max()
+        assert np.array_equal(got, ref) or diff <= 1e-6 * max(1.0, float(np.abs(ref).max())), (b, diff)
+        outs.append(got); refs.append(ref)
+    # a batched call (shared geometry) equals the per-image calls
+    dd = torch.from_numpy(np.stack([dots[0], dots[0][::-1].copy()])).to(cuda).contiguous()
+    cc = torch.tensor([n[0], n_max], dtype=torch.int32, device=cuda)
+    both = density_from_dots(dd, cc, scale=(384.0 / 480, 384.0 / 640), sigma=4.0, radius=7)
+    one = density_from_dots(dd[:1].contiguous(), cc[:1].contiguous(), scale=(384.0 / 480, 384.0 / 640), sigma=4.0, radius=7)
+    assert torch.equal(both[0], one[0])
