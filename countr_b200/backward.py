@@ -270,6 +270,10 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
     if side is not None or wstream is not None:
         torch.cuda.current_stream().wait_stream(eng.side_stream(dev))     # join the exemplar-CNN backward and the dW work
     keep.clear()
+    # Every parameter that just received a gradient is about to be changed by an optimizer, and torch's version counter
+    # cannot be relied on to say so (torch.optim.AdamW(fused=True) updates parameters without bumping `_version`, and so
+    # does anything that writes through `.data`): mark their 16-bit copies stale now, the next forward re-casts them.
+    wc.bump(params)
     eng.last_arena = arena             # trainers that all-reduce outside the autograd node pick the arena up here
     if eng.grad_allreduce is not None:
         eng.grad_allreduce(arena)      # data-parallel mean of every decoder gradient in one collective

@@ -1052,3 +1052,112 @@ extern "C" int countr_window_blend(const void* outs, int dtype, const int32_t* s
   COUNTR_CHECK_CUDA(cudaGetLastError());
   return COUNTR_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Batched refresh of the 16-bit GEMM / conv operand copies of the fp32 master weights: ONE launch per step instead of one
+// cast / transpose / pack launch per tensor (~50 launches of 2-3 us each after every optimizer step).
+//   entry = {src fp32, dst 16-bit, kind, R, C}:   kind 0  dst[i] = src[i]                  (R*C elements)
+//                                                 kind 1  dst[c][r] = src[r][c]            (fp32 [R][C] -> [C][R])
+//                                                 kind 2  conv pack mode 0 (Cout = R, Cin = C): dst[co][tap][ci] = w[co][ci][tap]
+//                                                 kind 3  conv pack mode 1:                     dst[ci][tap][co] = w[co][ci][8 - tap]
+//   blk_prefix[e] = first block of entry e (n_entries + 1 values); 256 threads per block:
+//   kind 0: 2048 elements per block; kind 1: one 32 x 32 tile per block; kind 2: one (co, 128 ci) slab per block;
+//   kind 3: one 32 x 32 tile of w viewed as [Cout][Cin*9] per block.
+// ------------------------------------------------------------------------------------------
+namespace countr {
+namespace {
+struct WREntry {
+  const float* src;
+  uint16_t* dst;
+  long long kind, R, C, pad;
+};
+
+__global__ void __launch_bounds__(256) weight_refresh_kernel(const WREntry* __restrict__ entries, const int* __restrict__ blk_prefix,
+                                                             int n_entries, int bf16) {
+  __shared__ int s_e;
+  __shared__ float tile[32][33];
+  if (threadIdx.x == 0) {
+    int e = 0;
+    while (e + 1 < n_entries && static_cast<int>(blockIdx.x) >= blk_prefix[e + 1]) ++e;
+    s_e = e;
+  }
+  __syncthreads();
+  const WREntry en = entries[s_e];
+  const int lb = blockIdx.x - blk_prefix[s_e];      // block index inside the entry
+  const int R = static_cast<int>(en.R), C = static_cast<int>(en.C);
+  if (en.kind == 0) {
+    const long long n = static_cast<long long>(R) * C;
+    const long long i = (static_cast<long long>(lb) * 256 + threadIdx.x) * 8;
+    if (i + 8 <= n && (reinterpret_cast<uintptr_t>(en.src) & 15u) == 0 && (reinterpret_cast<uintptr_t>(en.dst) & 15u) == 0) {
+      const float4 a = *reinterpret_cast<const float4*>(en.src + i), b = *reinterpret_cast<const float4*>(en.src + i + 4);
+      uint4 o;
+      o.x = pack2(a.x, a.y, bf16);
+      o.y = pack2(a.z, a.w, bf16);
+      o.z = pack2(b.x, b.y, bf16);
+      o.w = pack2(b.z, b.w, bf16);
+      *reinterpret_cast<uint4*>(en.dst + i) = o;
+    } else {
+      for (long long j = i; j < n && j < i + 8; ++j) en.dst[j] = static_cast<uint16_t>(pack2(en.src[j], 0.f, bf16) & 0xffffu);
+    }
+  } else if (en.kind == 1) {
+    const int tiles_c = (C + 31) / 32;
+    const int c0 = (lb % tiles_c) * 32, r0 = (lb / tiles_c) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+      const int r = r0 + i, c = c0 + tx;
+      tile[i][tx] = (r < R && c < C) ? en.src[static_cast<size_t>(r) * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, r = r0 + tx;
+      if (r < R && c < C) en.dst[static_cast<size_t>(c) * R + r] = static_cast<uint16_t>(pack2(tile[tx][i], 0.f, bf16) & 0xffffu);
+    }
+  } else if (en.kind == 2) {
+    // mode 0: dst[co][tap][ci] = w[co][ci][tap].  Block = (co, 128 input channels): 1152 contiguous floats in, 9 rows of
+    // 128 contiguous 16-bit values out (Cout = R, Cin = C).
+    __shared__ float cw[128 * 9];
+    const int cblocks = (C + 127) / 128;
+    const int co = lb / cblocks, ci0 = (lb % cblocks) * 128;
+    const int nci = min(128, C - ci0);
+    const float* sp = en.src + (static_cast<long long>(co) * C + ci0) * 9;
+    for (int i = threadIdx.x; i < nci * 9; i += 256) cw[i] = sp[i];
+    __syncthreads();
+    uint16_t* dp = en.dst + static_cast<long long>(co) * 9 * C + ci0;
+    for (int i = threadIdx.x; i < nci * 9; i += 256) {
+      const int tap = i / nci, ci = i - tap * nci;
+      dp[static_cast<long long>(tap) * C + ci] = static_cast<uint16_t>(pack2(cw[ci * 9 + tap], 0.f, bf16) & 0xffffu);
+    }
+  } else {
+    // mode 1: dst[ci][tap][co] = w[co][ci][8 - tap]: the transpose of w viewed as [Cout][Cin*9], with the 9 taps of every
+    // input channel written in reverse order.  Same 32 x 32 tiles as kind 1 (rows = co, columns = ci*9 + tap).
+    const int CC = C * 9;
+    const int tiles_c = (CC + 31) / 32;
+    const int c0 = (lb % tiles_c) * 32, r0 = (lb / tiles_c) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+      const int r = r0 + i, c = c0 + tx;
+      tile[i][tx] = (r < R && c < CC) ? en.src[static_cast<size_t>(r) * CC + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, r = r0 + tx;
+      if (r < R && c < CC) {
+        const int ci = c / 9, tap = c - ci * 9;
+        en.dst[(static_cast<size_t>(ci) * 9 + (8 - tap)) * R + r] = static_cast<uint16_t>(pack2(tile[tx][i], 0.f, bf16) & 0xffffu);
+      }
+    }
+  }
+}
+}  // namespace
+}  // namespace countr
+
+extern "C" int countr_weight_refresh(const void* entries, const int32_t* blk_prefix, int n_entries, int total_blocks, int bf16,
+                                     countr_stream_t stream_) {
+  using namespace countr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(entries && blk_prefix && n_entries > 0 && total_blocks > 0, "bad arguments");
+  weight_refresh_kernel<<<static_cast<unsigned>(total_blocks), 256, 0, stream>>>(reinterpret_cast<const WREntry*>(entries), blk_prefix,
+                                                                                n_entries, bf16);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}

@@ -46,6 +46,7 @@ class WeightCache:
     def __init__(self):
         self.cache = {}
         self.ext = {}          # id(p) -> counter bumped by trainers that update parameters with their own kernels
+        self._tables = {}      # (device, stale set) -> device job table of refresh_batch
 
     def bump(self, params):
         """Mark parameters as modified outside torch (torch's version counter did not move)."""
@@ -67,6 +68,62 @@ class WeightCache:
             if len(self.cache) > 4096:      # drop entries of dead parameters
                 self.cache = {k: e for k, e in self.cache.items() if e[0]() is not None}
         return ent[2]
+
+    # kind -> (countr_weight_refresh job code, shape of the 16-bit copy)
+    @staticmethod
+    def _job(p, kind):
+        n = p.shape[0]
+        k = p.numel() // n if n else 0
+        if kind == "w":
+            return 0, (n, k), (n, k)
+        if kind == "v":
+            return 0, tuple(p.shape), (1, p.numel())
+        if kind == "wt":
+            return 1, (k, n), (n, k)
+        cout, cin = p.shape[0], p.shape[1]
+        if kind == "c0":
+            return 2, (cout, 9 * cin), (cout, cin)
+        return 3, (cin, 9 * cout), (cout, cin)          # "c1"
+
+    def refresh_batch(self, plan):
+        """Bring the 16-bit copies of every (parameter, kind) in `plan` up to date with ONE kernel launch (instead of one
+        cast / transpose / pack launch per stale tensor — ~50 launches after every optimizer step of the fine-tune loop).
+        The device job table is cached per set of stale tensors, so a steady training loop (and a CUDA-graph capture after
+        warm-up) does no host-to-device traffic here."""
+        work = []
+        for p, kind in plan:
+            key = (id(p), kind)
+            ent = self.cache.get(key)
+            ver = (p.data_ptr(), p._version, self.ext.get(id(p), 0))
+            if ent is not None and ent[0]() is p and ent[1] == ver and ent[2].device == p.device:
+                continue
+            code, shape, rc = self._job(p, kind)
+            reuse = ent is not None and ent[2].device == p.device and ent[2].shape == torch.Size(shape)
+            buf = ent[2] if reuse else torch.empty(shape, dtype=F16, device=p.device)
+            self.cache[key] = (weakref.ref(p), ver, buf)
+            work.append((p.data_ptr(), buf.data_ptr(), code, rc[0], rc[1]))
+        if not work:
+            return 0
+        dev = plan[0][0].device
+        tkey = (str(dev), tuple(work))
+        tab = self._tables.get(tkey)
+        if tab is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("countr_b200: the weight-refresh table must be built outside CUDA-graph capture "
+                                   "(run one eager warm-up step before capturing)")
+            rows, prefix, nblk = [], [0], 0
+            for src, dst, code, r, c in work:
+                rows += [src, dst, code, r, c, 0]
+                n = r * c
+                nblk += ((n + 2047) // 2048 if code == 0 else ((r + 31) // 32) * ((c + 31) // 32) if code == 1 else
+                         r * ((c + 127) // 128) if code == 2 else ((r + 31) // 32) * ((9 * c + 31) // 32))
+                prefix.append(nblk)
+            tab = (torch.tensor(rows, dtype=torch.int64, device=dev), torch.tensor(prefix, dtype=torch.int32, device=dev), len(work), nblk)
+            if len(self._tables) > 64:
+                self._tables.clear()
+            self._tables[tkey] = tab
+        ops.weight_refresh(tab[0], tab[1], tab[2], tab[3])
+        return len(work)
 
     def w16(self, p):
         """[N, K] row-major copy (B operand of y = x W^T)."""
@@ -223,6 +280,29 @@ class Engine:
         return y32, y16
 
     # ------------------------------------------------------------------ decoder
+    @staticmethod
+    def decoder_weight_plan(m, shot_num, train):
+        """Every (parameter, operand-copy kind) the decoder forward — and, when training, its backward — will ask the
+        WeightCache for: 'w' row-major, 'wt' transposed (dX GEMMs), 'c0' / 'c1' packed conv filters (forward / dX)."""
+        plan = [(m.decoder_embed.weight, "w")]
+        ex = [m.decoder_proj2[0], m.decoder_proj3[0], m.decoder_proj4[0]]
+        if shot_num > 0:
+            plan += [(c.weight, "c0") for c in ex]
+        else:
+            plan.append((m.shot_token, "v"))
+        for blk in m.decoder_blocks:
+            lin = [blk.selfattn.qkv, blk.selfattn.proj, blk.attn.wq, blk.attn.wk, blk.attn.wv, blk.attn.proj, blk.mlp.fc1, blk.mlp.fc2]
+            plan += [(l.weight, "w") for l in lin]
+            if train:
+                plan += [(l.weight, "wt") for l in lin]
+        heads = [m.decode_head0[0], m.decode_head1[0], m.decode_head2[0], m.decode_head3[0]]
+        plan += [(c.weight, "c0") for c in heads]
+        if train:
+            plan += [(c.weight, "c1") for c in heads]
+            if shot_num > 0:
+                plan += [(c.weight, "c1") for c in ex]
+        return plan
+
     def decoder_forward(self, m, lat16, boxes, shot_num, B, out_dtype, save=None, pre=None):
         """lat16: fp16 [B*L, D] encoder output.  Returns the density map [B, 2^4*h, 2^4*w]."""
         dev = lat16.device

@@ -158,6 +158,8 @@ class SupervisedMAE(nn.Module):
         self._check(imgs)
         eng = engine()
         pre = None
+        # every stale 16-bit decoder weight copy is refreshed here in one launch, before the side stream forks
+        eng.wc.refresh_batch(eng.decoder_weight_plan(self, shot_num, self._needs_grad()))
         if shot_num > 0 and eng.overlap_exemplar:
             assert boxes.dim() == 5 and boxes.shape[1] >= shot_num, "boxes must be [N, K>=shot_num, 3, 64, 64]"
             train = self._needs_grad()

@@ -237,6 +237,7 @@ class MaskedAutoencoderViTNoCT(nn.Module):
         pe = self.patch_embed.proj
         ops.colsum(ge, G(pe.bias))
         _dw_linear(ge16, pk.view(B * Lk, -1), G(pe.weight).view(pe.weight.shape[0], -1))
+        wc.bump(params)      # gradient received => about to be updated; fused optimizers do not bump `_version` (see backward.py)
         eng.last_arena = arena
         if eng.grad_allreduce is not None:
             eng.grad_allreduce(arena)

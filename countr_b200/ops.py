@@ -142,6 +142,12 @@ def cast16(src32, dst16, scale=1.0):
     _count()
 
 
+def weight_refresh(entries_dev, prefix_dev, n_entries, total_blocks, bf16=False):
+    """One launch for a whole table of cast / transpose / conv-pack jobs (countr_weight_refresh)."""
+    check(lib().countr_weight_refresh(_ptr(entries_dev), _ptr(prefix_dev), n_entries, total_blocks, int(bf16), _stream()))
+    _count()
+
+
 def cast16_transpose(src32, dst16):
     R, C = src32.shape
     check(lib().countr_cast_transpose_f32_to_16(_ptr(src32), _ptr(dst16), R, C, _is_bf16(dst16), _stream()))

@@ -68,6 +68,7 @@ class FineTuner:
         """Forward, loss and backward; leaves the (scaled) gradients in `self.arena`.  Returns the loss (device scalar)."""
         m, eng = self.model, engine()
         B = imgs.shape[0]
+        eng.wc.refresh_batch(eng.decoder_weight_plan(m, shot_num, True))    # all stale 16-bit weight copies, one launch
         pre = eng.exemplar_async(m, boxes, shot_num, train=True) if (shot_num > 0 and eng.overlap_exemplar) else None
         _, lat16 = eng.encoder_forward(m, imgs)
         save = {}

@@ -278,6 +278,15 @@ int countr_density_from_dots(const double* dots, const int32_t* counts, int B, i
                              int canvas_h, int canvas_w, int y0, int x0, int H, int W, const double* weights, int radius,
                              float gain, float* tmp, float* out, countr_stream_t stream);
 
+/* Batched refresh of the 16-bit operand copies of fp32 master weights (one launch per optimizer step instead of one per
+ * tensor).  entries: device array of {const float* src; uint16* dst; int64 kind, R, C, pad} with kind 0 = cast of R*C
+ * elements, 1 = cast + transpose [R][C] -> [C][R], 2 / 3 = countr_conv_weight_pack mode 0 / 1 with Cout = R, Cin = C;
+ * blk_prefix[e] (n_entries + 1 values) = first 256-thread block of entry e: 2048 elements per block for kind 0, one 32x32
+ * tile per block for kind 1, one (co, 128 input channels) slab per block for kind 2, one 32x32 tile of the filter viewed
+ * as [Cout][Cin*9] per block for kind 3. */
+int countr_weight_refresh(const void* entries, const int32_t* blk_prefix, int n_entries, int total_blocks, int bf16,
+                          countr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -125,3 +125,39 @@ def test_loss_curve_tracks_reference(cuda, api):
     # the loss is quadratic in the map, so the 1e-3 map tolerance is 2e-3 on the loss before any optimizer feedback
     assert max(devs[:2]) < 2e-3
     assert max(devs) < 1e-2              # 16 Adam steps of fp16-operand arithmetic later (measured: <= 5e-3)
+
+
+@pytest.mark.parametrize("kind", ["fused", "data_write"])
+def test_parameter_updates_that_skip_the_version_counter_are_seen(cuda, kind):
+    """torch.optim.AdamW(fused=True) — what a fast training script uses — updates parameters WITHOUT bumping `Tensor._version`,
+    and so does a write through `.data`; the 16-bit operand copies must still follow the fp32 masters.  After one such update the
+    model must produce exactly what a freshly built model with the updated state_dict produces (the eval forward is
+    bit-reproducible)."""
+    import copy
+    m, sd, cfg = build("small", 1, cuda)
+    m.train()
+    imgs, boxes = synth.make_inputs(2, seed=300)
+    imgs, boxes = imgs.to(cuda), boxes.to(cuda)
+    out0 = m(imgs, boxes, 3)
+    (out0.float().sum() * 64.0).backward()
+    if kind == "fused":
+        opt = torch.optim.AdamW([p for p in m.parameters() if p.grad is not None], lr=3e-3, betas=(0.9, 0.95), fused=True)
+        v0 = m.decode_head3[0].weight._version
+        opt.step()
+        assert m.decode_head3[0].weight._version == v0, "torch now bumps the version in the fused path: the test premise changed"
+    else:
+        with torch.no_grad():
+            for p in m.parameters():
+                if p.grad is not None:
+                    p.data.add_(p.grad.sign(), alpha=-3e-3)
+    m.eval()
+    with torch.no_grad():
+        out1 = m(imgs, boxes, 3)
+    fresh, _, _ = build("small", 1, cuda)
+    fresh.load_state_dict(copy.deepcopy(m.state_dict()), strict=True)
+    fresh.eval()
+    with torch.no_grad():
+        ref = fresh(imgs, boxes, 3)
+    torch.cuda.synchronize()
+    assert not torch.equal(out1, out0.detach()), "the update did not change the output at all"
+    assert torch.equal(out1, ref), f"stale 16-bit weight copies: max |diff| = {(out1 - ref).abs().max().item():.3e}"
