@@ -209,6 +209,24 @@ class Engine:
             self._side[key] = torch.cuda.Stream(device=dev)
         return self._side[key]
 
+    def refresh_decoder_weights(self, m, shot_num, train, dev):
+        """WeightCache.refresh_batch over the decoder's plan.  With the side stream enabled the launch goes there and an event
+        recorded behind it is returned: the caller makes its stream wait for it before the first decoder kernel
+        (decoder_embed reads a refreshed copy before decoder_forward joins the exemplar branch).  Otherwise the refresh runs on
+        the current stream and None is returned."""
+        plan = self.decoder_weight_plan(m, shot_num, train)
+        if not self.overlap_exemplar:
+            self.wc.refresh_batch(plan)
+            return None
+        side = self.side_stream(dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            if self.wc.refresh_batch(plan) == 0:
+                return None
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return ev
+
     def exemplar_async(self, m, boxes, S, train):
         """Start decoder_proj1..4 on the side stream (it only depends on the boxes): ~45 tiny latency-bound
         launches that would otherwise sit on the critical path overlap the encoder instead.  The consumer calls

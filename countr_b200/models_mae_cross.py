@@ -158,14 +158,17 @@ class SupervisedMAE(nn.Module):
         self._check(imgs)
         eng = engine()
         pre = None
-        # every stale 16-bit decoder weight copy is refreshed here in one launch, before the side stream forks
-        eng.wc.refresh_batch(eng.decoder_weight_plan(self, shot_num, self._needs_grad()))
+        # every stale 16-bit decoder weight copy is refreshed in one launch — on the side stream, ahead of the exemplar CNN
+        # (the frozen encoder does not read them, so the ~50 us stay off the critical path)
+        refreshed = eng.refresh_decoder_weights(self, shot_num, self._needs_grad(), imgs.device)
         if shot_num > 0 and eng.overlap_exemplar:
             assert boxes.dim() == 5 and boxes.shape[1] >= shot_num, "boxes must be [N, K>=shot_num, 3, 64, 64]"
             train = self._needs_grad()
             with torch.no_grad():
                 pre = eng.exemplar_async(self, boxes, shot_num, train=train)   # overlaps the encoder
         _, lat16 = self._encode(imgs)
+        if refreshed is not None:
+            torch.cuda.current_stream().wait_event(refreshed)
         out_dtype = imgs.dtype if imgs.dtype in (F32, F16, torch.bfloat16) else F32
         return self._decode(lat16, boxes, shot_num, imgs.shape[0], out_dtype, pre)
 

@@ -68,9 +68,11 @@ class FineTuner:
         """Forward, loss and backward; leaves the (scaled) gradients in `self.arena`.  Returns the loss (device scalar)."""
         m, eng = self.model, engine()
         B = imgs.shape[0]
-        eng.wc.refresh_batch(eng.decoder_weight_plan(m, shot_num, True))    # all stale 16-bit weight copies, one launch
+        on_side = eng.refresh_decoder_weights(m, shot_num, True, imgs.device)    # all stale 16-bit weight copies, one launch
         pre = eng.exemplar_async(m, boxes, shot_num, train=True) if (shot_num > 0 and eng.overlap_exemplar) else None
         _, lat16 = eng.encoder_forward(m, imgs)
+        if on_side is not None:
+            torch.cuda.current_stream().wait_event(on_side)
         save = {}
         out = eng.decoder_forward(m, lat16, boxes, shot_num, B, F32, save=save, pre=pre)
         dout = torch.empty_like(out)
