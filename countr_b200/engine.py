@@ -47,6 +47,7 @@ class WeightCache:
         self.cache = {}
         self.ext = {}          # id(p) -> counter bumped by trainers that update parameters with their own kernels
         self._tables = {}      # (device, stale set) -> device job table of refresh_batch
+        self.lazy_fills = 0    # per-tensor refreshes done outside refresh_batch (diagnostic; tests/test_trainer_gpu.py)
 
     def bump(self, params):
         """Mark parameters as modified outside torch (torch's version counter did not move)."""
@@ -63,6 +64,7 @@ class WeightCache:
             reuse = ent is not None and ent[2].device == p.device and ent[2].shape == torch.Size(shape)
             buf = ent[2] if reuse else torch.empty(shape, dtype=F16, device=p.device)
             fill(p.detach(), buf)
+            self.lazy_fills += 1       # one launch per tensor: the batched refresh_batch() plans exist to keep this at zero
             ent = (weakref.ref(p), ver, buf)
             self.cache[key] = ent
             if len(self.cache) > 4096:      # drop entries of dead parameters

@@ -140,6 +140,15 @@ class MaskedAutoencoderViTNoCT(nn.Module):
         _lib.require_device()
         wc = engine().wc
         dev = imgs.device
+        # all stale 16-bit weight copies (every trainable tensor after an optimizer step) in one launch
+        train_plan = tape is not None
+        lin = [self.patch_embed.proj, self.decoder_embed, self.decoder_pred]
+        for blk in list(self.blocks) + list(self.decoder_blocks):
+            lin += [blk.attn.qkv, blk.attn.proj, blk.mlp.fc1, blk.mlp.fc2]
+        plan = [(l.weight, "w") for l in lin]
+        if train_plan:
+            plan += [(l.weight, "wt") for l in lin[1:]]       # the patch embedding needs no dX
+        wc.refresh_batch(plan)
         B, C, Himg, Wimg = imgs.shape
         P = self.patch_embed.patch_size[0]
         assert Himg == self.patch_embed.img_size[0] and Wimg == self.patch_embed.img_size[1], \

@@ -161,3 +161,33 @@ def test_parameter_updates_that_skip_the_version_counter_are_seen(cuda, kind):
     torch.cuda.synchronize()
     assert not torch.equal(out1, out0.detach()), "the update did not change the output at all"
     assert torch.equal(out1, ref), f"stale 16-bit weight copies: max |diff| = {(out1 - ref).abs().max().item():.3e}"
+
+
+@pytest.mark.parametrize("which", ["finetune", "pretrain"])
+def test_steady_training_step_refreshes_weights_in_one_launch(cuda, which):
+    """After an optimizer step every trainable tensor needs new 16-bit copies; the forward's refresh plan must cover every
+    (parameter, layout) the kernels ask for, so no per-tensor cast / transpose / pack launch happens (WeightCache.lazy_fills)."""
+    from countr_b200.engine import engine
+    eng = engine()
+    if which == "finetune":
+        m, sd, cfg = build("small", 1, cuda)
+        m.train()
+        imgs, boxes = synth.make_inputs(2, seed=310)
+        imgs, boxes = imgs.to(cuda), boxes.to(cuda)
+        run = lambda shot: m(imgs, boxes if shot else torch.empty(2, 0, device=cuda), shot).float().sum()
+        shots = [3, 0, 2]
+    else:
+        import models_mae_noct as N
+        m = N.MaskedAutoencoderViTNoCT(embed_dim=256, depth=2, num_heads=4, decoder_depth=1).to(cuda).train()
+        imgs = torch.rand(2, 3, 384, 384, device=cuda)
+        run = lambda shot: m(imgs, mask_ratio=0.5)[0]
+        shots = [0, 0, 0]
+    opt = torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=1e-4, fused=True)
+    for i, shot in enumerate(shots + shots):
+        if i == len(shots):
+            before = eng.wc.lazy_fills          # every shot count has been seen once: caches and job tables exist
+        opt.zero_grad(set_to_none=True)
+        (run(shot) * 16.0).backward()
+        opt.step()
+    torch.cuda.synchronize()
+    assert eng.wc.lazy_fills == before, f"{eng.wc.lazy_fills - before} per-tensor weight refreshes in steady-state steps"
