@@ -91,3 +91,52 @@ extern "C" int countr_density_from_dots(const double* dots, const int32_t* count
   COUNTR_CHECK_CUDA(cudaGetLastError());
   return COUNTR_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Exemplar crops: boxes[b][s] = Resize((64, 64))(image[b][:, y1:y2+1, x1:x2+1])     (util/FSC147.py:285-298, 343-351)
+// torchvision 0.14.1 (the reference's pin) resizes a float tensor with torch.nn.functional.interpolate(mode="bilinear",
+// align_corners=False) and no antialiasing; this is that arithmetic (ATen upsample_bilinear2d: source index
+// scale * (dst + 0.5) - 0.5 clamped at 0, scale = in / out in float, value = h0 (w0 a + w1 b) + h1 (w0 c + w1 d)).
+// ------------------------------------------------------------------------------------------
+namespace countr {
+namespace {
+__global__ void crop_resize_kernel(const float* __restrict__ img, long long sb, long long sc, long long sh, long long sw,
+                                   const int* __restrict__ rects, float* __restrict__ out, int B, int S, int C, int H, int W, int O) {
+  const long long total = static_cast<long long>(B) * S * C * O * O;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = static_cast<int>(idx % O), oy = static_cast<int>((idx / O) % O);
+  const int c = static_cast<int>((idx / (static_cast<long long>(O) * O)) % C);
+  const int s = static_cast<int>((idx / (static_cast<long long>(O) * O * C)) % S);
+  const int b = static_cast<int>(idx / (static_cast<long long>(O) * O * C * S));
+  const int* r = rects + (static_cast<long long>(b) * S + s) * 4;
+  const int y1 = max(0, min(H - 1, r[0])), x1 = max(0, min(W - 1, r[1]));
+  const int y2 = max(y1, min(H - 1, r[2])), x2 = max(x1, min(W - 1, r[3]));   // python slicing clips at the image border
+  const int h = y2 - y1 + 1, w = x2 - x1 + 1;
+  const float scale_h = static_cast<float>(h) / O, scale_w = static_cast<float>(w) / O;
+  float ry = scale_h * (oy + 0.5f) - 0.5f, rx = scale_w * (ox + 0.5f) - 0.5f;
+  ry = ry < 0.f ? 0.f : ry;
+  rx = rx < 0.f ? 0.f : rx;
+  const int iy0 = min(static_cast<int>(ry), h - 1), ix0 = min(static_cast<int>(rx), w - 1);
+  const int iy1 = iy0 + (iy0 < h - 1 ? 1 : 0), ix1 = ix0 + (ix0 < w - 1 ? 1 : 0);
+  const float ly1 = fminf(fmaxf(ry - iy0, 0.f), 1.f), lx1 = fminf(fmaxf(rx - ix0, 0.f), 1.f);
+  const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const float* p = img + b * sb + c * sc;
+  const float a = p[(y1 + iy0) * sh + (x1 + ix0) * sw], bq = p[(y1 + iy0) * sh + (x1 + ix1) * sw];
+  const float cq = p[(y1 + iy1) * sh + (x1 + ix0) * sw], d = p[(y1 + iy1) * sh + (x1 + ix1) * sw];
+  out[idx] = ly0 * (lx0 * a + lx1 * bq) + ly1 * (lx0 * cq + lx1 * d);
+}
+}  // namespace
+}  // namespace countr
+
+extern "C" int countr_crop_resize_boxes(const float* img, int64_t sb, int64_t sc, int64_t sh, int64_t sw, const int32_t* rects,
+                                        float* out, int B, int S, int C, int H, int W, int out_hw, countr_stream_t stream_) {
+  using namespace countr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(img && rects && out, "null pointer");
+  COUNTR_REQUIRE(B > 0 && S > 0 && C > 0 && H > 0 && W > 0 && out_hw > 0, "bad shape");
+  const long long total = static_cast<long long>(B) * S * C * out_hw * out_hw;
+  crop_resize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(img, sb, sc, sh, sw, rects, out, B, S, C, H, W, out_hw);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}

@@ -44,3 +44,19 @@ def density_from_dots(dots, counts, out_hw=(384, 384), scale=(1.0, 1.0), canvas_
                                          ctypes.c_void_p(wd.data_ptr()), r, float(gain), ctypes.c_void_p(tmp.data_ptr()),
                                          ctypes.c_void_p(out.data_ptr()), ops._stream()))
     return out
+
+
+def crop_resize_boxes(images, rects, out_hw=64):
+    """images: fp32 [B, C, H, W] on the device (any strides); rects: int32 [B, S, 4] = (y1, x1, y2, x2) inclusive, in pixels of
+    `images` (FSC147.py:287-296: the scaled exemplar boxes).  Returns fp32 [B, S, C, out_hw, out_hw] — the `boxes` input of
+    SupervisedMAE.forward — with torchvision 0.14.1's `transforms.Resize((64, 64))` arithmetic for tensors."""
+    assert images.is_cuda and images.dtype == torch.float32 and images.dim() == 4
+    assert rects.is_cuda and rects.dtype == torch.int32 and rects.dim() == 3 and rects.shape[0] == images.shape[0] and rects.shape[2] == 4
+    rects = rects.contiguous()
+    B, C, H, W = images.shape
+    S = rects.shape[1]
+    out = torch.empty(B, S, C, out_hw, out_hw, dtype=torch.float32, device=images.device)
+    sb, sc, sh, sw = images.stride()
+    check(lib().countr_crop_resize_boxes(ctypes.c_void_p(images.data_ptr()), sb, sc, sh, sw, ctypes.c_void_p(rects.data_ptr()),
+                                         ctypes.c_void_p(out.data_ptr()), B, S, C, H, W, out_hw, ops._stream()))
+    return out

@@ -287,6 +287,12 @@ int countr_density_from_dots(const double* dots, const int32_t* counts, int B, i
 int countr_weight_refresh(const void* entries, const int32_t* blk_prefix, int n_entries, int total_blocks, int bf16,
                           countr_stream_t stream);
 
+/* Exemplar crops (util/FSC147.py:285-298, 343-351): out[b][s] = Resize((out_hw, out_hw))(img[b][:, y1:y2+1, x1:x2+1]) with
+ * torchvision 0.14.1's tensor semantics (bilinear, align_corners=False, no antialias).  img: fp32, element strides
+ * (sb, sc, sh, sw); rects: int32 [B][S][4] = (y1, x1, y2, x2), inclusive, clipped to the image; out: fp32 [B][S][C][out_hw][out_hw]. */
+int countr_crop_resize_boxes(const float* img, int64_t sb, int64_t sc, int64_t sh, int64_t sw, const int32_t* rects, float* out,
+                             int B, int S, int C, int H, int W, int out_hw, countr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

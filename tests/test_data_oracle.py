@@ -76,3 +76,36 @@ def test_density_kernels_match_oracle(cuda, mode):
     both = density_from_dots(dd, cc, scale=(384.0 / 480, 384.0 / 640), sigma=4.0, radius=7)
     one = density_from_dots(dd[:1].contiguous(), cc[:1].contiguous(), scale=(384.0 / 480, 384.0 / 640), sigma=4.0, radius=7)
     assert torch.equal(both[0], one[0])
+
+
+def test_crop_resize_oracle_is_torchvision_without_antialias():
+    """The oracle's restatement equals torchvision's own Resize with antialias disabled (the 0.14.1 behaviour for tensors)."""
+    tv = pytest.importorskip("torchvision")
+    from torchvision import transforms
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(3, 120, 200, generator=g)
+    rects = [(10, 20, 57, 90), (0, 0, 119, 199), (30, 40, 33, 44), (100, 150, 119, 199)]
+    ref = D.crop_resize_boxes(img, rects)
+    for i, (y1, x1, y2, x2) in enumerate(rects):
+        tvb = transforms.Resize((64, 64), antialias=False)(img[:, y1:y2 + 1, x1:x2 + 1])
+        assert torch.allclose(ref[i], tvb, rtol=0, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_crop_resize_kernel_matches_oracle(cuda):
+    from countr_b200.data import crop_resize_boxes
+    g = torch.Generator().manual_seed(6)
+    imgs = torch.rand(3, 3, 384, 416, generator=g)
+    rects = torch.tensor([[[10, 20, 57, 90], [0, 0, 383, 415], [30, 40, 33, 44]],
+                          [[100, 150, 119, 199], [5, 5, 5, 5], [300, 350, 383, 415]],
+                          [[0, 0, 63, 63], [17, 3, 200, 9], [200, 100, 210, 300]]], dtype=torch.int32)
+    got = crop_resize_boxes(imgs.to(cuda), rects.to(cuda))
+    torch.cuda.synchronize()
+    assert got.shape == (3, 3, 3, 64, 64)
+    for b in range(3):
+        ref = D.crop_resize_boxes(imgs[b], [tuple(int(v) for v in r) for r in rects[b]])
+        assert torch.allclose(got[b].cpu(), ref, rtol=0, atol=2e-6), (b, (got[b].cpu() - ref).abs().max().item())
+    # a non-contiguous view (a 384-wide window of a wider image) gives the same crops as its contiguous copy
+    win = imgs.to(cuda)[:, :, :, 16:400]
+    r2 = torch.tensor([[[10, 20, 57, 90]], [[0, 0, 383, 383]], [[30, 40, 33, 44]]], dtype=torch.int32, device=cuda)
+    assert torch.equal(crop_resize_boxes(win, r2), crop_resize_boxes(win.contiguous(), r2))
