@@ -23,3 +23,16 @@ def cuda():
     from countr_b200 import _lib
     _lib.require_device()  # raises if the .so is missing or the device is not sm_100
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _deterministic_draws(request):
+    """Every test draws its random tensors from a seed derived from its own id: a threshold that holds for one draw and not
+    for another is a test bug, and the suite must give the same verdict on every fresh box."""
+    import zlib
+    import torch
+    seed = zlib.crc32(request.node.nodeid.encode()) & 0x7FFFFFFF
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+    yield
