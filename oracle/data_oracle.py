@@ -9,28 +9,30 @@ import numpy as np
 from scipy import ndimage
 
 
+def _dot_canvas(dots, H, W, new_H, new_W):
+    """One 1 per annotated point on the (new_H x new_W) resized canvas: row = min(new_H-1, int(y * new_H/H)), column likewise
+    (FSC147.py:263-265, 327-329).  Assignment, not accumulation: coincident points count once.  float64 products truncated
+    toward zero, exactly like Python's int() on the reference's numpy scalars."""
+    sh, sw = float(new_H) / H, float(new_W) / W
+    canvas = np.zeros((new_H, new_W), dtype=np.float32)
+    if len(dots):
+        d = np.asarray(dots, dtype=np.float64)
+        rows = np.minimum(new_H - 1, np.trunc(d[:, 1] * sh).astype(np.int64))
+        cols = np.minimum(new_W - 1, np.trunc(d[:, 0] * sw).astype(np.int64))
+        canvas[rows, cols] = 1
+    return canvas
+
+
 def train_density(dots, H, W, new_H, new_W, start, max_hw=384):
-    """FSC147.py:262-273.  dots: float64 [n, 2] (x, y) in original-image pixels; (H, W) original size."""
-    scale_factor_h = float(new_H) / H
-    scale_factor_w = float(new_W) / W
-    resized_density = np.zeros((new_H, new_W), dtype='float32')
-    for i in range(dots.shape[0]):
-        resized_density[min(new_H - 1, int(dots[i][1] * scale_factor_h))][min(new_W - 1, int(dots[i][0] * scale_factor_w))] = 1
-    reresized_density = resized_density[0:max_hw, start:start + max_hw]
-    reresized_density = ndimage.gaussian_filter(reresized_density, sigma=(1, 1), order=0)
-    return reresized_density * 60
+    """FSC147.py:262-273 (no-augmentation path).  dots: float64 [n, 2] (x, y) in original-image pixels; (H, W) original size;
+    the max_hw-wide window starting at column `start` is filtered with sigma = 1 (scipy's default truncate: radius 4)."""
+    window = _dot_canvas(dots, H, W, new_H, new_W)[:max_hw, start:start + max_hw]
+    return ndimage.gaussian_filter(window, sigma=(1, 1), order=0) * 60
 
 
 def val_density(dots, H, W, max_hw=384):
-    """FSC147.py:326-331."""
-    new_H = new_W = max_hw
-    scale_factor_h = float(new_H) / H
-    scale_factor_w = float(new_W) / W
-    resized_density = np.zeros((new_H, new_W), dtype='float32')
-    for i in range(dots.shape[0]):
-        resized_density[min(new_H - 1, int(dots[i][1] * scale_factor_h))][min(new_W - 1, int(dots[i][0] * scale_factor_w))] = 1
-    resized_density = ndimage.gaussian_filter(resized_density, sigma=4, radius=7, order=0)
-    return resized_density * 60
+    """FSC147.py:326-331: the whole image resized to max_hw x max_hw, sigma = 4 with an explicit radius of 7."""
+    return ndimage.gaussian_filter(_dot_canvas(dots, H, W, max_hw, max_hw), sigma=4, radius=7, order=0) * 60
 
 
 def crop_resize_boxes(resized_image, rects, out_hw=64):
