@@ -89,3 +89,30 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert "oracle" not in open(os.path.join(dirpath, f)).read(), f
+
+
+def test_decoder_weight_plan_covers_every_gemm_operand():
+    """The batched weight-refresh plan (Engine.decoder_weight_plan) must name every decoder weight that is consumed as a
+    16-bit GEMM / conv operand — a tensor missing from the plan falls back to a per-tensor refresh launch (and, before the
+    plan existed, fused optimizers left such copies stale).  Pure host logic: runs without a GPU."""
+    import models_mae_cross as M
+    from countr_b200.engine import Engine
+    m = M.SupervisedMAE(embed_dim=128, depth=1, num_heads=2, decoder_depth=2)
+    fp32_direct = {"decoder_proj1.0.weight", "decode_head3.3.weight"}       # direct conv / 1x1 dot kernels read the fp32 masters
+    names = {id(p): n for n, p in m.named_parameters()}
+    for shot, train in ((3, True), (0, True), (2, False), (0, False)):
+        plan = Engine.decoder_weight_plan(m, shot, train)
+        assert len(plan) == len({(id(p), k) for p, k in plan}), "duplicate (parameter, layout) in the plan"
+        kinds = {}
+        for p, k in plan:
+            kinds.setdefault(names[id(p)], set()).add(k)
+        want_w = [n for n, p in m.named_parameters()
+                  if p.ndim >= 2 and n not in fp32_direct and not n.startswith(("blocks.", "patch_embed.")) and "pos_embed" not in n
+                  and (shot > 0 or not n.startswith("decoder_proj"))]
+        for n in want_w:
+            fwd = "c0" if (n.startswith("decoder_proj") or n.startswith("decode_head")) else "w"
+            assert fwd in kinds.get(n, ()), (shot, train, n, kinds.get(n))
+            if train and n != "decoder_embed.weight":      # decoder_embed needs no dX: its input is the frozen encoder's output
+                assert ("c1" if fwd == "c0" else "wt") in kinds[n], (shot, train, n, kinds[n])
+        assert ("shot_token" in kinds) == (shot == 0)
+        assert not any(n.startswith(("blocks.", "patch_embed.")) for n in kinds), "encoder weights are frozen: not part of the per-step plan"
