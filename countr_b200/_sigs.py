@@ -1,5 +1,5 @@
 """argtypes / restype of the plain-argument entry points (include/countr_b200.h)."""
-from ctypes import c_double, c_float, c_int32, c_int64, c_void_p
+from ctypes import c_double, c_float, c_int32, c_int64, c_uint64, c_void_p
 
 P, I, L, F = c_void_p, c_int32, c_int64, c_float
 
@@ -32,12 +32,19 @@ SIGS = {
     "countr_mae_unshuffle": [P, P, P, P, P, I, I, I, I, P],
     "countr_mae_loss": [P, P, I, L, L, L, L, P, P, I, I, I, I, I, I, P],
     "countr_cast_scaled_f32_to_16": [P, P, P, L, I, P],
-    "countr_masked_mse": [P, I, P, P, P, P, I, I, I, F, P],
-    "countr_adamw_step": [P, I, P, I, P, P, P, P, F, F, F, F, F, P],
+    "countr_finetune_loss": [P, I, P, I, P, L, c_uint64, F, P, F, P, P, P, P, P, I, I, I, P],
+    "countr_grad_stats": [P, L, P, P, P],
+    "countr_adamw_update": [P, I, P, I, P, P, P, P, P, P, F, F, F, F, F, I, P],
     "countr_window_blend": [P, I, P, I, I, I, I, P, P],
     "countr_weight_refresh": [P, P, I, I, I, P],
     "countr_crop_resize_boxes": [P, L, L, L, L, P, P, I, I, I, I, I, I, P],
     "countr_density_from_dots": [P, P, I, I, c_double, c_double, I, I, I, I, I, I, P, I, F, P, P, P],
+}
+
+
+SIZE_QUERIES = {
+    "countr_finetune_loss_scratch_bytes": [I],
+    "countr_grad_stats_scratch_bytes": [],
 }
 
 
@@ -46,3 +53,7 @@ def declare(lib):
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = c_int32
+    for name, args in SIZE_QUERIES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = c_int64

@@ -17,7 +17,7 @@ all-reduce); they are returned to autograd, which accumulates them into `.grad` 
 import torch
 
 from . import ops
-from .dist import build_grad_arena
+from .dist import ARENA_TAIL, build_grad_arena, param_flag_index, usage_flags
 from .engine import F16, F32, _contig32
 
 
@@ -107,10 +107,12 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
     M = B * L
     Dd = m.decoder_embed.weight.shape[0]
 
-    # ---- flat gradient arena
-    names, params = m._decoder_params(shot_num)
-    arena, views = build_grad_arena(names, params, dev)
+    # ---- flat gradient arena: every decoder parameter (also the ones this shot_num does not reach, left at zero) + usage
+    # flags, so that all data-parallel ranks reduce the same layout whatever shot_num each of them drew (dist.py)
+    names, params = m._decoder_params(None)
+    arena, views = build_grad_arena(names, params, dev, tail=ARENA_TAIL)
     ops.zero_(arena)
+    arena[arena.numel() - ARENA_TAIL:].copy_(eng.usage_flags(shot_num, dev), non_blocking=True)
     grads = {"__names__": {id(p): n for n, p in zip(names, params)}}
     grads.update(views)
 
@@ -277,4 +279,13 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
     eng.last_arena = arena             # trainers that all-reduce outside the autograd node pick the arena up here
     if eng.grad_allreduce is not None:
         eng.grad_allreduce(arena)      # data-parallel mean of every decoder gradient in one collective
+        # DDP(find_unused_parameters=True) semantics for eager trainers: a parameter group this rank did not use but another
+        # rank did receives the averaged gradient too (autograd only returns gradients for this rank's own inputs).  Reading
+        # the two flags is a host sync; the graph-captured FineTuner path resolves them on the device instead.
+        flags = arena[arena.numel() - ARENA_TAIL:].tolist()
+        local = set(m._decoder_params(shot_num)[0])
+        for n, p in zip(names, params):
+            k = param_flag_index(n)
+            if k and n not in local and flags[k - 1] > 0:
+                p.grad = views[n].clone() if p.grad is None else p.grad + views[n]
     return grads

@@ -472,10 +472,9 @@ int launch_attention(const void* qkv, void* out, float* lse, int B, int L, int H
   if (rc) return rc;
   rc = make_tmap_4d_16b(&tkv, qkv, dims, str, boxk, sw);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     COUNTR_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<DH, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
-    attr_set = true;
   }
   AttnArgs p;
   p.out = reinterpret_cast<uint16_t*>(out);
@@ -791,10 +790,9 @@ extern "C" int countr_attention_bwd(const void* qkv, const void* out, const void
     if (rc) return rc;
   }
   constexpr uint32_t smem_bytes = 4 * kBwdMaxBlk * (128 * 32 * 2) + 2 * (128 * 128 * 2) + 64 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     COUNTR_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
   }
   AttnBwdArgs a;
   a.dO = reinterpret_cast<const uint16_t*>(dout);

@@ -835,10 +835,9 @@ extern "C" int countr_cross_attn_core_bwd(const void* q16, const float* k32, con
   COUNTR_REQUIRE(dh == 32 && D % 512 == 0 && S >= 1 && S <= kMaxShots && L % kTokPerBlock == 0,
                  "cross-attention backward supports dh=32, D%%512==0, S<=8, L%%32==0 (dh=%d D=%d S=%d L=%d)", dh, D, S, L);
   const size_t smem = (2ull * S * D + 2ull * kTokPerBlock * (D / 32) * S) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     COUNTR_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
   }
   COUNTR_REQUIRE(smem <= 96 * 1024, "shared memory %zu too large", smem);
   cross_attn_core_bwd_kernel<<<B * L / kTokPerBlock, 256, smem, stream>>>(

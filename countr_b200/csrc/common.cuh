@@ -65,6 +65,20 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE attribute: a call site remembers which devices it has
+// configured, so a second GPU driven from the same process gets its own call.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool need() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) return true;
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 // ---------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------

@@ -963,11 +963,10 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   }
   if (rc) return rc;
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     COUNTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     COUNTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
   }
   const int max_clusters = sms / p.cs;
   const int clusters = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;

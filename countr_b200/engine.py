@@ -92,7 +92,7 @@ class WeightCache:
         cast / transpose / pack launch per stale tensor — ~50 launches after every optimizer step of the fine-tune loop).
         The device job table is cached per set of stale tensors, so a steady training loop (and a CUDA-graph capture after
         warm-up) does no host-to-device traffic here."""
-        work = []
+        work, pending = [], []
         for p, kind in plan:
             key = (id(p), kind)
             ent = self.cache.get(key)
@@ -102,7 +102,7 @@ class WeightCache:
             code, shape, rc = self._job(p, kind)
             reuse = ent is not None and ent[2].device == p.device and ent[2].shape == torch.Size(shape)
             buf = ent[2] if reuse else torch.empty(shape, dtype=F16, device=p.device)
-            self.cache[key] = (weakref.ref(p), ver, buf)
+            pending.append((key, (weakref.ref(p), ver, buf)))      # committed only once the refresh kernel is enqueued
             work.append((p.data_ptr(), buf.data_ptr(), code, rc[0], rc[1]))
         if not work:
             return 0
@@ -125,7 +125,19 @@ class WeightCache:
                 self._tables.clear()
             self._tables[tkey] = tab
         ops.weight_refresh(tab[0], tab[1], tab[2], tab[3])
+        # a failed table build / launch raised above: the cache then still describes the old (stale, but initialised) copies
+        self.cache.update(pending)
         return len(work)
+
+    def invalidate(self, params=None):
+        """Out-of-band weight edits (EMA / weight averaging, `p.data.copy_()` on encoder weights, anything that neither moves
+        torch's version counter nor goes through a countr backward): mark the 16-bit copies of `params` (default: every
+        cached parameter) stale so the next forward re-casts them."""
+        if params is None:
+            for key in list(self.cache):
+                self.ext[key[0]] = self.ext.get(key[0], 0) + 1
+        else:
+            self.bump(params)
 
     def w16(self, p):
         """[N, K] row-major copy (B operand of y = x W^T)."""
@@ -161,13 +173,16 @@ class Engine:
         self.grad_allreduce = None
         self.last_arena = None          # flat fp32 gradient arena of the most recent backward
         self._side = {}                 # per-device side stream: the exemplar CNN runs concurrently with the encoder
+        self._flags = {}
         self.overlap_exemplar = True
         self.overlap_dw = True          # FIM weight / bias gradients on the side stream (backward.py)
 
     # ------------------------------------------------------------------ encoder
-    def encoder_forward(self, m, imgs):
+    def encoder_forward(self, m, imgs, keep=False):
         """m: SupervisedMAE-like module (patch_embed, pos_embed, blocks, norm).
-        Returns (latent fp32 [B, L, D], latent fp16 [B*L, D])."""
+        Returns (latent fp32 [B, L, D], latent fp16 [B*L, D]).  keep=True (training): the fp16 latent is saved for the decoder
+        backward (decoder_embed's weight gradient), so it gets its own buffer instead of the shared workspace slot that the next
+        forward — a validation pass, a second micro-batch, a sliding-window evaluation — would overwrite."""
         ops_ = ops
         dev = imgs.device
         B, C, Himg, Wimg = imgs.shape
@@ -200,9 +215,20 @@ class Engine:
             ops_.linear(h, wc.w16(blk.mlp.fc1.weight), u, bias=_contig32(blk.mlp.fc1.bias), act=1)
             ops_.linear(u, wc.w16(blk.mlp.fc2.weight), x, bias=_contig32(blk.mlp.fc2.bias), residual=x)
         lat32 = torch.empty(B, L, D, dtype=F32, device=dev)
-        lat16 = ws.get("lat16", (M, D), F16, dev)
+        lat16 = torch.empty(M, D, dtype=F16, device=dev) if keep else ws.get("lat16", (M, D), F16, dev)
         ops_.layernorm_fwd(x, _contig32(m.norm.weight), _contig32(m.norm.bias), m.norm.eps, y16=lat16, y32=lat32.view(M, D))
         return lat32, lat16
+
+    def usage_flags(self, shot_num, dev):
+        """Device constant written to the tail of the gradient arena (dist.usage_flags); built on first use, which must
+        happen outside CUDA-graph capture (the eager warm-up step)."""
+        from .dist import usage_flags
+        key = (str(dev), shot_num == 0)
+        t = self._flags.get(key)
+        if t is None:
+            t = torch.tensor(usage_flags(shot_num), dtype=F32, device=dev)
+            self._flags[key] = t
+        return t
 
     # ------------------------------------------------------------------ exemplar encoder
     def side_stream(self, dev):

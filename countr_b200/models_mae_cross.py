@@ -114,27 +114,32 @@ class SupervisedMAE(nn.Module):
 
     def _encode(self, imgs):
         self._check(imgs)
+        train = self._needs_grad()     # the backward keeps the 16-bit latent: it must not live in the shared workspace
         with torch.no_grad():
-            return engine().encoder_forward(self, imgs)
+            return engine().encoder_forward(self, imgs, keep=train)
 
     def forward_encoder(self, x):
         """[N,3,H,W] -> [N, L, D] (patch embed + pos + blocks + norm, models_mae_cross.py:136-148)."""
         lat32, _ = self._encode(x)
         return lat32 if x.dtype == F32 else lat32.to(x.dtype)
 
-    def _decoder_params(self, shot_num):
+    def _decoder_params(self, shot_num=None):
+        """Trainable decoder parameters in `named_parameters()` order; shot_num=None -> all of them (the gradient arena
+        layout), otherwise only the ones a step with `shot_num` exemplars reaches."""
         names, params = [], []
         for n, p in self.named_parameters():
             if not p.requires_grad or n.startswith(("patch_embed.", "blocks.", "norm.")):
                 continue
-            if (shot_num > 0 and n == "shot_token") or (shot_num == 0 and n.startswith("decoder_proj")):
+            if shot_num is not None and ((shot_num > 0 and n == "shot_token") or (shot_num == 0 and n.startswith("decoder_proj"))):
                 continue   # unused on this path: no gradient, like the reference (DDP find_unused_parameters)
             names.append(n)
             params.append(p)
         return names, params
 
     def _needs_grad(self):
-        return torch.is_grad_enabled() and any(p.requires_grad for p in self.decoder_embed.parameters())
+        if not torch.is_grad_enabled():
+            return False
+        return any(p.requires_grad for n, p in self.named_parameters() if not n.startswith(("patch_embed.", "blocks.", "norm.")))
 
     def _decode(self, lat16, y_, shot_num, B, out_dtype, pre=None):
         if self._needs_grad():

@@ -249,18 +249,49 @@ int countr_cast_scaled_f32_to_16(const float* src, const float* scale_ptr, void*
 /* ------------------------------------------------------------------------------------------
  * Script-side pieces of the fine-tune step as single kernels (used by countr_b200.train.FineTuner).
  * ------------------------------------------------------------------------------------------ */
-/* FSC_finetune_cross.py:290-295: loss = sum((out-gt)^2 * mask / (H*W)) / B  (mask [H][W] broadcast over the batch);
- * dout (optional, fp32 [B][H][W]) = d(loss * grad_scale)/d out */
-int countr_masked_mse(const void* out, int out_dtype, const float* gt, const float* mask, float* loss, float* dout, int B,
-                      int H, int W, float grad_scale, countr_stream_t stream);
-/* unscale + torch.optim.AdamW (decoupled weight decay, bias correction) over every tensor of a flat arena in one
- * launch.  tensors: device array of {float* param; int64 grad_off; int64 moment_off; int64 numel; float weight_decay;
- * int step_idx} (40 bytes);
- * chunks: device array of {int tensor, int chunk_of_1024}; step: device fp32 per-parameter step counters (incremented
- * here for the participating tensors, so the call is CUDA-graph replayable). */
-int countr_adamw_step(const void* tensors, int num_tensors, const void* chunks, int num_chunks, const float* grad,
-                      float* exp_avg, float* exp_avg_sq, float* step, float lr, float beta1, float beta2, float eps,
-                      float inv_scale, countr_stream_t stream);
+/* Device state block of the fused step (fp32[8], owned by the caller): [0] loss scale, [1] GradScaler growth tracker,
+ * [2] found_inf of the last countr_grad_stats (0/1), [3] global L2 norm of the UNSCALED gradients (util/misc.py:289-301
+ * get_grad_norm_), [4] learning rate, [5] step counter (drives the device-side mask draw).  Keeping these on the device
+ * lets a captured CUDA graph follow the lr schedule (lr_sched.adjust_learning_rate, FSC_finetune_cross.py:270) and the
+ * dynamic loss scale (torch.cuda.amp.GradScaler, util/misc.py:260-280) without re-capture. */
+#define COUNTR_ST_SCALE 0
+#define COUNTR_ST_GROWTH 1
+#define COUNTR_ST_FOUND_INF 2
+#define COUNTR_ST_GRAD_NORM 3
+#define COUNTR_ST_LR 4
+#define COUNTR_ST_STEP 5
+
+/* FSC_finetune_cross.py:290-303 in one launch.  out / gt: [B][H][W] of dtype code 0 fp32 / 1 fp16 / 2 bf16.
+ *   mask != NULL : fp32 keep-mask, element (b, i) at mask[b * mask_bstride + i] (mask_bstride 0 = one [H][W] mask tiled over
+ *                  the batch, as np.tile does at :291-293)
+ *   mask == NULL : the mask is drawn on the device, Bernoulli(keep_prob) per pixel, the same draw for every image of the
+ *                  batch, from a counter-based generator keyed by (seed, state[5], pixel); mask_out (optional, uint8
+ *                  [H][W]) receives it
+ *   result[0] = sum((out-gt)^2 * mask / (H*W)) / B;  result[1] = batch MAE and result[2] = batch MSE of the counts
+ *   counts (optional) [B][2] = {out.sum()/60, gt.sum()/60} per image (:298-303)
+ *   dout (optional, fp32 [B][H][W]) = d(loss * scale)/d out with scale = state[0] if state != NULL else grad_scale
+ * scratch: countr_finetune_loss_scratch_bytes(B) bytes, 8-byte aligned, its first 8 bytes zero before the first call.
+ * All reductions run in a fixed order (bit-reproducible). */
+int countr_finetune_loss(const void* out, int out_dtype, const void* gt, int gt_dtype, const float* mask, int64_t mask_bstride,
+                         uint64_t seed, float keep_prob, const float* state, float grad_scale, float* dout, uint8_t* mask_out,
+                         void* scratch, float* result, float* counts, int B, int H, int W, countr_stream_t stream);
+int64_t countr_finetune_loss_scratch_bytes(int B);
+/* GradScaler.unscale_ inf check + get_grad_norm_ over the flat (still scaled) gradient arena: state[2] = any non-finite,
+ * state[3] = ||grad||_2 / state[0].  scratch: countr_grad_stats_scratch_bytes() bytes, first 8 bytes zero before the first call. */
+int countr_grad_stats(const float* grad, int64_t n, void* scratch, float* state, countr_stream_t stream);
+int64_t countr_grad_stats_scratch_bytes(void);
+/* unscale + torch.optim.AdamW (decoupled weight decay, bias correction) over every tensor of a flat arena in one launch,
+ * then the per-parameter step counters and GradScaler.update().  Skipped entirely (parameters, moments and counters
+ * untouched, scale *= backoff_factor) when state[2] != 0; lr = state[4], 1/scale = 1/state[0].
+ * tensors: device array of {float* param; int64 grad_off; int64 moment_off; int64 numel; float weight_decay; int step_idx;
+ * int flag_idx; int pad} (48 bytes); a tensor with flag_idx k > 0 is updated only when flags[k-1] != 0 (flags: device
+ * floats, e.g. the tail of the all-reduced gradient arena saying which optional parameter groups were used on any rank —
+ * DDP(find_unused_parameters=True) semantics, FSC_finetune_cross.py:230).
+ * chunks: device array of {int tensor, int chunk_of_1024}; step: device fp32 per-parameter step counters.
+ * growth_interval <= 0 keeps the loss scale static. */
+int countr_adamw_update(const void* tensors, int num_tensors, const void* chunks, int num_chunks, const float* grad,
+                        const float* flags, float* exp_avg, float* exp_avg_sq, float* step, float* state, float beta1, float beta2,
+                        float eps, float growth_factor, float backoff_factor, int growth_interval, countr_stream_t stream);
 
 /* Sliding-window evaluation blend (demo.py:124-160; FSC_test_cross(few-shot).py:322-349): outs [nw][H][Wwin] are the
  * density maps of the windows at columns starts[i] (visited left to right); density [H][W] receives the running

@@ -165,6 +165,72 @@ def gen_curve(ref, out_dir):
     np.savez_compressed(os.path.join(out_dir, "small_curve.npz"), **res)
 
 
+def gen_base_b8(ref, out_dir):
+    """The benchmarked configuration itself (BASELINE configs[1]): base model, batch 8, 3 exemplars — density map,
+    encoder latent and every decoder gradient of the fine-tune loss from the UNMODIFIED reference (fp32, CPU)."""
+    cfg = synth.CONFIGS["base"]
+    sd = synth.make_state_dict(cfg, seed=0)
+    m = build_ref_model(ref, cfg, sd).train()
+    imgs, boxes = synth.make_inputs(8, seed=1234)
+    gt, mask = synth.make_targets(8, seed=4321)
+    with torch.no_grad():
+        latent = m.forward_encoder(imgs)
+    out = m(imgs, boxes, 3)
+    loss = O.finetune_loss(out, gt, mask)
+    loss.backward()
+    res = {"loss": loss.detach().numpy(), "out_pool8": pool8(out.detach()).numpy(), "out_sum": out.detach().sum((1, 2)).numpy(),
+           "out_rows": out.detach()[:, [0, 100, 383]].numpy(),
+           "latent_sub": latent[:, ::8, ::8].numpy(), "latent_rownorm": latent.norm(dim=-1).numpy(),
+           "latent_norm": latent.norm().numpy()}
+    tot = 0.0
+    for name, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        gflat = p.grad.flatten()
+        res[f"g/{name}/norm"] = gflat.norm().numpy()
+        res[f"g/{name}/sum"] = gflat.sum().numpy()
+        res[f"g/{name}/head"] = gflat[:16].numpy()
+        tot += float(gflat.double().norm() ** 2)
+    res["g_total_norm"] = np.array(tot ** 0.5)
+    np.savez_compressed(os.path.join(out_dir, "base_b8.npz"), **res)
+    print(f"base_b8: loss={loss.item():.6f} counts={(out.detach().sum((1, 2)) / 60).tolist()} |g|={tot ** 0.5:.6e}")
+
+
+NOCT_BASE = dict(img_size=384, patch_size=16, embed_dim=768, depth=12, num_heads=12, decoder_embed_dim=512, decoder_depth=8,
+                 decoder_num_heads=16, mlp_ratio=4, eps=1e-6)
+
+
+def gen_noct_base(ref, out_dir):
+    """MAE pre-training at the benchmarked geometry (models_mae_noct.mae_vit_base_patch16, BASELINE configs[4]), batch 4,
+    mask_ratio 0.5: loss, prediction summary and every parameter-gradient norm from the UNMODIFIED reference."""
+    from functools import partial
+    from oracle import noct_oracle as NO
+    cfg = NOCT_BASE
+    sd = NO.make_state_dict(cfg, seed=5)
+    m = ref.noct.MaskedAutoencoderViTNoCT(img_size=384, patch_size=16, embed_dim=cfg["embed_dim"], depth=cfg["depth"],
+                                          num_heads=cfg["num_heads"], decoder_embed_dim=512, decoder_depth=cfg["decoder_depth"],
+                                          decoder_num_heads=16, mlp_ratio=4, norm_layer=partial(nn.LayerNorm, eps=1e-6),
+                                          norm_pix_loss=False)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    imgs, _ = synth.make_inputs(4, seed=92)
+    torch.manual_seed(321)
+    loss, pred, mask = m(imgs, mask_ratio=0.5)
+    loss.backward()
+    out = {"loss": loss.detach().numpy(), "mask": mask.numpy(), "pred_rowsum": pred.detach().sum(-1).numpy(),
+           "pred_head": pred.detach()[:, :4, :64].numpy()}
+    tot = 0.0
+    for name, p in m.named_parameters():
+        if p.grad is not None:
+            out[f"g/{name}/norm"] = p.grad.norm().numpy()
+            out[f"g/{name}/head"] = p.grad.flatten()[:16].numpy()
+            tot += float(p.grad.double().norm() ** 2)
+    out["g_total_norm"] = np.array(tot ** 0.5)
+    np.savez_compressed(os.path.join(out_dir, "noct_base.npz"), **out)
+    print(f"noct_base: loss={loss.item():.6f} |g|={tot ** 0.5:.6e}")
+
+
 def pool8(x):
     return torch.nn.functional.avg_pool2d(x[:, None], 8)[:, 0]
 
@@ -177,6 +243,10 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     if "--curve-only" in sys.argv:
         return gen_curve(ref, out_dir)
+    if "--base-b8-only" in sys.argv:
+        return gen_base_b8(ref, out_dir)
+    if "--noct-base-only" in sys.argv:
+        return gen_noct_base(ref, out_dir)
 
     # ---- C1: base model, one image, 3 exemplars, eval, fp32 (demo.py path) ----
     cfg = synth.CONFIGS["base"]
@@ -223,6 +293,8 @@ def main():
     np.savez_compressed(os.path.join(out_dir, "small_grads.npz"), **grads)
     gen_noct(ref, out_dir)
     gen_curve(ref, out_dir)
+    gen_base_b8(ref, out_dir)
+    gen_noct_base(ref, out_dir)
     for f in sorted(os.listdir(out_dir)):
         print(f, os.path.getsize(os.path.join(out_dir, f)))
 

@@ -118,8 +118,8 @@ NOCT_SMALL = dict(img_size=384, patch_size=16, embed_dim=256, depth=2, num_heads
                   decoder_num_heads=16, mlp_ratio=4, eps=1e-6)
 
 
-def noct_noise(n, l):
-    torch.manual_seed(123)          # the reference's forward draws torch.rand(N, L) first (models_mae_noct.py:118)
+def noct_noise(n, l, seed=123):
+    torch.manual_seed(seed)         # the reference's forward draws torch.rand(N, L) first (models_mae_noct.py:118)
     return torch.rand(n, l)
 
 
@@ -142,3 +142,20 @@ def test_noct_oracle_matches_reference(norm_pix):
     for k in train:
         ref_norm = float(g[f"{tag}/g/{k}/norm"])
         assert abs(sd[k].grad.norm().item() - ref_norm) <= 1e-3 * ref_norm + 1e-9, k
+
+
+def test_oracle_matches_reference_at_the_benchmarked_config():
+    """tests/golden/base_b8.npz is the UNMODIFIED reference on the bench workload (base model, batch 8, 3 shots).  The images of
+    a batch are independent, so the oracle is pinned on the first two of them here (the GPU test pins the gradients)."""
+    g = np.load(os.path.join(GOLD, "base_b8.npz"))
+    cfg = synth.CONFIGS["base"]
+    sd = synth.make_state_dict(cfg, seed=0)
+    imgs, boxes = synth.make_inputs(8, seed=1234)
+    with torch.no_grad():
+        lat = O.forward_encoder(sd, cfg, imgs[:2])
+        out = O.forward(sd, cfg, imgs[:2], boxes[:2], 3)
+    pool = torch.nn.functional.avg_pool2d(out[:, None], 8)[:, 0]
+    assert rel(lat[:, ::8, ::8], g["latent_sub"][:2]) < 2e-5
+    assert rel(lat.norm(dim=-1), g["latent_rownorm"][:2]) < 2e-5
+    assert rel(pool, g["out_pool8"][:2]) < 2e-5
+    assert rel(out.sum((1, 2)), g["out_sum"][:2]) < 2e-5

@@ -12,22 +12,142 @@ from test_parity_gpu import build
 pytestmark = pytest.mark.gpu
 
 
-def test_masked_mse_and_adamw_kernels(cuda):
+def _loss_call(out, gt, mask, state=None, scale=1.0, seed=0, keep=0.8, want_mask=False, bstride=0):
     from countr_b200 import ops
     from countr_b200._lib import check, lib
-    B, H, W = 3, 96, 96
-    out = torch.randn(B, H, W, device=cuda, requires_grad=True)
-    gt = torch.rand(B, H, W, device=cuda)
-    mask = (torch.rand(H, W, device=cuda) < 0.8).float()
-    ref = ((out - gt) ** 2 * mask / (H * W)).sum() / B
-    (ref * 7.0).backward()
-    loss = torch.zeros((), device=cuda)
-    dout = torch.empty(B, H, W, device=cuda)
-    check(lib().countr_masked_mse(ctypes.c_void_p(out.data_ptr()), 0, ctypes.c_void_p(gt.data_ptr()), ctypes.c_void_p(mask.data_ptr()),
-                                  ctypes.c_void_p(loss.data_ptr()), ctypes.c_void_p(dout.data_ptr()), B, H, W, 7.0, ops._stream()))
+    B, H, W = out.shape
+    P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())     # noqa: E731
+    code = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+    dev = out.device
+    scratch = torch.zeros(int(lib().countr_finetune_loss_scratch_bytes(B)) // 8, dtype=torch.float64, device=dev)
+    result = torch.zeros(3, device=dev)
+    counts = torch.zeros(B, 2, device=dev)
+    dout = torch.empty(B, H, W, device=dev)
+    mask_out = torch.zeros(H, W, dtype=torch.uint8, device=dev) if want_mask else None
+    for _ in range(2):        # twice: the ticket must be left at zero for the next launch (CUDA-graph replay)
+        check(lib().countr_finetune_loss(P(out), code[out.dtype], P(gt), code[gt.dtype], P(mask), bstride, seed, keep, P(state), scale,
+                                         P(dout), P(mask_out), P(scratch), P(result), P(counts), B, H, W, ops._stream()))
     torch.cuda.synchronize()
-    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item()) + 1e-7
-    assert torch.allclose(dout, out.grad, rtol=1e-5, atol=1e-9)
+    return result, counts, dout, mask_out
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("per_image_mask", [False, True])
+def test_finetune_loss_kernel(cuda, dtype, per_image_mask):
+    """FSC_finetune_cross.py:290-303 in one launch: loss, its gradient, per-image counts, batch MAE / MSE."""
+    from oracle import train_oracle as TO
+    B, H, W = 3, 96, 96
+    out = torch.randn(B, H, W, device=cuda).to(dtype).requires_grad_(True)
+    gt = torch.rand(B, H, W, device=cuda).to(dtype)
+    mask = (torch.rand((B, H, W) if per_image_mask else (H, W), device=cuda) < 0.8).float()
+    ref, pred, gtc, mae, mse = TO.loss_and_counts(out.float(), gt.float(), mask)
+    (ref * 7.0).backward()
+    result, counts, dout, _ = _loss_call(out.detach(), gt, mask, scale=7.0, bstride=H * W if per_image_mask else 0)
+    assert abs(result[0].item() - ref.item()) < 1e-5 * abs(ref.item()) + 1e-7
+    assert torch.allclose(dout, out.grad.float(), rtol=1e-3 if dtype == torch.float16 else 1e-5, atol=1e-9)
+    assert torch.allclose(counts[:, 0], pred.detach(), rtol=1e-5, atol=1e-5) and torch.allclose(counts[:, 1], gtc, rtol=1e-5, atol=1e-5)
+    assert abs(result[1].item() - mae.item()) < 1e-4 * abs(mae.item()) + 1e-6
+    assert abs(result[2].item() - mse.item()) < 1e-4 * abs(mse.item()) + 1e-6
+
+
+def test_device_side_bernoulli_mask(cuda):
+    """mask == NULL: the Bernoulli(0.8) pixel mask (np.random.binomial at FSC_finetune_cross.py:290) is drawn on the device,
+    one draw per step shared by the batch; bit-identical to the numpy restatement, a fresh draw every step."""
+    from oracle import train_oracle as TO
+    B, H, W = 2, 384, 384
+    out = torch.randn(B, H, W, device=cuda)
+    gt = torch.rand(B, H, W, device=cuda)
+    state = torch.zeros(8, device=cuda)
+    state[0] = 512.0
+    masks = []
+    for step in (0, 1, 5):
+        state[5] = float(step)
+        result, counts, dout, mk = _loss_call(out, gt, None, state=state, seed=1234, want_mask=True)
+        want = torch.from_numpy(TO.bernoulli_mask(1234, step, H * W).reshape(H, W))
+        assert torch.equal(mk.cpu(), want)
+        ref = TO.loss_and_counts(out, gt, want.to(cuda).float())[0]
+        assert abs(result[0].item() - ref.item()) < 1e-5 * abs(ref.item())
+        assert torch.allclose(dout, 2 * (out - gt) * want.to(cuda).float() / (H * W * B) * 512.0, rtol=1e-5, atol=1e-9)
+        masks.append(want)
+    assert all(abs(m.float().mean().item() - 0.8) < 5e-3 for m in masks)
+    assert (masks[0] != masks[1]).float().mean() > 0.25          # independent draws differ on 2 * .8 * .2 = 32 % of the pixels
+
+
+def test_grad_stats_and_overflow_skip(cuda):
+    """util/misc.py:260-301: unscale_ + inf check + get_grad_norm_, optimizer step skipped and scale halved on overflow,
+    scale doubled after growth_interval clean steps; lr and the scale are read from the device state block."""
+    from countr_b200 import ops
+    from countr_b200._lib import check, lib
+    from oracle import train_oracle as TO
+    import numpy as np
+    P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())     # noqa: E731
+    n = 4 * 1000 + 8
+    ps = [torch.randn(1000, device=cuda), torch.randn(30, 100, device=cuda), torch.randn(8, device=cuda)]
+    flag_idx = [0, 0, 1]
+    arena = torch.zeros(n + 4, device=cuda)
+    offs = [0, 1000, 4000]
+    rec = np.zeros(3, dtype=np.dtype([("param", "<u8"), ("goff", "<i8"), ("moff", "<i8"), ("numel", "<i8"), ("wd", "<f4"),
+                                      ("step_idx", "<i4"), ("flag_idx", "<i4"), ("pad", "<i4")]))
+    chunks = []
+    for i, p in enumerate(ps):
+        rec[i] = (p.data_ptr(), offs[i], offs[i], p.numel(), 0.05 if p.ndim > 1 else 0.0, i, flag_idx[i], 0)
+        chunks += [(i, c) for c in range((p.numel() + 1023) // 1024)]
+    tensors = torch.from_numpy(rec.view(np.uint8).copy()).to(cuda)
+    chunks_t = torch.tensor(chunks, dtype=torch.int32, device=cuda)
+    m1, m2, steps = torch.zeros(n, device=cuda), torch.zeros(n, device=cuda), torch.zeros(3, device=cuda)
+    state = torch.zeros(8, device=cuda)
+    state[0], state[4] = 1024.0, 1e-3
+    scratch = torch.zeros(int(lib().countr_grad_stats_scratch_bytes()) // 8, dtype=torch.float64, device=cuda)
+    ref_p = [p.clone() for p in ps]
+    opt = torch.optim.AdamW([{"params": [ref_p[0], ref_p[2]], "weight_decay": 0.0}, {"params": [ref_p[1]], "weight_decay": 0.05}],
+                            lr=1e-3, betas=(0.9, 0.95))
+    scaler = TO.ScalerState(1024.0, interval=3)
+
+    def run(grads, flags, lr):
+        state[4] = lr
+        arena.zero_()
+        for g, o in zip(grads, offs):
+            arena[o:o + g.numel()] = g.flatten() * state[0]
+        arena[n:n + 4] = torch.tensor(flags, device=cuda)
+        check(lib().countr_grad_stats(P(arena), n, P(scratch), P(state), ops._stream()))
+        check(lib().countr_adamw_update(P(tensors), 3, P(chunks_t), len(chunks), P(arena), ctypes.c_void_p(arena.data_ptr() + 4 * n),
+                                        P(m1), P(m2), P(steps), P(state), 0.9, 0.95, 1e-8, 2.0, 0.5, 3, ops._stream()))
+        torch.cuda.synchronize()
+
+    g = torch.Generator(device="cpu").manual_seed(0)
+    plan = [("ok", 1e-3), ("inf", 1e-3), ("ok", 5e-4), ("ok", 5e-4), ("nan", 2e-4), ("ok", 2e-4), ("ok", 2e-4), ("ok", 2e-4), ("unused", 2e-4)]
+    for kind, lr in plan:
+        grads = [torch.randn(p.shape, generator=g).to(cuda) for p in ps]
+        flags = [1.0, 0.0, 0.0, 0.0]
+        if kind == "inf":
+            grads[1][3, 7] = float("inf")
+        if kind == "nan":
+            grads[0][11] = float("nan")
+        if kind == "unused":
+            flags[0] = 0.0
+            grads[2].zero_()                  # absent gradients are zero-filled in the arena
+        before = [p.clone() for p in ps]
+        scale_before = state[0].item()
+        run(grads, flags, lr)
+        bad = kind in ("inf", "nan")
+        assert bool(state[2].item()) == bad
+        if bad:
+            assert all(torch.equal(a, b) for a, b in zip(ps, before)), "an overflowed step must not touch the parameters"
+        else:
+            want = TO.grad_norm(grads if kind != "unused" else grads[:2]).item()
+            assert abs(state[3].item() - want) < 1e-4 * want
+            for grp in opt.param_groups:
+                grp["lr"] = lr
+            for rp, gg in zip(ref_p, grads):
+                rp.grad = gg.clone()
+            if kind == "unused":
+                ref_p[2].grad = None          # DDP find_unused_parameters: no gradient anywhere -> the optimizer skips it
+            opt.step()
+            for a, b in zip(ps, ref_p):
+                assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+        scaler.update(bad)
+        assert state[0].item() == scaler.scale, (kind, state[0].item(), scaler.scale, scale_before)
+    assert steps.tolist() == [7.0, 7.0, 6.0] and state[5].item() == len(plan)
 
 
 @pytest.mark.parametrize("shots", [[3, 3, 3], [3, 0, 2]])
