@@ -41,6 +41,12 @@ static EncodeTiledFn get_encode() {
 
 int make_tmap_4d_16b(CUtensorMap* out, const void* base, const uint64_t dims[4],
                      const uint64_t strides[4], const uint32_t box[4], TmapSwizzle swizzle) {
+  return make_tmap_4d(out, base, 2, dims, strides, box, swizzle);
+}
+
+int make_tmap_4d(CUtensorMap* out, const void* base, int elt_bytes, const uint64_t dims[4], const uint64_t strides[4],
+                 const uint32_t box[4], TmapSwizzle swizzle) {
+  COUNTR_REQUIRE(elt_bytes == 2 || elt_bytes == 4, "tensor map element size %d unsupported", elt_bytes);
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(COUNTR_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   COUNTR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0, "tensor map base %p not 16-byte aligned", base);
@@ -53,7 +59,7 @@ int make_tmap_4d_16b(CUtensorMap* out, const void* base, const uint64_t dims[4],
                    (unsigned long long)dims[i], box[i]);
   }
   for (int i = 1; i < 4; ++i) {
-    gstr[i - 1] = strides[i] * 2ull;  // bytes
+    gstr[i - 1] = strides[i] * static_cast<unsigned long long>(elt_bytes);  // bytes
     COUNTR_REQUIRE((gstr[i - 1] & 15ull) == 0, "tensor map stride %d (%llu B) not a multiple of 16 B", i,
                    (unsigned long long)gstr[i - 1]);
   }
@@ -61,7 +67,7 @@ int make_tmap_4d_16b(CUtensorMap* out, const void* base, const uint64_t dims[4],
                           : swizzle == TMAP_SW_64 ? CU_TENSOR_MAP_SWIZZLE_64B
                           : swizzle == TMAP_SW_32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                                   : CU_TENSOR_MAP_SWIZZLE_NONE;
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), gdim, gstr, bx, es,
+  CUresult r = enc(out, elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstr, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)

@@ -49,15 +49,19 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kStages = 4;
+constexpr int kMaxStages = 8;
 constexpr int kMaxBN = 256;
 constexpr uint32_t kABytes = BM * BK * 2;       // 16 KB
-constexpr uint32_t kBBytes = kMaxBN * BK * 2;   // 32 KB
-constexpr uint32_t kStageBytes = kABytes + kBBytes;
-constexpr int kEpiWarps = 8;                     // 2 per TMEM lane quarter: they split the 32-column chunks
+constexpr int kEpiWarps = 8;                     // 2 per TMEM lane quarter: they split the column chunks
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr uint32_t kStageBufBytes = 32 * 32 * 4;  // per epilogue warp: one 32 x 32 fp32 chunk, XOR-swizzled (transpose staging)
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * kStageBufBytes;
+constexpr uint32_t kEpiBufBytes = 32 * 128;      // one epilogue staging buffer: 32 rows x 128 bytes (XOR / SWIZZLE_128B layout)
+// Dynamic shared memory (the 227 KB opt-in maximum), laid out by the host per launch (GemmArgs):
+//   [0, nstages * stage_bytes)                    operand ring: A 16 KB + B bn x 128 B per stage (pair mode: half of B)
+//   [epi_off, + 8 warps * nbuf * 4 KB)            epilogue staging, 1024-byte aligned (TMA SWIZZLE_128B source / destination)
+//   [kBarOff, + 512)                              mbarriers + TMEM base address
+constexpr uint32_t kSmemBytes = 232448;
+constexpr uint32_t kBarOff = kSmemBytes - 1024 /*alignment slack*/ - 512;
+constexpr uint32_t kPairStageBytes = 32768;
 
 struct GemmArgs {
   int M, N, K;
@@ -68,6 +72,11 @@ struct GemmArgs {
   int split_k, k_per_split;
   int m_tiles, n_tiles, total_tiles;   // total_tiles counts CLUSTER tiles (cs consecutive m tiles x one n tile)
   int epi64;                           // 1: 16-bit outputs drain 64 columns per round (COUNTR_EPI64=0 turns it off for A/B runs)
+  int nstages, stage_bytes;            // operand ring
+  int epi_off, nbuf;                   // epilogue staging: offset, buffers per epilogue warp (1 or 2)
+  int epi_mode;                        // 0: LSU stores (all modes); 1: 16-bit tile through TMA stores; 2: fp32 tile through TMA
+                                       // stores / reduce-adds, residual through TMA loads
+  int box_x;                           // conv: x extent of one warp's 32-pixel store box
   int pair;                            // 1: CTA pair (cta_group::2): 256 x bn tile over two SMs, 6 stages of 32 KB
   int cs, m_groups;                    // cluster size (CTAs sharing the B tile via TMA multicast), ceil(m_tiles / cs)
   // conv mode
@@ -124,18 +133,18 @@ __device__ __forceinline__ float2 unpack_16b(uint32_t v, int bf16) {
 template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const GemmArgs p) {
+            const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // 192 KB of operand stages: 4 x (A 16 KB + B 32 KB), or in pair mode 6 x (A 16 KB + half of B 16 KB)
-  const int nstages = kPair ? 6 : kStages;
-  const uint32_t stage_bytes = kPair ? 32768u : kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* full = bars;                 // [6]
-  uint64_t* empty = bars + 6;            // [6]
-  uint64_t* tmem_full = bars + 12;       // [2]
-  uint64_t* tmem_empty = bars + 14;      // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+  const int nstages = p.nstages;
+  const uint32_t stage_bytes = p.stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
+  uint64_t* full = bars;                 // [8]
+  uint64_t* empty = bars + 8;            // [8]
+  uint64_t* tmem_full = bars + 16;       // [2]
+  uint64_t* tmem_empty = bars + 18;      // [2]
+  uint64_t* res_full = bars + 20;        // [8 warps][2 buffers]: residual chunk landed (epi_mode 2)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 36);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -156,6 +165,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], kPair ? 2 * kEpiWarps : kEpiWarps);   // pair: the leader waits for both CTAs' epilogues
     }
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_full[i], 1);
+    if (p.epi_mode != 0) tma_prefetch_desc(&tma_c);
+    if (p.epi_mode == 2 && p.residual != nullptr) tma_prefetch_desc(&tma_r);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -362,13 +374,231 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     // output row, a warp instruction touches 4 lines.  All elementwise work happens in the coalesced mapping.
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
     const int egroup = (warp - 2) >> 2;  // which share of the column chunks this warp drains
-    const uint32_t stg = smem_u32(smem + kStages * kStageBytes + 256) + (warp - 2) * kStageBufBytes;   // shared-space address
+    const uint32_t stg = smem_u32(smem + p.epi_off) + (warp - 2) * p.nbuf * kEpiBufBytes;   // shared-space address (1024-aligned)
     const int rr = lane >> 3, c4 = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
     int trt = 0;
+    uint64_t* const my_res = res_full + 2 * (warp - 2);
+    uint32_t nst = 0;          // staging rounds of this warp so far (buffer = nst % nbuf); warp-uniform
+    uint32_t res_uses[2] = {0, 0};   // residual loads consumed per staging buffer (mbarrier phase bookkeeping)
     for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
       const TileCoord t = decode_tile(p, tile, rank);
+      if (p.epi_mode != 0) {
+        // =========================== TMA epilogue ===========================
+        // Everything happens in the TMEM mapping (lane == accumulator row): bias / GELU / GroupNorm statistics / residual
+        // add on the registers tcgen05.ld delivers, the row is written into a SWIZZLE_128B staging buffer (32 rows x 128 B per
+        // warp, conflict-free: 16-byte chunk q of row r sits at chunk q ^ (r & 7)) and ONE elected lane hands the 4 KB box to
+        // the TMA unit (UTMASTG), which also clips row / column tails.  No transpose read-back, no per-row address
+        // arithmetic, no LSU global stores; the next round's TMEM read overlaps the store.
+        const int n0 = t.n * p.bn;
+        const bool first_split = (t.s == 0);
+        const int r_in_tile = quarter * 32 + lane;
+        int c1, c2v, c3;       // tensor-map coordinates 1..3 of this warp's 32-row box
+        bool row_ok;
+        if (p.conv == 1) {
+          const int x0 = (t.m % p.tiles_x) * p.bx, y0 = (t.m / p.tiles_x) * p.by;
+          c1 = x0 + (quarter * 32) % p.bx;
+          c2v = y0 + (quarter * 32) / p.bx;
+          c3 = t.b1;
+          row_ok = (x0 + r_in_tile % p.bx < p.W) && (y0 + r_in_tile / p.bx < p.H);
+        } else {
+          c1 = t.m * BM + quarter * 32;
+          c2v = t.b2;
+          c3 = t.b1;
+          row_ok = c1 + lane < p.M;
+        }
+        const bool use_bias = p.bias != nullptr && first_split;
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
+        const uint32_t rowoff = static_cast<uint32_t>(lane) * 128u;
+        if (p.epi_mode == 1) {
+          if (tile == cluster_id) pdl_wait();   // bias comes from earlier kernels; C may still be read by them
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kMaxBN;
+          for (int cc = egroup; cc < p.bn / 64; cc += kEpiWarps / 4) {
+            const int col0 = n0 + cc * 64;
+            if (col0 >= p.N) break;
+            float4 bq[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (use_bias) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+            }
+            uint32_t r[2][32];
+            tmem_ld_32x32b_x32(t_row + cc * 64, r[0]);
+            tmem_ld_32x32b_x32(t_row + cc * 64 + 32, r[1]);
+            tmem_ld_wait();
+            const uint32_t buf = stg + (nst % p.nbuf) * kEpiBufBytes;
+            if (nst >= static_cast<uint32_t>(p.nbuf)) {      // the store that last used this buffer has read it
+              if (lane == 0) { if (p.nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+              __syncwarp();
+            }
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] = fmaf(__uint_as_float(r[hf][4 * j]), p.alpha, bq[j].x);
+                v[4 * j + 1] = fmaf(__uint_as_float(r[hf][4 * j + 1]), p.alpha, bq[j].y);
+                v[4 * j + 2] = fmaf(__uint_as_float(r[hf][4 * j + 2]), p.alpha, bq[j].z);
+                v[4 * j + 3] = fmaf(__uint_as_float(r[hf][4 * j + 3]), p.alpha, bq[j].w);
+              }
+              if (hf == 0 && use_bias) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 32 + 4 * j));
+              }
+              if (p.gn_stats != nullptr) {
+                float s1 = 0.f, s2 = 0.f;
+                if (row_ok) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) {
+                    s1 += v[j];
+                    s2 = fmaf(v[j], v[j], s2);
+                  }
+                }
+                s1 = warp_sum(s1);
+                s2 = warp_sum(s2);
+                if (lane == 0) {
+                  double* st = p.gn_stats + (static_cast<long long>(t.b1) * (p.N / 32) + (col0 + hf * 32) / 32) * 2;
+                  atomicAdd(st, static_cast<double>(s1));
+                  atomicAdd(st + 1, static_cast<double>(s2));
+                }
+              }
+              if (p.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  const float2 gq = gelu_erf2(make_float2(v[j], v[j + 1]));
+                  v[j] = gq.x;
+                  v[j + 1] = gq.y;
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint32_t w0, w1, w2, w3;
+                if (p.bf16) {
+                  w0 = pack_16b(v[8 * q], v[8 * q + 1], 1); w1 = pack_16b(v[8 * q + 2], v[8 * q + 3], 1);
+                  w2 = pack_16b(v[8 * q + 4], v[8 * q + 5], 1); w3 = pack_16b(v[8 * q + 6], v[8 * q + 7], 1);
+                } else {
+                  w0 = pack_16b(v[8 * q], v[8 * q + 1], 0); w1 = pack_16b(v[8 * q + 2], v[8 * q + 3], 0);
+                  w2 = pack_16b(v[8 * q + 4], v[8 * q + 5], 0); w3 = pack_16b(v[8 * q + 6], v[8 * q + 7], 0);
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + rowoff + (((hf * 4 + q) ^ sw) << 4)),
+                             "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                             : "memory");
+              }
+            }
+            fence_proxy_async_smem();      // generic-proxy writes of this lane -> visible to the TMA unit
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tma_c, buf, col0, c1, c2v, c3);
+              bulk_commit();
+            }
+            ++nst;
+          }
+        } else {
+          // ---------------- fp32 tile: 32 columns (128 bytes per row) per round; optional residual (TMA-loaded into the
+          // staging buffer ahead of time, added in place) and split-K accumulation (TMA reduce-add)
+          const bool use_res = p.residual != nullptr && first_split;
+          const int nchunks = min(p.bn, p.N - n0) / 32;
+          const int mine = nchunks > egroup ? (nchunks - egroup + 1) / 2 : 0;       // chunks egroup, egroup + 2, ...
+          if (tile == cluster_id) pdl_wait();   // residual / bias come from earlier kernels; C may still be read by them
+          const uint32_t nst0 = nst;           // round counter at the start of this tile: chunk k uses buffer (nst0 + k) % nbuf
+          auto load_res = [&](int k) {          // lane 0: residual chunk k of this warp -> its staging buffer
+            const uint32_t b = (nst0 + static_cast<uint32_t>(k)) % p.nbuf;
+            mbar_arrive_expect_tx(&my_res[b], kEpiBufBytes);
+            tma_load_4d(smem + p.epi_off + ((warp - 2) * p.nbuf + b) * kEpiBufBytes, &tma_r, &my_res[b],
+                        n0 + (egroup + 2 * k) * 32, c1, c2v, c3);
+          };
+          if (use_res && mine > 0) {            // issued BEFORE the accumulator is waited for: lands during the main loop
+            if (lane == 0) {
+              bulk_wait_read<0>();              // the previous tile's stores have read both buffers
+              load_res(0);
+              if (p.nbuf == 2 && mine > 1) load_res(1);
+            }
+            __syncwarp();
+          }
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kMaxBN;
+          for (int k = 0; k < mine; ++k) {
+            const int col0 = n0 + (egroup + 2 * k) * 32;
+            const uint32_t bsel = (nst0 + static_cast<uint32_t>(k)) % p.nbuf;
+            const uint32_t buf = stg + bsel * kEpiBufBytes;
+            float4 bq[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (use_bias) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+            }
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + (egroup + 2 * k) * 32, r);
+            if (use_res) {
+              // the store of round k-1 has read its buffer -> refill it with the residual of chunk k-1+nbuf
+              if (k >= 1 && k - 1 + p.nbuf < mine) {
+                if (lane == 0) {
+                  bulk_wait_read<0>();
+                  load_res(k - 1 + p.nbuf);
+                }
+                __syncwarp();
+              }
+              mbar_wait(&my_res[bsel], res_uses[bsel] & 1u);
+              ++res_uses[bsel];
+            } else if (nst0 + k >= static_cast<uint32_t>(p.nbuf)) {
+              if (lane == 0) { if (p.nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+              __syncwarp();
+            }
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j] = fmaf(__uint_as_float(r[4 * j]), p.alpha, bq[j].x);
+              v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), p.alpha, bq[j].y);
+              v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), p.alpha, bq[j].z);
+              v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), p.alpha, bq[j].w);
+            }
+            if (use_res) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float4 rv;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(rv.x), "=f"(rv.y), "=f"(rv.z), "=f"(rv.w)
+                             : "r"(buf + rowoff + ((static_cast<uint32_t>(q) ^ sw) << 4))
+                             : "memory");
+                v[4 * q] += rv.x; v[4 * q + 1] += rv.y; v[4 * q + 2] += rv.z; v[4 * q + 3] += rv.w;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(buf + rowoff + ((static_cast<uint32_t>(q) ^ sw) << 4)),
+                           "f"(v[4 * q]), "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
+                           : "memory");
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (p.atomic) tma_reduce_add_4d(&tma_c, buf, col0, c1, c2v, c3);
+              else tma_store_4d(&tma_c, buf, col0, c1, c2v, c3);
+              bulk_commit();
+            }
+          }
+          nst = nst0 + static_cast<uint32_t>(mine);
+        }
+        // accumulator drained (it lives in registers / shared memory now): hand the TMEM stage back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kPair && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+          else mbar_arrive(&tmem_empty[acc]);
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      }
+      // =========================== LSU epilogue (every mode) ===========================
       // rows handled by this lane in the coalesced mapping: r_in_tile = quarter*32 + 4*it + rr, it = 0..7
       int rowi[8];            // logical row (residual / aux addressing); c_off = cbase + rowi * ldc
       uint32_t vmask = 0;
@@ -778,6 +1008,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
   }
 
+  if (p.epi_mode != 0 && warp >= 2 && lane == 0) bulk_wait_all<0>();   // this warp's TMA stores have been performed
   tc_fence_before();
   if (p.cs > 1) cluster_sync_all(); else __syncthreads();   // no peer may still signal this CTA's barriers after it exits
   if (threadIdx.x == 0) TR(3);
@@ -963,6 +1194,61 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   }
   if (rc) return rc;
 
+  // ---- epilogue mode: TMA stores wherever the tile is plain (see the kernel), LSU stores for the rest
+  static int epi_tma = -1;
+  if (epi_tma < 0) {
+    const char* e = getenv("COUNTR_EPI_TMA");
+    epi_tma = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  const int c_elt = d->out_f32 ? 4 : 2;
+  const long long sc1e = d->sc1, sc2e = d->sc2;
+  const bool c_strides_ok = (d->ldc * c_elt) % 16 == 0 && (nb1 <= 1 || conv || (sc1e * c_elt) % 16 == 0) &&
+                            (nb2 <= 1 || conv || (sc2e * c_elt) % 16 == 0) && (!conv || (sc1e * c_elt) % 16 == 0);
+  p.epi_mode = 0;
+  if (epi_tma && c_strides_ok && d->aux == nullptr) {
+    if (!d->out_f32 && d->residual == nullptr && !d->atomic && bn % 64 == 0 && d->N % 64 == 0 && (d->act == 0 || d->act == 1)) p.epi_mode = 1;
+    else if (d->out_f32 && d->act == 0 && d->gn_stats == nullptr && d->res_mod == 0 && d->N % 32 == 0 &&
+             (d->residual == nullptr || ((d->ldr * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->residual) & 15u) == 0 && !d->atomic &&
+                                         nb1 * nb2 == 1 && !conv)))
+      p.epi_mode = 2;
+  }
+  // ---- shared-memory layout
+  p.stage_bytes = p.pair ? static_cast<int>(kPairStageBytes) : static_cast<int>(kABytes) + bn * 128;
+  p.nbuf = 2;
+  int room = static_cast<int>(kBarOff) - kEpiWarps * p.nbuf * static_cast<int>(kEpiBufBytes);
+  if (room / p.stage_bytes < 4) {          // keep at least four operand stages: one staging buffer per warp instead
+    p.nbuf = 1;
+    room = static_cast<int>(kBarOff) - kEpiWarps * static_cast<int>(kEpiBufBytes);
+  }
+  p.nstages = room / p.stage_bytes;
+  if (p.nstages > kMaxStages) p.nstages = kMaxStages;
+  p.epi_off = p.nstages * p.stage_bytes;    // stage_bytes is a multiple of 4096: the staging area stays 1024-byte aligned
+  p.box_x = conv ? (p.bx < 32 ? p.bx : 32) : 32;
+
+  CUtensorMap tc = ta, tr = ta;             // placeholders when unused (never dereferenced)
+  if (p.epi_mode != 0) {
+    const uint32_t bcols = d->out_f32 ? 32u : 64u;
+    if (conv) {
+      const uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->conv_w, (uint64_t)d->conv_h, (uint64_t)nb1};
+      const uint64_t str[4] = {1, (uint64_t)d->ldc, (uint64_t)d->ldc * d->conv_w, (uint64_t)d->sc1};
+      const uint32_t box[4] = {bcols, (uint32_t)p.box_x, (uint32_t)(32 / p.box_x), 1};
+      rc = make_tmap_4d(&tc, d->c, c_elt, dims, str, box, TMAP_SW_128);
+    } else {
+      const uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->M, (uint64_t)nb2, (uint64_t)nb1};
+      const uint64_t str[4] = {1, (uint64_t)d->ldc, (uint64_t)(nb2 > 1 ? d->sc2 : d->ldc), (uint64_t)(nb1 > 1 ? d->sc1 : d->ldc)};
+      const uint32_t box[4] = {bcols, 32, 1, 1};
+      rc = make_tmap_4d(&tc, d->c, c_elt, dims, str, box, TMAP_SW_128);
+    }
+    if (rc) return rc;
+    if (p.epi_mode == 2 && d->residual != nullptr) {
+      const uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->M, 1, 1};
+      const uint64_t str[4] = {1, (uint64_t)d->ldr, (uint64_t)d->ldr, (uint64_t)d->ldr};
+      const uint32_t box[4] = {32, 32, 1, 1};
+      rc = make_tmap_4d(&tr, d->residual, 4, dims, str, box, TMAP_SW_128);
+      if (rc) return rc;
+    }
+  }
+
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
     COUNTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -984,7 +1270,7 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = p.cs > 1 ? 2 : 1;   // plain (non-cluster) launch path for single-CTA tiles
-  if (p.pair) COUNTR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<true>, ta, tb, p));
-  else COUNTR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<false>, ta, tb, p));
+  if (p.pair) COUNTR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<true>, ta, tb, tc, tr, p));
+  else COUNTR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<false>, ta, tb, tc, tr, p));
   return COUNTR_OK;
 }

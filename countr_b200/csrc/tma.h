@@ -20,6 +20,10 @@ enum TmapSwizzle : int { TMAP_SW_NONE = 0, TMAP_SW_32 = 1, TMAP_SW_64 = 2, TMAP_
 int make_tmap_4d_16b(CUtensorMap* out, const void* base, const uint64_t dims[4],
                      const uint64_t strides[4], const uint32_t box[4], TmapSwizzle swizzle);
 
+// Same for any element size (2: 16-bit payload, 4: fp32 — the fp32 type matters for TMA reduce-add stores).
+int make_tmap_4d(CUtensorMap* out, const void* base, int elt_bytes, const uint64_t dims[4], const uint64_t strides[4],
+                 const uint32_t box[4], TmapSwizzle swizzle);
+
 int num_sms();
 
 }  // namespace countr

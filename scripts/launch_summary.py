@@ -1,17 +1,18 @@
 """Summarise an ncu launch list (--metrics gpu__time_duration.sum --csv) of `bench.py --steps 1 --no-graph`:
-the last fine-tune step (from the last patchify launch on), per-kernel totals and the phase boundaries."""
+the last fine-tune step — from its weight_refresh launch (the first kernel of a step: the decoder weight re-cast and the
+exemplar CNN run on the side stream BEFORE the encoder's patchify) to the optimizer update — per-kernel totals."""
 import csv, sys, collections
 
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]
 hdr, rows = rows[0], rows[1:]
 ki, vi, gi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Metric Unit")
 seq = [(r[ki], r[gi], float(r[vi].replace(",", "")) * (1e-3 if r[ui].startswith("n") else 1.0)) for r in rows]
-starts = [i for i, s in enumerate(seq) if "patchify" in s[0]]
+starts = [i for i, s in enumerate(seq) if "weight_refresh" in s[0]] or [i for i, s in enumerate(seq) if "patchify" in s[0]]
 step = seq[starts[-1]:]
 # cut the per-kernel timing loop / input generation that follows the step
 end = len(step)
 for i, s in enumerate(step):
-    if "multi_tensor_apply" in s[0]:
+    if "multi_tensor_apply" in s[0] or "adam_finish" in s[0]:
         end = i + 1
 step = step[:end]
 verbose = len(sys.argv) > 2

@@ -48,16 +48,20 @@ def test_reference_script_loop_runs_unchanged(cuda, tmp_path):
         assert 0 < x["n_grads"] < n_all
     dev32 = [abs(x["loss32"] - g["loss"][i]) / g["loss"][i] for i, x in enumerate(applied)]
     dev16 = [abs(x["loss16"] - g["loss"][i]) / g["loss"][i] for i, x in enumerate(applied)]
-    cdev = [float(np.abs(np.array(x["count"]) - g["count"][i]).max() / np.abs(g["count"][i]).max()) for i, x in enumerate(applied)]
+    cscale = float(np.abs(g["count"]).max())        # the counts swing through zero along the curve: deviations relative to their range
+    cdev = [float(np.abs(np.array(x["count"]) - g["count"][i]).max() / cscale) for i, x in enumerate(applied)]
     print("\n[script loop] relative loss deviation per applied step (fp32 restatement of the fp16 map):", " ".join(f"{d:.1e}" for d in dev32))
     print("[script loop] same for the script's own fp16 loss expression:", " ".join(f"{d:.1e}" for d in dev16))
-    print("[script loop] relative count deviation per step:", " ".join(f"{d:.1e}" for d in cdev))
+    print("[script loop] count deviation per step, relative to the largest |count| of the curve:", " ".join(f"{d:.1e}" for d in cdev))
     assert max(dev32[:2]) < 4e-3          # fp16 density map (5e-4 per pixel) on top of the 1e-3 map tolerance
     assert max(dev32) < 2e-2              # 16 AdamW steps later
     assert max(dev16) < 5e-2              # the script's fp16 loss sums pixel terms quantised to the fp16 subnormal grid
     assert max(cdev) < 5e-3
     worst = (0.0, "")
     for n, d in res["deltas"].items():
+        if n.endswith((".attn.wk.bias", ".selfattn.qkv.bias")) or (n.startswith("decoder_proj") and n.endswith(".bias")):
+            continue      # (partly) exactly-zero true gradient — key bias under the softmax shift, conv bias in front of InstanceNorm:
+                          # Adam turns pure rounding noise into full-size steps there
         gold = float(g[f"final/{n}/delta_norm"])
         if gold == 0.0:
             assert d == 0.0, n                 # frozen encoder
