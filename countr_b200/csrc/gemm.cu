@@ -193,6 +193,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     int stage = 0;
     uint32_t phase = 0;
     int trk = 0;
+    if (!kPair && p.conv == 0 && p.cs == 1 && p.a_mn == p.b_mn) {
+      // ---- fast paths: plain Linear (both operands K-major) and dW = dY^T X (both MN-major), single CTA.  The general
+      // loop below evaluates every mode per k-block (~100 instructions, ~390 clk per k-block measured): fine under a
+      // 128 x 256 tile (512 clk of MMA per k-block) but it starves the tensor pipe at N tiles of 128 / 64 (256 / 128 clk).
+      const bool mn = p.a_mn != 0;
+      const int nboxb = p.bn >> 6;
+      const uint32_t tx = kABytes + b_bytes;
+      for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+        const TileCoord t = decode_tile(p, tile, rank);
+        const int k_begin = t.s * p.k_per_split;
+        const int k_end = min(p.K, k_begin + p.k_per_split);
+        const int nkb = (k_end - k_begin + BK - 1) / BK;
+        const int m0 = t.m * BM, n0 = t.n * p.bn;
+        if (tile == cluster_id) pdl_wait();   // first tile: the operands come from earlier kernels
+        int k = k_begin;
+        for (int kb = 0; kb < nkb; ++kb, k += BK) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          TR(16 + trk); ++trk;
+          uint8_t* sa = smem + stage * stage_bytes;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[stage], tx);
+            if (!mn) {
+              tma_load_4d(sa, &tma_a, &full[stage], k, m0, t.b2, t.b1);
+              tma_load_4d(sa + kABytes, &tma_b, &full[stage], k, n0, t.b2, t.b1);
+            } else {
+              tma_load_4d(sa, &tma_a, &full[stage], m0, k, t.b2, t.b1);
+              tma_load_4d(sa + 8192, &tma_a, &full[stage], m0 + 64, k, t.b2, t.b1);
+              for (int i = 0; i < nboxb; ++i)
+                tma_load_4d(sa + kABytes + i * 8192, &tma_b, &full[stage], n0 + i * 64, k, t.b2, t.b1);
+            }
+          }
+          __syncwarp();
+          TR(256 + trk - 1);
+          if (++stage == nstages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    } else
     for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
       const TileCoord t = decode_tile(p, tile, rank);
       const int k_begin = t.s * p.k_per_split;
@@ -414,6 +454,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (p.epi_mode == 1) {
           if (tile == cluster_id) pdl_wait();   // bias comes from earlier kernels; C may still be read by them
           mbar_wait(&tmem_full[acc], acc_phase);
+          if (warp == 2) TR(1024 + 2 * trt);
           tc_fence_after();
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kMaxBN;
           for (int cc = egroup; cc < p.bn / 64; cc += kEpiWarps / 4) {
@@ -520,6 +561,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             __syncwarp();
           }
           mbar_wait(&tmem_full[acc], acc_phase);
+          if (warp == 2) TR(1024 + 2 * trt);
           tc_fence_after();
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kMaxBN;
           for (int k = 0; k < mine; ++k) {
@@ -586,6 +628,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           nst = nst0 + static_cast<uint32_t>(mine);
         }
         // accumulator drained (it lives in registers / shared memory now): hand the TMEM stage back to the MMA warp
+        if (warp == 2) TR(1025 + 2 * trt);
+        ++trt;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256) finetune_loss_kernel(const void* __restri
   const float gmul = 2.f * inv_norm * scale;
   float a_loss = 0.f, a_pred = 0.f, a_gt = 0.f;
   const long long base = static_cast<long long>(b) * HW;
+#pragma unroll 4
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
     float m;
     if (mask != nullptr) m = mask[b * mask_bstride + i];
@@ -80,26 +81,32 @@ __global__ void __launch_bounds__(256) finetune_loss_kernel(const void* __restri
     last = atomicAdd(ticket, 1) == static_cast<int>(gridDim.x * gridDim.y) - 1;
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
-    // fixed summation order: the loss and the metrics are bit-reproducible run to run
+  if (last) {
+    // fixed summation order (thread b sums image b's partials in index order, thread 0 combines the images in order): the
+    // loss and the metrics are bit-reproducible run to run
+    __shared__ double fin[3][256];
     __threadfence();
-    double loss = 0., mae = 0., mse = 0.;
-    for (int bb = 0; bb < B; ++bb) {
-      double p = 0., g = 0.;
-      for (int k = 0; k < static_cast<int>(gridDim.x); ++k) {
-        const volatile double* pp = partial + (static_cast<long long>(bb) * gridDim.x + k) * 3;
-        loss += pp[0]; p += pp[1]; g += pp[2];
+    const int nblk = static_cast<int>(gridDim.x);
+    for (int bb = threadIdx.x; bb < B; bb += blockDim.x) {
+      double l = 0., pr = 0., g = 0.;
+      for (int k = 0; k < nblk; ++k) {
+        const double* pp = partial + (static_cast<long long>(bb) * nblk + k) * 3;
+        l += __ldcg(pp); pr += __ldcg(pp + 1); g += __ldcg(pp + 2);
       }
-      const float pc = static_cast<float>(p / 60.0), gc = static_cast<float>(g / 60.0);
+      const float pc = static_cast<float>(pr / 60.0), gc = static_cast<float>(g / 60.0);
       if (counts != nullptr) { counts[2 * bb] = pc; counts[2 * bb + 1] = gc; }
       const float err = fabsf(pc - gc);
-      mae += static_cast<double>(err);
-      mse += static_cast<double>(err * err);
+      fin[0][bb] = l; fin[1][bb] = static_cast<double>(err); fin[2][bb] = static_cast<double>(err * err);     // B <= 256 (host check)
     }
-    result[0] = static_cast<float>(loss * static_cast<double>(inv_norm));
-    result[1] = static_cast<float>(mae / B);
-    result[2] = static_cast<float>(mse / B);
-    *ticket = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double loss = 0., mae = 0., mse = 0.;
+      for (int bb = 0; bb < B; ++bb) { loss += fin[0][bb]; mae += fin[1][bb]; mse += fin[2][bb]; }
+      result[0] = static_cast<float>(loss * static_cast<double>(inv_norm));
+      result[1] = static_cast<float>(mae / B);
+      result[2] = static_cast<float>(mse / B);
+      *ticket = 0;
+    }
   }
 }
 
@@ -113,6 +120,7 @@ __global__ void __launch_bounds__(256) grad_stats_kernel(const float* __restrict
   int nonfinite = 0;
   const long long n4 = n >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(grad);
+#pragma unroll 4
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 v = g4[i];
     acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
@@ -136,20 +144,30 @@ __global__ void __launch_bounds__(256) grad_stats_kernel(const float* __restrict
     last = atomicAdd(ticket, 1) == static_cast<int>(gridDim.x) - 1;
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
+  if (last) {
+    // fixed order: thread i sums partials i, i + 256, ...; thread 0 combines the 256 sums in index order
+    __shared__ double fin[256];
+    __shared__ int finbad[256];
     __threadfence();
     double s = 0.;
     int nf = 0;
-    for (int k = 0; k < static_cast<int>(gridDim.x); ++k) {
-      const volatile double* pp = partial + 2 * k;
-      s += pp[0];
-      nf |= pp[1] != 0.0;
+    for (int k = threadIdx.x; k < static_cast<int>(gridDim.x); k += blockDim.x) {
+      s += __ldcg(partial + 2 * k);
+      nf |= __ldcg(partial + 2 * k + 1) != 0.0;
     }
-    const float scale = state[ST_SCALE];
-    const float norm = static_cast<float>(sqrt(s)) / scale;
-    state[ST_FOUND_INF] = (nf || !isfinite(norm)) ? 1.f : 0.f;
-    state[ST_GRAD_NORM] = norm;
-    *ticket = 0;
+    fin[threadIdx.x] = s;
+    finbad[threadIdx.x] = nf;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.;
+      int bad_any = 0;
+      for (int k = 0; k < 256; ++k) { tot += fin[k]; bad_any |= finbad[k]; }
+      const float scale = state[ST_SCALE];
+      const float norm = static_cast<float>(sqrt(tot)) / scale;
+      state[ST_FOUND_INF] = (bad_any || !isfinite(norm)) ? 1.f : 0.f;
+      state[ST_GRAD_NORM] = norm;
+      *ticket = 0;
+    }
   }
 }
 
@@ -239,7 +257,7 @@ extern "C" int countr_finetune_loss(const void* out, int out_dtype, const void* 
                                     countr_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(out && gt && scratch && result && out_dtype >= 0 && out_dtype <= 2 && gt_dtype >= 0 && gt_dtype <= 2, "bad arguments");
-  COUNTR_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 4096, "bad shape B=%d H=%d W=%d", B, H, W);
+  COUNTR_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 256, "bad shape B=%d H=%d W=%d (B <= 256)", B, H, W);
   COUNTR_REQUIRE(mask != nullptr || (keep_prob >= 0.f && keep_prob <= 1.f), "keep_prob must be in [0, 1]");
   COUNTR_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 7u) == 0, "scratch must be 8-byte aligned");
   // scratch: one int ticket (8 bytes, zero before the FIRST call; the kernel leaves it at zero) + B * 36 * 3 doubles

@@ -37,14 +37,15 @@ def test_finetune_loss_kernel(cuda, dtype, per_image_mask):
     """FSC_finetune_cross.py:290-303 in one launch: loss, its gradient, per-image counts, batch MAE / MSE."""
     from oracle import train_oracle as TO
     B, H, W = 3, 96, 96
-    out = torch.randn(B, H, W, device=cuda).to(dtype).requires_grad_(True)
+    out = torch.randn(B, H, W, device=cuda).to(dtype)
     gt = torch.rand(B, H, W, device=cuda).to(dtype)
     mask = (torch.rand((B, H, W) if per_image_mask else (H, W), device=cuda) < 0.8).float()
-    ref, pred, gtc, mae, mse = TO.loss_and_counts(out.float(), gt.float(), mask)
+    out32 = out.float().requires_grad_(True)         # the kernel reads the 16-bit values and computes in fp32
+    ref, pred, gtc, mae, mse = TO.loss_and_counts(out32, gt.float(), mask)
     (ref * 7.0).backward()
-    result, counts, dout, _ = _loss_call(out.detach(), gt, mask, scale=7.0, bstride=H * W if per_image_mask else 0)
+    result, counts, dout, _ = _loss_call(out, gt, mask, scale=7.0, bstride=H * W if per_image_mask else 0)
     assert abs(result[0].item() - ref.item()) < 1e-5 * abs(ref.item()) + 1e-7
-    assert torch.allclose(dout, out.grad.float(), rtol=1e-3 if dtype == torch.float16 else 1e-5, atol=1e-9)
+    assert torch.allclose(dout, out32.grad, rtol=1e-5, atol=1e-9)
     assert torch.allclose(counts[:, 0], pred.detach(), rtol=1e-5, atol=1e-5) and torch.allclose(counts[:, 1], gtc, rtol=1e-5, atol=1e-5)
     assert abs(result[1].item() - mae.item()) < 1e-4 * abs(mae.item()) + 1e-6
     assert abs(result[2].item() - mse.item()) < 1e-4 * abs(mse.item()) + 1e-6
