@@ -373,6 +373,80 @@ __device__ __forceinline__ void umma_commit_2cta_mc(uint64_t* bar, uint16_t cta_
       "h"(cta_mask)
       : "memory");
 }
+// One 64-wide k-block of the GEMM main loop as ONE instruction sequence: a non-blocking probe of the NEXT stage's `full`
+// barrier, four tcgen05.mma (k-steps of 16) issued by the elected lane, the commit that frees the stage and (last k-block)
+// the commit that publishes the accumulator.  The probe's result is only read after the MMAs have been issued, so the
+// barrier round trip (~150 clk for test_wait) hides behind the ~60 clk each UTCHMMA takes to issue instead of preceding it
+// (measured with scripts/trace_gemm.py: the issue loop, not the tensor pipe or TMA, paced the 128 x 64..192 tiles at
+// 410 + bn/2 clk per k-block against a pipe time of 2*bn).  Executed by the WHOLE warp; returns 1 when the probed barrier
+// phase has completed.  kGroup = 1: single CTA; 2: CTA pair (commits are multicast to both CTAs, mask 3).
+template <int kGroup>
+__device__ __forceinline__ uint32_t umma_kblock(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t a_step, uint32_t b_step,
+                                                uint32_t idesc, uint32_t accumulate, uint32_t empty_bar, uint32_t acc_bar,
+                                                uint32_t is_last, uint32_t probe_bar, uint32_t probe_parity) {
+  uint32_t ready;
+  const uint64_t as = a_step, bs = b_step;
+  if (kGroup == 1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q, e, l;\n\t"
+        ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q, [%11], %12;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "setp.ne.b32 l, %10, 0;\n\t"
+        "and.pred l, l, e;\n\t"
+        "add.u64 a1, %2, %4;\n\t"
+        "add.u64 b1, %3, %5;\n\t"
+        "add.u64 a2, a1, %4;\n\t"
+        "add.u64 b2, b1, %5;\n\t"
+        "add.u64 a3, a2, %4;\n\t"
+        "add.u64 b3, b2, %5;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %6, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %6, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a2, b2, %6, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a3, b3, %6, 1;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+        "@l tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t"
+        "}\n"
+        : "=r"(ready)
+        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "l"(as), "l"(bs), "r"(idesc), "r"(accumulate), "r"(empty_bar), "r"(acc_bar),
+          "r"(is_last), "r"(probe_bar), "r"(probe_parity)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q, e, l;\n\t"
+        ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        ".reg .b16 m;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q, [%11], %12;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "setp.ne.b32 l, %10, 0;\n\t"
+        "and.pred l, l, e;\n\t"
+        "mov.b16 m, 3;\n\t"
+        "add.u64 a1, %2, %4;\n\t"
+        "add.u64 b1, %3, %5;\n\t"
+        "add.u64 a2, a1, %4;\n\t"
+        "add.u64 b2, b1, %5;\n\t"
+        "add.u64 a3, a2, %4;\n\t"
+        "add.u64 b3, b2, %5;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%1], %2, %3, %6, p;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a1, b1, %6, 1;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a2, b2, %6, 1;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a3, b3, %6, 1;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], m;\n\t"
+        "@l tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%9], m;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t"
+        "}\n"
+        : "=r"(ready)
+        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "l"(as), "l"(bs), "r"(idesc), "r"(accumulate), "r"(empty_bar), "r"(acc_bar),
+          "r"(is_last), "r"(probe_bar), "r"(probe_parity)
+        : "memory");
+  }
+  return ready;
+}
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(kCols)

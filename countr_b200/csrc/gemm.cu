@@ -23,6 +23,8 @@
 #include "common.cuh"
 #include "tma.h"
 
+#include <algorithm>
+
 namespace countr {
 
 // Optional in-kernel timeline (clock64 stamps of one CTA's producer / MMA / epilogue roles) for scripts/trace_gemm.py.
@@ -30,7 +32,8 @@ namespace countr {
 #ifdef COUNTR_TRACE
 __device__ long long* g_trace = nullptr;
 __device__ int g_trace_cta = 0;
-__device__ int g_dbg = 0;   // experiment knobs: 1 = skip the C stores, 2 = skip the residual loads
+__device__ int g_dbg = 0;   // experiment knobs: 1 = skip the C stores, 2 = skip the residual loads, 4 = no TMA operand loads
+                            // (fast-path producer), 8 = no MMAs (single-CTA path)
 #define DBG_INIT const int dbg_ = g_dbg
 #define DBG(bit) (dbg_ & (bit))
 #define TR_INIT long long* const tr_ = (g_trace != nullptr && static_cast<int>(blockIdx.x) == g_trace_cta) ? g_trace : nullptr
@@ -71,6 +74,7 @@ struct GemmArgs {
   int bf16;
   int split_k, k_per_split;
   int m_tiles, n_tiles, total_tiles;   // total_tiles counts CLUSTER tiles (cs consecutive m tiles x one n tile)
+  uint32_t mg_magic, nt_magic, sk_magic, nb2_magic;   // fast_div constants of m_groups, n_tiles, split_k, nb2
   int epi64;                           // 1: 16-bit outputs drain 64 columns per round (COUNTR_EPI64=0 turns it off for A/B runs)
   int nstages, stage_bytes;            // operand ring
   int epi_off, nbuf;                   // epilogue staging: offset, buffers per epilogue warp (1 or 2)
@@ -101,16 +105,26 @@ struct TileCoord {
   int m, n, s, b1, b2;
 };
 
+// idx / d for idx * d < 2^32 with the host-computed magic = floor(2^32 / d) + 1 (d > 1): a multiply-high instead of the
+// ~100-clk emulated integer division — five of them per tile decode were ~0.5 us of every kernel's prologue.
+__device__ __forceinline__ int fast_div(int idx, int d, uint32_t magic) {
+  return d == 1 ? idx : static_cast<int>(__umulhi(static_cast<uint32_t>(idx), magic));
+}
+
 __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int idx, int rank) {
   TileCoord t;
-  t.m = (idx % p.m_groups) * p.cs + rank;
-  idx /= p.m_groups;
-  t.n = idx % p.n_tiles;
-  idx /= p.n_tiles;
-  t.s = idx % p.split_k;
-  idx /= p.split_k;
-  t.b2 = idx % p.nb2;
-  t.b1 = idx / p.nb2;
+  int q = fast_div(idx, p.m_groups, p.mg_magic);
+  t.m = (idx - q * p.m_groups) * p.cs + rank;
+  idx = q;
+  q = fast_div(idx, p.n_tiles, p.nt_magic);
+  t.n = idx - q * p.n_tiles;
+  idx = q;
+  q = fast_div(idx, p.split_k, p.sk_magic);
+  t.s = idx - q * p.split_k;
+  idx = q;
+  q = fast_div(idx, p.nb2, p.nb2_magic);
+  t.b2 = idx - q * p.nb2;
+  t.b1 = q;
   return t;
 }
 
@@ -143,8 +157,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   uint64_t* empty = bars + 8;            // [8]
   uint64_t* tmem_full = bars + 16;       // [2]
   uint64_t* tmem_empty = bars + 18;      // [2]
-  uint64_t* res_full = bars + 20;        // [8 warps][2 buffers]: residual chunk landed (epi_mode 2)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 36);
+  uint64_t* res_full = bars + 20;        // [8 warps][3 buffers]: residual chunk landed (epi_mode 2)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 44);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -165,7 +179,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], kPair ? 2 * kEpiWarps : kEpiWarps);   // pair: the leader waits for both CTAs' epilogues
     }
-    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_full[i], 1);
+    for (int i = 0; i < 3 * kEpiWarps; ++i) mbar_init(&res_full[i], 1);
     if (p.epi_mode != 0) tma_prefetch_desc(&tma_c);
     if (p.epi_mode == 2 && p.residual != nullptr) tma_prefetch_desc(&tma_r);
     fence_mbar_init();
@@ -212,7 +226,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           mbar_wait(&empty[stage], phase ^ 1);
           TR(16 + trk); ++trk;
           uint8_t* sa = smem + stage * stage_bytes;
-          if (elect_one()) {
+          if (DBG(4)) {
+            if (elect_one()) mbar_arrive(&full[stage]);
+          } else if (elect_one()) {
             mbar_arrive_expect_tx(&full[stage], tx);
             if (!mn) {
               tma_load_4d(sa, &tma_a, &full[stage], k, m0, t.b2, t.b1);
@@ -223,6 +239,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               for (int i = 0; i < nboxb; ++i)
                 tma_load_4d(sa + kABytes + i * 8192, &tma_b, &full[stage], n0 + i * 64, k, t.b2, t.b1);
             }
+          }
+          __syncwarp();
+          TR(256 + trk - 1);
+          if (++stage == nstages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    } else if (kPair && p.conv == 0 && !p.a_mn && !p.b_mn) {
+      // ---- fast path: plain Linear on a CTA pair (both operands K-major): this CTA's 128 rows of A and its half of the B tile;
+      // every byte is credited to the LEADER's full barrier
+      const uint32_t tx2 = 2 * (kABytes + b_bytes);
+      const int nhalf = p.bn / 2;
+      for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+        const TileCoord t = decode_tile(p, tile, rank);
+        const int k_begin = t.s * p.k_per_split;
+        const int k_end = min(p.K, k_begin + p.k_per_split);
+        const int nkb = (k_end - k_begin + BK - 1) / BK;
+        const int m0 = t.m * BM, n0 = t.n * p.bn + rank * nhalf;
+        if (tile == cluster_id) pdl_wait();
+        int k = k_begin;
+        for (int kb = 0; kb < nkb; ++kb, k += BK) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          TR(16 + trk); ++trk;
+          uint8_t* sa = smem + stage * stage_bytes;
+          const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], tx2);
+            tma_load_4d_2sm(sa, &tma_a, full_leader, k, m0, t.b2, t.b1);
+            tma_load_4d_2sm(sa + kABytes, &tma_b, full_leader, k, n0, t.b2, t.b1);
           }
           __syncwarp();
           TR(256 + trk - 1);
@@ -359,6 +406,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       // MN-major: 64-wide MN blocks 8192 B apart (LBO), 8-row k groups 1024 B apart (SBO); +2048 B per 16-row k-step
       const uint32_t a_step = p.a_mn ? (2048u >> 4) : (32u >> 4);
       const uint32_t b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
+      uint32_t ready = 0;       // the `full` barrier of the CURRENT stage was already seen complete by the previous k-block's probe
+      const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+      const bool fused_issue = p.cs == 1 || kPair;     // multicast clusters (experiments only) keep the plain sequence
       for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
         const TileCoord t = decode_tile(p, tile, rank);
         const int k_begin = t.s * p.k_per_split;
@@ -368,36 +418,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kMaxBN;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full[stage], phase);
+          if (!ready) mbar_wait(&full[stage], phase);
           TR(512 + trk); ++trk;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint32_t sb = sa + kABytes;
           const uint64_t a_desc = p.a_mn ? make_smem_desc_sw128(sa, 8192, 1024) : make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t b_desc = p.b_mn ? make_smem_desc_sw128(sb, 8192, 1024) : make_smem_desc_sw128(sb, 16, 1024);
-          if (elect_one()) {
-            if (kPair) {
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == nstages) {
+            nstage = 0;
+            nphase ^= 1;
+          }
+          if (fused_issue && !DBG(8)) {
+            // probe of the next stage + 4 MMAs + commits in one sequence (common.cuh: umma_kblock)
+            ready = umma_kblock<kPair ? 2 : 1>(d_tmem, a_desc, b_desc, a_step, b_step, idesc, kb != 0 ? 1u : 0u,
+                                                empty0 + stage * 8, smem_u32(&tmem_full[acc]), kb == nkb - 1 ? 1u : 0u,
+                                                full0 + nstage * 8, nphase);
+          } else {
+            ready = 0;
+            if (elect_one()) {
+              if (!DBG(8)) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                umma_f16_ss_2cta(d_tmem, a_desc + static_cast<uint64_t>(a_step * k), b_desc + static_cast<uint64_t>(b_step * k),
-                                 idesc, (kb | k) != 0);
-              umma_commit_2cta_mc(&empty[stage], 3);                       // frees the stage in BOTH CTAs
-              if (kb == nkb - 1) umma_commit_2cta_mc(&tmem_full[acc], 3);  // wakes BOTH epilogues
-            } else {
-#pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                umma_f16_ss(d_tmem, a_desc + static_cast<uint64_t>(a_step * k), b_desc + static_cast<uint64_t>(b_step * k),
-                            idesc, (kb | k) != 0);
-              if (p.cs > 1) umma_commit_mc(&empty[stage], mc_mask); else umma_commit(&empty[stage]);
-              if (kb == nkb - 1) umma_commit(&tmem_full[acc]);
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_f16_ss(d_tmem, a_desc + static_cast<uint64_t>(a_step * k), b_desc + static_cast<uint64_t>(b_step * k),
+                              idesc, (kb | k) != 0);
+              }
+              if (kPair) {
+                umma_commit_2cta_mc(&empty[stage], 3);
+                if (kb == nkb - 1) umma_commit_2cta_mc(&tmem_full[acc], 3);
+              } else {
+                if (p.cs > 1) umma_commit_mc(&empty[stage], mc_mask); else umma_commit(&empty[stage]);
+                if (kb == nkb - 1) umma_commit(&tmem_full[acc]);
+              }
             }
           }
           __syncwarp();
           TR(768 + trk - 1);
-          if (++stage == nstages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          stage = nstage;
+          phase = nphase;
         }
         if (++acc == 2) {
           acc = 0;
@@ -419,9 +479,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     int acc = 0;
     uint32_t acc_phase = 0;
     int trt = 0;
-    uint64_t* const my_res = res_full + 2 * (warp - 2);
+    uint64_t* const my_res = res_full + 3 * (warp - 2);
     uint32_t nst = 0;          // staging rounds of this warp so far (buffer = nst % nbuf); warp-uniform
-    uint32_t res_uses[2] = {0, 0};   // residual loads consumed per staging buffer (mbarrier phase bookkeeping)
+    uint32_t res_uses[3] = {0, 0, 0};   // residual loads consumed per staging buffer (mbarrier phase bookkeeping)
     for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
       const TileCoord t = decode_tile(p, tile, rank);
       if (p.epi_mode != 0) {
@@ -453,6 +513,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const uint32_t rowoff = static_cast<uint32_t>(lane) * 128u;
         if (p.epi_mode == 1) {
           if (tile == cluster_id) pdl_wait();   // bias comes from earlier kernels; C may still be read by them
+          // bias of this warp's column chunks, one column per lane, fetched BEFORE the accumulator is waited for (the L2 round
+          // trip hides behind the main loop); the row-per-lane arithmetic below reads column j's value with a shuffle
+          float blane[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+          if (use_bias) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int col0 = n0 + (egroup + 2 * i) * 64;
+              if (egroup + 2 * i < p.bn / 64 && col0 < p.N) {
+                blane[i][0] = __ldg(p.bias + col0 + lane);
+                blane[i][1] = __ldg(p.bias + col0 + 32 + lane);
+              }
+            }
+          }
           mbar_wait(&tmem_full[acc], acc_phase);
           if (warp == 2) TR(1024 + 2 * trt);
           tc_fence_after();
@@ -460,36 +533,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int cc = egroup; cc < p.bn / 64; cc += kEpiWarps / 4) {
             const int col0 = n0 + cc * 64;
             if (col0 >= p.N) break;
-            float4 bq[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (use_bias) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
-            }
+            const bool second = cc != egroup;
+            const float bl0 = second ? blane[1][0] : blane[0][0], bl1 = second ? blane[1][1] : blane[0][1];
             uint32_t r[2][32];
             tmem_ld_32x32b_x32(t_row + cc * 64, r[0]);
             tmem_ld_32x32b_x32(t_row + cc * 64 + 32, r[1]);
             tmem_ld_wait();
             const uint32_t buf = stg + (nst % p.nbuf) * kEpiBufBytes;
             if (nst >= static_cast<uint32_t>(p.nbuf)) {      // the store that last used this buffer has read it
-              if (lane == 0) { if (p.nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+              if (lane == 0) { if (p.nbuf == 3) bulk_wait_read<2>(); else if (p.nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
               __syncwarp();
             }
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
               float v[32];
+              const float blh = hf == 0 ? bl0 : bl1;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                v[4 * j] = fmaf(__uint_as_float(r[hf][4 * j]), p.alpha, bq[j].x);
-                v[4 * j + 1] = fmaf(__uint_as_float(r[hf][4 * j + 1]), p.alpha, bq[j].y);
-                v[4 * j + 2] = fmaf(__uint_as_float(r[hf][4 * j + 2]), p.alpha, bq[j].z);
-                v[4 * j + 3] = fmaf(__uint_as_float(r[hf][4 * j + 3]), p.alpha, bq[j].w);
-              }
-              if (hf == 0 && use_bias) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 32 + 4 * j));
-              }
+              for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[hf][j]), p.alpha, __shfl_sync(0xffffffffu, blh, j));
               if (p.gn_stats != nullptr) {
                 float s1 = 0.f, s2 = 0.f;
                 if (row_ok) {
@@ -554,11 +614,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           };
           if (use_res && mine > 0) {            // issued BEFORE the accumulator is waited for: lands during the main loop
             if (lane == 0) {
-              bulk_wait_read<0>();              // the previous tile's stores have read both buffers
+              bulk_wait_read<0>();              // the previous tile's stores have read every buffer
               load_res(0);
-              if (p.nbuf == 2 && mine > 1) load_res(1);
+              if (p.nbuf >= 2 && mine > 1) load_res(1);
+              if (p.nbuf >= 3 && mine > 2) load_res(2);
             }
             __syncwarp();
+          }
+          // bias of this warp's chunks, one column per lane (see the 16-bit path)
+          float blane[4] = {0.f, 0.f, 0.f, 0.f};
+          if (use_bias) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (i < mine) blane[i] = __ldg(p.bias + n0 + (egroup + 2 * i) * 32 + lane);
           }
           mbar_wait(&tmem_full[acc], acc_phase);
           if (warp == 2) TR(1024 + 2 * trt);
@@ -568,13 +636,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const int col0 = n0 + (egroup + 2 * k) * 32;
             const uint32_t bsel = (nst0 + static_cast<uint32_t>(k)) % p.nbuf;
             const uint32_t buf = stg + bsel * kEpiBufBytes;
-            float4 bq[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (use_bias) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
-            }
+            const float blk_ = k == 0 ? blane[0] : k == 1 ? blane[1] : k == 2 ? blane[2] : blane[3];
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_row + (egroup + 2 * k) * 32, r);
             if (use_res) {
@@ -589,18 +651,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               mbar_wait(&my_res[bsel], res_uses[bsel] & 1u);
               ++res_uses[bsel];
             } else if (nst0 + k >= static_cast<uint32_t>(p.nbuf)) {
-              if (lane == 0) { if (p.nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+              if (lane == 0) { if (p.nbuf == 3) bulk_wait_read<2>(); else if (p.nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
               __syncwarp();
             }
             tmem_ld_wait();
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[4 * j] = fmaf(__uint_as_float(r[4 * j]), p.alpha, bq[j].x);
-              v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), p.alpha, bq[j].y);
-              v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), p.alpha, bq[j].z);
-              v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), p.alpha, bq[j].w);
-            }
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, __shfl_sync(0xffffffffu, blk_, j));
             if (use_res) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
@@ -1052,7 +1109,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
   }
 
-  if (p.epi_mode != 0 && warp >= 2 && lane == 0) bulk_wait_all<0>();   // this warp's TMA stores have been performed
+  // the staging buffers must outlive the TMA unit's READS of them; the global writes themselves complete asynchronously and
+  // are ordered before grid completion like any other store (same contract as CUTLASS's tma_store_wait)
+  if (p.epi_mode != 0 && warp >= 2 && lane == 0) bulk_wait_read<0>();
   tc_fence_before();
   if (p.cs > 1) cluster_sync_all(); else __syncthreads();   // no peer may still signal this CTA's barriers after it exits
   if (threadIdx.x == 0) TR(3);
@@ -1171,6 +1230,12 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   p.cs = cs;
   p.m_groups = (p.m_tiles + cs - 1) / cs;
   p.total_tiles = p.m_groups * p.n_tiles * p.split_k * nb1 * nb2;
+  {
+    auto magic = [](int d) { return d > 1 ? static_cast<uint32_t>((1ull << 32) / static_cast<uint64_t>(d)) + 1u : 0u; };
+    p.mg_magic = magic(p.m_groups); p.nt_magic = magic(p.n_tiles); p.sk_magic = magic(p.split_k); p.nb2_magic = magic(nb2);
+    COUNTR_REQUIRE(static_cast<long long>(p.total_tiles) * std::max(std::max(p.m_groups, p.n_tiles), std::max(p.split_k, nb2)) < (1ll << 32),
+                   "tile count %d too large for the fast tile decode", p.total_tiles);
+  }
 
   p.C = d->c; p.ldc = d->ldc; p.sc1 = d->sc1; p.sc2 = d->sc2;
   p.out_f32 = d->out_f32; p.atomic = d->atomic;
@@ -1263,6 +1328,21 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   if (room / p.stage_bytes < 4) {          // keep at least four operand stages: one staging buffer per warp instead
     p.nbuf = 1;
     room = static_cast<int>(kBarOff) - kEpiWarps * static_cast<int>(kEpiBufBytes);
+  }
+  // fp32 + residual tiles with three 32-column chunks per epilogue warp (bn = 192: proj / fc2 of the encoder): a third staging
+  // buffer lets the WHOLE residual tile land during the main loop, so the exposed epilogue of these one-tile-per-CTA GEMMs is
+  // TMEM read + add + store per chunk instead of a residual round trip per chunk — as long as three operand stages remain
+  {
+    static int nbuf3 = -1;
+    if (nbuf3 < 0) {
+      const char* e = getenv("COUNTR_EPI_NBUF3");
+      nbuf3 = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    const int room3 = static_cast<int>(kBarOff) - kEpiWarps * 3 * static_cast<int>(kEpiBufBytes);
+    if (nbuf3 && p.epi_mode == 2 && d->residual != nullptr && bn == 192 && p.nbuf == 2 && room3 / p.stage_bytes >= 3) {
+      p.nbuf = 3;
+      room = room3;
+    }
   }
   p.nstages = room / p.stage_bytes;
   if (p.nstages > kMaxStages) p.nstages = kMaxStages;

@@ -58,13 +58,13 @@ def run(name, m, n, k, mode, bn=0, pair=0, cluster=0, cta=0, show=14):
     print("    first tile, warp 2, per chunk (start, tmem loaded, transposed, stores issued):", [tuple(C[i:i + 4]) for i in range(0, len(C), 4)])
 
 
-lib.countr_debug_set_knobs(0)
+lib.countr_debug_set_knobs.argtypes = [ctypes.c_int]
 M = 4608
-run("fim fc2 res", M, 512, 2048, "res", show=10)
-run("fim fc2 res pair", M, 512, 2048, "res", bn=128, pair=1, show=10)
-run("fim proj res", M, 512, 512, "res", show=10)
-run("enc qkv f16", M, 2304, 768, "f16", show=10)
-run("enc qkv f16 cta100", M, 2304, 768, "f16", cta=100, show=10)
-run("enc fc2 res", M, 768, 3072, "res", show=10)
-run("enc fc1 gelu", M, 3072, 768, "gelu", show=10)
-run("kv", 24, 512, 512, "f32", show=10)
+lib.countr_debug_set_knobs(0)
+run("enc fc2 res", M, 768, 3072, "res", show=8)
+run("fim fc2 res", M, 512, 2048, "res", show=8)
+run("enc qkv f16", M, 2304, 768, "f16", show=8)
+run("enc proj res", M, 768, 768, "res", show=8)
+run("enc fc1 gelu", M, 3072, 768, "gelu", show=8)
+run("fim fc2 res pair", M, 512, 2048, "res", bn=128, pair=1, show=8)
+run("N=1024 bn256 pair", M, 1024, 4096, "f16", bn=256, pair=1, show=8)
