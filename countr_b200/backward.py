@@ -183,28 +183,44 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
             fn()
 
     def new_g16():
-        # the 16-bit residual gradient is read by side-stream dW GEMMs: a fresh buffer per LayerNorm backward
-        return torch.empty(M, Dd, dtype=F16, device=dev) if wstream is not None else g16
+        # the 16-bit residual gradient is read by the deferred dW GEMMs: a fresh buffer per LayerNorm backward
+        return torch.empty(M, Dd, dtype=F16, device=dev)
+
+    # Weight and bias gradients of the Linear layers are leaves of the backward graph: they are only RECORDED here and
+    # computed at the end by one grouped tcgen05 launch (+ one grouped column-sum launch) over all of them — 17 GEMMs and
+    # 8 column sums that would otherwise sit between the dX GEMMs of the latency-bound chain, each with its own launch,
+    # prologue, pipeline fill and exposed epilogue (csrc/grouped.cu).  eng.defer_dw = False restores the per-layer launches.
+    defer = getattr(eng, "defer_dw", True)
+    dw_jobs, cs_jobs = [], []
+
+    def dW(dy16, x16, p):
+        if defer:
+            dw_jobs.append((dy16, x16, G(p).view(p.shape[0], -1)))
+        else:
+            off(lambda: _dw_linear(dy16, x16, G(p)), dy16)
+
+    def dB(dy, p):
+        if defer:
+            cs_jobs.append((dy, G(p)))
+        else:
+            off(lambda: ops.colsum(dy, G(p)), dy)
     for bi, (blk, s) in enumerate(zip(blocks_rev, reversed(sv["blocks"]))):
         H = blk.selfattn.num_heads
         dhd = Dd // H
         hid = blk.mlp.fc1.weight.shape[0]
         # --- MLP: x3 = x2 + fc2(gelu(fc1(LN2 x2)))
-        off(lambda g16=g16: _dw_linear(g16, s["u"], G(blk.mlp.fc2.weight)), g16)
+        dW(g16, s["u"], blk.mlp.fc2.weight)
         dpre = torch.empty(M, hid, dtype=F16, device=dev)
         ops.linear(g16, wc.w16_t(blk.mlp.fc2.weight), dpre, act=2, aux=s["pre"])
-
-        def _fc1_grads(dpre=dpre):
-            ops.colsum(dpre, G(blk.mlp.fc1.bias))
-            _dw_linear(dpre, s["h2"], G(blk.mlp.fc1.weight))
-        off(_fc1_grads, dpre)
+        dB(dpre, blk.mlp.fc1.bias)
+        dW(dpre, s["h2"], blk.mlp.fc1.weight)
         ops.linear(dpre, wc.w16_t(blk.mlp.fc1.weight), dh)
         g16 = new_g16()
         ops.layernorm_bwd(dh, s["x2"], _contig32(blk.norm2.weight), s["mean2"], s["rstd2"], g, G(blk.norm2.weight),
                           G(blk.norm2.bias), accumulate=True, dx16=g16, dx_colsum=G(blk.attn.proj.bias))
         # --- cross attention: x2 = x1 + proj(core(wq(LN1 x1), wk(y), wv(y)))
         ca = blk.attn
-        off(lambda g16=g16: _dw_linear(g16, s["c16"], G(ca.proj.weight)), g16)
+        dW(g16, s["c16"], ca.proj.weight)
         dc = torch.empty(M, Dd, dtype=F16, device=dev)
         ops.linear(g16, wc.w16_t(ca.proj.weight), dc)
         dq = torch.empty(M, Dd, dtype=F16, device=dev)
@@ -214,10 +230,8 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
         ops.zero_(dv32)
         ops.cross_attn_core_bwd(s["q16"], s["k32"], s["v32"], s["probs"], dc, dq, dk32, dv32, B, L, S, Dd, dhd, ca.scale,
                                 kv_broadcast=kvb)
-        def _wq_grads(dq=dq):
-            ops.colsum(dq, G(ca.wq.bias))
-            _dw_linear(dq, s["h1"], G(ca.wq.weight))
-        off(_wq_grads, dq)
+        dB(dq, ca.wq.bias)
+        dW(dq, s["h1"], ca.wq.weight)
         ops.linear(dq, wc.w16_t(ca.wq.weight), dh)
         def _kv_grads(dk32=dk32, dv32=dv32):
             # everything downstream of dK / dV only feeds the exemplar branch (dL/dy), never the token stream
@@ -226,10 +240,14 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
             keep.extend((dk16, dv16))
             ops.cast16(dk32, dk16)
             ops.cast16(dv32, dv16)
-            ops.colsum(dk32, G(ca.wk.bias))
-            ops.colsum(dv32, G(ca.wv.bias))
-            _dw_linear(dk16, y16, G(ca.wk.weight))
-            _dw_linear(dv16, y16, G(ca.wv.weight))
+            if defer:
+                cs_jobs.extend(((dk32, G(ca.wk.bias)), (dv32, G(ca.wv.bias))))
+                dw_jobs.extend(((dk16, y16, G(ca.wk.weight)), (dv16, y16, G(ca.wv.weight))))
+            else:
+                ops.colsum(dk32, G(ca.wk.bias))
+                ops.colsum(dv32, G(ca.wv.bias))
+                _dw_linear(dk16, y16, G(ca.wk.weight))
+                _dw_linear(dv16, y16, G(ca.wv.weight))
             ops.linear(dk16, wc.w16_t(ca.wk.weight), dy32, residual=dy32)
             ops.linear(dv16, wc.w16_t(ca.wv.weight), dy32, residual=dy32)
         off(_kv_grads, dk32, dv32)
@@ -250,15 +268,13 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
                           G(blk.norm1.bias), accumulate=True, dx16=g16, dx_colsum=G(blk.selfattn.proj.bias))
         # --- self attention: x1 = x0 + proj(attn(qkv(LN0 x0)))
         sa = blk.selfattn
-        off(lambda g16=g16: _dw_linear(g16, s["att"], G(sa.proj.weight)), g16)
+        dW(g16, s["att"], sa.proj.weight)
         datt = torch.empty(M, Dd, dtype=F16, device=dev)
         ops.linear(g16, wc.w16_t(sa.proj.weight), datt)
         dqkv = attention_backward(s["qkv"], s["lse"], datt, B, L, H, dhd, sa.scale, att=s["att"])
 
-        def _qkv_grads(dqkv=dqkv):
-            ops.colsum(dqkv, G(sa.qkv.bias))
-            _dw_linear(dqkv, s["h0"], G(sa.qkv.weight))
-        off(_qkv_grads, dqkv)
+        dB(dqkv, sa.qkv.bias)
+        dW(dqkv, s["h0"], sa.qkv.weight)
         ops.linear(dqkv, wc.w16_t(sa.qkv.weight), dh)
         nxt_bias = blocks_rev[bi + 1].mlp.fc2.bias if bi + 1 < n_blocks else m.decoder_embed.bias
         g16 = new_g16()
@@ -267,10 +283,16 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
 
     # ---- decoder_embed: weight / bias only (its input is the frozen encoder's output)
     de = m.decoder_embed
-    _dw_linear(g16, sv["lat16"], G(de.weight))
+    if defer:
+        dw_jobs.append((g16, sv["lat16"], G(de.weight)))
+    else:
+        _dw_linear(g16, sv["lat16"], G(de.weight))
 
     if side is not None or wstream is not None:
-        torch.cuda.current_stream().wait_stream(eng.side_stream(dev))     # join the exemplar-CNN backward and the dW work
+        torch.cuda.current_stream().wait_stream(eng.side_stream(dev))     # join the exemplar-CNN backward and the k/v work
+    if defer:
+        ops.grouped_colsum(cs_jobs)
+        ops.grouped_dw(dw_jobs)
     keep.clear()
     # Every parameter that just received a gradient is about to be changed by an optimizer, and torch's version counter
     # cannot be relied on to say so (torch.optim.AdamW(fused=True) updates parameters without bumping `_version`, and so

@@ -181,7 +181,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
     for (int i = 0; i < 3 * kEpiWarps; ++i) mbar_init(&res_full[i], 1);
     if (p.epi_mode != 0) tma_prefetch_desc(&tma_c);
-    if (p.epi_mode == 2 && p.residual != nullptr) tma_prefetch_desc(&tma_r);
+    if ((p.epi_mode == 2 && p.residual != nullptr) || (p.epi_mode == 1 && p.aux != nullptr)) tma_prefetch_desc(&tma_r);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -526,6 +526,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               }
             }
           }
+          // act == 2 (GELU' of the saved pre-activation, fc2's dX): this warp's chunks of `aux` are TMA-loaded into its staging
+          // buffers ahead of the accumulator (host: nbuf covers the chunks per warp) and the product is formed in place
+          const bool aux_in = p.act == 2, aux_out = p.act == 1 && p.aux != nullptr;
+          if (aux_in) {
+            if (lane == 0) {
+              bulk_wait_read<0>();            // the previous tile's stores have read the buffers
+              for (int i = 0; i < 2; ++i) {
+                const int cc = egroup + 2 * i;
+                if (cc < p.bn / 64 && n0 + cc * 64 < p.N) {
+                  mbar_arrive_expect_tx(&my_res[i], kEpiBufBytes);
+                  tma_load_4d(smem + p.epi_off + ((warp - 2) * p.nbuf + i) * kEpiBufBytes, &tma_r, &my_res[i], n0 + cc * 64, c1, c2v, c3);
+                }
+              }
+            }
+            __syncwarp();
+          }
           mbar_wait(&tmem_full[acc], acc_phase);
           if (warp == 2) TR(1024 + 2 * trt);
           tc_fence_after();
@@ -539,8 +555,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             tmem_ld_32x32b_x32(t_row + cc * 64, r[0]);
             tmem_ld_32x32b_x32(t_row + cc * 64 + 32, r[1]);
             tmem_ld_wait();
-            const uint32_t buf = stg + (nst % p.nbuf) * kEpiBufBytes;
-            if (nst >= static_cast<uint32_t>(p.nbuf)) {      // the store that last used this buffer has read it
+            // plain: rotate the staging buffers; aux_in: chunk i lives in buffer i; aux_out: buffer 0 = C chunk, buffer 1 = aux chunk
+            const uint32_t buf = (aux_in ? (second ? 1u : 0u) : aux_out ? 0u : (nst % p.nbuf)) * kEpiBufBytes + stg;
+            const uint32_t buf2 = stg + kEpiBufBytes;
+            if (aux_in) {
+              const int bi = second ? 1 : 0;
+              mbar_wait(&my_res[bi], res_uses[bi] & 1u);
+              ++res_uses[bi];
+            } else if (aux_out) {
+              if (nst > 0) {
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+              }
+            } else if (nst >= static_cast<uint32_t>(p.nbuf)) {      // the store that last used this buffer has read it
               if (lane == 0) { if (p.nbuf == 3) bulk_wait_read<2>(); else if (p.nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
               __syncwarp();
             }
@@ -567,12 +594,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                   atomicAdd(st + 1, static_cast<double>(s2));
                 }
               }
+              if (aux_out) {
+                // the pre-activation (saved for the backward) goes out through the second staging buffer
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint32_t w0 = pack_16b(v[8 * q], v[8 * q + 1], p.bf16), w1 = pack_16b(v[8 * q + 2], v[8 * q + 3], p.bf16);
+                  const uint32_t w2 = pack_16b(v[8 * q + 4], v[8 * q + 5], p.bf16), w3 = pack_16b(v[8 * q + 6], v[8 * q + 7], p.bf16);
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf2 + rowoff + (((hf * 4 + q) ^ sw) << 4)),
+                               "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                               : "memory");
+                }
+              }
               if (p.act == 1) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
                   const float2 gq = gelu_erf2(make_float2(v[j], v[j + 1]));
                   v[j] = gq.x;
                   v[j + 1] = gq.y;
+                }
+              } else if (aux_in) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint32_t a0, a1, a2, a3;
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                               : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                               : "r"(buf + rowoff + (((hf * 4 + q) ^ sw) << 4))
+                               : "memory");
+                  const float2 g0 = gelu_erf_grad2(unpack_16b(a0, p.bf16)), g1 = gelu_erf_grad2(unpack_16b(a1, p.bf16));
+                  const float2 g2 = gelu_erf_grad2(unpack_16b(a2, p.bf16)), g3 = gelu_erf_grad2(unpack_16b(a3, p.bf16));
+                  v[8 * q] *= g0.x; v[8 * q + 1] *= g0.y; v[8 * q + 2] *= g1.x; v[8 * q + 3] *= g1.y;
+                  v[8 * q + 4] *= g2.x; v[8 * q + 5] *= g2.y; v[8 * q + 6] *= g3.x; v[8 * q + 7] *= g3.y;
                 }
               }
 #pragma unroll
@@ -594,6 +645,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             __syncwarp();
             if (lane == 0) {
               tma_store_4d(&tma_c, buf, col0, c1, c2v, c3);
+              if (aux_out) tma_store_4d(&tma_r, buf2, col0, c1, c2v, c3);
               bulk_commit();
             }
             ++nst;
@@ -1314,9 +1366,18 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   const bool c_strides_ok = (d->ldc * c_elt) % 16 == 0 && (nb1 <= 1 || conv || (sc1e * c_elt) % 16 == 0) &&
                             (nb2 <= 1 || conv || (sc2e * c_elt) % 16 == 0) && (!conv || (sc1e * c_elt) % 16 == 0);
   p.epi_mode = 0;
-  if (epi_tma && c_strides_ok && d->aux == nullptr) {
-    if (!d->out_f32 && d->residual == nullptr && !d->atomic && bn % 64 == 0 && d->N % 64 == 0 && (d->act == 0 || d->act == 1)) p.epi_mode = 1;
-    else if (d->out_f32 && d->act == 0 && d->gn_stats == nullptr && d->res_mod == 0 && d->N % 32 == 0 &&
+  // aux (fc1's saved pre-activation: an extra 16-bit output with act 1, an extra 16-bit input with act 2) also goes through TMA when
+  // it is a plain [M, N] matrix
+  static int epi_aux = -1;
+  if (epi_aux < 0) {
+    const char* e = getenv("COUNTR_EPI_AUX");
+    epi_aux = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  const bool aux_tma = d->aux == nullptr || (epi_aux && !d->out_f32 && !conv && nb1 * nb2 == 1 && (d->ldaux * 2) % 16 == 0 &&
+                                              (reinterpret_cast<uintptr_t>(d->aux) & 15u) == 0 && (d->act == 1 || d->act == 2));
+  if (epi_tma && c_strides_ok && aux_tma) {
+    if (!d->out_f32 && d->residual == nullptr && !d->atomic && bn % 64 == 0 && d->N % 64 == 0 && (d->act == 0 || d->act == 1 || d->act == 2)) p.epi_mode = 1;
+    else if (d->aux == nullptr && d->out_f32 && d->act == 0 && d->gn_stats == nullptr && d->res_mod == 0 && d->N % 32 == 0 &&
              (d->residual == nullptr || ((d->ldr * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->residual) & 15u) == 0 && !d->atomic &&
                                          nb1 * nb2 == 1 && !conv)))
       p.epi_mode = 2;
@@ -1325,7 +1386,8 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   p.stage_bytes = p.pair ? static_cast<int>(kPairStageBytes) : static_cast<int>(kABytes) + bn * 128;
   p.nbuf = 2;
   int room = static_cast<int>(kBarOff) - kEpiWarps * p.nbuf * static_cast<int>(kEpiBufBytes);
-  if (room / p.stage_bytes < 4) {          // keep at least four operand stages: one staging buffer per warp instead
+  const bool aux_needs_two = p.epi_mode == 1 && d->aux != nullptr;   // the aux epilogues address staging buffers 0 and 1
+  if (room / p.stage_bytes < 4 && !aux_needs_two) {          // keep at least four operand stages: one staging buffer per warp instead
     p.nbuf = 1;
     room = static_cast<int>(kBarOff) - kEpiWarps * static_cast<int>(kEpiBufBytes);
   }
@@ -1364,6 +1426,13 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
       rc = make_tmap_4d(&tc, d->c, c_elt, dims, str, box, TMAP_SW_128);
     }
     if (rc) return rc;
+    if (p.epi_mode == 1 && d->aux != nullptr) {
+      const uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->M, 1, 1};
+      const uint64_t str[4] = {1, (uint64_t)d->ldaux, (uint64_t)d->ldaux, (uint64_t)d->ldaux};
+      const uint32_t box[4] = {64, 32, 1, 1};
+      rc = make_tmap_4d(&tr, d->aux, 2, dims, str, box, TMAP_SW_128);
+      if (rc) return rc;
+    }
     if (p.epi_mode == 2 && d->residual != nullptr) {
       const uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->M, 1, 1};
       const uint64_t str[4] = {1, (uint64_t)d->ldr, (uint64_t)d->ldr, (uint64_t)d->ldr};

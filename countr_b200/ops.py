@@ -240,6 +240,49 @@ def colsum(x, out32):
     _count()
 
 
+class _DwProblem(ctypes.Structure):
+    _fields_ = [("dy", ctypes.c_void_p), ("x", ctypes.c_void_p), ("dw", ctypes.c_void_p), ("ld_dy", ctypes.c_int64),
+                ("ld_x", ctypes.c_int64), ("ld_dw", ctypes.c_int64), ("tokens", ctypes.c_int32), ("n_out", ctypes.c_int32),
+                ("k_in", ctypes.c_int32), ("pad_", ctypes.c_int32)]
+
+
+class _ColsumProblem(ctypes.Structure):
+    _fields_ = [("x", ctypes.c_void_p), ("out", ctypes.c_void_p), ("rows", ctypes.c_int64), ("ld", ctypes.c_int64),
+                ("cols", ctypes.c_int32), ("dtype", ctypes.c_int32)]
+
+
+MAX_GROUP = 32
+
+
+def grouped_dw(problems):
+    """problems: list of (dy16 [tokens, n_out], x16 [tokens, k_in], dw32 [n_out, k_in]);  dw32 += dy16^T @ x16 for all of them in
+    one persistent launch per 32 problems (countr_grouped_dw)."""
+    for i in range(0, len(problems), MAX_GROUP):
+        chunk = problems[i:i + MAX_GROUP]
+        arr = (_DwProblem * len(chunk))()
+        for j, (dy, x, dw) in enumerate(chunk):
+            assert dy.dtype in (F16, BF16) and x.dtype == dy.dtype and dw.dtype == torch.float32
+            assert dy.shape[0] == x.shape[0] and dw.shape == (dy.shape[1], x.shape[1]) and dy.stride(1) == 1 and x.stride(1) == 1
+            assert dw.is_contiguous()
+            arr[j] = _DwProblem(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), dy.stride(0), x.stride(0), dw.stride(0), dy.shape[0],
+                                dy.shape[1], x.shape[1], 0)
+        check(lib().countr_grouped_dw(arr, len(chunk), _is_bf16(chunk[0][0]), _stream()))
+        _count()
+
+
+def grouped_colsum(problems):
+    """problems: list of (x [rows, cols], out32 [cols]);  out32 += column sums, one launch per 32 problems."""
+    for i in range(0, len(problems), MAX_GROUP):
+        chunk = problems[i:i + MAX_GROUP]
+        arr = (_ColsumProblem * len(chunk))()
+        for j, (x, out) in enumerate(chunk):
+            cols = x.shape[-1]
+            assert x.is_contiguous() and out.dtype == torch.float32 and out.numel() == cols
+            arr[j] = _ColsumProblem(x.data_ptr(), out.data_ptr(), x.numel() // cols, cols, cols, _DTYPE_CODE[x.dtype])
+        check(lib().countr_grouped_colsum(arr, len(chunk), _stream()))
+        _count()
+
+
 def softmax_bwd_rows(s16, dp16, lse, scale):
     L = s16.shape[-1]
     check(lib().countr_softmax_bwd_rows(_ptr(s16), _ptr(dp16), _ptr(lse), s16.numel() // L, L, scale, _is_bf16(s16), _stream()))

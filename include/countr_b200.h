@@ -208,6 +208,32 @@ int countr_gn_bwd_apply(const void* raw, const void* dyh, const double* stats, c
                         countr_stream_t stream);
 /* out[n] += sum_r x[r][n]  (Linear bias gradients); dtype code of x: 0 fp32, 1 fp16, 2 bf16 */
 int countr_colsum(const void* x, int dtype, float* out, int64_t R, int N, int64_t ld, countr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Deferred weight / bias gradients of a backward pass in ONE launch each.
+ * countr_grouped_dw: for every problem i  dw_i[n_out][k_in] (fp32, pre-zeroed or carrying earlier contributions) +=
+ *   dy_i[tokens][n_out]^T x_i[tokens][k_in]  (16-bit operands, fp32 accumulate; one persistent tcgen05 kernel walks the
+ *   concatenated, token-split tile list of all problems and accumulates through TMA reduce-add).
+ * countr_grouped_colsum: out_i[cols] += column sums of x_i[rows][cols] (dtype 0 fp32, 1 fp16, 2 bf16).
+ * replaces: the mm(dY^T, X) and sum(dY, 0) halves of autograd's addmm backward for every nn.Linear of the decoder
+ *   (models_crossvit.py:55-57,77,80,104-108; models_mae_cross.py:39) and of models_mae_noct under FSC_pretrain.py.
+ * ------------------------------------------------------------------------------------------ */
+#define COUNTR_MAX_GROUP 32
+typedef struct countr_dw_problem {
+  const void* dy;   /* [tokens][ld_dy] 16-bit */
+  const void* x;    /* [tokens][ld_x] 16-bit */
+  float* dw;        /* [n_out][ld_dw] fp32 */
+  int64_t ld_dy, ld_x, ld_dw;
+  int32_t tokens, n_out, k_in, pad_;
+} countr_dw_problem;
+int countr_grouped_dw(const countr_dw_problem* probs, int n, int bf16, countr_stream_t stream);
+typedef struct countr_colsum_problem {
+  const void* x;
+  float* out;
+  int64_t rows, ld;
+  int32_t cols, dtype;
+} countr_colsum_problem;
+int countr_grouped_colsum(const countr_colsum_problem* probs, int n, countr_stream_t stream);
 /* _softmax_backward_data on materialised rows (self-attention backward of the FIM):
  * in place S <- P = exp(S - lse), dP <- dS = scale * P * (dP - sum_j P_j dP_j) */
 int countr_softmax_bwd_rows(void* s_io, void* dp_io, const float* lse, int64_t rows, int L, float scale, int bf16,

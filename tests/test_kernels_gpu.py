@@ -155,6 +155,58 @@ def test_gemm_epilogues(cuda):
     assert_close(y, lin + pos.repeat(M // 576, 1), 2e-5, "pos-embed residual")
 
 
+def test_grouped_dw_and_colsum(cuda):
+    """Every dW = dY^T X (and bias gradient) of a backward pass in one launch each: mixed shapes, a token count that is not a
+    multiple of 64 (zero-filled k tail), a 24-token problem (the k/v projections of the exemplars), output widths that are not
+    multiples of the 128 x 256 tile, accumulation on top of earlier contributions."""
+    from countr_b200 import ops
+    shapes = [(4608, 512, 2048), (4608, 2048, 512), (4608, 1536, 512), (24, 512, 512), (1000, 512, 768), (4608, 512, 512), (333, 192, 320)]
+    dws, refs, probs, cprobs, crefs = [], [], [], [], []
+    for i, (tok, n_out, k_in) in enumerate(shapes):
+        dy = _rand16((tok, n_out), cuda, seed=40 + i, scale=0.5)
+        x = _rand16((tok, k_in), cuda, seed=60 + i, scale=0.5)
+        dw = torch.randn(n_out, k_in, device=cuda)
+        refs.append(dw.double() + dy.double().t() @ x.double())
+        probs.append((dy, x, dw))
+        db = torch.randn(n_out, device=cuda)
+        crefs.append(db.double() + dy.double().sum(0))
+        cprobs.append((dy, db))
+    x32 = torch.randn(24, 512, device=cuda)
+    db32 = torch.zeros(512, device=cuda)
+    cprobs.append((x32, db32))
+    crefs.append(x32.double().sum(0))
+    ops.grouped_dw(probs)
+    ops.grouped_colsum(cprobs)
+    torch.cuda.synchronize()
+    for (tok, n_out, k_in), (_, _, dw), ref in zip(shapes, probs, refs):
+        assert_close(dw, ref.float(), 2e-5, f"grouped dW tokens={tok} {n_out}x{k_in}")
+    for (_, db), ref in zip(cprobs, crefs):
+        assert_close(db, ref.float(), 2e-5, "grouped colsum")
+
+
+@pytest.mark.parametrize("M,N,K", [(4608, 2048, 512), (1000, 2048, 512), (4608, 512, 2048), (333, 1536, 512)])
+def test_gemm_aux_epilogues_tma(cuda, M, N, K):
+    """fc1 forward with the saved pre-activation (second 16-bit output) and fc2's dX with the GELU' multiply (16-bit input),
+    both through the TMA epilogue, at the FIM / encoder shapes and with ragged row counts (the TMA unit clips the tails)."""
+    from countr_b200 import ops
+    a = _rand16((M, K), cuda, seed=18, scale=0.5)
+    w = _rand16((N, K), cuda, seed=19, scale=0.05)
+    bias = torch.randn(N, device=cuda)
+    lin = a.float() @ w.float().t() + bias
+    pre = torch.zeros(M, N, device=cuda, dtype=torch.float16)
+    u = torch.zeros(M, N, device=cuda, dtype=torch.float16)
+    ops.linear(a, w, u, bias=bias, act=1, aux=pre)
+    torch.cuda.synchronize()
+    assert_close(pre, lin, 1e-3, "pre-activation")
+    assert_close(u, F.gelu(lin), 1e-3, "gelu")
+    g = torch.zeros(M, N, device=cuda, dtype=torch.float16)
+    ops.linear(a, w, g, act=2, aux=pre)
+    torch.cuda.synchronize()
+    x_ = pre.float().requires_grad_(True)
+    F.gelu(x_).sum().backward()
+    assert_close(g, (a.float() @ w.float().t()) * x_.grad, 1.5e-3, "gelu bwd")
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 24, 24, 512, 256), (2, 48, 48, 256, 256), (1, 96, 96, 256, 256),
                                             (3, 32, 32, 64, 128), (3, 16, 16, 128, 256), (3, 8, 8, 256, 512)])
 def test_conv3x3(cuda, B, H, W, Cin, Cout):
