@@ -8,7 +8,7 @@ SIGS = {
     "countr_layernorm_fwd": [P, P, P, P, P, P, P, I, I, F, I, P],
     "countr_layernorm_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, P],
     "countr_attention_fwd": [P, P, P, I, I, I, I, F, I, P],
-    "countr_attention_bwd": [P, P, P, P, P, I, I, I, I, F, I, P],
+    "countr_attention_bwd": [P, P, P, P, P, P, I, I, I, I, F, I, P],
     "countr_cross_attn_core": [P, P, P, P, P, I, I, I, I, I, F, I, I, P],
     "countr_cast_f32_to_16": [P, P, L, F, I, P],
     "countr_cast_transpose_f32_to_16": [P, P, I, I, I, P],
@@ -47,6 +47,7 @@ SIGS = {
 SIZE_QUERIES = {
     "countr_finetune_loss_scratch_bytes": [I],
     "countr_grad_stats_scratch_bytes": [],
+    "countr_attention_bwd_workspace_bytes": [I, I, I, I],
 }
 
 

@@ -32,14 +32,38 @@ def _dw_linear(dy16, x16, dw32):
              atomic=True, split_k=split)
 
 
+class GradJobs:
+    """Deferred weight / bias gradients of a backward pass.  They are leaves of the backward graph, so the schedules only
+    RECORD them (operands must stay alive and unmodified) and `flush()` computes all of them with one grouped tcgen05 launch
+    per 32 weight gradients and one grouped column-sum launch per 32 bias gradients (csrc/grouped.cu) — instead of a
+    launch + prologue + pipeline fill + exposed epilogue per layer in the middle of the latency-bound dX chain."""
+
+    def __init__(self):
+        self.dw, self.cs = [], []
+
+    def dW(self, dy16, x16, dw32):
+        self.dw.append((dy16, x16, dw32.view(dw32.shape[0], -1)))
+
+    def dB(self, x, out32):
+        self.cs.append((x, out32.view(-1)))
+
+    def flush(self):
+        if self.cs:
+            ops.grouped_colsum(self.cs)
+        if self.dw:
+            ops.grouped_dw(self.dw)
+        self.dw, self.cs = [], []
+
+
 def attention_backward(qkv, lse, datt, B, L, H, dh, scale, att=None, fused=True):
     """qkv fp16 [B*L, 3*H*dh] (packed), lse fp32 [B,H,L], datt fp16 [B*L, H*dh] -> dqkv fp16 [B*L, 3*H*dh].
-    head_dim 32 (the FIM) runs the fused flash-style kernel (needs the forward output `att`); other head sizes use
-    batched tcgen05 GEMMs over materialised [B,H,L,L] scores plus a row softmax-backward."""
+    head_dim 32 (the FIM, the pre-training decoder) and 64 (the pre-training encoder) run the fused flash-style kernels (they
+    need the forward output `att`); other head sizes use batched tcgen05 GEMMs over materialised [B,H,L,L] scores plus a row
+    softmax-backward."""
     dev = qkv.device
     D = H * dh
     row = 3 * D
-    if fused and att is not None and dh == 32 and L <= 640:
+    if fused and att is not None and ((dh == 32 and L <= 640) or dh == 64):
         dqkv = torch.empty(B * L, row, dtype=F16, device=dev)
         ops.attention_bwd(qkv, att, datt, lse, dqkv, B, L, H, dh, scale)
         return dqkv

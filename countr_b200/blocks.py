@@ -6,7 +6,7 @@ is trained too; the fine-tune path has its own in-place (frozen encoder) and FIM
 import torch
 
 from . import ops
-from .backward import _dw_linear, attention_backward
+from .backward import attention_backward
 from .engine import F16, F32, _contig32
 
 
@@ -37,9 +37,13 @@ def vit_block_forward(wc, blk, x, B, L, save):
     return x2
 
 
-def vit_block_backward(wc, blk, s, g, g16, G):
-    """g (fp32) / g16 (its fp16 copy) hold dL/dx_out on entry and dL/dx_in on exit (updated in place).
-    G(param) -> the fp32 gradient view to accumulate into."""
+def vit_block_backward(wc, blk, s, g, g16, G, jobs, next_bias=None):
+    """g (fp32, updated in place) holds dL/dx_out on entry and dL/dx_in on exit; g16 is the fp16 copy of the entry gradient.
+    Returns the fp16 copy of the exit gradient (a fresh buffer: the deferred weight-gradient jobs keep reading the old ones).
+    G(param) -> the fp32 gradient view to accumulate into; jobs: backward.GradJobs (weight / bias gradients are deferred);
+    next_bias: bias of the Linear that consumed x_in's producer (fc2 of the block below, patch-embed / decoder_embed), its
+    gradient = column sums of the exit gradient, emitted by the last LayerNorm backward.  The caller provides the column sums
+    of the ENTRY gradient (this block's fc2.bias) the same way."""
     dev = g.device
     M, D = g.shape
     H = blk.attn.num_heads
@@ -48,23 +52,24 @@ def vit_block_backward(wc, blk, s, g, g16, G):
     B, L = s["B"], s["L"]
     dh = torch.empty(M, D, dtype=F32, device=dev)
     # MLP
-    ops.colsum(g, G(blk.mlp.fc2.bias))
-    _dw_linear(g16, s["u"], G(blk.mlp.fc2.weight))
+    jobs.dW(g16, s["u"], G(blk.mlp.fc2.weight))
     dpre = torch.empty(M, hid, dtype=F16, device=dev)
     ops.linear(g16, wc.w16_t(blk.mlp.fc2.weight), dpre, act=2, aux=s["pre"])
-    ops.colsum(dpre, G(blk.mlp.fc1.bias))
-    _dw_linear(dpre, s["h2"], G(blk.mlp.fc1.weight))
+    jobs.dB(dpre, G(blk.mlp.fc1.bias))
+    jobs.dW(dpre, s["h2"], G(blk.mlp.fc1.weight))
     ops.linear(dpre, wc.w16_t(blk.mlp.fc1.weight), dh)
+    g16 = torch.empty(M, D, dtype=F16, device=dev)
     ops.layernorm_bwd(dh, s["x1"], _contig32(blk.norm2.weight), s["mean2"], s["rstd2"], g, G(blk.norm2.weight), G(blk.norm2.bias),
-                      accumulate=True, dx16=g16)
+                      accumulate=True, dx16=g16, dx_colsum=G(blk.attn.proj.bias))
     # attention
-    ops.colsum(g, G(blk.attn.proj.bias))
-    _dw_linear(g16, s["att"], G(blk.attn.proj.weight))
+    jobs.dW(g16, s["att"], G(blk.attn.proj.weight))
     datt = torch.empty(M, D, dtype=F16, device=dev)
     ops.linear(g16, wc.w16_t(blk.attn.proj.weight), datt)
     dqkv = attention_backward(s["qkv"], s["lse"], datt, B, L, H, dhd, blk.attn.scale, att=s["att"])
-    ops.colsum(dqkv, G(blk.attn.qkv.bias))
-    _dw_linear(dqkv, s["h1"], G(blk.attn.qkv.weight))
+    jobs.dB(dqkv, G(blk.attn.qkv.bias))
+    jobs.dW(dqkv, s["h1"], G(blk.attn.qkv.weight))
     ops.linear(dqkv, wc.w16_t(blk.attn.qkv.weight), dh)
+    g16 = torch.empty(M, D, dtype=F16, device=dev)
     ops.layernorm_bwd(dh, s["x0"], _contig32(blk.norm1.weight), s["mean1"], s["rstd1"], g, G(blk.norm1.weight), G(blk.norm1.bias),
-                      accumulate=True, dx16=g16)
+                      accumulate=True, dx16=g16, dx_colsum=None if next_bias is None else G(next_bias))
+    return g16

@@ -742,6 +742,259 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
   }
 }
 
+
+// ================================================================================================
+// Fused self-attention BACKWARD for head_dim 64 (the encoder of the MAE pre-training step, models_mae_noct.py:137-152
+// under autograd).  Whole-head residency does not fit at dh = 64 (Q, K, V, dO of 576 tokens = 288 KB; dQ of every query
+// block + dV + dK + S + dP = 704 TMEM columns), so the work is split FlashAttention-2 style:
+//   one CTA = one (batch, head, 128-KEY block j): K_j, V_j stay in shared memory, the query blocks stream through
+//   (Q_i, dO_i), dV_j / dK_j accumulate in tensor memory over i, and each pair's dQ_i contribution (128 x 64 fp32)
+//   is added to an fp32 [B][L][H][64] workspace with vector reductions; countr_attention_bwd converts the workspace
+//   into the Q slots of dqkv afterwards.  TMEM: dV 64 + dK 64 + dQ 64 + S 128 + dP 128 = 448 columns.
+// Any L (one CTA per key block); out-of-range rows are zero-filled by TMA and get lse = delta = 0.
+// ================================================================================================
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attention_bwd64_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
+                       const AttnBwdArgs p, float* __restrict__ dq32) {
+  constexpr int DH = 64;
+  constexpr uint32_t kBlkBytes = 128 * DH * 2;       // 16 KB
+  constexpr uint32_t kTileBytes = 128 * 128 * 2;     // 32 KB: P or dS tile
+  constexpr uint32_t kOffK = 0, kOffV = kBlkBytes, kOffQ = 2 * kBlkBytes /*[2 buffers]*/, kOffdO = 4 * kBlkBytes /*[2]*/;
+  constexpr uint32_t kOffP = 6 * kBlkBytes, kOffdS = kOffP + kTileBytes, kOffBar = kOffdS + kTileBytes;
+  constexpr uint32_t tdV = 0, tdK = 64, tdQ = 128, tS = 256, tP = 384;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* bar_q = bar_kv + 1;      // [2]: Q_i / dO_i landed in buffer i & 1
+  uint64_t* bar_s = bar_kv + 3;      // S, dP of the pair are in TMEM
+  uint64_t* bar_e = bar_kv + 4;      // dV / dK / dQ MMAs of the pair have completed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_kv + 5);
+
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int r = quarter * 32 + lane;                 // row inside a 128-row block
+  const int nblk = (p.L + 127) / 128;
+  const int j = blockIdx.x % nblk;
+  const int bh = blockIdx.x / nblk;
+  const int h = bh % p.H, b = bh / p.H;
+  const int D = p.H * DH;
+
+  pdl_trigger();
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_qkv);
+    tma_prefetch_desc(&tma_do);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_q + 1, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_e, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+  pdl_wait();   // qkv / out / dout come from earlier kernels, dq32 was zeroed by one
+
+  auto load_q = [&](int i) {       // warp 0, whole warp
+    const int buf = i & 1;
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar_q + buf, 2u * kBlkBytes);
+      tma_load_4d(smem + kOffQ + buf * kBlkBytes, &tma_qkv, bar_q + buf, 0, i * 128, h, b);
+      tma_load_4d(smem + kOffdO + buf * kBlkBytes, &tma_do, bar_q + buf, 0, i * 128, h, b);
+    }
+    __syncwarp();
+  };
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar_kv, 2u * kBlkBytes);
+      tma_load_4d(smem + kOffK, &tma_qkv, bar_kv, 0, j * 128, p.H + h, b);
+      tma_load_4d(smem + kOffV, &tma_qkv, bar_kv, 0, j * 128, 2 * p.H + h, b);
+    }
+    __syncwarp();
+    load_q(0);
+    if (nblk > 1) load_q(1);
+  }
+
+  const float sl2 = p.scale * 1.44269504088896340736f;
+  const uint32_t idesc_s = make_idesc_f16(128, 128, false, false, p.bf16 != 0);
+  const uint32_t idesc_mm = make_idesc_f16(128, DH, true, true, p.bf16 != 0);   // A = P^T / dS^T (MN-major), B MN-major
+  const uint32_t idesc_km = make_idesc_f16(128, DH, false, true, p.bf16 != 0);  // A = dS (K-major), B MN-major
+  const uint32_t sP = smem_u32(smem + kOffP), sdS = smem_u32(smem + kOffdS);
+  const uint32_t aK = smem_u32(smem + kOffK), aV = smem_u32(smem + kOffV);
+
+  for (int i = 0; i < nblk; ++i) {
+    const int buf = i & 1;
+    // per-row constants of this thread's query row (overlaps the TMA loads / the previous pair's MMAs)
+    float lse2 = 0.f, delta = 0.f;
+    {
+      const int q = i * 128 + r;
+      if (q < p.L) {
+        lse2 = p.lse[(static_cast<long long>(b) * p.H + h) * p.L + q] * 1.44269504088896340736f;
+        const uint4* po = reinterpret_cast<const uint4*>(p.O + (static_cast<long long>(b) * p.L + q) * D + h * DH);
+        const uint4* pd = reinterpret_cast<const uint4*>(p.dO + (static_cast<long long>(b) * p.L + q) * D + h * DH);
+        float acc = 0.f;
+#pragma unroll
+        for (int v = 0; v < DH / 8; ++v) {
+          const uint4 a = po[v], c = pd[v];
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            float2 fa, fc;
+            if (p.bf16) {
+              fa = make_float2(__uint_as_float(aw[w] << 16), __uint_as_float(aw[w] & 0xffff0000u));
+              fc = make_float2(__uint_as_float(cw[w] << 16), __uint_as_float(cw[w] & 0xffff0000u));
+            } else {
+              fa = __half22float2(*reinterpret_cast<const __half2*>(&aw[w]));
+              fc = __half22float2(*reinterpret_cast<const __half2*>(&cw[w]));
+            }
+            acc += fa.x * fc.x + fa.y * fc.y;
+          }
+        }
+        delta = acc;
+      }
+    }
+    const uint32_t aQ = smem_u32(smem + kOffQ + buf * kBlkBytes), adO = smem_u32(smem + kOffdO + buf * kBlkBytes);
+    if (warp == 0) {
+      if (i == 0) mbar_wait(bar_kv, 0);
+      mbar_wait(bar_q + buf, (i >> 1) & 1);
+      tc_fence_after();
+      const uint64_t dq = make_desc(aQ, 16, 1024, 2u), dk = make_desc(aK, 16, 1024, 2u);
+      const uint64_t dd = make_desc(adO, 16, 1024, 2u), dv = make_desc(aV, 16, 1024, 2u);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_f16_ss(tmem_base + tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_f16_ss(tmem_base + tP, dd + 2 * k, dv + 2 * k, idesc_s, k != 0);
+        umma_commit(bar_s);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar_s, i & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi) {
+      const int g = half * 2 + gi;
+      uint32_t rs[32], rp[32];
+      tmem_ld_32x32b_x32(t_lane + tS + g * 32, rs);
+      tmem_ld_32x32b_x32(t_lane + tP + g * 32, rp);
+      tmem_ld_wait();
+      float pv[32], dsv[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        pv[c] = ex2_approx(fmaf(__uint_as_float(rs[c]), sl2, -lse2));
+        dsv[c] = pv[c] * (__uint_as_float(rp[c]) - delta) * p.scale;
+      }
+      const uint32_t row_off = (g >> 1) * (128 * 128) + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o, o2;
+        o.x = pack2(pv[8 * q + 0], pv[8 * q + 1], p.bf16);
+        o.y = pack2(pv[8 * q + 2], pv[8 * q + 3], p.bf16);
+        o.z = pack2(pv[8 * q + 4], pv[8 * q + 5], p.bf16);
+        o.w = pack2(pv[8 * q + 6], pv[8 * q + 7], p.bf16);
+        o2.x = pack2(dsv[8 * q + 0], dsv[8 * q + 1], p.bf16);
+        o2.y = pack2(dsv[8 * q + 2], dsv[8 * q + 3], p.bf16);
+        o2.z = pack2(dsv[8 * q + 4], dsv[8 * q + 5], p.bf16);
+        o2.w = pack2(dsv[8 * q + 6], dsv[8 * q + 7], p.bf16);
+        const uint32_t off = row_off + ((((g & 1) * 4 + q) ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(smem + kOffP + off) = o;
+        *reinterpret_cast<uint4*>(smem + kOffdS + off) = o2;
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // 16 query rows (dV, dK) / 16 keys (dQ) per step
+          const uint64_t p_mn = make_desc(sP + ks * 2048, 16384, 1024, 2u);
+          const uint64_t ds_mn = make_desc(sdS + ks * 2048, 16384, 1024, 2u);
+          const uint64_t ds_k = make_desc(sdS + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024, 2u);
+          umma_f16_ss(tmem_base + tdV, p_mn, make_desc(adO + ks * 2048, 16, 1024, 2u), idesc_mm, (i | ks) != 0);
+          umma_f16_ss(tmem_base + tdK, ds_mn, make_desc(aQ + ks * 2048, 16, 1024, 2u), idesc_mm, (i | ks) != 0);
+          umma_f16_ss(tmem_base + tdQ, ds_k, make_desc(aK + ks * 2048, 16, 1024, 2u), idesc_km, ks != 0);
+        }
+        umma_commit(bar_e);
+      }
+      __syncwarp();
+    }
+    // dQ contribution of this pair: thread (query row r, column half) adds its 32 columns to the fp32 workspace
+    mbar_wait(bar_e, i & 1);
+    tc_fence_after();
+    if (warp == 0 && i + 2 < nblk) load_q(i + 2);     // this pair's Q / dO buffer is free again
+    {
+      const int q = i * 128 + r;
+      uint32_t rq[32];
+      tmem_ld_32x32b_x32(t_lane + tdQ + half * 32, rq);
+      tmem_ld_wait();
+      if (q < p.L) {
+        float* dst = dq32 + ((static_cast<long long>(b) * p.L + q) * p.H + h) * DH + half * 32;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c), "f"(__uint_as_float(rq[4 * c])),
+                       "f"(__uint_as_float(rq[4 * c + 1])), "f"(__uint_as_float(rq[4 * c + 2])), "f"(__uint_as_float(rq[4 * c + 3]))
+                       : "memory");
+      }
+    }
+    tc_fence_before();
+    __syncthreads();   // S / dP / dQ columns and the P / dS tiles are rewritten by the next pair
+  }
+  // dV_j, dK_j complete (the last bar_e covered every MMA): thread (key row r, column half) writes its 32 columns of each
+  tc_fence_after();
+  {
+    const int key = j * 128 + r;
+    uint32_t rv[32], rk[32];
+    tmem_ld_32x32b_x32(t_lane + tdV + half * 32, rv);
+    tmem_ld_32x32b_x32(t_lane + tdK + half * 32, rk);
+    tmem_ld_wait();
+    if (key < p.L) {
+      uint16_t* base = p.dqkv + (static_cast<long long>(b) * p.L + key) * (3 * D) + h * DH + half * 32;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 ov, ok;
+        ov.x = pack2(__uint_as_float(rv[8 * q + 0]), __uint_as_float(rv[8 * q + 1]), p.bf16);
+        ov.y = pack2(__uint_as_float(rv[8 * q + 2]), __uint_as_float(rv[8 * q + 3]), p.bf16);
+        ov.z = pack2(__uint_as_float(rv[8 * q + 4]), __uint_as_float(rv[8 * q + 5]), p.bf16);
+        ov.w = pack2(__uint_as_float(rv[8 * q + 6]), __uint_as_float(rv[8 * q + 7]), p.bf16);
+        ok.x = pack2(__uint_as_float(rk[8 * q + 0]), __uint_as_float(rk[8 * q + 1]), p.bf16);
+        ok.y = pack2(__uint_as_float(rk[8 * q + 2]), __uint_as_float(rk[8 * q + 3]), p.bf16);
+        ok.z = pack2(__uint_as_float(rk[8 * q + 4]), __uint_as_float(rk[8 * q + 5]), p.bf16);
+        ok.w = pack2(__uint_as_float(rk[8 * q + 6]), __uint_as_float(rk[8 * q + 7]), p.bf16);
+        *reinterpret_cast<uint4*>(base + 2 * D + 8 * q) = ov;   // V slot
+        *reinterpret_cast<uint4*>(base + D + 8 * q) = ok;       // K slot
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// dq32 [B*L][H*64] fp32 -> the Q slots of dqkv [B*L][3][H*64] (16-bit); thread = 8 columns
+__global__ void __launch_bounds__(256) dq_cast_kernel(const float* __restrict__ dq32, uint16_t* __restrict__ dqkv, long long rows, int D,
+                                                      int bf16) {
+  pdl_trigger();
+  pdl_wait();
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int per_row = D / 8;
+  if (idx >= rows * per_row) return;
+  const long long row = idx / per_row;
+  const int c = static_cast<int>(idx - row * per_row) * 8;
+  const float4 a = *reinterpret_cast<const float4*>(dq32 + row * D + c), b4 = *reinterpret_cast<const float4*>(dq32 + row * D + c + 4);
+  uint4 o;
+  o.x = pack2(a.x, a.y, bf16); o.y = pack2(a.z, a.w, bf16); o.z = pack2(b4.x, b4.y, bf16); o.w = pack2(b4.z, b4.w, bf16);
+  *reinterpret_cast<uint4*>(dqkv + row * 3 * D + c) = o;
+}
+
 }  // namespace
 }  // namespace countr
 
@@ -766,33 +1019,36 @@ extern "C" int countr_attention_fwd(const void* qkv, void* out, float* lse, int 
   return set_error(COUNTR_ERR_UNSUPPORTED, "attention head_dim %d not supported (32 or 64)", dh);
 }
 
-extern "C" int countr_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int L, int H,
-                                    int dh, float scale, int bf16, countr_stream_t stream_) {
+extern "C" int64_t countr_attention_bwd_workspace_bytes(int B, int L, int H, int dh) {
+  return dh == 64 ? static_cast<int64_t>(B) * L * H * dh * 4 : 0;
+}
+
+extern "C" int countr_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* workspace,
+                                    int B, int L, int H, int dh, float scale, int bf16, countr_stream_t stream_) {
   using namespace countr;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(qkv && out && dout && lse && dqkv, "null pointer");
-  COUNTR_REQUIRE(dh == 32, "fused attention backward supports head_dim 32 (got %d)", dh);
-  COUNTR_REQUIRE(L >= 1 && L <= 128 * kBwdMaxBlk, "fused attention backward supports L <= %d (got %d)", 128 * kBwdMaxBlk, L);
+  COUNTR_REQUIRE(dh == 32 || dh == 64, "fused attention backward supports head_dim 32 and 64 (got %d)", dh);
+  COUNTR_REQUIRE(L >= 1 && (dh == 64 || L <= 128 * kBwdMaxBlk), "fused attention backward (head_dim 32) supports L <= %d (got %d)",
+                 128 * kBwdMaxBlk, L);
+  COUNTR_REQUIRE(dh == 32 || (workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0),
+                 "head_dim 64 needs a 16-byte aligned workspace of countr_attention_bwd_workspace_bytes()");
   const int D = H * dh;
+  const TmapSwizzle sw = dh == 64 ? TMAP_SW_128 : TMAP_SW_64;
   CUtensorMap tq, td;
   {
     const uint64_t dims[4] = {(uint64_t)dh, (uint64_t)L, (uint64_t)(3 * H), (uint64_t)B};
     const uint64_t str[4] = {1, (uint64_t)(3 * D), (uint64_t)dh, (uint64_t)L * 3 * D};
     const uint32_t box[4] = {(uint32_t)dh, 128, 1, 1};
-    int rc = make_tmap_4d_16b(&tq, qkv, dims, str, box, TMAP_SW_64);
+    int rc = make_tmap_4d_16b(&tq, qkv, dims, str, box, sw);
     if (rc) return rc;
   }
   {
     const uint64_t dims[4] = {(uint64_t)dh, (uint64_t)L, (uint64_t)H, (uint64_t)B};
     const uint64_t str[4] = {1, (uint64_t)D, (uint64_t)dh, (uint64_t)L * D};
     const uint32_t box[4] = {(uint32_t)dh, 128, 1, 1};
-    int rc = make_tmap_4d_16b(&td, dout, dims, str, box, TMAP_SW_64);
+    int rc = make_tmap_4d_16b(&td, dout, dims, str, box, sw);
     if (rc) return rc;
-  }
-  constexpr uint32_t smem_bytes = 4 * kBwdMaxBlk * (128 * 32 * 2) + 2 * (128 * 128 * 2) + 64 + 1024;
-  static PerDeviceOnce attr_once;
-  if (attr_once.need()) {
-    COUNTR_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   }
   AttnBwdArgs a;
   a.dO = reinterpret_cast<const uint16_t*>(dout);
@@ -802,6 +1058,26 @@ extern "C" int countr_attention_bwd(const void* qkv, const void* out, const void
   a.B = B; a.L = L; a.H = H;
   a.scale = scale;
   a.bf16 = bf16;
+  if (dh == 64) {
+    constexpr uint32_t smem64 = 6 * (128 * 64 * 2) + 2 * (128 * 128 * 2) + 64 + 1024;
+    static PerDeviceOnce attr64;
+    if (attr64.need())
+      COUNTR_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
+    float* dq32 = reinterpret_cast<float*>(workspace);
+    const long long rows = static_cast<long long>(B) * L;
+    COUNTR_CHECK_CUDA(cudaMemsetAsync(dq32, 0, static_cast<size_t>(rows) * D * 4, stream));
+    const int nblk = (L + 127) / 128;
+    COUNTR_CHECK_CUDA(launch_pdl(attention_bwd64_kernel, dim3(B * H * nblk), dim3(kBwdThreads), smem64, stream, tq, td, a, dq32));
+    const long long n = rows * (D / 8);
+    COUNTR_CHECK_CUDA(launch_pdl(dq_cast_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, stream,
+                                 static_cast<const float*>(dq32), a.dqkv, rows, D, bf16));
+    return COUNTR_OK;
+  }
+  constexpr uint32_t smem_bytes = 4 * kBwdMaxBlk * (128 * 32 * 2) + 2 * (128 * 128 * 2) + 64 + 1024;
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
+    COUNTR_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  }
   COUNTR_CHECK_CUDA(launch_pdl(attention_bwd_kernel<32>, dim3(B * H), dim3(kBwdThreads), smem_bytes, stream, tq, td, a));
   return COUNTR_OK;
 }

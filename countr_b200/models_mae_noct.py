@@ -21,7 +21,7 @@ from . import _lib, ops
 from .blocks import vit_block_backward, vit_block_forward
 from .dist import build_grad_arena
 from .engine import F16, F32, _contig32, engine
-from .backward import _dw_linear
+from .backward import GradJobs
 from .pos_embed import get_2d_sincos_pos_embed
 from .vit import Block, PatchEmbed
 
@@ -208,44 +208,47 @@ class MaskedAutoencoderViTNoCT(nn.Module):
         ids = {id(p): n for n, p in zip(names, params)}
         G = lambda p: views[ids[id(p)]]  # noqa: E731
         e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)  # noqa: E731
+        jobs = GradJobs()     # every weight / bias gradient is deferred to two grouped launches at the end (backward.GradJobs)
         # predictor
         dp16 = e(t["dpred"].shape, F16)
         ops.cast16_scaled(t["dpred"], g_loss.detach().to(F32).contiguous(), dp16)
-        ops.colsum(dp16, G(self.decoder_pred.bias))
-        _dw_linear(dp16, t["f16"], G(self.decoder_pred.weight))
+        jobs.dB(dp16, G(self.decoder_pred.bias))
+        jobs.dW(dp16, t["f16"], G(self.decoder_pred.weight))
         dh = e((B * L, Dd), F32)
         ops.linear(dp16, wc.w16_t(self.decoder_pred.weight), dh)
         g, g16 = e((B * L, Dd), F32), e((B * L, Dd), F16)
         dn = self.decoder_norm
-        ops.layernorm_bwd(dh, t["x_dec"], _contig32(dn.weight), t["mean_d"], t["rstd_d"], g, G(dn.weight), G(dn.bias), accumulate=False, dx16=g16)
-        for blk, s in zip(reversed(list(self.decoder_blocks)), reversed(t["dec"])):
-            vit_block_backward(wc, blk, s, g, g16, G)
+        dblocks, eblocks = list(self.decoder_blocks), list(self.blocks)
+        ops.layernorm_bwd(dh, t["x_dec"], _contig32(dn.weight), t["mean_d"], t["rstd_d"], g, G(dn.weight), G(dn.bias), accumulate=False, dx16=g16,
+                          dx_colsum=G(dblocks[-1].mlp.fc2.bias))
+        for k in range(len(dblocks) - 1, -1, -1):
+            g16 = vit_block_backward(wc, dblocks[k], t["dec"][k], g, g16, G, jobs, next_bias=dblocks[k - 1].mlp.fc2.bias if k > 0 else None)
         # un-shuffle backward: d x_[b, j] = g[b, ids_shuffle[b, j]]; rows j < Lk belong to the kept tokens, the rest
         # all received the shared mask_token
         if L > Lk:
             gm = e((B, L - Lk, Dd), F32)
             ops.gather_rows(g.view(B, L, Dd), t["ids_masked"], gm)
-            ops.colsum(gm.view(B * (L - Lk), Dd), G(self.mask_token).view(-1))
+            jobs.dB(gm.view(B * (L - Lk), Dd), G(self.mask_token))
         gk = e((B, Lk, Dd), F32)
         ops.gather_rows(g.view(B, L, Dd), t["ids_keep"], gk)
         gk16 = e((B * Lk, Dd), F16)
         ops.cast16(gk.view(B * Lk, Dd), gk16)
         de = self.decoder_embed
-        ops.colsum(gk.view(B * Lk, Dd), G(de.bias))
-        _dw_linear(gk16, t["lat16"], G(de.weight))
+        jobs.dB(gk.view(B * Lk, Dd), G(de.bias))
+        jobs.dW(gk16, t["lat16"], G(de.weight))
         dhe = e((B * Lk, D), F32)
         ops.linear(gk16, wc.w16_t(de.weight), dhe)
         ge, ge16 = e((B * Lk, D), F32), e((B * Lk, D), F16)
         ops.layernorm_bwd(dhe, t["x_enc"], _contig32(self.norm.weight), t["mean_e"], t["rstd_e"], ge, G(self.norm.weight), G(self.norm.bias),
-                          accumulate=False, dx16=ge16)
-        for blk, s in zip(reversed(list(self.blocks)), reversed(t["enc"])):
-            vit_block_backward(wc, blk, s, ge, ge16, G)
+                          accumulate=False, dx16=ge16, dx_colsum=G(eblocks[-1].mlp.fc2.bias))
+        pe = self.patch_embed.proj
+        for k in range(len(eblocks) - 1, -1, -1):
+            ge16 = vit_block_backward(wc, eblocks[k], t["enc"][k], ge, ge16, G, jobs, next_bias=eblocks[k - 1].mlp.fc2.bias if k > 0 else pe.bias)
         # patch embedding: only the kept tokens carry gradient
         pk = e((B, Lk, t["patches"].shape[1]), F16)
         ops.gather_rows(t["patches"].view(B, L, -1), t["ids_keep"], pk)
-        pe = self.patch_embed.proj
-        ops.colsum(ge, G(pe.bias))
-        _dw_linear(ge16, pk.view(B * Lk, -1), G(pe.weight).view(pe.weight.shape[0], -1))
+        jobs.dW(ge16, pk.view(B * Lk, -1), G(pe.weight))
+        jobs.flush()
         wc.bump(params)      # gradient received => about to be updated; fused optimizers do not bump `_version` (see backward.py)
         eng.last_arena = arena
         if eng.grad_allreduce is not None:

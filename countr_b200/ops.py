@@ -126,9 +126,13 @@ def attention_fwd(qkv16, out16, B, L, H, dh, scale, lse=None):
 
 
 def attention_bwd(qkv16, out16, dout16, lse, dqkv16, B, L, H, dh, scale):
-    check(lib().countr_attention_bwd(_ptr(qkv16), _ptr(out16), _ptr(dout16), _ptr(lse), _ptr(dqkv16), B, L, H, dh, scale,
+    ws = None
+    nbytes = int(lib().countr_attention_bwd_workspace_bytes(B, L, H, dh))
+    if nbytes:
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=qkv16.device)     # fp32 dQ accumulator (head_dim 64)
+    check(lib().countr_attention_bwd(_ptr(qkv16), _ptr(out16), _ptr(dout16), _ptr(lse), _ptr(dqkv16), _ptr(ws), B, L, H, dh, scale,
                                      _is_bf16(qkv16), _stream()))
-    _count()
+    _count(3 if nbytes else 1)
 
 
 def cross_attn_core(q16, k32, v32, out16, B, L, S, D, dh, scale, probs=None, kv_broadcast=False):

@@ -125,11 +125,15 @@ int countr_layernorm_bwd(const float* dy, const float* x, const float* gamma, co
 int countr_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int dh, float scale,
                          int bf16, countr_stream_t stream);
 
-/* Fused flash-style backward of the same op for head_dim 32 (the FIM self-attention): given qkv, the forward
- * output `out`, its gradient `dout` ([B*L][H*dh]) and lse, writes dqkv [B][L][3][H][dh].  No [B,H,L,L] tensor is
- * materialised.  replaces: autograd of models_crossvit.py:87-91 (bmm / _softmax_backward_data / bmm). */
-int countr_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int L, int H,
-                         int dh, float scale, int bf16, countr_stream_t stream);
+/* Fused flash-style backward of the same op: given qkv, the forward output `out`, its gradient `dout` ([B*L][H*dh]) and
+ * lse, writes dqkv [B][L][3][H][dh].  No [B,H,L,L] tensor is materialised.
+ *   head_dim 32 (the FIM self-attention, L <= 640): one CTA per (batch, head), everything resident, workspace unused (NULL).
+ *   head_dim 64 (the MAE pre-training encoder, any L): one CTA per (batch, head, 128-key block); dQ is accumulated in the
+ *   fp32 workspace (countr_attention_bwd_workspace_bytes, 16-byte aligned; zeroed here) and converted into dqkv at the end.
+ * replaces: autograd of models_crossvit.py:87-91 / timm Attention (bmm / _softmax_backward_data / bmm). */
+int64_t countr_attention_bwd_workspace_bytes(int B, int L, int H, int dh);
+int countr_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* workspace, int B,
+                         int L, int H, int dh, float scale, int bf16, countr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Cross-attention core for a handful of exemplar tokens (S <= 8): per token and head

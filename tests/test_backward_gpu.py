@@ -93,7 +93,8 @@ def test_colsum_and_softmax_bwd(cuda):
 
 
 @pytest.mark.parametrize("B,L,H,dh,fused", [(2, 576, 16, 32, True), (2, 576, 16, 32, False), (1, 200, 3, 32, True), (1, 640, 2, 32, True),
-                                             (1, 288, 4, 64, False)])
+                                             (1, 288, 4, 64, False), (2, 288, 12, 64, True), (1, 576, 3, 64, True), (1, 200, 2, 64, True),
+                                             (3, 144, 2, 64, True)])
 def test_attention_backward(cuda, B, L, H, dh, fused):
     from countr_b200 import ops
     from countr_b200.backward import attention_backward
