@@ -38,6 +38,8 @@ SIGS = {
     "countr_window_blend": [P, I, P, I, I, I, I, P, P],
     "countr_weight_refresh": [P, P, I, I, I, P],
     "countr_crop_resize_boxes": [P, L, L, L, L, P, P, I, I, I, I, I, I, P],
+    "countr_crop_resize": [P, L, L, L, L, P, P, I, I, I, I, I, I, I, P],
+    "countr_rect_mass": [P, I, I, P, I, F, P, P],
     "countr_grouped_dw": [P, I, I, P],
     "countr_grouped_colsum": [P, I, P],
     "countr_density_from_dots": [P, P, I, I, c_double, c_double, I, I, I, I, I, I, P, I, F, P, P, P],

@@ -28,12 +28,13 @@ def vit_block_forward(wc, blk, x, B, L, save):
     ops.linear(att, wc.w16(blk.attn.proj.weight), x1, bias=_contig32(blk.attn.proj.bias), residual=x)
     h2, mean2, rstd2 = e((M, D), F16), e((M,), F32), e((M,), F32)
     ops.layernorm_fwd(x1, _contig32(blk.norm2.weight), _contig32(blk.norm2.bias), blk.norm2.eps, y16=h2, mean=mean2, rstd=rstd2)
-    u, pre = e((M, hid), F16), e((M, hid), F16)
+    u, pre = e((M, hid), F16), (e((M, hid), F16) if save is not None else None)     # the pre-activation is only kept for the backward
     ops.linear(h2, wc.w16(blk.mlp.fc1.weight), u, bias=_contig32(blk.mlp.fc1.bias), act=1, aux=pre)
     x2 = e((M, D), F32)
     ops.linear(u, wc.w16(blk.mlp.fc2.weight), x2, bias=_contig32(blk.mlp.fc2.bias), residual=x1)
-    save.append(dict(x0=x, h1=h1, mean1=mean1, rstd1=rstd1, qkv=qkv, att=att, lse=lse, x1=x1, h2=h2, mean2=mean2, rstd2=rstd2,
-                     u=u, pre=pre, B=B, L=L))
+    if save is not None:
+        save.append(dict(x0=x, h1=h1, mean1=mean1, rstd1=rstd1, qkv=qkv, att=att, lse=lse, x1=x1, h2=h2, mean2=mean2, rstd2=rstd2,
+                         u=u, pre=pre, B=B, L=L))
     return x2
 
 

@@ -979,6 +979,89 @@ attention_bwd64_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid
   }
 }
 
+// ================================================================================================
+// Generic-head-size forward (CUDA cores, fp32): head dims the tcgen05 kernels are not instantiated for — mae_vit_huge_patch14
+// (models_mae_cross.py:226-231: 1280 / 16 = 80 channels per head, 27 x 27 = 729 tokens).  One warp per query row, 8 rows per
+// block; K / V stream through shared memory in 64-key chunks shared by the 8 warps; lanes own keys for Q.K^T and output
+// channels for P.V; online softmax in fp32.  Same arithmetic and outputs (out, lse) as attention_fwd_kernel.  Not a
+// benchmarked configuration: it exists so that every factory of the reference runs.
+// ================================================================================================
+constexpr int kGenMaxDh = 128, kGenKeys = 64;
+__global__ void __launch_bounds__(256) attention_fwd_generic_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out,
+                                                                     float* __restrict__ lse, int L, int H, int dh, float scale_log2,
+                                                                     int bf16) {
+  extern __shared__ float gsm[];
+  const int pitch = dh + 1;                       // odd pitch in words: conflict-free row-per-lane reads
+  float* sk = gsm;                                // [64][pitch]
+  float* sv = sk + kGenKeys * pitch;              // [64][pitch]
+  float* sq = sv + kGenKeys * pitch;              // [8][dh]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q = blockIdx.x * 8 + warp;
+  const long long row = 3ll * H * dh;
+  pdl_trigger();
+  pdl_wait();
+  auto ld16 = [&](const uint16_t* p) {
+    return bf16 ? __uint_as_float(static_cast<uint32_t>(*p) << 16) : __half2float(*reinterpret_cast<const __half*>(p));
+  };
+  if (q < L)
+    for (int d = lane; d < dh; d += 32) sq[warp * dh + d] = ld16(qkv + (static_cast<long long>(b) * L + q) * row + h * dh + d);
+  float m_run = -INFINITY, l_run = 0.f;
+  float o[kGenMaxDh / 32];
+#pragma unroll
+  for (int t = 0; t < kGenMaxDh / 32; ++t) o[t] = 0.f;
+  for (int k0 = 0; k0 < L; k0 += kGenKeys) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kGenKeys * dh; i += blockDim.x) {
+      const int kk = i / dh, d = i - kk * dh;
+      const int key = k0 + kk;
+      float kv = 0.f, vv = 0.f;
+      if (key < L) {
+        const uint16_t* base = qkv + (static_cast<long long>(b) * L + key) * row + h * dh + d;
+        kv = ld16(base + static_cast<long long>(H) * dh);
+        vv = ld16(base + 2ll * H * dh);
+      }
+      sk[kk * pitch + d] = kv;
+      sv[kk * pitch + d] = vv;
+    }
+    __syncthreads();
+    if (q >= L) continue;
+    float s0 = 0.f, s1 = 0.f;
+    for (int d = 0; d < dh; ++d) {
+      const float qd = sq[warp * dh + d];
+      s0 = fmaf(qd, sk[lane * pitch + d], s0);
+      s1 = fmaf(qd, sk[(lane + 32) * pitch + d], s1);
+    }
+    s0 = (k0 + lane < L) ? s0 * scale_log2 : -INFINITY;
+    s1 = (k0 + lane + 32 < L) ? s1 * scale_log2 : -INFINITY;
+    const float mx = warp_max(fmaxf(s0, s1));
+    const float m_new = fmaxf(m_run, mx);
+    const float corr = exp2f(m_run - m_new);         // first chunk: exp2(-inf) = 0
+    const float p0 = exp2f(s0 - m_new), p1 = exp2f(s1 - m_new);
+    l_run = l_run * corr + warp_sum(p0 + p1);
+    m_run = m_new;
+#pragma unroll
+    for (int t = 0; t < kGenMaxDh / 32; ++t) o[t] *= corr;
+    for (int j = 0; j < kGenKeys; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, j < 32 ? p0 : p1, j & 31);
+#pragma unroll
+      for (int t = 0; t < kGenMaxDh / 32; ++t) {
+        const int d = lane + 32 * t;
+        if (d < dh) o[t] = fmaf(pj, sv[j * pitch + d], o[t]);
+      }
+    }
+  }
+  if (q >= L) return;
+  const float inv = 1.f / l_run;
+  uint16_t* orow = out + (static_cast<long long>(b) * L + q) * (H * dh) + h * dh;
+#pragma unroll
+  for (int t = 0; t < kGenMaxDh / 32; ++t) {
+    const int d = lane + 32 * t;
+    if (d < dh) orow[d] = static_cast<uint16_t>(pack2(o[t] * inv, 0.f, bf16) & 0xffffu);
+  }
+  if (lse != nullptr && lane == 0) lse[(static_cast<long long>(b) * H + h) * L + q] = (m_run + log2f(l_run)) * 0.69314718055994531f;
+}
+
 // dq32 [B*L][H*64] fp32 -> the Q slots of dqkv [B*L][3][H*64] (16-bit); thread = 8 columns
 __global__ void __launch_bounds__(256) dq_cast_kernel(const float* __restrict__ dq32, uint16_t* __restrict__ dqkv, long long rows, int D,
                                                       int bf16) {
@@ -1016,7 +1099,19 @@ extern "C" int countr_attention_fwd(const void* qkv, void* out, float* lse, int 
                             : launch_attention<64, false>(qkv, out, lse, B, L, H, scale, bf16, stream);
   if (dh == 32) return bf16 ? launch_attention<32, true>(qkv, out, lse, B, L, H, scale, bf16, stream)
                             : launch_attention<32, false>(qkv, out, lse, B, L, H, scale, bf16, stream);
-  return set_error(COUNTR_ERR_UNSUPPORTED, "attention head_dim %d not supported (32 or 64)", dh);
+  COUNTR_REQUIRE(dh >= 8 && dh <= kGenMaxDh && dh % 8 == 0, "attention head_dim %d not supported (32 / 64 on tensor cores, any multiple of 8 up to %d otherwise)",
+                 dh, kGenMaxDh);
+  {
+    // head sizes without a tcgen05 instantiation (mae_vit_huge_patch14: 80): generic CUDA-core kernel
+    const size_t smem = (2ull * kGenKeys * (dh + 1) + 8ull * dh) * sizeof(float);
+    static PerDeviceOnce attr_gen;
+    if (attr_gen.need())
+      COUNTR_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    COUNTR_CHECK_CUDA(launch_pdl(attention_fwd_generic_kernel, dim3((L + 7) / 8, H, B), dim3(256), smem, stream,
+                                 reinterpret_cast<const uint16_t*>(qkv), reinterpret_cast<uint16_t*>(out), lse, L, H, dh,
+                                 scale * 1.44269504088896340736f, bf16));
+    return COUNTR_OK;
+  }
 }
 
 extern "C" int64_t countr_attention_bwd_workspace_bytes(int B, int L, int H, int dh) {

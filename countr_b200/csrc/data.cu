@@ -101,19 +101,20 @@ extern "C" int countr_density_from_dots(const double* dots, const int32_t* count
 namespace countr {
 namespace {
 __global__ void crop_resize_kernel(const float* __restrict__ img, long long sb, long long sc, long long sh, long long sw,
-                                   const int* __restrict__ rects, float* __restrict__ out, int B, int S, int C, int H, int W, int O) {
-  const long long total = static_cast<long long>(B) * S * C * O * O;
+                                   const int* __restrict__ rects, float* __restrict__ out, int B, int S, int C, int H, int W, int OH, int OW) {
+  const long long total = static_cast<long long>(B) * S * C * OH * OW;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int ox = static_cast<int>(idx % O), oy = static_cast<int>((idx / O) % O);
-  const int c = static_cast<int>((idx / (static_cast<long long>(O) * O)) % C);
-  const int s = static_cast<int>((idx / (static_cast<long long>(O) * O * C)) % S);
-  const int b = static_cast<int>(idx / (static_cast<long long>(O) * O * C * S));
+  const int ox = static_cast<int>(idx % OW), oy = static_cast<int>((idx / OW) % OH);
+  const long long plane = static_cast<long long>(OH) * OW;
+  const int c = static_cast<int>((idx / plane) % C);
+  const int s = static_cast<int>((idx / (plane * C)) % S);
+  const int b = static_cast<int>(idx / (plane * C * S));
   const int* r = rects + (static_cast<long long>(b) * S + s) * 4;
   const int y1 = max(0, min(H - 1, r[0])), x1 = max(0, min(W - 1, r[1]));
   const int y2 = max(y1, min(H - 1, r[2])), x2 = max(x1, min(W - 1, r[3]));   // python slicing clips at the image border
   const int h = y2 - y1 + 1, w = x2 - x1 + 1;
-  const float scale_h = static_cast<float>(h) / O, scale_w = static_cast<float>(w) / O;
+  const float scale_h = static_cast<float>(h) / OH, scale_w = static_cast<float>(w) / OW;
   float ry = scale_h * (oy + 0.5f) - 0.5f, rx = scale_w * (ox + 0.5f) - 0.5f;
   ry = ry < 0.f ? 0.f : ry;
   rx = rx < 0.f ? 0.f : rx;
@@ -126,17 +127,57 @@ __global__ void crop_resize_kernel(const float* __restrict__ img, long long sb, 
   const float cq = p[(y1 + iy1) * sh + (x1 + ix0) * sw], d = p[(y1 + iy1) * sh + (x1 + ix1) * sw];
   out[idx] = ly0 * (lx0 * a + lx1 * bq) + ly1 * (lx0 * cq + lx1 * d);
 }
+
+// sum over the inclusive pixel rectangles (y1, x1, y2, x2) of map / divisor, all rectangles added into out[0]
+// (test-time normalisation: the density mass under the exemplar boxes, FSC_test_cross(few-shot).py:353-359)
+__global__ void __launch_bounds__(256) rect_mass_kernel(const float* __restrict__ map, int H, int W, const int* __restrict__ rects,
+                                                        float divisor, float* __restrict__ out) {
+  const int* r = rects + blockIdx.x * 4;
+  // python slicing: negative / oversized bounds clip at the border
+  const int y1 = max(0, r[0]), x1 = max(0, r[1]), y2 = min(H - 1, r[2]), x2 = min(W - 1, r[3]);
+  float acc = 0.f;
+  if (y2 >= y1 && x2 >= x1) {
+    const int w = x2 - x1 + 1, n = (y2 - y1 + 1) * w;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += map[static_cast<long long>(y1 + i / w) * W + x1 + i % w] / divisor;
+  }
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(out, t);
+  }
+}
 }  // namespace
 }  // namespace countr
 
-extern "C" int countr_crop_resize_boxes(const float* img, int64_t sb, int64_t sc, int64_t sh, int64_t sw, const int32_t* rects,
-                                        float* out, int B, int S, int C, int H, int W, int out_hw, countr_stream_t stream_) {
+extern "C" int countr_crop_resize(const float* img, int64_t sb, int64_t sc, int64_t sh, int64_t sw, const int32_t* rects, float* out,
+                                  int B, int S, int C, int H, int W, int out_h, int out_w, countr_stream_t stream_) {
   using namespace countr;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(img && rects && out, "null pointer");
-  COUNTR_REQUIRE(B > 0 && S > 0 && C > 0 && H > 0 && W > 0 && out_hw > 0, "bad shape");
-  const long long total = static_cast<long long>(B) * S * C * out_hw * out_hw;
-  crop_resize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(img, sb, sc, sh, sw, rects, out, B, S, C, H, W, out_hw);
+  COUNTR_REQUIRE(B > 0 && S > 0 && C > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0, "bad shape");
+  const long long total = static_cast<long long>(B) * S * C * out_h * out_w;
+  crop_resize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(img, sb, sc, sh, sw, rects, out, B, S, C, H, W, out_h,
+                                                                                     out_w);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_crop_resize_boxes(const float* img, int64_t sb, int64_t sc, int64_t sh, int64_t sw, const int32_t* rects,
+                                        float* out, int B, int S, int C, int H, int W, int out_hw, countr_stream_t stream_) {
+  return countr_crop_resize(img, sb, sc, sh, sw, rects, out, B, S, C, H, W, out_hw, out_hw, stream_);
+}
+
+extern "C" int countr_rect_mass(const float* map, int H, int W, const int32_t* rects, int n_rects, float divisor, float* out,
+                                countr_stream_t stream_) {
+  using namespace countr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(map && rects && out && H > 0 && W > 0 && n_rects > 0 && divisor != 0.f, "bad arguments");
+  rect_mass_kernel<<<n_rects, 256, 0, stream>>>(map, H, W, rects, divisor, out);
   COUNTR_CHECK_CUDA(cudaGetLastError());
   return COUNTR_OK;
 }

@@ -109,6 +109,27 @@ __global__ void patchify_kernel(const void* __restrict__ img, int dtype, long lo
   *reinterpret_cast<uint4*>(out + row * (static_cast<long long>(C) * P * P) + col) = pack8(f, bf16);
 }
 
+// Any patch size / image size (mae_vit_huge_patch14: 14-px patches on a 384-px image -> 27 x 27 patches, the last 6 pixels of
+// every row / column are dropped like Conv2d(stride = kernel) drops them): one thread per output element, rows padded with
+// zeros to `ld` elements (a multiple of 8: TMA needs 16-byte row pitches).
+__global__ void patchify_generic_kernel(const void* __restrict__ img, int dtype, long long sb, long long sc, long long sh, long long sw,
+                                        uint16_t* __restrict__ out, int B, int C, int H, int W, int P, int ld, int bf16) {
+  const int gw = W / P, gh = H / P;
+  const long long total = static_cast<long long>(B) * gh * gw * ld;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int col = static_cast<int>(idx % ld);
+  const long long row = idx / ld;
+  float v = 0.f;
+  if (col < C * P * P) {
+    const int kx = col % P, ky = (col / P) % P, c = col / (P * P);
+    const int px = static_cast<int>(row % gw), py = static_cast<int>((row / gw) % gh), b = static_cast<int>(row / (static_cast<long long>(gw) * gh));
+    v = load_any(img, b * sb + c * sc + static_cast<long long>(py * P + ky) * sh + static_cast<long long>(px * P + kx) * sw, dtype);
+  }
+  float f[8] = {v, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  out[idx] = static_cast<uint16_t>(pack8(f, bf16).x & 0xffffu);
+}
+
 // ------------------------------------------------------------------------------------------
 // Conv2d 3x3 weight [Cout][Cin][3][3] fp32 -> GEMM B operand, 16-bit:
 //   mode 0 (forward):  out[co][(ky*3+kx)*Cin + ci] = w[co][ci][ky][kx]
@@ -646,7 +667,7 @@ __global__ void __launch_bounds__(256) inorm_relu_pool_kernel(const uint16_t* __
 // probs [M][Hh][S] fp32 (optional, saved for backward).  dh == 32, D % 512 == 0, S <= 8.
 // One warp per token: lane l owns channels [16l,16l+16) of each 512-chunk (= half a head).
 // ------------------------------------------------------------------------------------------
-constexpr int kMaxShots = 8;
+constexpr int kMaxShots = 16;     // forward: evaluation passes every annotated exemplar box (FSC_test_cross(few-shot).py:261); training uses <= 3
 __global__ void __launch_bounds__(256) cross_attn_core_kernel(const uint16_t* __restrict__ q16, const float* __restrict__ k32,
                                                                const float* __restrict__ v32, uint16_t* __restrict__ out16,
                                                                float* __restrict__ probs, int L, int S, int D, float scale,
@@ -866,7 +887,16 @@ extern "C" int countr_patchify(const void* img, int dtype, int64_t sb, int64_t s
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(img && out, "null pointer");
   COUNTR_REQUIRE(dtype >= 0 && dtype <= 2, "image dtype code %d", dtype);
-  COUNTR_REQUIRE(P % 8 == 0 && H % P == 0 && W % P == 0, "patch size %d must be a multiple of 8 dividing %dx%d", P, H, W);
+  COUNTR_REQUIRE(P > 0 && H >= P && W >= P, "patch size %d vs image %dx%d", P, H, W);
+  if (P % 8 != 0 || H % P != 0 || W % P != 0) {
+    // generic path: row pitch = C*P*P rounded up to a multiple of 8, zero padded (see the header)
+    const int ld = (C * P * P + 7) & ~7;
+    const long long n = static_cast<long long>(B) * (H / P) * (W / P) * ld;
+    patchify_generic_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(img, dtype, sb, sc, sh, sw,
+                                                                                     reinterpret_cast<uint16_t*>(out), B, C, H, W, P, ld, bf16);
+    COUNTR_CHECK_CUDA(cudaGetLastError());
+    return COUNTR_OK;
+  }
   const long long total = static_cast<long long>(B) * (H / P) * (W / P) * C * P * (P / 8);
   patchify_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(img, dtype, sb, sc, sh, sw,
                                                                                  reinterpret_cast<uint16_t*>(out), B, C, H, W, P, bf16);
@@ -990,6 +1020,10 @@ extern "C" int countr_cross_attn_core(const void* q16, const float* k32, const f
   while (L % tpb) tpb >>= 1;
   const int blocks = B * L / tpb;
   const size_t smem = 2ull * S * D * sizeof(float);
+  COUNTR_REQUIRE(smem <= 160 * 1024, "exemplar tokens do not fit in shared memory (S=%d D=%d)", S, D);
+  static PerDeviceOnce attr_once;
+  if (attr_once.need())
+    COUNTR_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   cross_attn_core_kernel<<<blocks, 256, smem, stream>>>(reinterpret_cast<const uint16_t*>(q16), k32, v32,
                                                        reinterpret_cast<uint16_t*>(out16), probs, L, S, D, scale, tpb, bf16,
                                                        kv_broadcast ? 0ll : static_cast<long long>(S) * D);

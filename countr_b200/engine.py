@@ -193,12 +193,20 @@ class Engine:
         M = B * L
         D = m.pos_embed.shape[-1]
         ws, wc = self.ws, self.wc
-        patches = ws.get("patches", (M, C * P * P), F16, dev)
+        Kp = C * P * P
+        ld = (Kp + 7) & ~7             # TMA row pitch: multiple of 16 bytes (14-px patches: 588 -> 592, zero padded)
+        patches = ws.get("patches", (M, ld), F16, dev)
         ops_.patchify(imgs, patches, P)
         x = ws.get("enc_x", (M, D), F32, dev)
         pe = m.patch_embed.proj
-        ops_.linear(patches, wc.w16(pe.weight), x, bias=_contig32(pe.bias), residual=_contig32(m.pos_embed).reshape(L, D),
-                    res_mod=L)
+        w_pe = wc.w16(pe.weight)
+        if ld != Kp:
+            # not a benchmarked configuration (mae_vit_huge_patch14 only): zero-padded copy of the filter matrix per forward
+            wpad = ws.get("pe_wpad", (D, ld), F16, dev)
+            wpad.zero_()
+            wpad[:, :Kp].copy_(w_pe)
+            w_pe = wpad
+        ops_.linear(patches, w_pe, x, bias=_contig32(pe.bias), residual=_contig32(m.pos_embed).reshape(L, D), res_mod=L)
         h = ws.get("enc_h", (M, D), F16, dev)
         for blk in m.blocks:
             H = blk.attn.num_heads

@@ -255,10 +255,68 @@ class MaskedAutoencoderViTNoCT(nn.Module):
             eng.grad_allreduce(arena)
         return views
 
-    # -- reference API
+    # -- reference API: the staged calls (models_mae_noct.py:137-198).  forward() runs the same schedule fused and is the only
+    # differentiable entry point (FSC_pretrain.py:263 calls nothing else); the staged calls are inference-only inspection hooks.
+    def _refresh(self):
+        lin = [self.patch_embed.proj, self.decoder_embed, self.decoder_pred]
+        for blk in list(self.blocks) + list(self.decoder_blocks):
+            lin += [blk.attn.qkv, blk.attn.proj, blk.mlp.fc1, blk.mlp.fc2]
+        engine().wc.refresh_batch([(l.weight, "w") for l in lin])
+
+    @torch.no_grad()
     def forward_encoder(self, x, mask_ratio):
-        raise NotImplementedError("countr_b200: use forward(imgs, mask_ratio); the staged forward_encoder/forward_decoder/forward_loss "
-                                  "calls of the reference are fused into one kernel schedule here")
+        """imgs [N, 3, H, W] -> (latent fp32 [N, L_keep, D], mask [N, L], ids_restore [N, L])   (models_mae_noct.py:137-152)"""
+        if not x.is_cuda:
+            raise _lib.CountrError("countr_b200 runs on a B200 (sm_100a) only: got a CPU tensor and there is no CPU fallback")
+        _lib.require_device()
+        self._refresh()
+        wc, dev = engine().wc, x.device
+        B, C, Himg, Wimg = x.shape
+        P = self.patch_embed.patch_size[0]
+        L, D = (Himg // P) * (Wimg // P), self.pos_embed.shape[-1]
+        patches = torch.empty(B * L, C * P * P, dtype=F16, device=dev)
+        ops.patchify(x, patches, P)
+        x_full = torch.empty(B * L, D, dtype=F32, device=dev)
+        pe = self.patch_embed.proj
+        ops.linear(patches, wc.w16(pe.weight), x_full, bias=_contig32(pe.bias), residual=_contig32(self.pos_embed).reshape(L, D), res_mod=L)
+        Lk, ids_shuffle, ids_restore, mask = self._masking_indices(B, L, mask_ratio, dev)
+        h = torch.empty(B * Lk, D, dtype=F32, device=dev)
+        ops.gather_rows(x_full.view(B, L, D), ids_shuffle[:, :Lk].contiguous(), h.view(B, Lk, D))
+        for blk in self.blocks:
+            h = vit_block_forward(wc, blk, h, B, Lk, None)
+        lat = torch.empty(B, Lk, D, dtype=F32, device=dev)
+        ops.layernorm_fwd(h, _contig32(self.norm.weight), _contig32(self.norm.bias), self.norm.eps, y32=lat.view(B * Lk, D))
+        return lat, mask, ids_restore
+
+    @torch.no_grad()
+    def forward_decoder(self, x, ids_restore):
+        """latent [N, L_keep, D], ids_restore [N, L] -> pred fp32 [N, L, p*p*3]   (models_mae_noct.py:154-175)"""
+        self._refresh()
+        wc, dev = engine().wc, x.device
+        B, Lk, D = x.shape
+        L = ids_restore.shape[1]
+        Dd = self.decoder_embed.weight.shape[0]
+        lat16 = torch.empty(B * Lk, D, dtype=F16, device=dev)
+        ops.cast16(x.detach().to(F32).contiguous().view(B * Lk, D), lat16)
+        xk = torch.empty(B * Lk, Dd, dtype=F32, device=dev)
+        ops.linear(lat16, wc.w16(self.decoder_embed.weight), xk, bias=_contig32(self.decoder_embed.bias))
+        xd = torch.empty(B * L, Dd, dtype=F32, device=dev)
+        ops.mae_unshuffle(xk.view(B, Lk, Dd), ids_restore.contiguous(), _contig32(self.mask_token).reshape(Dd),
+                          _contig32(self.decoder_pos_embed).reshape(L, Dd), xd.view(B, L, Dd))
+        for blk in self.decoder_blocks:
+            xd = vit_block_forward(wc, blk, xd, B, L, None)
+        f16 = torch.empty(B * L, Dd, dtype=F16, device=dev)
+        ops.layernorm_fwd(xd, _contig32(self.decoder_norm.weight), _contig32(self.decoder_norm.bias), self.decoder_norm.eps, y16=f16)
+        pred = torch.empty(B, L, self.decoder_pred.weight.shape[0], dtype=F32, device=dev)
+        ops.linear(f16, wc.w16(self.decoder_pred.weight), pred.view(B * L, -1), bias=_contig32(self.decoder_pred.bias))
+        return pred
+
+    @torch.no_grad()
+    def forward_loss(self, imgs, pred, mask):
+        """Mean over ALL patches of the per-patch MSE — the reference replaces `mask` by ones (models_mae_noct.py:193-195)."""
+        loss = torch.empty((), dtype=F32, device=imgs.device)
+        ops.mae_loss(pred.detach().to(F32).contiguous(), imgs, loss, None, self.patch_embed.patch_size[0], self.norm_pix_loss)
+        return loss
 
     def forward(self, imgs, mask_ratio=0.75):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):

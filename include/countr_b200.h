@@ -155,7 +155,9 @@ int countr_cast_f32_to_16(const float* src, void* dst, int64_t n, float scale, i
 int countr_cast_transpose_f32_to_16(const float* src, void* dst, int R, int C, int bf16, countr_stream_t stream);
 /* PatchEmbed gather (timm PatchEmbed.proj as a GEMM; models_mae_cross.py:27,138): NCHW image of
  * dtype code {0 fp32, 1 fp16, 2 bf16} with element strides (sb,sc,sh,sw) -> out16 [B*gh*gw][C*P*P],
- * columns ordered (c, ky, kx) like Conv2d.weight.view(out, -1). */
+ * columns ordered (c, ky, kx) like Conv2d.weight.view(out, -1).  Patch sizes that are not a multiple of 8 or do not divide
+ * the image (mae_vit_huge_patch14: P = 14 on 384 px -> 27 x 27 patches, trailing pixels dropped like the strided Conv2d
+ * drops them): rows are [B*(H/P)*(W/P)][ld], ld = C*P*P rounded up to a multiple of 8, zero padded. */
 int countr_patchify(const void* img, int dtype, int64_t sb, int64_t sc, int64_t sh, int64_t sw, void* out,
                     int B, int C, int H, int W, int P, int bf16, countr_stream_t stream);
 /* Conv2d 3x3 weight [Cout][Cin][3][3] fp32 -> B operand of the implicit GEMM:
@@ -353,6 +355,15 @@ int countr_weight_refresh(const void* entries, const int32_t* blk_prefix, int n_
  * (sb, sc, sh, sw); rects: int32 [B][S][4] = (y1, x1, y2, x2), inclusive, clipped to the image; out: fp32 [B][S][C][out_hw][out_hw]. */
 int countr_crop_resize_boxes(const float* img, int64_t sb, int64_t sc, int64_t sh, int64_t sw, const int32_t* rects, float* out,
                              int B, int S, int C, int H, int W, int out_hw, countr_stream_t stream);
+/* Same resize arithmetic with a rectangular output: out fp32 [B][S][C][out_h][out_w].  Used by the evaluation path that tiles an
+ * image with tiny exemplars into 3 x 3 crops and blows each crop up to the full frame (FSC_test_cross(few-shot).py:273-285:
+ * TF.crop + transforms.Resize((h, w))). */
+int countr_crop_resize(const float* img, int64_t sb, int64_t sc, int64_t sh, int64_t sw, const int32_t* rects, float* out, int B,
+                       int S, int C, int H, int W, int out_h, int out_w, countr_stream_t stream);
+/* out[0] += sum over n_rects inclusive pixel rectangles (y1, x1, y2, x2; clipped like python slices) of map[y][x] / divisor —
+ * the exemplar-box density mass of the test-time normalisation (FSC_test_cross(few-shot).py:353-359, demo.py:162-169). */
+int countr_rect_mass(const float* map, int H, int W, const int32_t* rects, int n_rects, float divisor, float* out,
+                     countr_stream_t stream);
 
 #ifdef __cplusplus
 }

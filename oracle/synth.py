@@ -20,6 +20,10 @@ CONFIGS = {
     # ViT-L/16 geometry (embed 1024, 16 heads of 64; models_mae_cross.py:218-223) with a 4-block FIM (:232-237), shallow
     "large_fim4": dict(img_size=384, patch_size=16, embed_dim=1024, depth=2, num_heads=16, decoder_embed_dim=512,
                        decoder_depth=4, decoder_num_heads=16, mlp_ratio=4, eps=1e-6),
+    # ViT-H/14 geometry (models_mae_cross.py:226-231): 14-px patches -> 27 x 27 = 729 tokens, 1280 / 16 = 80 channels per head,
+    # 432 x 432 density map; shallow encoder
+    "huge_d2": dict(img_size=384, patch_size=14, embed_dim=1280, depth=2, num_heads=16, decoder_embed_dim=512,
+                    decoder_depth=2, decoder_num_heads=16, mlp_ratio=4, eps=1e-6),
     "small": dict(img_size=384, patch_size=16, embed_dim=256, depth=2, num_heads=4, decoder_embed_dim=512,
                   decoder_depth=2, decoder_num_heads=16, mlp_ratio=4, eps=1e-6),
 }

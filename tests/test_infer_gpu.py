@@ -53,3 +53,34 @@ def test_sliding_window_matches_reference_loop(cuda, w, shot):
     # same kernels, but the batched forward picks other tile shapes / statistics splits than batch 1, so fp16 roundings differ
     assert rel(dens, ref) < 1e-3, (w, window_starts(w))
     assert abs(cnt.item() - ref.sum().item() / 60) < 1e-3 * abs(ref.sum().item() / 60)
+
+
+@pytest.mark.parametrize("w,pos,tiled", [(512, [(40, 60, 130, 170), (200, 300, 290, 420), (10, 10, 380, 500)], False),
+                                         (384, [(100, 100, 106, 107), (200, 220, 260, 300), (20, 30, 200, 380)], True),
+                                         (512, [(5, 5, 12, 13), (50, 60, 58, 66), (300, 400, 306, 409)], True)])
+def test_evaluate_image_matches_cpu_oracle(cuda, w, pos, tiled):
+    """FSC_test_cross(few-shot).py:258-359 end to end — 3 x 3 tiling for tiny exemplars (crop + bilinear blow-up + one batched
+    forward over all crops x windows), count, test-time normalisation — against the CPU restatement (oracle/infer_oracle.py)
+    driving the CPU oracle model: the CUDA path is checked against an independent implementation, forward included."""
+    from countr_b200.infer import evaluate_image, small_exemplar_count
+    from oracle import countr_oracle as O
+    from oracle import infer_oracle as IO
+    m, sd, cfg = build("small", 1, cuda)
+    m.eval()
+    g = torch.Generator().manual_seed(7 * w + len(pos))
+    samples = torch.rand(1, 3, 384, w, generator=g)
+    boxes = torch.rand(1, 3, 3, 64, 64, generator=g)
+    assert (small_exemplar_count(pos) >= 1) == tiled
+    with torch.no_grad():
+        ref_cnt, ref_maps = IO.evaluate_image(lambda im, bx, s: O.forward(sd, cfg, im.contiguous(), bx, s), samples, boxes, pos)
+        ref_raw, _ = IO.evaluate_image(lambda im, bx, s: O.forward(sd, cfg, im.contiguous(), bx, s), samples, boxes, pos, normalization=False) \
+            if not tiled else (None, None)
+    cnt, dens = evaluate_image(m, samples.to(cuda), boxes.to(cuda), pos)
+    ref = torch.stack(ref_maps) if tiled else ref_maps[0]
+    assert dens.shape == ref.shape
+    assert rel(dens, ref) < 2e-3, rel(dens, ref)
+    assert abs(cnt.item() - ref_cnt) < 2e-3 * abs(ref_cnt) + 1e-6, (cnt.item(), ref_cnt)
+    if ref_raw is not None:
+        raw, _ = evaluate_image(m, samples.to(cuda), boxes.to(cuda), pos, normalization=False)
+        assert abs(raw.item() - ref_raw) < 2e-3 * abs(ref_raw) + 1e-6
+        print(f"[evaluate_image] w={w}: count {ref_raw:.3f} -> normalised {ref_cnt:.3f}")

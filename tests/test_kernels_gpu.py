@@ -282,7 +282,8 @@ def test_layernorm(cuda, rows, D):
 # ------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,L,H,dh", [(1, 128, 1, 64), (2, 576, 12, 64), (2, 576, 16, 32), (1, 288, 12, 64), (1, 200, 2, 32)])
+@pytest.mark.parametrize("B,L,H,dh", [(1, 128, 1, 64), (2, 576, 12, 64), (2, 576, 16, 32), (1, 288, 12, 64), (1, 200, 2, 32),
+                                      (1, 729, 16, 80), (2, 100, 3, 48)])     # the last two: generic head sizes (ViT-H: 80)
 def test_attention_fwd(cuda, B, L, H, dh):
     from countr_b200 import ops
     qkv = _rand16((B, L, 3, H, dh), cuda, seed=12, scale=1.5)
@@ -323,7 +324,7 @@ def test_attention_fwd_growing_scores(cuda):
 def test_cross_attn_core(cuda):
     from countr_b200 import ops
     B, L, D, dh = 2, 576, 512, 32
-    for S in (1, 2, 3, 5):
+    for S in (1, 2, 3, 5, 9, 16):      # evaluation passes every annotated box (up to 16); training uses <= 3
         q = _rand16((B * L, D), cuda, seed=13)
         k = torch.randn(B, S, D, device=cuda)
         v = torch.randn(B, S, D, device=cuda)

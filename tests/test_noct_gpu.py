@@ -80,3 +80,21 @@ def test_noct_eval_and_masking_api(cuda):
     xm, mk, ids = m.random_masking(x, 0.5)
     assert xm.shape == (2, 288, 256) and torch.equal(xm, torch.gather(x, 1, torch.argsort(ids, 1)[:, :288].unsqueeze(-1).repeat(1, 1, 256)))
     assert torch.equal(m.unpatchify(m.patchify(imgs)), imgs)
+
+
+def test_noct_staged_api_matches_fused_forward(cuda):
+    """forward_encoder -> forward_decoder -> forward_loss (the reference's staged calls, models_mae_noct.py:137-198) give what the
+    fused forward() gives for the same masking noise."""
+    import models_mae_noct as N
+    torch.manual_seed(5)
+    m = N.MaskedAutoencoderViTNoCT(embed_dim=256, depth=2, num_heads=4, decoder_depth=2).to(cuda).eval()
+    imgs = torch.rand(2, 3, 384, 384, device=cuda)
+    m._noise_override = noct_noise(2, 576)
+    with torch.no_grad():
+        loss, pred, mask = m(imgs, mask_ratio=0.5)
+        lat, mask2, ids_restore = m.forward_encoder(imgs, 0.5)
+        pred2 = m.forward_decoder(lat, ids_restore)
+        loss2 = m.forward_loss(imgs, pred2, mask2)
+    assert lat.shape == (2, 288, 256) and torch.equal(mask, mask2)
+    assert rel(pred2, pred) < 2e-3          # the staged path re-casts the fp32 latent to 16 bit between the stages
+    assert abs(loss2.item() - loss.item()) < 2e-3 * abs(loss.item())

