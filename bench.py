@@ -216,8 +216,21 @@ class Env:
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         _lib.require_device()
+        self.sm_budget = None
         if self.world > 1:
             import datetime
+            # The gradient all-reduce overlaps compute (the next batch's frozen encoder / the rest of the backward).  Our GEMM and
+            # attention kernels are persistent — one CTA (pair) per SM — so a collective that needs SMs while they run would
+            # push part of every grid into a second wave.  Leave four SMs to NCCL (144-CTA grids lose nothing on the Linear and
+            # attention shapes: 432 tiles = 3 x 144, 288 attention items = 2 x 144) and cap the collective at four CTAs.
+            # (fine-tune only: measured at N = 2, 4.32 -> 4.23 ms per step.  The pre-training step's 446.6 MB all-reduce needs NCCL's
+            # full CTA count; its sliced overlap — models_mae_noct grad_slice_hook, --overlap-pretrain — did not pay at N = 2:
+            # 20.2 ms against 19.7 ms for one all-reduce between the backward and the update graph.)
+            overlap = (args.workload == "finetune" and not args.no_overlap) or (args.workload == "pretrain" and args.overlap_pretrain)
+            if overlap:
+                os.environ.setdefault("NCCL_MAX_CTAS", "4")
+                os.environ.setdefault("NCCL_MAX_NCHANNELS", "4")
+                self.sm_budget = int(_lib.lib().countr_set_sm_budget(int(os.environ.get("COUNTR_SM_BUDGET", "144"))))
             dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=180))   # a stuck collective aborts
         self.steps, self.warmup = args.steps, max(args.warmup, 3)
 
@@ -252,8 +265,16 @@ class Env:
         return flag.item() != 0
 
     def done(self):
+        """Leave without tearing NCCL down: destroy_process_group() can block forever while CUDA graphs that captured
+        collectives are alive (observed at N = 2: the JSON line was out, the processes never exited).  Everything is flushed
+        and every rank has passed the last barrier, so a hard exit loses nothing."""
         if self.world > 1:
-            self.dist.destroy_process_group()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            try:
+                self.barrier()
+            finally:
+                os._exit(0)
 
 
 def eager_warmup(torch, fn, n=3):
@@ -726,7 +747,7 @@ def run_finetune(env, args):
                    + (" + NCCL grad all-reduce (avg)" if world > 1 else ""),
                    "cuda_graph": graphs is not None, "schedule": mode,
                    "step_api": "countr_b200.train.FineTuner" if use_tuner else "script loop (autograd + torch.optim.AdamW)",
-                   "loss_scale": loss_scale,
+                   "loss_scale": loss_scale, "sm_budget": env.sm_budget,
                    "l2": "per-step working set (~1.5 GB of activations) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": round(e2e, 2), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / n_e2e, 4), "h2d": "prefetched on a copy stream during the previous step"},
@@ -891,8 +912,31 @@ def run_pretrain(env, args):
                 for gr in grads:
                     dist.all_reduce(gr, op=dist.ReduceOp.AVG)
 
+    # N > 1, overlapped: the backward hands the arena to `slice_hook` in two pieces — [decoder_embed .. end] as soon as the decoder
+    # backward is done, the encoder part at the end — and each piece is all-reduced on the comm stream while the main stream
+    # keeps computing; the update waits for both.  The whole step (NCCL kernels included) is captured in ONE CUDA graph.
+    overlapped = world > 1 and args.overlap_pretrain
+    comm = torch.cuda.Stream() if world > 1 else None
+
+    def slice_hook(sl):
+        comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(comm):
+            dist.all_reduce(sl, op=dist.ReduceOp.AVG)
+
+    def step_overlapped():
+        eng.grad_slice_hook = slice_hook
+        try:
+            fwd_bwd()
+        finally:
+            eng.grad_slice_hook = None
+        torch.cuda.current_stream().wait_stream(comm)
+        update()
+
     def step_eager():
         opt.zero_grad(set_to_none=True)
+        if overlapped:
+            step_overlapped()
+            return
         fwd_bwd()
         allreduce()
         update()
@@ -908,6 +952,11 @@ def run_pretrain(env, args):
                 with torch.cuda.graph(g1):
                     fwd_bwd()
                     update()
+                graphs = (g1,)
+            elif overlapped:
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    step_overlapped()
                 graphs = (g1,)
             else:
                 g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
@@ -985,8 +1034,9 @@ def run_pretrain(env, args):
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME["pretrain"], "global_batch": B * world,
                        "step": "forward + full backward (encoder trained) + unscale + torch.optim.AdamW(fused)" +
-                               (" + NCCL all-reduce (avg) of the flat 446.6 MB gradient arena" if world > 1 else ""),
-                       "cuda_graph": graphs is not None, "loss_scale": scale,
+                               (" + NCCL all-reduce (avg) of the flat 446.6 MB gradient arena" if world > 1 else "") +
+                               (" in two pieces overlapped with the backward" if overlapped else ""),
+                       "cuda_graph": graphs is not None, "loss_scale": scale, "sm_budget": env.sm_budget,
                        "l2": "per-step working set exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": round(e2e, 2), "unit": "images/s", "h2d_bytes_per_step": d_imgs.numel() * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms_e2e / n, 4), "h2d": "fp32 images prefetched on a copy stream during the previous step"},
@@ -1011,6 +1061,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the parity / sustained-window / eager_b200 / script_mode legs")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: do not overlap the all-reduce with the next batch's encoder")
+    ap.add_argument("--overlap-pretrain", action="store_true",
+                    help="N > 1, pretrain: all-reduce the gradient arena in slices during the backward (experimental; slower at N = 2)")
     ap.add_argument("--script-loop", action="store_true",
                     help="drive the fine-tune step with the reference script's own loop (model() -> loss.backward() -> torch.optim.AdamW) "
                          "instead of countr_b200.train.FineTuner; both run the same forward / backward kernels")

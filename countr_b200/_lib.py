@@ -53,6 +53,8 @@ def _declare(lib):
     lib.countr_version.restype = c_char_p
     lib.countr_check_device.restype = c_int32
     lib.countr_num_sms.restype = c_int32
+    lib.countr_set_sm_budget.argtypes = [c_int32]
+    lib.countr_set_sm_budget.restype = c_int32
     lib.countr_gemm.argtypes = [POINTER(GemmDesc), c_void_p]
     lib.countr_gemm.restype = c_int32
     from . import _sigs  # noqa: WPS433  (plain-argument entry points)

@@ -89,13 +89,19 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+static int g_sm_budget = 0;   // 0 = every SM; set by countr_set_sm_budget (data-parallel runs leave a few SMs to NCCL)
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
+    const char* e = getenv("COUNTR_SM_BUDGET");
+    if (e != nullptr && g_sm_budget == 0) g_sm_budget = atoi(e);
   }
+  // persistent kernels size their grids with this: an even number (CTA pairs), never more than the device has
+  if (g_sm_budget > 0 && g_sm_budget < n) return g_sm_budget & ~1;
   return n;
 }
 
@@ -121,6 +127,11 @@ int countr_check_device(void) {
 }
 
 int countr_num_sms(void) { return countr::num_sms(); }
+
+int countr_set_sm_budget(int n) {
+  countr::g_sm_budget = n > 0 ? n : 0;
+  return countr::num_sms();
+}
 
 int countr_memset_zero(void* ptr, size_t bytes, countr_stream_t stream) {
   if (cudaMemsetAsync(ptr, 0, bytes, reinterpret_cast<cudaStream_t>(stream)) != cudaSuccess)

@@ -29,6 +29,11 @@ const char* countr_last_error(void);
 const char* countr_version(void);
 int countr_check_device(void);
 int countr_num_sms(void);
+/* Persistent kernels launch one CTA (or CTA pair) per SM.  A data-parallel trainer that overlaps its NCCL gradient all-reduce with
+ * compute sets a budget below the device's SM count (e.g. 144 of 148) so that the collective's CTAs find free SMs instead of
+ * queueing behind — and splitting into a second wave — the persistent grids.  n <= 0 restores "all SMs"; returns the value in
+ * effect (also settable with the COUNTR_SM_BUDGET environment variable). */
+int countr_set_sm_budget(int n);
 /* cudaMemsetAsync(ptr, 0, bytes) on `stream` (statistics / split-K accumulators) */
 int countr_memset_zero(void* ptr, size_t bytes, countr_stream_t stream);
 
