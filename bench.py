@@ -880,10 +880,14 @@ def run_pretrain(env, args):
     B = PER_GPU_BATCH["pretrain"]
     torch.manual_seed(0)
     model = models_mae_noct.mae_vit_base_patch16(norm_pix_loss=True).to(dev).train()     # FSC_pretrain.py --norm_pix_loss
-    opt = torch.optim.AdamW(param_groups(model, 0.05), lr=1e-5, betas=(0.9, 0.95), fused=True, capturable=True)
+    from countr_b200.train import ArenaAdamW
+    scale = 1024.0
+    names, params = model._trainable()
+    # unscale + inf check + grad norm + AdamW (timm add_weight_decay grouping) + GradScaler.update as three kernels over the flat
+    # gradient arena the backward leaves behind (util/misc.py:260-301 / FSC_pretrain.py:226-228, 296-300)
+    opt = ArenaAdamW(names, params, lr=1e-5, weight_decay=0.05, betas=(0.9, 0.95), loss_scale=scale, dynamic_scale=False)
     eng = engine()
     eng.grad_allreduce = None
-    scale = 1024.0
     g = torch.Generator().manual_seed(99 + rank)
     host = [torch.rand(B, 3, 384, 384, generator=g).pin_memory() for _ in range(2)]
     d_imgs = torch.empty(B, 3, 384, 384, device=dev)
@@ -896,21 +900,16 @@ def run_pretrain(env, args):
         (loss * scale).backward()
         d_loss.copy_(loss.detach())
 
+    def zero_grad():
+        for p in params:
+            p.grad = None
+
     def update():
-        grads = [p.grad for p in model.parameters() if p.grad is not None]
-        torch._foreach_mul_(grads, 1.0 / scale)
-        opt.step()
+        opt.step(eng.last_arena)
 
     def allreduce():
         if world > 1:
-            a = eng.last_arena
-            grads = [p.grad for p in model.parameters() if p.grad is not None]
-            base = a.untyped_storage().data_ptr()
-            if all(gr.untyped_storage().data_ptr() == base for gr in grads):
-                dist.all_reduce(a, op=dist.ReduceOp.AVG)          # ONE collective over the flat 446.6 MB arena
-            else:
-                for gr in grads:
-                    dist.all_reduce(gr, op=dist.ReduceOp.AVG)
+            dist.all_reduce(eng.last_arena, op=dist.ReduceOp.AVG)          # ONE collective over the flat 446.6 MB arena
 
     # N > 1, overlapped: the backward hands the arena to `slice_hook` in two pieces — [decoder_embed .. end] as soon as the decoder
     # backward is done, the encoder part at the end — and each piece is all-reduced on the comm stream while the main stream
@@ -933,7 +932,7 @@ def run_pretrain(env, args):
         update()
 
     def step_eager():
-        opt.zero_grad(set_to_none=True)
+        zero_grad()
         if overlapped:
             step_overlapped()
             return
@@ -946,7 +945,7 @@ def run_pretrain(env, args):
     n0 = ops.LAUNCHES[0]
     if not args.no_graph:
         try:
-            opt.zero_grad(set_to_none=True)
+            zero_grad()
             if world == 1:
                 g1 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g1):
@@ -1033,7 +1032,7 @@ def run_pretrain(env, args):
             "warmup": env.warmup, "ms_per_step": round(ms_dev / env.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME["pretrain"], "global_batch": B * world,
-                       "step": "forward + full backward (encoder trained) + unscale + torch.optim.AdamW(fused)" +
+                       "step": "forward + full backward (encoder trained) + inf check / grad norm / unscale + AdamW (countr_b200.train.ArenaAdamW)" +
                                (" + NCCL all-reduce (avg) of the flat 446.6 MB gradient arena" if world > 1 else "") +
                                (" in two pieces overlapped with the backward" if overlapped else ""),
                        "cuda_graph": graphs is not None, "loss_scale": scale, "sm_budget": env.sm_budget,

@@ -241,7 +241,7 @@ struct ColsumProb {
   const void* x;
   float* out;
   long long R, ld;
-  int N, dtype, rows_per_block, col_blocks, block_begin;
+  int N, dtype, rows_per_block, col_blocks, block_begin, vec8;
 };
 struct ColsumArgs {
   int nprob;
@@ -254,33 +254,58 @@ __global__ void __launch_bounds__(256) grouped_colsum_kernel(const __grid_consta
   const ColsumProb& q = g.pr[pi];
   const int local = blockIdx.x - q.block_begin;
   const int cb = local % q.col_blocks, rb = local / q.col_blocks;
-  // thread = 2 columns; blockDim.x = 128 threads along N, blockDim.y = 2 row lanes
-  const int c = (cb * 128 + threadIdx.x) * 2;
   pdl_trigger();
   pdl_wait();
   const long long r0 = static_cast<long long>(rb) * q.rows_per_block;
   const long long r1 = min(q.R, r0 + q.rows_per_block);
-  float a0 = 0.f, a1 = 0.f;
-  if (c < q.N) {
+  __shared__ float red[8][257];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 column groups of 8 x 8 row lanes: 16-byte loads
+  const int c = (cb * 32 + tx) * 8;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  if (q.vec8) {
+    if (c < q.N) {
 #pragma unroll 4
-    for (long long r = r0 + threadIdx.y; r < r1; r += 2) {
-      if (q.dtype == 0) {
-        const float2 v = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(q.x) + r * q.ld + c);
-        a0 += v.x; a1 += v.y;
-      } else {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(q.x) + r * q.ld + c);
-        if (q.dtype == 2) { a0 += __uint_as_float(w << 16); a1 += __uint_as_float(w & 0xffff0000u); }
-        else { const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w)); a0 += v.x; a1 += v.y; }
+      for (long long r = r0 + ty; r < r1; r += 8) {
+        if (q.dtype == 0) {
+          const float4 v0 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(q.x) + r * q.ld + c);
+          const float4 v1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(q.x) + r * q.ld + c + 4);
+          a[0] += v0.x; a[1] += v0.y; a[2] += v0.z; a[3] += v0.w; a[4] += v1.x; a[5] += v1.y; a[6] += v1.z; a[7] += v1.w;
+        } else {
+          const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(q.x) + r * q.ld + c);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (q.dtype == 2) { a[2 * j] += __uint_as_float(w[j] << 16); a[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u); }
+            else { const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w[j])); a[2 * j] += v.x; a[2 * j + 1] += v.y; }
+          }
+        }
       }
     }
+  } else {
+    // narrow / unaligned matrices: scalar loads, same thread layout
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (c + j < q.N)
+        for (long long r = r0 + ty; r < r1; r += 8) {
+          if (q.dtype == 0) a[j] += reinterpret_cast<const float*>(q.x)[r * q.ld + c + j];
+          else {
+            const uint16_t hv = reinterpret_cast<const uint16_t*>(q.x)[r * q.ld + c + j];
+            a[j] += q.dtype == 2 ? __uint_as_float(static_cast<uint32_t>(hv) << 16) : __half2float(*reinterpret_cast<const __half*>(&hv));
+          }
+        }
+    }
   }
-  __shared__ float red[2][256];
-  red[threadIdx.y][threadIdx.x * 2] = a0;
-  red[threadIdx.y][threadIdx.x * 2 + 1] = a1;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ty][tx * 8 + j] = a[j];
   __syncthreads();
-  if (threadIdx.y == 0 && c < q.N) {
-    atomicAdd(q.out + c, red[0][threadIdx.x * 2] + red[1][threadIdx.x * 2]);
-    if (c + 1 < q.N) atomicAdd(q.out + c + 1, red[0][threadIdx.x * 2 + 1] + red[1][threadIdx.x * 2 + 1]);
+  {
+    const int col = threadIdx.x;          // 256 columns of the block, one per thread
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][col];
+    if (cb * 256 + col < q.N) atomicAdd(q.out + cb * 256 + col, t);
   }
 }
 
@@ -296,17 +321,18 @@ extern "C" int countr_grouped_colsum(const countr_colsum_problem* probs, int n, 
   int blocks = 0;
   for (int i = 0; i < n; ++i) {
     const countr_colsum_problem& d = probs[i];
-    COUNTR_REQUIRE(d.x && d.out && d.rows > 0 && d.cols > 0 && d.cols % 2 == 0 && d.ld % 2 == 0 && d.dtype >= 0 && d.dtype <= 2,
+    COUNTR_REQUIRE(d.x && d.out && d.rows > 0 && d.cols > 0 && d.ld >= d.cols && d.dtype >= 0 && d.dtype <= 2,
                    "problem %d: bad arguments", i);
     ColsumProb& q = g.pr[i];
     q.x = d.x; q.out = d.out; q.R = d.rows; q.ld = d.ld; q.N = d.cols; q.dtype = d.dtype;
-    q.col_blocks = (d.cols / 2 + 127) / 128;
-    q.rows_per_block = 64;            // 256 columns x 64 rows per block: ~2000 blocks for the decoder's bias gradients
+    q.col_blocks = (d.cols + 255) / 256;
+    q.vec8 = (d.cols % 8 == 0 && d.ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d.x) & 15u) == 0) ? 1 : 0;
+    q.rows_per_block = 128;           // 256 columns x 128 rows per block
     const long long row_blocks = (d.rows + q.rows_per_block - 1) / q.rows_per_block;
     q.block_begin = blocks;
     blocks += q.col_blocks * static_cast<int>(row_blocks);
   }
-  COUNTR_CHECK_CUDA(launch_pdl(grouped_colsum_kernel, dim3(blocks), dim3(128, 2), 0, stream, g));
+  COUNTR_CHECK_CUDA(launch_pdl(grouped_colsum_kernel, dim3(blocks), dim3(256), 0, stream, g));
   return COUNTR_OK;
 }
 

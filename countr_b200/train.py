@@ -170,3 +170,66 @@ class FineTuner:
             self.allreduce(self.arena)
         self.update()
         return loss
+
+
+class ArenaAdamW:
+    """GradScaler.unscale_ / inf check / get_grad_norm_ / AdamW / GradScaler.update (util/misc.py:260-301 + torch.optim.AdamW with
+    the timm add_weight_decay grouping, FSC_pretrain.py:226-228) over a flat fp32 gradient arena, as three kernels: the same
+    device-side state block and update kernels FineTuner uses, for any model whose backward leaves its gradients in one arena
+    (models_mae_noct: `engine().last_arena`).
+
+        opt = ArenaAdamW(*model._trainable(), lr=..., weight_decay=0.05, betas=(0.9, 0.95), loss_scale=1024.0)
+        (loss * opt.scale()).backward();  opt.step(engine().last_arena)
+    """
+
+    def __init__(self, names, params, lr=1e-5, weight_decay=0.05, betas=(0.9, 0.95), eps=1e-8, loss_scale=65536.0, dynamic_scale=True,
+                 growth_factor=2.0, backoff_factor=0.5, growth_interval=2000):
+        self.names, self.params = list(names), list(params)
+        self.betas, self.eps = betas, eps
+        self.growth, self.backoff = float(growth_factor), float(backoff_factor)
+        self.interval = int(growth_interval) if dynamic_scale else 0
+        self.dev = self.params[0].device
+        st = [0.0] * 8
+        st[ST_SCALE], st[ST_LR] = float(loss_scale), float(lr)
+        self.state = torch.tensor(st, dtype=F32, device=self.dev)
+        self._lr_host = torch.zeros(1, dtype=F32).pin_memory() if torch.cuda.is_available() else torch.zeros(1)
+        self._stats_scratch = torch.zeros(int(lib().countr_grad_stats_scratch_bytes()) // 8, dtype=torch.float64, device=self.dev)
+        self.n_grad = arena_size(self.params)
+        self.exp_avg = torch.zeros(self.n_grad, dtype=F32, device=self.dev)
+        self.exp_avg_sq = torch.zeros(self.n_grad, dtype=F32, device=self.dev)
+        self.step_count = torch.zeros(len(self.names), dtype=F32, device=self.dev)
+        self._flags = torch.zeros(ARENA_TAIL, dtype=F32, device=self.dev)          # no optional parameter groups
+        rec = np.zeros(len(self.names), dtype=np.dtype([("param", "<u8"), ("goff", "<i8"), ("moff", "<i8"), ("numel", "<i8"), ("wd", "<f4"),
+                                                        ("step_idx", "<i4"), ("flag_idx", "<i4"), ("pad", "<i4")]))
+        chunks, off = [], 0
+        for i, (n, p) in enumerate(zip(self.names, self.params)):
+            assert p.dtype == F32 and p.is_contiguous()
+            wd = 0.0 if (p.ndim == 1 or n.endswith(".bias")) else weight_decay
+            rec[i] = (p.data_ptr(), off, off, p.numel(), wd, i, 0, 0)
+            chunks += [(i, c) for c in range((p.numel() + 1023) // 1024)]
+            off += (p.numel() + 3) // 4 * 4
+        self._tensors = torch.from_numpy(rec.view(np.uint8).copy()).to(self.dev)
+        self._chunks = torch.tensor(chunks, dtype=torch.int32, device=self.dev)
+        self._n_chunks = len(chunks)
+
+    def scale(self):
+        """The current loss scale as a device scalar (multiply the loss by it before backward)."""
+        return self.state[ST_SCALE]
+
+    def set_lr(self, lr):
+        self._lr_host[0] = float(lr)
+        self.state[ST_LR:ST_LR + 1].copy_(self._lr_host, non_blocking=True)
+
+    def metrics(self):
+        s = self.state.tolist()
+        return dict(grad_norm=s[ST_GRAD_NORM], loss_scale=s[ST_SCALE], found_inf=bool(s[ST_FOUND_INF]), lr=s[ST_LR], step=int(s[ST_STEP]))
+
+    @torch.no_grad()
+    def step(self, arena):
+        assert arena.numel() >= self.n_grad and arena.dtype == F32
+        check(lib().countr_grad_stats(_p(arena), self.n_grad, _p(self._stats_scratch), _p(self.state), ops._stream()))
+        check(lib().countr_adamw_update(_p(self._tensors), len(self.names), _p(self._chunks), self._n_chunks, _p(arena), _p(self._flags),
+                                        _p(self.exp_avg), _p(self.exp_avg_sq), _p(self.step_count), _p(self.state), self.betas[0],
+                                        self.betas[1], self.eps, self.growth, self.backoff, self.interval, ops._stream()))
+        ops._count(3)
+        engine().wc.bump(self.params)

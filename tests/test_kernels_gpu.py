@@ -175,6 +175,10 @@ def test_grouped_dw_and_colsum(cuda):
     db32 = torch.zeros(512, device=cuda)
     cprobs.append((x32, db32))
     crefs.append(x32.double().sum(0))
+    for shape, dt in (((100, 6), torch.float16), ((33, 10), torch.float32), ((700, 264), torch.float16)):   # widths off the 8-column fast path
+        xo = torch.randn(shape, device=cuda).to(dt)
+        cprobs.append((xo, torch.zeros(shape[1], device=cuda)))
+        crefs.append(xo.double().sum(0))
     ops.grouped_dw(probs)
     ops.grouped_colsum(cprobs)
     torch.cuda.synchronize()

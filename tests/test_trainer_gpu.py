@@ -312,3 +312,42 @@ def test_steady_training_step_refreshes_weights_in_one_launch(cuda, which):
         opt.step()
     torch.cuda.synchronize()
     assert eng.wc.lazy_fills == before, f"{eng.wc.lazy_fills - before} per-tensor weight refreshes in steady-state steps"
+
+
+def test_arena_adamw_matches_torch(cuda):
+    """ArenaAdamW (the pre-training step's optimizer: unscale + inf check + grad norm + AdamW + GradScaler.update over a flat arena)
+    against torch.optim.AdamW with the timm add_weight_decay grouping, three steps, plus the overflow skip."""
+    from countr_b200.dist import build_grad_arena
+    from countr_b200.train import ArenaAdamW
+    torch.manual_seed(3)
+    shapes = {"a.weight": (64, 48), "a.bias": (64,), "norm.weight": (48,), "tok": (1, 1, 48), "b.weight": (33, 7, 3, 3)}
+    params = [torch.nn.Parameter(torch.randn(s, device=cuda)) for s in shapes.values()]
+    names = list(shapes)
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in params]
+    decay = [r for n, r in zip(names, ref) if not (r.ndim == 1 or n.endswith(".bias"))]
+    no_decay = [r for n, r in zip(names, ref) if r.ndim == 1 or n.endswith(".bias")]
+    topt = torch.optim.AdamW([{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": 0.05}], lr=1e-3, betas=(0.9, 0.95))
+    opt = ArenaAdamW(names, params, lr=1e-3, weight_decay=0.05, betas=(0.9, 0.95), loss_scale=512.0, dynamic_scale=True)
+    for step in range(3):
+        arena, views = build_grad_arena(names, params, cuda)
+        arena.zero_()
+        total = 0.0
+        for n, r in zip(names, ref):
+            gr = torch.randn_like(r)
+            r.grad = gr.clone()
+            views[n].copy_(gr * 512.0)
+            total += gr.double().pow(2).sum().item()
+        opt.step(arena)
+        topt.step()
+        m = opt.metrics()
+        assert not m["found_inf"] and abs(m["grad_norm"] - total ** 0.5) < 1e-4 * total ** 0.5
+    for n, p, r in zip(names, params, ref):
+        assert torch.allclose(p, r, rtol=2e-5, atol=2e-6), n
+    before = [p.detach().clone() for p in params]
+    arena, views = build_grad_arena(names, params, cuda)
+    arena.zero_()
+    views["a.weight"][0, 0] = float("inf")
+    opt.step(arena)
+    m = opt.metrics()
+    assert m["found_inf"] and m["loss_scale"] == 256.0                       # skipped, scale backed off
+    assert all(torch.equal(p, b) for p, b in zip(params, before))
