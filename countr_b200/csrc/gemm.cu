@@ -1273,8 +1273,13 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   // auto policy (cta_pair == 0): pairs for the big implicit-GEMM convolutions, where the larger operand reuse
   // (32 KB instead of 48 KB of smem fill per k-block and SM) is worth +13 % (1.10 -> 1.24 PF/s on decode_head3);
   // neutral on the mid-size Linear layers, which are latency- not throughput-bound (profiles/r1_bench_gemm_pair.log).
-  const bool pair_auto = bn == 256 && ((conv && static_cast<long long>(p.m_tiles) * nb1 >= 128) ||
-                                       (conv_dw && p.m_tiles % 2 == 0 && d->K >= 64 * 64));
+  // ... and for long-K Linear layers whose tile list is a single wave of CTA pairs (the encoder's fc2: K = 3072, 72 pairs of
+  // 256 x 192): the pair's main loop runs at the tensor floor (384 clk per k-block against 456 for one CTA), which outweighs
+  // its longer prologue once there are ~48 k-blocks (fp32 + residual: 22.0 -> 20.0 us; no gain at K <= 2048)
+  const bool pair_auto = (bn == 256 && ((conv && static_cast<long long>(p.m_tiles) * nb1 >= 128) ||
+                                        (conv_dw && p.m_tiles % 2 == 0 && d->K >= 64 * 64))) ||
+                         (!conv && !conv_dw && !d->a_mn && !d->b_mn && bn == 192 && d->K >= 3072 && p.m_tiles % 2 == 0 && split_k == 1 &&
+                          nb1 * nb2 == 1 && (p.m_tiles / 2) * ((d->N + bn - 1) / bn) <= sms / 2);
   p.pair = (pair_ok && (d->cta_pair > 0 || (d->cta_pair == 0 && pair_auto))) ? 1 : 0;
   int cs = p.pair ? 2 : (d->cluster > 0 ? d->cluster : 1);
   if (cs != 1 && cs != 2 && cs != 4) cs = 1;
