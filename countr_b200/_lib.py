@@ -42,6 +42,7 @@ class GemmDesc(Structure):
         ("ldr", c_int64),
         ("res_mod", c_int32),
         ("gn_stats", c_void_p),
+        ("ln_x16", c_void_p), ("ld_x16", c_int64), ("ln_stats", c_void_p), ("ln_colsum", c_void_p), ("ln_dim", c_int32), ("ln_eps", c_float),
     ]
 
 

@@ -99,6 +99,12 @@ struct GemmArgs {
   long long ldr;
   int res_mod;
   double* gn_stats;
+  // LayerNorm folded into the neighbouring GEMMs (see countr_gemm_desc)
+  uint16_t* ln_x16;
+  long long ld_x16;
+  float* ln_stats;
+  const float* ln_colsum;
+  float ln_inv_dim, ln_eps;
 };
 
 struct TileCoord {
@@ -515,6 +521,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           if (tile == cluster_id) pdl_wait();   // bias comes from earlier kernels; C may still be read by them
           // bias of this warp's column chunks, one column per lane, fetched BEFORE the accumulator is waited for (the L2 round
           // trip hides behind the main loop); the row-per-lane arithmetic below reads column j's value with a shuffle
+          // LayerNorm consumer: this lane's row statistics (eight fixed-order partials written by the producer GEMM) and the
+          // column sums of W * diag(gamma), one column per lane like the bias
+          const bool ln_in = p.ln_colsum != nullptr;
+          float ln_rstd = 1.f, ln_nmr = 0.f;          // rstd and -rstd * mean of this lane's row
+          float slane[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+          if (ln_in) {
+            float s1 = 0.f, s2 = 0.f;
+            if (row_ok) {
+              const float4* sp = reinterpret_cast<const float4*>(p.ln_stats + static_cast<long long>(c1 + lane) * 16);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 q4 = sp[i];
+                s1 += q4.x; s2 += q4.y; s1 += q4.z; s2 += q4.w;
+              }
+            }
+            const float mean = s1 * p.ln_inv_dim;
+            const float var = fmaxf(s2 * p.ln_inv_dim - mean * mean, 0.f);
+            ln_rstd = rsqrtf(var + p.ln_eps);
+            ln_nmr = -ln_rstd * mean;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int col0 = n0 + (egroup + 2 * i) * 64;
+              if (egroup + 2 * i < p.bn / 64 && col0 < p.N) {
+                slane[i][0] = __ldg(p.ln_colsum + col0 + lane);
+                slane[i][1] = __ldg(p.ln_colsum + col0 + 32 + lane);
+              }
+            }
+          }
           float blane[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
           if (use_bias) {
 #pragma unroll
@@ -551,6 +585,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if (col0 >= p.N) break;
             const bool second = cc != egroup;
             const float bl0 = second ? blane[1][0] : blane[0][0], bl1 = second ? blane[1][1] : blane[0][1];
+            const float sl0 = second ? slane[1][0] : slane[0][0], sl1 = second ? slane[1][1] : slane[0][1];
             uint32_t r[2][32];
             tmem_ld_32x32b_x32(t_row + cc * 64, r[0]);
             tmem_ld_32x32b_x32(t_row + cc * 64 + 32, r[1]);
@@ -575,8 +610,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             for (int hf = 0; hf < 2; ++hf) {
               float v[32];
               const float blh = hf == 0 ? bl0 : bl1;
+              if (ln_in) {
+                const float slh = hf == 0 ? sl0 : sl1;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[hf][j]), p.alpha, __shfl_sync(0xffffffffu, blh, j));
+                for (int j = 0; j < 32; ++j)
+                  v[j] = fmaf(__uint_as_float(r[hf][j]), ln_rstd, fmaf(ln_nmr, __shfl_sync(0xffffffffu, slh, j), __shfl_sync(0xffffffffu, blh, j)));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[hf][j]), p.alpha, __shfl_sync(0xffffffffu, blh, j));
+              }
               if (p.gn_stats != nullptr) {
                 float s1 = 0.f, s2 = 0.f;
                 if (row_ok) {
@@ -684,6 +726,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           if (warp == 2) TR(1024 + 2 * trt);
           tc_fence_after();
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kMaxBN;
+          float ln_s1 = 0.f, ln_s2 = 0.f;       // LayerNorm producer: sum / sum of squares of this lane's row over this warp's chunks
           for (int k = 0; k < mine; ++k) {
             const int col0 = n0 + (egroup + 2 * k) * 32;
             const uint32_t bsel = (nst0 + static_cast<uint32_t>(k)) % p.nbuf;
@@ -721,6 +764,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 v[4 * q] += rv.x; v[4 * q + 1] += rv.y; v[4 * q + 2] += rv.z; v[4 * q + 3] += rv.w;
               }
             }
+            if (p.ln_x16 != nullptr) {
+              // the consumer GEMM reads these rows as its 16-bit A operand and normalises in its epilogue
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                ln_s1 += v[j];
+                ln_s2 = fmaf(v[j], v[j], ln_s2);
+              }
+            }
 #pragma unroll
             for (int q = 0; q < 8; ++q)
               asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(buf + rowoff + ((static_cast<uint32_t>(q) ^ sw) << 4)),
@@ -733,8 +784,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               else tma_store_4d(&tma_c, buf, col0, c1, c2v, c3);
               bulk_commit();
             }
+            if (p.ln_x16 != nullptr) {
+              // 16-bit copy of the chunk, read back from the staging buffer (the TMA store only reads it too) in the transposed
+              // mapping — 8 lanes cover 64 contiguous bytes of one row, 4 rows per instruction — instead of 32 scattered 16-byte
+              // row pieces per instruction from the lane == row mapping
+#pragma unroll 1
+              for (int it = 0; it < 8; ++it) {
+                const int rw = it * 4 + rr;
+                float4 f;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
+                             : "r"(buf + rw * 128 + ((c4 ^ (rw & 7)) << 4))
+                             : "memory");
+                if (c1 + rw < p.M)
+                  *reinterpret_cast<uint2*>(p.ln_x16 + static_cast<long long>(c1 + rw) * p.ld_x16 + col0 + c4 * 4) =
+                      make_uint2(pack_16b(f.x, f.y, p.bf16), pack_16b(f.z, f.w, p.bf16));
+              }
+            }
           }
           nst = nst0 + static_cast<uint32_t>(mine);
+          if (p.ln_x16 != nullptr && row_ok)
+            *reinterpret_cast<float2*>(p.ln_stats + static_cast<long long>(c1 + lane) * 16 + (t.n * 2 + egroup) * 2) = make_float2(ln_s1, ln_s2);
         }
         // accumulator drained (it lives in registers / shared memory now): hand the TMEM stage back to the MMA warp
         if (warp == 2) TR(1025 + 2 * trt);
@@ -1301,6 +1371,8 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
   p.act = d->act; p.aux = d->aux; p.ldaux = d->ldaux;
   p.residual = d->residual; p.ldr = d->ldr; p.res_mod = d->res_mod;
   p.gn_stats = d->gn_stats;
+  p.ln_x16 = reinterpret_cast<uint16_t*>(d->ln_x16); p.ld_x16 = d->ld_x16; p.ln_stats = d->ln_stats; p.ln_colsum = d->ln_colsum;
+  p.ln_inv_dim = d->ln_dim > 0 ? 1.0f / static_cast<float>(d->ln_dim) : 0.f; p.ln_eps = d->ln_eps;
   {
     static int epi64 = -1;
     if (epi64 < 0) {
@@ -1386,6 +1458,18 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
              (d->residual == nullptr || ((d->ldr * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->residual) & 15u) == 0 && !d->atomic &&
                                          nb1 * nb2 == 1 && !conv)))
       p.epi_mode = 2;
+  }
+  if (d->ln_x16 != nullptr || d->ln_colsum != nullptr) {
+    COUNTR_REQUIRE(d->ln_stats != nullptr && (reinterpret_cast<uintptr_t>(d->ln_stats) & 15u) == 0, "LayerNorm folding needs 16-byte aligned ln_stats");
+    COUNTR_REQUIRE(!conv && !conv_dw && nb1 * nb2 == 1 && split_k == 1, "LayerNorm folding: plain GEMM only");
+    if (d->ln_x16 != nullptr) {
+      COUNTR_REQUIRE(p.epi_mode == 2 && p.n_tiles * 2 <= 8 && bn % 64 == 0 && d->N % 64 == 0 && d->ld_x16 % 8 == 0 &&
+                         (reinterpret_cast<uintptr_t>(d->ln_x16) & 15u) == 0 && d->ln_colsum == nullptr,
+                     "LayerNorm producer needs the fp32 TMA epilogue, at most four N tiles of an even number of 32-column chunks per warp");
+    } else {
+      COUNTR_REQUIRE(p.epi_mode == 1 && d->ln_dim == d->K && d->alpha == 1.0f && d->aux == nullptr,
+                     "LayerNorm consumer needs the 16-bit TMA epilogue, ln_dim == K, alpha == 1 and no aux");
+    }
   }
   // ---- shared-memory layout
   p.stage_bytes = p.pair ? static_cast<int>(kPairStageBytes) : static_cast<int>(kABytes) + bn * 128;

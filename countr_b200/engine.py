@@ -15,6 +15,7 @@ Reference correspondence: encoder_forward = SupervisedMAE.forward_encoder (model
 136-148); decoder_forward = forward_decoder (:150-199).
 """
 import math
+import os
 import weakref
 
 import torch
@@ -176,8 +177,31 @@ class Engine:
         self._flags = {}
         self.overlap_exemplar = True
         self.overlap_dw = True          # FIM weight / bias gradients on the side stream (backward.py)
+        self.fold_layernorm = os.environ.get("COUNTR_FOLD_LN", "0") == "1"     # encoder: LayerNorm folded into the neighbouring GEMM epilogues
+        self._folded = {}
 
     # ------------------------------------------------------------------ encoder
+    def folded_linear(self, norm, lin):
+        """Operands of a Linear with the LayerNorm in front of it folded in (frozen encoder; cached until any of the four tensors
+        changes): W' = 16-bit(W diag(gamma)), colsum[n] = sum_k W'[n, k] (of the ROUNDED values the tensor core multiplies),
+        bias' = b + W beta.  Init-time torch arithmetic, not on the hot path."""
+        ps = (norm.weight, norm.bias, lin.weight, lin.bias)
+        key = tuple(id(p) for p in ps)
+        stamp = tuple((p.data_ptr(), p._version, self.wc.ext.get(id(p), 0)) for p in ps)
+        ent = self._folded.get(key)
+        if ent is None or ent[0] != stamp:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("countr_b200: folded LayerNorm operands must be built outside CUDA-graph capture "
+                                   "(run one eager warm-up step before capturing)")
+            with torch.no_grad():
+                w = lin.weight.detach().to(F32)
+                w16 = (w * norm.weight.detach().to(F32)[None, :]).to(F16).contiguous()
+                colsum = w16.double().sum(1).to(F32).contiguous()
+                bias = (lin.bias.detach().double() + w.double() @ norm.bias.detach().double()).to(F32).contiguous()
+            ent = (stamp, w16, colsum, bias)
+            self._folded[key] = ent
+        return ent[1], ent[2], ent[3]
+
     def encoder_forward(self, m, imgs, keep=False):
         """m: SupervisedMAE-like module (patch_embed, pos_embed, blocks, norm).
         Returns (latent fp32 [B, L, D], latent fp16 [B*L, D]).  keep=True (training): the fp16 latent is saved for the decoder
@@ -208,20 +232,46 @@ class Engine:
             w_pe = wpad
         ops_.linear(patches, w_pe, x, bias=_contig32(pe.bias), residual=_contig32(m.pos_embed).reshape(L, D), res_mod=L)
         h = ws.get("enc_h", (M, D), F16, dev)
-        for blk in m.blocks:
+        # LayerNorm folded into the GEMMs around it (csrc/gemm.cu, countr_gemm_desc): proj / fc2 also emit a 16-bit copy of the
+        # residual stream and per-row statistics partials, fc1 / the next block's qkv multiply that copy by W diag(gamma) and
+        # normalise in their epilogue.  23 of the encoder's 25 LayerNorm launches disappear; block 0's norm1 (fed by the patch
+        # embedding) and the final norm (fp32 + 16-bit outputs) stay kernels.  Needs D / 4 to be a GEMM tile width.
+        # OFF by default (COUNTR_FOLD_LN=1 / Engine.fold_layernorm turn it on): measured on B200 at B = 8 inside the CUDA graph the
+        # 23 saved launches (~5.6 us each) are paid back by ~3 us of extra epilogue per GEMM on 46 GEMMs — encoder 1347 us folded
+        # vs 1331 us with LayerNorm kernels (profiles/README.md).  It wins where launches are synchronous (the scripts'
+        # CUDA_LAUNCH_BLOCKING=1).
+        fold = self.fold_layernorm and D % 4 == 0 and (D // 4) in (128, 192, 256)
+        x16 = ws.get("enc_x16", (M, D), F16, dev) if fold else None
+        st = ws.get("enc_lnstats", (M, 8, 2), F32, dev) if fold else None
+        nblk = len(m.blocks)
+        for bi, blk in enumerate(m.blocks):
             H = blk.attn.num_heads
             dh = D // H
             hid = blk.mlp.fc1.weight.shape[0]
             qkv = ws.get("enc_qkv", (M, 3 * D), F16, dev)
             att = ws.get("enc_att", (M, D), F16, dev)
             u = ws.get("enc_u", (M, hid), F16, dev)
-            ops_.layernorm_fwd(x, _contig32(blk.norm1.weight), _contig32(blk.norm1.bias), blk.norm1.eps, y16=h)
-            ops_.linear(h, wc.w16(blk.attn.qkv.weight), qkv, bias=_contig32(blk.attn.qkv.bias))
+            if fold and bi > 0:
+                wq, sq, bq = self.folded_linear(blk.norm1, blk.attn.qkv)
+                ops_.linear(x16, wq, qkv, bias=bq, ln_stats=st, ln_colsum=sq, ln_eps=blk.norm1.eps)
+            else:
+                ops_.layernorm_fwd(x, _contig32(blk.norm1.weight), _contig32(blk.norm1.bias), blk.norm1.eps, y16=h)
+                ops_.linear(h, wc.w16(blk.attn.qkv.weight), qkv, bias=_contig32(blk.attn.qkv.bias))
             ops_.attention_fwd(qkv, att, B, L, H, dh, blk.attn.scale)
-            ops_.linear(att, wc.w16(blk.attn.proj.weight), x, bias=_contig32(blk.attn.proj.bias), residual=x)
-            ops_.layernorm_fwd(x, _contig32(blk.norm2.weight), _contig32(blk.norm2.bias), blk.norm2.eps, y16=h)
-            ops_.linear(h, wc.w16(blk.mlp.fc1.weight), u, bias=_contig32(blk.mlp.fc1.bias), act=1)
-            ops_.linear(u, wc.w16(blk.mlp.fc2.weight), x, bias=_contig32(blk.mlp.fc2.bias), residual=x)
+            if fold:
+                ops_.linear(att, wc.w16(blk.attn.proj.weight), x, bias=_contig32(blk.attn.proj.bias), residual=x, bn=D // 4, ln_x16=x16,
+                            ln_stats=st)
+                w1, s1, b1 = self.folded_linear(blk.norm2, blk.mlp.fc1)
+                ops_.linear(x16, w1, u, bias=b1, act=1, ln_stats=st, ln_colsum=s1, ln_eps=blk.norm2.eps)
+            else:
+                ops_.linear(att, wc.w16(blk.attn.proj.weight), x, bias=_contig32(blk.attn.proj.bias), residual=x)
+                ops_.layernorm_fwd(x, _contig32(blk.norm2.weight), _contig32(blk.norm2.bias), blk.norm2.eps, y16=h)
+                ops_.linear(h, wc.w16(blk.mlp.fc1.weight), u, bias=_contig32(blk.mlp.fc1.bias), act=1)
+            if fold and bi + 1 < nblk:
+                ops_.linear(u, wc.w16(blk.mlp.fc2.weight), x, bias=_contig32(blk.mlp.fc2.bias), residual=x, bn=D // 4, ln_x16=x16,
+                            ln_stats=st)
+            else:
+                ops_.linear(u, wc.w16(blk.mlp.fc2.weight), x, bias=_contig32(blk.mlp.fc2.bias), residual=x)
         lat32 = torch.empty(B, L, D, dtype=F32, device=dev)
         lat16 = torch.empty(M, D, dtype=F16, device=dev) if keep else ws.get("lat16", (M, D), F16, dev)
         ops_.layernorm_fwd(x, _contig32(m.norm.weight), _contig32(m.norm.bias), m.norm.eps, y16=lat16, y32=lat32.view(M, D))

@@ -35,7 +35,8 @@ def _count(n=1):
 
 def gemm(a, b, c, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, nb1=1, nb2=1,
          sa=(0, 0), sb=(0, 0), sc=(0, 0), bias=None, act=0, aux=None, ldaux=0, residual=None, ldr=0,
-         res_mod=0, alpha=1.0, atomic=False, split_k=1, bn=0, conv=None, gn_stats=None, conv_dw=None, cluster=0, pair=0):
+         res_mod=0, alpha=1.0, atomic=False, split_k=1, bn=0, conv=None, gn_stats=None, conv_dw=None, cluster=0, pair=0,
+         ln_x16=None, ln_stats=None, ln_colsum=None, ln_dim=0, ln_eps=0.0):
     """C = epilogue(alpha * A @ B^T); see countr_gemm_desc for the layout rules."""
     assert a.dtype in (F16, BF16) and b.dtype == a.dtype
     d = GemmDesc()
@@ -65,19 +66,29 @@ def gemm(a, b, c, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, nb1=1, nb2=
     d.ldr = ldr
     d.res_mod = res_mod
     d.gn_stats = gn_stats.data_ptr() if gn_stats is not None else None
+    if ln_stats is not None:        # LayerNorm folded into this GEMM's epilogue (producer: ln_x16, consumer: ln_colsum)
+        d.ln_stats = ln_stats.data_ptr()
+        d.ln_x16 = ln_x16.data_ptr() if ln_x16 is not None else None
+        d.ld_x16 = ln_x16.stride(0) if ln_x16 is not None else 0
+        d.ln_colsum = ln_colsum.data_ptr() if ln_colsum is not None else None
+        d.ln_dim, d.ln_eps = ln_dim, ln_eps
     check(lib().countr_gemm(ctypes.byref(d), _stream()))
     _count()
     return c
 
 
-def linear(x16, w16, out, bias=None, act=0, aux=None, residual=None, res_mod=0, alpha=1.0):
-    """out[M,N] = epi(x16[M,K] @ w16[N,K]^T); residual is fp32 [M or res_mod, N] (may alias out)."""
+def linear(x16, w16, out, bias=None, act=0, aux=None, residual=None, res_mod=0, alpha=1.0, bn=0, ln_x16=None, ln_stats=None,
+           ln_colsum=None, ln_eps=0.0):
+    """out[M,N] = epi(x16[M,K] @ w16[N,K]^T); residual is fp32 [M or res_mod, N] (may alias out).
+    LayerNorm folding (countr_gemm_desc): producer — ln_x16 [M,N] 16-bit + ln_stats [M,8,2] fp32 receive a 16-bit copy of `out` and
+    its row-statistics partials; consumer — x16 is such a copy, w16 = W * diag(gamma), ln_colsum[n] = sum_k w16[n,k], bias = b + W beta."""
     M, K = x16.shape
     N = w16.shape[0]
     assert w16.shape[1] == K and out.shape == (M, N)
     return gemm(x16, w16, out, M, N, K, lda=x16.stride(0), ldb=w16.stride(0), ldc=out.stride(0), bias=bias,
                 act=act, aux=aux, ldaux=aux.stride(0) if aux is not None else 0, residual=residual,
-                ldr=residual.stride(0) if residual is not None else 0, res_mod=res_mod, alpha=alpha)
+                ldr=residual.stride(0) if residual is not None else 0, res_mod=res_mod, alpha=alpha, bn=bn, ln_x16=ln_x16,
+                ln_stats=ln_stats, ln_colsum=ln_colsum, ln_dim=K, ln_eps=ln_eps)
 
 
 def conv3x3(x16, w16, out, bias=None, gn_stats=None, pair=0):

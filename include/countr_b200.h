@@ -99,6 +99,19 @@ typedef struct countr_gemm_desc {
   int64_t ldr;
   int32_t res_mod;
   double* gn_stats;      /* conv mode: [B][N/32][2] (sum, sum of squares) += over 32-channel groups */
+  /* LayerNorm folded into the GEMMs on either side of it (the frozen encoder: Block.norm1 / norm2 between proj|fc2 and
+   * qkv|fc1, timm Block.forward).  PRODUCER (fp32 out + residual): ln_x16 = 16-bit copy of the output rows [M][ld_x16] and
+   * ln_stats = float2 [M][8] partial (sum, sum of squares) of every output row, slot 2 * n_tile + column half (no atomics:
+   * bit-reproducible).  CONSUMER (16-bit out; A = that 16-bit copy, B = W * diag(gamma)): ln_stats != NULL with ln_colsum:
+   *   C[r][c] = rstd_r * acc[r][c] - rstd_r * mean_r * ln_colsum[c] + bias[c],
+   * ln_colsum[c] = sum_k B[c][k], bias = b + W beta, mean / rstd from the eight partials over ln_dim columns (eps ln_eps).
+   * Algebraically LayerNorm(x) W^T + b with the statistics taken from the fp32 values. */
+  void* ln_x16;
+  int64_t ld_x16;
+  float* ln_stats;
+  const float* ln_colsum;
+  int32_t ln_dim;
+  float ln_eps;
 } countr_gemm_desc;
 
 int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream);

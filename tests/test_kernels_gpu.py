@@ -155,6 +155,41 @@ def test_gemm_epilogues(cuda):
     assert_close(y, lin + pos.repeat(M // 576, 1), 2e-5, "pos-embed residual")
 
 
+@pytest.mark.parametrize("M,D,N2,act", [(4608, 768, 2304, 0), (1000, 768, 3072, 1), (4608, 512, 2048, 1), (333, 1024, 1024, 0)])
+def test_layernorm_folded_into_gemms(cuda, M, D, N2, act):
+    """LayerNorm between two Linear layers without a LayerNorm kernel: the producer GEMM (fp32 out + residual) also emits the
+    16-bit copy of its rows and row-statistics partials, the consumer GEMM multiplies by W diag(gamma) and normalises in its
+    epilogue.  Against fp32 torch: x = a W1^T + b1 + res; y = act(LayerNorm(x) W2^T + b2)."""
+    from countr_b200 import ops
+    K1 = 512
+    a = _rand16((M, K1), cuda, seed=70, scale=0.5)
+    w1 = _rand16((D, K1), cuda, seed=71, scale=0.05)
+    b1 = torch.randn(D, device=cuda)
+    res = torch.randn(M, D, device=cuda) * 2 + 0.5            # non-zero row means
+    gamma, beta = torch.rand(D, device=cuda) + 0.5, torch.randn(D, device=cuda) * 0.1
+    w2 = torch.randn(N2, D, device=cuda) * 0.05
+    b2 = torch.randn(N2, device=cuda)
+    x = res.clone()
+    x16 = torch.zeros(M, D, device=cuda, dtype=torch.float16)
+    st = torch.zeros(M, 8, 2, device=cuda)
+    ops.linear(a, w1, x, bias=b1, residual=x, bn=D // 4, ln_x16=x16, ln_stats=st)
+    x_ref = a.float() @ w1.float().t() + b1 + res
+    torch.cuda.synchronize()
+    assert_close(x, x_ref, 2e-5, "producer output")
+    assert_close(x16, x_ref, 1e-3, "16-bit copy")
+    assert_close(st.view(M, 8, 2)[:, :, 0].sum(1), x_ref.sum(1), 1e-4, "row sums")
+    w2f = (w2 * gamma[None, :]).half().contiguous()
+    colsum = w2f.double().sum(1).float().contiguous()
+    bias2 = (b2.double() + w2.double() @ beta.double()).float().contiguous()
+    y = torch.zeros(M, N2, device=cuda, dtype=torch.float16)
+    ops.linear(x16, w2f, y, bias=bias2, act=act, ln_stats=st, ln_colsum=colsum, ln_eps=1e-6)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x_ref, (D,), gamma, beta, 1e-6) @ w2.t() + b2
+    if act:
+        ref = F.gelu(ref)
+    assert_close(y, ref, 2e-3, "folded LayerNorm + Linear")
+
+
 def test_grouped_dw_and_colsum(cuda):
     """Every dW = dY^T X (and bias gradient) of a backward pass in one launch each: mixed shapes, a token count that is not a
     multiple of 64 (zero-filled k tail), a 24-token problem (the k/v projections of the exemplars), output widths that are not
