@@ -1,0 +1,26 @@
+#!/bin/bash
+# Round-2 final evidence (one GPU): whole GPU suite, the three bench workloads, launch lists, the ncu captures the first pass missed.
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/r2_tests_final.log; cat gpurun_out/r2_tests_final.log
+timeout 600 python bench.py > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err; cut -c1-200 gpurun_out/r2_bench_final.json
+timeout 300 python bench.py --workload infer0 --no-cpu-baseline > gpurun_out/r2_bench_infer0.json 2> gpurun_out/r2_bench_infer0.err; cut -c1-200 gpurun_out/r2_bench_infer0.json
+timeout 300 python bench.py --workload pretrain --no-cpu-baseline > gpurun_out/r2_bench_pretrain.json 2> gpurun_out/r2_bench_pretrain.err; cut -c1-200 gpurun_out/r2_bench_pretrain.json
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_reference_arm.json 2>/dev/null; cut -c1-200 gpurun_out/r2_bench_reference_arm.json
+bash scripts/gpu_launch_list.sh r2_launches_final > /dev/null 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none --csv --log-file gpurun_out/r2_launches_pretrain_final.csv python bench.py --workload pretrain --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-extras > /dev/null 2>&1
+python scripts/cublas_compare.py > gpurun_out/r2_cublas_final.log 2>&1; tail -10 gpurun_out/r2_cublas_final.log
+python scripts/time_stages.py 2>&1 | tail -2 > gpurun_out/r2_time_stages.log; cat gpurun_out/r2_time_stages.log
+STEP="python bench.py --steps 1 --warmup 2 --no-graph --no-cpu-baseline --no-extras"
+cap() {   # name, kernel regex, launch skip
+  timeout 300 ncu --set full --clock-control none --import-source on -k "regex:$2" --launch-skip $3 --launch-count 1 -f -o gpurun_out/$1 $STEP > /dev/null 2>&1
+  python scripts/ncu_summary.py gpurun_out/$1.ncu-rep gpurun_out/$1.json > /dev/null 2>&1 && echo "captured $1"
+}
+cap r2_ncu_gn_bwd_reduce1 gn_relu_bwd_reduce_kernel 8
+cap r2_ncu_gn_bwd_reduce0 gn_relu_bwd_reduce_kernel 9
+cap r2_ncu_attn_fwd64 attention_fwd_kernel 28
+cap r2_ncu_grouped_colsum grouped_colsum_kernel 2
+for w in conv attn; do
+  timeout 200 ncu --set full --clock-control none --import-source on --launch-skip 4 --launch-count 1 -f -o gpurun_out/r2_ncu_prof_$w python scripts/prof_gemm.py $w > /dev/null 2>&1
+  python scripts/ncu_summary.py gpurun_out/r2_ncu_prof_$w.ncu-rep gpurun_out/r2_ncu_prof_$w.json > /dev/null 2>&1 && echo "captured $w"
+done
+rm -f gpurun_out/*.ncu-rep
