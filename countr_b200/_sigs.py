@@ -6,7 +6,8 @@ P, I, L, F = c_void_p, c_int32, c_int64, c_float
 SIGS = {
     "countr_memset_zero": [P, c_int64, P],
     "countr_layernorm_fwd": [P, P, P, P, P, P, P, I, I, F, I, P],
-    "countr_layernorm_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, P],
+    "countr_layernorm_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, P],
+    "countr_layernorm_bwd_blocks": [I],
     "countr_attention_fwd": [P, P, P, I, I, I, I, F, I, P],
     "countr_attention_bwd": [P, P, P, P, P, P, I, I, I, I, F, I, P],
     "countr_cross_attn_core": [P, P, P, P, P, I, I, I, I, I, F, I, I, P],

@@ -168,6 +168,11 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
         ops.gn_bwd_apply(raw, dyh, stats, gsum, gamma, dyh, G(conv.bias), gn.num_groups, gn.eps)   # in place: dyh -> d_raw
         d_next = _conv_grads(dyh, inp, conv, grads, wc, F32 if i == 0 else F16)
 
+    # weight / bias / LayerNorm-parameter gradients are deferred to grouped launches at the end (see GradJobs)
+    defer = getattr(eng, "defer_dw", True)
+    jobs = GradJobs() if defer else None
+    dw_jobs, cs_jobs = (jobs.dw, jobs.cs) if defer else ([], [])
+
     # ---- decoder_norm
     g = torch.empty(M, Dd, dtype=F32, device=dev)       # gradient of the fp32 residual stream
     g16 = torch.empty(M, Dd, dtype=F16, device=dev)
@@ -176,7 +181,7 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
     # every LayerNorm backward also emits the column sums of the residual gradient it produces = the bias gradient of the
     # Linear that consumes it next (fc2 of the block below, the two attention projections, decoder_embed)
     ops.layernorm_bwd(d_next.view(M, Dd), sv["x_final"], _contig32(dn.weight), sv["meanf"], sv["rstdf"], g, G(dn.weight),
-                      G(dn.bias), accumulate=False, dx16=g16, dx_colsum=G(blocks_rev[0].mlp.fc2.bias))
+                      G(dn.bias), accumulate=False, dx16=g16, dx_colsum=G(blocks_rev[0].mlp.fc2.bias), jobs=jobs)
 
     # ---- FIM blocks (models_crossvit.py:152-156 reversed)
     y16 = sv["y16"]
@@ -214,8 +219,6 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
     # computed at the end by one grouped tcgen05 launch (+ one grouped column-sum launch) over all of them — 17 GEMMs and
     # 8 column sums that would otherwise sit between the dX GEMMs of the latency-bound chain, each with its own launch,
     # prologue, pipeline fill and exposed epilogue (csrc/grouped.cu).  eng.defer_dw = False restores the per-layer launches.
-    defer = getattr(eng, "defer_dw", True)
-    dw_jobs, cs_jobs = [], []
 
     def dW(dy16, x16, p):
         if defer:
@@ -241,7 +244,7 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
         ops.linear(dpre, wc.w16_t(blk.mlp.fc1.weight), dh)
         g16 = new_g16()
         ops.layernorm_bwd(dh, s["x2"], _contig32(blk.norm2.weight), s["mean2"], s["rstd2"], g, G(blk.norm2.weight),
-                          G(blk.norm2.bias), accumulate=True, dx16=g16, dx_colsum=G(blk.attn.proj.bias))
+                          G(blk.norm2.bias), accumulate=True, dx16=g16, dx_colsum=G(blk.attn.proj.bias), jobs=jobs)
         # --- cross attention: x2 = x1 + proj(core(wq(LN1 x1), wk(y), wv(y)))
         ca = blk.attn
         dW(g16, s["c16"], ca.proj.weight)
@@ -289,7 +292,7 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
                 _exemplar_backward(m, sv, boxes, S, dy32, grads, wc, G)
         g16 = new_g16()
         ops.layernorm_bwd(dh, s["x1"], _contig32(blk.norm1.weight), s["mean1"], s["rstd1"], g, G(blk.norm1.weight),
-                          G(blk.norm1.bias), accumulate=True, dx16=g16, dx_colsum=G(blk.selfattn.proj.bias))
+                          G(blk.norm1.bias), accumulate=True, dx16=g16, dx_colsum=G(blk.selfattn.proj.bias), jobs=jobs)
         # --- self attention: x1 = x0 + proj(attn(qkv(LN0 x0)))
         sa = blk.selfattn
         dW(g16, s["att"], sa.proj.weight)
@@ -303,7 +306,7 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
         nxt_bias = blocks_rev[bi + 1].mlp.fc2.bias if bi + 1 < n_blocks else m.decoder_embed.bias
         g16 = new_g16()
         ops.layernorm_bwd(dh, s["x0"], _contig32(blk.norm0.weight), s["mean0"], s["rstd0"], g, G(blk.norm0.weight),
-                          G(blk.norm0.bias), accumulate=True, dx16=g16, dx_colsum=G(nxt_bias))
+                          G(blk.norm0.bias), accumulate=True, dx16=g16, dx_colsum=G(nxt_bias), jobs=jobs)
 
     # ---- decoder_embed: weight / bias only (its input is the frozen encoder's output)
     de = m.decoder_embed
@@ -315,8 +318,7 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
     if side is not None or wstream is not None:
         torch.cuda.current_stream().wait_stream(eng.side_stream(dev))     # join the exemplar-CNN backward and the k/v work
     if defer:
-        ops.grouped_colsum(cs_jobs)
-        ops.grouped_dw(dw_jobs)
+        jobs.flush()
     keep.clear()
     # Every parameter that just received a gradient is about to be changed by an optimizer, and torch's version counter
     # cannot be relied on to say so (torch.optim.AdamW(fused=True) updates parameters without bumping `_version`, and so

@@ -61,7 +61,7 @@ def vit_block_backward(wc, blk, s, g, g16, G, jobs, next_bias=None):
     ops.linear(dpre, wc.w16_t(blk.mlp.fc1.weight), dh)
     g16 = torch.empty(M, D, dtype=F16, device=dev)
     ops.layernorm_bwd(dh, s["x1"], _contig32(blk.norm2.weight), s["mean2"], s["rstd2"], g, G(blk.norm2.weight), G(blk.norm2.bias),
-                      accumulate=True, dx16=g16, dx_colsum=G(blk.attn.proj.bias))
+                      accumulate=True, dx16=g16, dx_colsum=G(blk.attn.proj.bias), jobs=jobs)
     # attention
     jobs.dW(g16, s["att"], G(blk.attn.proj.weight))
     datt = torch.empty(M, D, dtype=F16, device=dev)
@@ -72,5 +72,5 @@ def vit_block_backward(wc, blk, s, g, g16, G, jobs, next_bias=None):
     ops.linear(dqkv, wc.w16_t(blk.attn.qkv.weight), dh)
     g16 = torch.empty(M, D, dtype=F16, device=dev)
     ops.layernorm_bwd(dh, s["x0"], _contig32(blk.norm1.weight), s["mean1"], s["rstd1"], g, G(blk.norm1.weight), G(blk.norm1.bias),
-                      accumulate=True, dx16=g16, dx_colsum=None if next_bias is None else G(next_bias))
+                      accumulate=True, dx16=g16, dx_colsum=None if next_bias is None else G(next_bias), jobs=jobs)
     return g16

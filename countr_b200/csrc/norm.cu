@@ -9,6 +9,8 @@
 #include "../../include/countr_b200.h"
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace countr {
 namespace {
 
@@ -84,7 +86,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                              const float* __restrict__ rstd_in, float* __restrict__ dx,
                                                              uint16_t* __restrict__ dx16, float* __restrict__ dgamma,
                                                              float* __restrict__ dbeta, float* __restrict__ dx_colsum, int rows,
-                                                             int D, int accumulate, int rows_per_warp, int bf16) {
+                                                             int D, int accumulate, int rows_per_warp, int bf16,
+                                                             float* __restrict__ partials) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   pdl_trigger();
@@ -166,9 +169,32 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       }
     }
   }
-  // block-level reduction of dgamma/dbeta over the 8 warps, then one atomic per column per block
+  // block-level reduction of dgamma/dbeta over the 8 warps, then one atomic per column per block — or, with `partials`
+  // ([3][gridDim.x][D]: dgamma, dbeta, column sums of dx), one plain store per column per block: the caller sums the
+  // block rows later (grouped column sums at the end of the backward), so the kernel has no same-address atomics and can
+  // run four blocks per SM
   __shared__ float4 red[8][32];
   const int w = threadIdx.x >> 5;
+  if (partials != nullptr) {
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        red[w][lane] = pass == 0 ? dg[i] : pass == 1 ? db[i] : dxs[i];
+        __syncthreads();
+        if (w == 0) {
+          float4 a = red[0][lane];
+#pragma unroll
+          for (int k = 1; k < 8; ++k) {
+            a.x += red[k][lane].x; a.y += red[k][lane].y; a.z += red[k][lane].z; a.w += red[k][lane].w;
+          }
+          reinterpret_cast<float4*>(partials + (static_cast<size_t>(pass) * gridDim.x + blockIdx.x) * D)[lane + 32 * i] = a;
+        }
+        __syncthreads();
+      }
+    }
+    return;
+  }
   if (dgamma == nullptr && dx_colsum == nullptr) return;
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
@@ -218,12 +244,39 @@ extern "C" int countr_layernorm_fwd(const float* x, const float* gamma, const fl
   return COUNTR_OK;
 }
 
+namespace {
+// grid of the partial-sums mode: four 8-warp blocks per SM (no atomics to contend on, memory latency is what is left)
+void ln_bwd_partial_grid(int rows, int* rpw, int* blocks) {
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    const char* e = getenv("COUNTR_LN_BWD_BLOCKS_PER_SM");
+    per_sm = e != nullptr ? atoi(e) : 1;
+    if (per_sm < 1) per_sm = 1;
+  }
+  const int target_warps = 148 * 8 * per_sm;
+  int r = (rows + target_warps - 1) / target_warps;
+  if (r < 1) r = 1;
+  const int warps = (rows + r - 1) / r;
+  *rpw = r;
+  *blocks = (warps + 7) / 8;
+}
+}  // namespace
+
+extern "C" int countr_layernorm_bwd_blocks(int rows) {
+  int rpw, blocks;
+  ln_bwd_partial_grid(rows, &rpw, &blocks);
+  return blocks;
+}
+
 extern "C" int countr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
                                     const float* rstd, float* dx, void* dx16, float* dgamma, float* dbeta, float* dx_colsum,
-                                    int rows, int D, int accumulate, int bf16, countr_stream_t stream_) {
+                                    float* partials, int rows, int D, int accumulate, int bf16, countr_stream_t stream_) {
   using namespace countr;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(dy && x && gamma && mean && rstd && dx, "null pointer");
+  COUNTR_REQUIRE(partials == nullptr || (dgamma == nullptr && dbeta == nullptr && dx_colsum == nullptr &&
+                                         (reinterpret_cast<uintptr_t>(partials) & 15u) == 0),
+                 "partials mode: 16-byte aligned [3][countr_layernorm_bwd_blocks(rows)][D] buffer, dgamma / dbeta / dx_colsum NULL");
   COUNTR_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "dgamma/dbeta must both be given or both NULL");
   COUNTR_REQUIRE(rows > 0 && D % 128 == 0 && D <= 1536, "LayerNorm width %d unsupported", D);
   // one wave of 8-warp blocks: fewer blocks = fewer same-address dgamma/dbeta atomics
@@ -231,11 +284,12 @@ extern "C" int countr_layernorm_bwd(const float* dy, const float* x, const float
   int rpw = (rows + target_warps - 1) / target_warps;
   if (rpw < 1) rpw = 1;
   const int warps = (rows + rpw - 1) / rpw;
-  const int blocks = (warps + 7) / 8;
+  int blocks = (warps + 7) / 8;
+  if (partials != nullptr) ln_bwd_partial_grid(rows, &rpw, &blocks);
 #define LN_CASE(NV)                                                                                       \
   case NV:                                                                                                \
     COUNTR_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel<NV>, dim3(blocks), dim3(256), 0, stream, dy, x, gamma, mean, rstd, dx,  \
-                                 reinterpret_cast<uint16_t*>(dx16), dgamma, dbeta, dx_colsum, rows, D, accumulate, rpw, bf16)); \
+                                 reinterpret_cast<uint16_t*>(dx16), dgamma, dbeta, dx_colsum, rows, D, accumulate, rpw, bf16, partials)); \
     break;
   switch (D / 128) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(8) LN_CASE(10) LN_CASE(12)

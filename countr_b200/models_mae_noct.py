@@ -220,7 +220,7 @@ class MaskedAutoencoderViTNoCT(nn.Module):
         dn = self.decoder_norm
         dblocks, eblocks = list(self.decoder_blocks), list(self.blocks)
         ops.layernorm_bwd(dh, t["x_dec"], _contig32(dn.weight), t["mean_d"], t["rstd_d"], g, G(dn.weight), G(dn.bias), accumulate=False, dx16=g16,
-                          dx_colsum=G(dblocks[-1].mlp.fc2.bias))
+                          dx_colsum=G(dblocks[-1].mlp.fc2.bias), jobs=jobs)
         for k in range(len(dblocks) - 1, -1, -1):
             g16 = vit_block_backward(wc, dblocks[k], t["dec"][k], g, g16, G, jobs, next_bias=dblocks[k - 1].mlp.fc2.bias if k > 0 else None)
         # un-shuffle backward: d x_[b, j] = g[b, ids_shuffle[b, j]]; rows j < Lk belong to the kept tokens, the rest
@@ -261,7 +261,7 @@ class MaskedAutoencoderViTNoCT(nn.Module):
         ops.linear(gk16, wc.w16_t(de.weight), dhe)
         ge, ge16 = e((B * Lk, D), F32), e((B * Lk, D), F16)
         ops.layernorm_bwd(dhe, t["x_enc"], _contig32(self.norm.weight), t["mean_e"], t["rstd_e"], ge, G(self.norm.weight), G(self.norm.bias),
-                          accumulate=False, dx16=ge16, dx_colsum=G(eblocks[-1].mlp.fc2.bias))
+                          accumulate=False, dx16=ge16, dx_colsum=G(eblocks[-1].mlp.fc2.bias), jobs=jobs)
         pe = self.patch_embed.proj
         for k in range(len(eblocks) - 1, -1, -1):
             ge16 = vit_block_backward(wc, eblocks[k], t["enc"][k], ge, ge16, G, jobs, next_bias=eblocks[k - 1].mlp.fc2.bias if k > 0 else pe.bias)

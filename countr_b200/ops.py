@@ -123,11 +123,23 @@ def layernorm_fwd(x, gamma, beta, eps, y16=None, y32=None, mean=None, rstd=None)
     _count()
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma=None, dbeta=None, accumulate=False, dx16=None, dx_colsum=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma=None, dbeta=None, accumulate=False, dx16=None, dx_colsum=None, jobs=None):
+    """jobs (backward.GradJobs): dgamma / dbeta / dx_colsum are not accumulated with atomics by this kernel; it writes per-block
+    partial sums and three column-sum jobs are recorded instead (summed by the grouped launch at the end of the backward), which
+    also lets the kernel run four blocks per SM."""
     rows, D = x.shape
+    partials = None
+    if jobs is not None and dgamma is not None:
+        nblk = int(lib().countr_layernorm_bwd_blocks(rows))
+        partials = torch.empty(3, nblk, D, dtype=torch.float32, device=x.device)
+        jobs.dB(partials[0], dgamma)
+        jobs.dB(partials[1], dbeta)
+        if dx_colsum is not None:
+            jobs.dB(partials[2], dx_colsum)
+        dgamma = dbeta = dx_colsum = None
     check(lib().countr_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dx16), _ptr(dgamma),
-                                     _ptr(dbeta), _ptr(dx_colsum), rows, D, int(accumulate), _is_bf16(dx16) if dx16 is not None else 0,
-                                     _stream()))
+                                     _ptr(dbeta), _ptr(dx_colsum), _ptr(partials), rows, D, int(accumulate),
+                                     _is_bf16(dx16) if dx16 is not None else 0, _stream()))
     _count()
 
 

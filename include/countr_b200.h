@@ -128,10 +128,14 @@ int countr_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
                          countr_stream_t stream);
 /* dx (+)= LN'(dy); dx16 (optional) = 16-bit copy of the updated dx (next GEMM's operand);
  * dgamma/dbeta (optional, pre-zeroed or carrying earlier contributions) +=;
- * dx_colsum [D] (optional) += column sums of the updated dx = bias gradient of the next Linear up the chain */
+ * dx_colsum [D] (optional) += column sums of the updated dx = bias gradient of the next Linear up the chain.
+ * partials != NULL (then dgamma / dbeta / dx_colsum must be NULL): no atomics — every block writes its sums of
+ * dgamma, dbeta and of the updated dx to partials[3][countr_layernorm_bwd_blocks(rows)][D]; the caller adds the block rows up
+ * later (countr_grouped_colsum at the end of the backward). */
+int countr_layernorm_bwd_blocks(int rows);
 int countr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
-                         const float* rstd, float* dx, void* dx16, float* dgamma, float* dbeta, float* dx_colsum, int rows,
-                         int D, int accumulate, int bf16, countr_stream_t stream);
+                         const float* rstd, float* dx, void* dx16, float* dgamma, float* dbeta, float* dx_colsum, float* partials,
+                         int rows, int D, int accumulate, int bf16, countr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused multi-head self-attention forward: softmax(scale * Q K^T) V, flash-style on tcgen05.
