@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma/dbeta partials per block -> atomics.
 // dy is fp32.  dx is ADDED to dx_accum when accumulate != 0 (the residual branch gradient).
 template <int NV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ mean_in,
                                                              const float* __restrict__ rstd_in, float* __restrict__ dx,
@@ -96,46 +96,26 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 #pragma unroll
   for (int i = 0; i < NV; ++i) dg[i] = db[i] = dxs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  // software pipeline over the rows of this warp: the loads of row r+1 are in flight while row r is reduced and stored
-  // (the per-row chain load -> two warp reductions -> store was fully exposed: 19 us per launch for 47 MB)
+  // Two blocks per SM (16 warps) hide the row-to-row latency; an explicit one-row prefetch cost 2 x NV float4 registers and kept
+  // the kernel at one block per SM (156 registers).
   const int row0 = warp * rows_per_warp;
-  float4 xn[NV], dn[NV];
-  float mean_n = 0.f, rstd_n = 0.f;
-  if (row0 < rows) {
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row0) * D);
-    const float4* dr = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row0) * D);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      xn[i] = xr[lane + 32 * i];
-      dn[i] = dr[lane + 32 * i];
-    }
-    mean_n = mean_in[row0];
-    rstd_n = rstd_in[row0];
-  }
   float4 gm[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) gm[i] = __ldg(g4 + lane + 32 * i);
   for (int rr = 0; rr < rows_per_warp; ++rr) {
     const int row = row0 + rr;
     if (row >= rows) break;
-    const float mean = mean_n, rstd = rstd_n;
     float4 xc[NV], dc[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      xc[i] = xn[i];
-      dc[i] = dn[i];
-    }
-    if (rr + 1 < rows_per_warp && row + 1 < rows) {
-      const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row + 1) * D);
-      const float4* dr = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row + 1) * D);
+    {
+      const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+      const float4* dr = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * D);
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        xn[i] = xr[lane + 32 * i];
-        dn[i] = dr[lane + 32 * i];
+        xc[i] = xr[lane + 32 * i];
+        dc[i] = dr[lane + 32 * i];
       }
-      mean_n = mean_in[row + 1];
-      rstd_n = rstd_in[row + 1];
     }
+    const float mean = mean_in[row], rstd = rstd_in[row];
     float4 xh[NV], gy[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -245,12 +225,13 @@ extern "C" int countr_layernorm_fwd(const float* x, const float* gamma, const fl
 }
 
 namespace {
-// grid of the partial-sums mode: four 8-warp blocks per SM (no atomics to contend on, memory latency is what is left)
+// grid of the partial-sums mode: two 8-warp blocks per SM (what 128 registers allow; no atomics to contend on, memory latency is
+// what is left)
 void ln_bwd_partial_grid(int rows, int* rpw, int* blocks) {
   static int per_sm = 0;
   if (per_sm == 0) {
     const char* e = getenv("COUNTR_LN_BWD_BLOCKS_PER_SM");
-    per_sm = e != nullptr ? atoi(e) : 1;
+    per_sm = e != nullptr ? atoi(e) : 2;     // measured: 2 blocks per SM 1875 vs 1902 us (fine-tune backward), 18.2 vs 19.1 ms (pre-train step)
     if (per_sm < 1) per_sm = 1;
   }
   const int target_warps = 148 * 8 * per_sm;
