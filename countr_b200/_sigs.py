@@ -41,6 +41,10 @@ SIGS = {
     "countr_crop_resize_boxes": [P, L, L, L, L, P, P, I, I, I, I, I, I, P],
     "countr_crop_resize": [P, L, L, L, L, P, P, I, I, I, I, I, I, I, P],
     "countr_rect_mass": [P, I, I, P, I, F, P, P],
+    "countr_aug_noise_clamp": [P, P, L, F, c_uint64, P],
+    "countr_aug_color_jitter": [P, P, P, P, I, I, I, P],
+    "countr_aug_gaussian_blur": [P, P, P, P, I, I, I, I, I, P],
+    "countr_aug_hflip": [P, P, P, I, I, I, I, P],
     "countr_grouped_dw": [P, I, I, P],
     "countr_grouped_colsum": [P, I, P],
     "countr_density_from_dots": [P, P, I, I, c_double, c_double, I, I, I, I, I, I, P, I, F, P, P, P],

@@ -13,6 +13,8 @@
 #include "../../include/countr_b200.h"
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace countr {
 namespace {
 
@@ -178,6 +180,207 @@ extern "C" int countr_rect_mass(const float* map, int H, int W, const int32_t* r
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(map && rects && out && H > 0 && W > 0 && n_rects > 0 && divisor != 0.f, "bad arguments");
   rect_mass_kernel<<<n_rects, 256, 0, stream>>>(map, H, W, rects, divisor, out);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+
+// ==========================================================================================
+// Training-time augmentations on the device (util/FSC147.py:133-143, 371-374): Gaussian noise + clamp, torchvision's
+// ColorJitter (brightness / contrast / saturation / hue in a sampled order, tensor arithmetic of
+// torchvision.transforms.functional) and GaussianBlur(kernel_size=(7, 9), sigma ~ U[0.1, 2]), horizontal flip.  The random
+// PARAMETERS (factors, order, sigma, flip decision) are the caller's (host RNG streams cannot be reproduced on the device);
+// given the same parameters the pixel arithmetic is torchvision's.  Images are fp32 [B][3][H][W] contiguous.
+// ==========================================================================================
+namespace countr {
+namespace {
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+
+// out = clamp(img + N(0, std), 0, 1); counter-based generator (one 64-bit hash per pixel pair, Box-Muller)
+__global__ void __launch_bounds__(256) noise_clamp_kernel(const float* __restrict__ img, float* __restrict__ out, long long n, float stddev,
+                                                          unsigned long long seed) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
+  if (i >= n) return;
+  const uint64_t h = mix64(seed ^ mix64(static_cast<uint64_t>(i)));
+  const float u1 = (static_cast<float>(static_cast<uint32_t>(h)) + 0.5f) * 2.3283064365386963e-10f;          // (0, 1)
+  const float u2 = (static_cast<float>(static_cast<uint32_t>(h >> 32)) + 0.5f) * 2.3283064365386963e-10f;
+  const float r = sqrtf(-2.f * logf(u1)) * stddev;
+  float sn, cs;
+  sincospif(2.f * u2, &sn, &cs);
+  out[i] = fminf(fmaxf(img[i] + r * cs, 0.f), 1.f);
+  if (i + 1 < n) out[i + 1] = fminf(fmaxf(img[i + 1] + r * sn, 0.f), 1.f);
+}
+
+__device__ __forceinline__ float gray_of(float r, float g, float b) { return 0.2989f * r + 0.587f * g + 0.114f * b; }
+
+// mean[b] += sum of the grayscale image (fp64 accumulation); the caller divides by H*W
+__global__ void __launch_bounds__(256) gray_sum_kernel(const float* __restrict__ img, double* __restrict__ sum, int HW) {
+  const int b = blockIdx.y;
+  const float* p = img + static_cast<long long>(b) * 3 * HW;
+  double acc = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
+    acc += static_cast<double>(gray_of(p[i], p[HW + i], p[2 * HW + i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    atomicAdd(sum + b, t);
+  }
+}
+
+// one ColorJitter operation on every pixel of image b: op[b] in {0 brightness, 1 contrast, 2 saturation, 3 hue, -1 skip}
+__global__ void __launch_bounds__(256) color_op_kernel(float* __restrict__ img, const int* __restrict__ op, const float* __restrict__ factor,
+                                                       const double* __restrict__ gray_sum, int HW) {
+  const int b = blockIdx.y;
+  const int which = op[b];
+  if (which < 0) return;
+  const float f = factor[b];
+  float* p = img + static_cast<long long>(b) * 3 * HW;
+  const float mean = which == 1 ? static_cast<float>(gray_sum[b] / HW) : 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    float r = p[i], g = p[HW + i], bl = p[2 * HW + i];
+    if (which == 0) {            // _blend(img, 0, f)
+      r = fminf(fmaxf(f * r, 0.f), 1.f); g = fminf(fmaxf(f * g, 0.f), 1.f); bl = fminf(fmaxf(f * bl, 0.f), 1.f);
+    } else if (which == 1 || which == 2) {
+      const float m = which == 1 ? mean : gray_of(r, g, bl);
+      r = fminf(fmaxf(f * r + (1.f - f) * m, 0.f), 1.f);
+      g = fminf(fmaxf(f * g + (1.f - f) * m, 0.f), 1.f);
+      bl = fminf(fmaxf(f * bl + (1.f - f) * m, 0.f), 1.f);
+    } else {                     // hue: _rgb2hsv, h = (h + f) % 1, _hsv2rgb
+      const float maxc = fmaxf(r, fmaxf(g, bl)), minc = fminf(r, fminf(g, bl));
+      const bool eqc = maxc == minc;
+      const float cr = maxc - minc;
+      const float sat = cr / (eqc ? 1.f : maxc);
+      const float div = eqc ? 1.f : cr;
+      const float rc = (maxc - r) / div, gc = (maxc - g) / div, bc = (maxc - bl) / div;
+      float h = 0.f;
+      if (maxc == r) h = bc - gc;
+      else if (maxc == g) h = 2.f + rc - bc;
+      else h = 4.f + gc - rc;
+      h = fmodf(h / 6.f + 1.f, 1.f);
+      h = h + f;
+      h = h - floorf(h);         // python % 1.0
+      const float v = maxc;
+      const float i6 = floorf(h * 6.f);
+      const float fr = h * 6.f - i6;
+      int ii = static_cast<int>(i6) % 6;
+      if (ii < 0) ii += 6;
+      const float pp = fminf(fmaxf(v * (1.f - sat), 0.f), 1.f);
+      const float qq = fminf(fmaxf(v * (1.f - sat * fr), 0.f), 1.f);
+      const float tt = fminf(fmaxf(v * (1.f - sat * (1.f - fr)), 0.f), 1.f);
+      switch (ii) {
+        case 0: r = v; g = tt; bl = pp; break;
+        case 1: r = qq; g = v; bl = pp; break;
+        case 2: r = pp; g = v; bl = tt; break;
+        case 3: r = pp; g = qq; bl = v; break;
+        case 4: r = tt; g = pp; bl = v; break;
+        default: r = v; g = pp; bl = qq; break;
+      }
+    }
+    p[i] = r; p[HW + i] = g; p[2 * HW + i] = bl;
+  }
+}
+
+// separable Gaussian blur with reflect padding; weights as torchvision's _get_gaussian_kernel1d (fp32), sigma per image.
+// horizontal != 0: along x with `k` taps, else along y.
+__global__ void __launch_bounds__(256) gauss_blur_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ sigma,
+                                                         int H, int W, int k, int horizontal) {
+  const int b = blockIdx.z;
+  const long long plane = static_cast<long long>(H) * W;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= 3 * plane) return;
+  const int x = static_cast<int>(idx % W), y = static_cast<int>((idx / W) % H), c = static_cast<int>(idx / plane);
+  const float sg = sigma[b];
+  const float half = (k - 1) * 0.5f;
+  float wsum = 0.f, acc = 0.f;
+  const float* p = in + (static_cast<long long>(b) * 3 + c) * plane;
+  for (int t = 0; t < k; ++t) {
+    const float xx = (-half + t) / sg;
+    const float w = expf(-0.5f * xx * xx);
+    wsum += w;
+    int q = (horizontal ? x : y) + t - k / 2;
+    const int n = horizontal ? W : H;
+    if (q < 0) q = -q;                       // reflect (no edge repeat)
+    if (q >= n) q = 2 * n - 2 - q;
+    acc += w * (horizontal ? p[static_cast<long long>(y) * W + q] : p[static_cast<long long>(q) * W + x]);
+  }
+  out[(static_cast<long long>(b) * 3 + c) * plane + static_cast<long long>(y) * W + x] = acc / wsum;
+}
+
+// horizontal flip of the images whose flag is set (planes = channels per image); otherwise copy
+__global__ void __launch_bounds__(256) hflip_kernel(const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ flag, int planes,
+                                                    int H, int W) {
+  const int b = blockIdx.y;
+  const long long n = static_cast<long long>(planes) * H * W;
+  const bool flip = flag[b] != 0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W);
+    out[b * n + i] = in[b * n + (flip ? i - x + (W - 1 - x) : i)];
+  }
+}
+
+}  // namespace
+}  // namespace countr
+
+extern "C" int countr_aug_noise_clamp(const float* img, float* out, int64_t n, float stddev, uint64_t seed, countr_stream_t stream_) {
+  using namespace countr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(img && out && n > 0 && stddev >= 0.f, "bad arguments");
+  const long long threads = (n + 1) / 2;
+  noise_clamp_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(img, out, n, stddev, seed);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_aug_color_jitter(float* img, const int32_t* ops, const float* factors, double* scratch, int B, int H, int W,
+                                       countr_stream_t stream_) {
+  using namespace countr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(img && ops && factors && scratch && B > 0 && H > 0 && W > 0, "bad arguments");
+  const int HW = H * W;
+  dim3 grid(static_cast<unsigned>(std::min(592, (HW + 255) / 256)), B);
+  // four passes (ColorJitter applies its four functions one after the other in the sampled order); pass j of image b runs
+  // ops[j][b] with factors[j][b]; the contrast pass needs the mean of the CURRENT grayscale image, recomputed per pass
+  for (int j = 0; j < 4; ++j) {
+    COUNTR_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * B, stream));
+    gray_sum_kernel<<<grid, 256, 0, stream>>>(img, scratch, HW);
+    color_op_kernel<<<grid, 256, 0, stream>>>(img, ops + static_cast<long long>(j) * B, factors + static_cast<long long>(j) * B, scratch, HW);
+  }
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_aug_gaussian_blur(const float* img, float* tmp, float* out, const float* sigma, int B, int H, int W, int kx, int ky,
+                                        countr_stream_t stream_) {
+  using namespace countr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(img && tmp && out && sigma && B > 0 && H > ky / 2 && W > kx / 2 && kx % 2 == 1 && ky % 2 == 1 && kx <= 31 && ky <= 31,
+                 "bad arguments (odd kernel sizes smaller than twice the image)");
+  const long long n = 3ll * H * W;
+  dim3 grid(static_cast<unsigned>((n + 255) / 256), 1, B);
+  gauss_blur_kernel<<<grid, 256, 0, stream>>>(img, tmp, sigma, H, W, kx, 1);
+  gauss_blur_kernel<<<grid, 256, 0, stream>>>(tmp, out, sigma, H, W, ky, 0);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_aug_hflip(const float* in, float* out, const int32_t* flags, int B, int planes, int H, int W, countr_stream_t stream_) {
+  using namespace countr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(in && out && flags && in != out && B > 0 && planes > 0 && H > 0 && W > 0, "bad arguments (out of place)");
+  const long long n = static_cast<long long>(planes) * H * W;
+  dim3 grid(static_cast<unsigned>(std::min<long long>(1184, (n + 255) / 256)), B);
+  hflip_kernel<<<grid, 256, 0, stream>>>(in, out, flags, planes, H, W);
   COUNTR_CHECK_CUDA(cudaGetLastError());
   return COUNTR_OK;
 }

@@ -387,6 +387,24 @@ int countr_crop_resize(const float* img, int64_t sb, int64_t sc, int64_t sh, int
 int countr_rect_mass(const float* map, int H, int W, const int32_t* rects, int n_rects, float divisor, float* out,
                      countr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training-time augmentations on the device (util/FSC147.py:133-143, 371-374, 176-180).  The random PARAMETERS are the caller's;
+ * given the same parameters the pixel arithmetic is numpy's / torchvision's.  Images: fp32 [B][3][H][W], contiguous.
+ *   countr_aug_noise_clamp   out = clamp(img + N(0, stddev), 0, 1)   (counter-based generator keyed by `seed`; :133-137)
+ *   countr_aug_color_jitter  torchvision ColorJitter in place: pass j (0..3) applies ops[j][b] in {0 brightness, 1 contrast,
+ *                            2 saturation, 3 hue, -1 none} with factors[j][b] to image b (transforms.functional.adjust_*, :372);
+ *                            scratch: B doubles
+ *   countr_aug_gaussian_blur torchvision GaussianBlur(kernel_size=(kx, ky)) with sigma[b] (reflect padding, :373); tmp: image-sized
+ *   countr_aug_hflip         TF.hflip of the images whose flag is set, `planes` channels per image (image and density map, :176-180)
+ * Not built: imgaug's Affine with keypoints (:146-171) and the mosaic collage (:183-262).
+ * ------------------------------------------------------------------------------------------ */
+int countr_aug_noise_clamp(const float* img, float* out, int64_t n, float stddev, uint64_t seed, countr_stream_t stream);
+int countr_aug_color_jitter(float* img, const int32_t* ops, const float* factors, double* scratch, int B, int H, int W,
+                            countr_stream_t stream);
+int countr_aug_gaussian_blur(const float* img, float* tmp, float* out, const float* sigma, int B, int H, int W, int kx, int ky,
+                             countr_stream_t stream);
+int countr_aug_hflip(const float* in, float* out, const int32_t* flags, int B, int planes, int H, int W, countr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
