@@ -1350,7 +1350,16 @@ extern "C" int countr_gemm(const countr_gemm_desc* d, countr_stream_t stream_) {
                                         (conv_dw && p.m_tiles % 2 == 0 && d->K >= 64 * 64))) ||
                          (!conv && !conv_dw && !d->a_mn && !d->b_mn && bn == 192 && d->K >= 3072 && p.m_tiles % 2 == 0 && split_k == 1 &&
                           nb1 * nb2 == 1 && (p.m_tiles / 2) * ((d->N + bn - 1) / bn) <= sms / 2);
-  p.pair = (pair_ok && (d->cta_pair > 0 || (d->cta_pair == 0 && pair_auto))) ? 1 : 0;
+  // large-M Linear layers run as CTA pairs (less shared-memory fill and L2 traffic per flop; these long kernels are power-limited);
+  // COUNTR_PAIR_LINEAR=<min m_tiles> moves the threshold (0 = never)
+  static int pair_linear = -1;
+  if (pair_linear < 0) {
+    const char* e = getenv("COUNTR_PAIR_LINEAR");
+    pair_linear = e != nullptr ? atoi(e) : 64;     // default: from 64 m tiles on (M >= 8192: B = 128 inference 33.6 -> 32.8 ms, pre-train step 18.27 -> 17.91 ms)
+  }
+  const bool pair_forced = pair_linear > 0 && !conv && !conv_dw && !d->a_mn && !d->b_mn && p.m_tiles >= pair_linear && p.m_tiles % 2 == 0 &&
+                           split_k == 1 && nb1 * nb2 == 1;
+  p.pair = (pair_ok && (d->cta_pair > 0 || (d->cta_pair == 0 && (pair_auto || pair_forced)))) ? 1 : 0;
   int cs = p.pair ? 2 : (d->cluster > 0 ? d->cluster : 1);
   if (cs != 1 && cs != 2 && cs != 4) cs = 1;
   while (cs > 1 && (p.m_tiles < cs || (d->b_mn || conv_dw ? (bn / 64) % cs != 0 : (bn % (8 * cs)) != 0))) cs >>= 1;
