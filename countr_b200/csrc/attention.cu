@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "tma.h"
 
+#include <stdlib.h>
 #include <type_traits>
 
 namespace countr {
@@ -457,6 +458,399 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
   }
+}
+
+// ================================================================================================
+// Four-tile variant of the forward kernel.  The two-tile kernel above is bound by the MUFU (exp2) and keeps it busy only two
+// thirds of the time: the two query tiles of a CTA move through S load -> row max -> exp -> P hand-off in lock-step, and one
+// warp per SM sub-partition cannot saturate the unit on its own (profiles/r2_attention_fwd.md).  Here a CTA works on FOUR
+// 128-query tiles of one (batch, head) at once with 64-key chunks: S_t is 64 TMEM columns (4 x 64 + 4 x 64 for O = all 512),
+// sixteen softmax warps (four per sub-partition, 64 S values per thread and chunk) drift apart naturally, so some warp is
+// always in its exp phase.  One work item = one head's four tiles (576 tokens: 4 tiles + one 64-row remainder item).
+// ================================================================================================
+constexpr int NT4 = 4;                     // query tiles in flight per CTA
+constexpr int KC4 = 64;                    // keys per chunk
+constexpr int KS4 = 4;                     // K / V ring stages
+// TWO MMA-issuing warps: a tcgen05.mma costs ~60-85 clk to issue (csrc/gemm.cu), and with 16-key k-steps and 64-wide tiles this
+// kernel issues 8 of them per (tile, chunk) — one warp issuing S = Q K^T and P.V in turn was the bottleneck (3300 of the
+// 5100 clk per chunk step), and its in-order barrier waits kept the tiles in lock-step.
+constexpr int kSoftmaxWarps4 = 16, kMmaWarp4 = 16, kPvWarp4 = 17, kTmaWarp4 = 18;
+constexpr int kThreads4 = 32 * 19;
+
+template <int DH>
+struct Attn4Smem {
+  static constexpr uint32_t kRowBytes = DH * 2;
+  static constexpr uint32_t kQBytes = BQ * kRowBytes;
+  static constexpr uint32_t kKBytes = KC4 * kRowBytes;
+  static constexpr uint32_t kPBytes = BQ * KC4 * 2;            // [128 x 128 B], one SWIZZLE_128B column block
+  static constexpr uint32_t kOffQ = 0;                         // [NT4]
+  static constexpr uint32_t kOffK = NT4 * kQBytes;             // [KS4]
+  static constexpr uint32_t kOffV = kOffK + KS4 * kKBytes;
+  static constexpr uint32_t kOffP = kOffV + KS4 * kKBytes;     // [NT4]
+  static constexpr uint32_t kOffBar = kOffP + NT4 * kPBytes;
+  static constexpr uint32_t kTotal = kOffBar + 512 + 1024;
+};
+
+struct Attn4Args {
+  uint16_t* out;
+  float* lse;
+  int B, L, H;
+  float scale_log2;
+  int n_full, n_items, full_groups;     // items [0, n_full): four-tile groups (bh-major inside a group index), then the remainders
+};
+
+template <int DH, bool kBf16>
+__global__ void __launch_bounds__(kThreads4, 1)
+attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, const Attn4Args p) {
+  using SM = Attn4Smem<DH>;
+  constexpr uint32_t kLayout = DH == 64 ? 2u : 4u;            // SWIZZLE_128B : SWIZZLE_64B
+  constexpr uint32_t kSboK = DH == 64 ? 1024u : 512u;
+  constexpr uint32_t kVStep = 16 * SM::kRowBytes;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
+  uint64_t* q_full = bars;                 // [1]
+  uint64_t* q_empty = bars + 1;            // [1]
+  uint64_t* k_full = bars + 2;             // [KS4]
+  uint64_t* k_empty = k_full + KS4;
+  uint64_t* v_full = k_empty + KS4;
+  uint64_t* v_empty = v_full + KS4;
+  uint64_t* s_full = v_empty + KS4;        // [NT4]
+  uint64_t* s_free = s_full + NT4;
+  uint64_t* p_full = s_free + NT4;
+  uint64_t* p_free = p_full + NT4;
+  uint64_t* o_full = p_free + NT4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + NT4);
+
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int nchunks = (p.L + KC4 - 1) / KC4;
+  const int BH = p.B * p.H;
+  const int tiles_total = (p.L + BQ - 1) / BQ;
+  // it-th work item of this CTA (-1: done).  With fewer four-tile items than CTAs every such item gets its own CTA and the
+  // remainder items (a fraction of a tile each) are spread over the CTAs that are left.
+  auto cta_item = [&](int it) -> int {
+    const int grid = static_cast<int>(gridDim.x), cta = static_cast<int>(blockIdx.x);
+    if (p.n_full < grid && p.n_items > p.n_full) {
+      if (cta < p.n_full) return it == 0 ? cta : -1;
+      const int r = (cta - p.n_full) + it * (grid - p.n_full);
+      return p.n_full + r < p.n_items ? p.n_full + r : -1;
+    }
+    const int item = cta + it * grid;
+    return item < p.n_items ? item : -1;
+  };
+  auto item_bh = [&](int item) { return item < p.n_full ? item % BH : item - p.n_full; };
+  auto item_group = [&](int item) { return item < p.n_full ? item / BH : p.full_groups; };
+  auto item_ntiles = [&](int item) { return min(NT4, tiles_total - NT4 * item_group(item)); };
+
+  pdl_trigger();
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_kv);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < KS4; ++s) {
+      mbar_init(k_full + s, 1);
+      mbar_init(k_empty + s, 1);
+      mbar_init(v_full + s, 1);
+      mbar_init(v_empty + s, 1);
+    }
+    for (int t = 0; t < NT4; ++t) {
+      mbar_init(s_full + t, 1);
+      mbar_init(s_free + t, 4);
+      mbar_init(p_full + t, 4);
+      mbar_init(p_free + t, 1);
+      mbar_init(o_full + t, 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp4) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+
+  if (warp == kTmaWarp4) {
+    int j = 0;
+    for (int it = 0;; ++it) {
+      const int item = cta_item(it);
+      if (item < 0) break;
+      const int bh = item_bh(item), h = bh % p.H, b = bh / p.H, g = item_group(item), nt = item_ntiles(item);
+      if (it > 0) mbar_wait(q_empty, (it - 1) & 1);          // the previous item's last S = Q K^T has read the Q tiles
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, nt * SM::kQBytes);
+        for (int t = 0; t < nt; ++t)
+          tma_load_4d(smem + SM::kOffQ + t * SM::kQBytes, &tma_q, q_full, 0, (NT4 * g + t) * BQ, h, b);
+      }
+      __syncwarp();
+      for (int c = 0; c < nchunks; ++c, ++j) {
+        const int s = j % KS4;
+        const uint32_t ph = static_cast<uint32_t>(j / KS4) & 1u;
+        if (j >= KS4) mbar_wait(k_empty + s, ph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(k_full + s, SM::kKBytes);
+          tma_load_4d(smem + SM::kOffK + s * SM::kKBytes, &tma_kv, k_full + s, 0, c * KC4, p.H + h, b);
+        }
+        __syncwarp();
+        if (j >= KS4) mbar_wait(v_empty + s, ph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(v_full + s, SM::kKBytes);
+          tma_load_4d(smem + SM::kOffV + s * SM::kKBytes, &tma_kv, v_full + s, 0, c * KC4, 2 * p.H + h, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kMmaWarp4) {
+    // ---- S = Q K^T issuer: runs as far ahead as the s_free hand-backs and the K ring allow
+    const uint32_t idesc_s = make_idesc_f16(BQ, KC4, false, false, kBf16);
+    const uint32_t sQ = smem_u32(smem + SM::kOffQ), sK = smem_u32(smem + SM::kOffK);
+    int n_s0 = 0, n_s1 = 0, n_s2 = 0, n_s3 = 0;      // S tiles issued so far per query tile
+    int j = 0;
+    for (int it = 0;; ++it) {
+      const int item = cta_item(it);
+      if (item < 0) break;
+      const int nt = item_ntiles(item);
+      mbar_wait(q_full, it & 1);
+      for (int c = 0; c < nchunks; ++c, ++j) {
+        const int s = j % KS4;
+        mbar_wait(k_full + s, static_cast<uint32_t>(j / KS4) & 1u);
+#pragma unroll
+        for (int t = 0; t < NT4; ++t) {
+          if (t < nt) {
+            int& n_s = t == 0 ? n_s0 : t == 1 ? n_s1 : t == 2 ? n_s2 : n_s3;
+            if (n_s > 0) mbar_wait(s_free + t, (n_s - 1) & 1);
+            tc_fence_after();
+            const uint64_t a_desc = make_desc(sQ + t * SM::kQBytes, 16, kSboK, kLayout);
+            const uint64_t b_desc = make_desc(sK + s * SM::kKBytes, 16, kSboK, kLayout);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < DH / 16; ++k)
+                umma_f16_ss(tmem_base + 256 + t * KC4, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc_s,
+                            k != 0);
+              umma_commit(s_full + t);
+              if (t == nt - 1) {
+                umma_commit(k_empty + s);
+                if (c == nchunks - 1) umma_commit(q_empty);
+              }
+            }
+            __syncwarp();
+            ++n_s;
+          }
+        }
+      }
+    }
+  } else if (warp == kPvWarp4) {
+    // ---- O += P V issuer
+    const uint32_t idesc_o = make_idesc_f16(BQ, DH, false, true, kBf16);
+    const uint32_t sV = smem_u32(smem + SM::kOffV), sP = smem_u32(smem + SM::kOffP);
+    int n_p0 = 0, n_p1 = 0, n_p2 = 0, n_p3 = 0;      // P.V products issued so far per query tile
+    int j = 0;
+    for (int it = 0;; ++it) {
+      const int item = cta_item(it);
+      if (item < 0) break;
+      const int nt = item_ntiles(item);
+      for (int c = 0; c < nchunks; ++c, ++j) {
+        const int s = j % KS4;
+        const int valid = min(KC4, p.L - c * KC4);
+        const int ksteps = ((valid + 31) / 32) * 2;
+        mbar_wait(v_full + s, static_cast<uint32_t>(j / KS4) & 1u);
+#pragma unroll
+        for (int t = 0; t < NT4; ++t) {
+          if (t < nt) {
+            int& n_p = t == 0 ? n_p0 : t == 1 ? n_p1 : t == 2 ? n_p2 : n_p3;
+            mbar_wait(p_full + t, n_p & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t a_desc = make_desc(sP + t * SM::kPBytes + k * 32, 16, 1024, 2u);
+                const uint64_t b_desc = make_desc(sV + s * SM::kKBytes + k * kVStep, 16, kSboK, kLayout);
+                umma_f16_ss(tmem_base + t * 64, a_desc, b_desc, idesc_o, (c | k) != 0);
+              }
+              umma_commit(p_free + t);
+              if (c == nchunks - 1) umma_commit(o_full + t);
+              if (t == nt - 1) umma_commit(v_empty + s);
+            }
+            __syncwarp();
+            ++n_p;
+          }
+        }
+      }
+    }
+  } else {
+    const int t = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t t_s = t_lane + 256 + t * KC4, t_o = t_lane + t * 64;
+    const uint32_t prow = smem_u32(smem + SM::kOffP + t * SM::kPBytes + (row >> 3) * 1024 + (row & 7) * 128) | ((row & 7) << 4);
+    int n_c = 0, n_o = 0;
+    for (int it = 0;; ++it) {
+      const int item = cta_item(it);
+      if (item < 0) break;
+      if (t >= item_ntiles(item)) continue;
+      const int bh = item_bh(item), h = bh % p.H, b = bh / p.H;
+      const int q0 = (NT4 * item_group(item) + t) * BQ;
+      if (q0 + quarter * 32 >= p.L) {
+        for (int c = 0; c < nchunks; ++c, ++n_c) {
+          mbar_wait(s_full + t, n_c & 1);
+          if (lane == 0) mbar_arrive(s_free + t);
+          if (lane == 0) mbar_arrive(p_full + t);
+          mbar_wait(p_free + t, n_c & 1);
+        }
+        ++n_o;
+        continue;
+      }
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int c = 0; c < nchunks; ++c) {
+        const int valid = min(KC4, p.L - c * KC4);
+        const int groups = (valid + 31) / 32;
+        mbar_wait(s_full + t, n_c & 1);
+        tc_fence_after();
+        uint32_t r[2][32];
+        tmem_ld_32x32b_x32(t_s, r[0]);
+        if (groups > 1) tmem_ld_32x32b_x32(t_s + 32, r[1]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free + t);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int lim = valid - g * 32;
+          if (lim > 0 && lim < 32) {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj)
+              if (jj >= lim) r[g][jj] = 0xff800000u;
+          }
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          if (g < groups) {
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 8) {
+              mx4[0] = fmaxf(mx4[0], fmaxf(__uint_as_float(r[g][jj + 0]), __uint_as_float(r[g][jj + 1])));
+              mx4[1] = fmaxf(mx4[1], fmaxf(__uint_as_float(r[g][jj + 2]), __uint_as_float(r[g][jj + 3])));
+              mx4[2] = fmaxf(mx4[2], fmaxf(__uint_as_float(r[g][jj + 4]), __uint_as_float(r[g][jj + 5])));
+              mx4[3] = fmaxf(mx4[3], fmaxf(__uint_as_float(r[g][jj + 6]), __uint_as_float(r[g][jj + 7])));
+            }
+          }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        const float m_cand = fmaxf(m_run, mx * p.scale_log2);
+        float corr = 1.f;
+        if (m_cand - m_run > 8.f) {
+          corr = ex2_approx(m_run - m_cand);
+          m_run = m_cand;
+        }
+        bool rescaled = false;
+        if (n_c > 0) {
+          mbar_wait(p_free + t, (n_c - 1) & 1);
+          tc_fence_after();
+          if (c > 0 && __any_sync(0xffffffffu, corr != 1.f)) {
+            rescaled = true;
+#pragma unroll
+            for (int d0 = 0; d0 < DH; d0 += 16) {
+              uint32_t o[16];
+              tmem_ld_32x32b_x16(t_o + d0, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) o[jj] = __float_as_uint(__uint_as_float(o[jj]) * corr);
+              tmem_st_32x32b_x16(t_o + d0, o);
+            }
+          }
+        }
+        const float2 sc2 = splat2(p.scale_log2), nm2 = splat2(-m_run);
+        float2 ls2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          if (g < groups) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t w[4];
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const float2 x = fma2(make_float2(__uint_as_float(r[g][8 * q + 2 * jj]), __uint_as_float(r[g][8 * q + 2 * jj + 1])), sc2, nm2);
+                const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                ls2[jj & 1] = add2(ls2[jj & 1], e);
+                w[jj] = pack2(e.x, e.y, kBf16);
+              }
+              st_shared_v4(prow ^ ((g * 4 + q) << 4), make_uint4(w[0], w[1], w[2], w[3]));
+            }
+          }
+        l_run = l_run * corr + ((ls2[0].x + ls2[0].y) + (ls2[1].x + ls2[1].y));
+        if (rescaled) tmem_st_wait();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full + t);
+        ++n_c;
+      }
+      mbar_wait(o_full + t, n_o & 1);
+      ++n_o;
+      tc_fence_after();
+      const float inv_l = 1.f / l_run;
+      const int q = q0 + row;
+      uint16_t* orow = p.out + (static_cast<long long>(b) * p.L + q) * (p.H * DH) + h * DH;
+#pragma unroll
+      for (int d0 = 0; d0 < DH; d0 += 16) {
+        uint32_t o[16];
+        tmem_ld_32x32b_x16(t_o + d0, o);
+        tmem_ld_wait();
+        if (q < p.L) {
+          uint4 o0, o1;
+          o0.x = pack2(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l, kBf16);
+          o0.y = pack2(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l, kBf16);
+          o0.z = pack2(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l, kBf16);
+          o0.w = pack2(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l, kBf16);
+          o1.x = pack2(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l, kBf16);
+          o1.y = pack2(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l, kBf16);
+          o1.z = pack2(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l, kBf16);
+          o1.w = pack2(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l, kBf16);
+          *reinterpret_cast<uint4*>(orow + d0) = o0;
+          *reinterpret_cast<uint4*>(orow + d0 + 8) = o1;
+        }
+      }
+      if (p.lse != nullptr && q < p.L)
+        p.lse[(static_cast<long long>(b) * p.H + h) * p.L + q] = (m_run + log2f(l_run)) * 0.69314718055994531f;
+      tc_fence_before();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp4) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int DH, bool kBf16>
+int launch_attention4(const void* qkv, void* out, float* lse, int B, int L, int H, float scale, cudaStream_t stream) {
+  using SM = Attn4Smem<DH>;
+  CUtensorMap tq, tkv;
+  const uint64_t dims[4] = {(uint64_t)DH, (uint64_t)L, (uint64_t)(3 * H), (uint64_t)B};
+  const uint64_t str[4] = {1, (uint64_t)(3 * H * DH), (uint64_t)DH, (uint64_t)L * 3 * H * DH};
+  const uint32_t boxq[4] = {DH, BQ, 1, 1}, boxk[4] = {DH, KC4, 1, 1};
+  const TmapSwizzle sw = DH == 64 ? TMAP_SW_128 : TMAP_SW_64;
+  int rc = make_tmap_4d_16b(&tq, qkv, dims, str, boxq, sw);
+  if (rc) return rc;
+  rc = make_tmap_4d_16b(&tkv, qkv, dims, str, boxk, sw);
+  if (rc) return rc;
+  static PerDeviceOnce attr_once;
+  if (attr_once.need())
+    COUNTR_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd4_kernel<DH, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+  Attn4Args p;
+  p.out = reinterpret_cast<uint16_t*>(out);
+  p.lse = lse;
+  p.B = B; p.L = L; p.H = H;
+  p.scale_log2 = scale * 1.44269504088896340736f;
+  const int tiles = (L + BQ - 1) / BQ;
+  p.full_groups = tiles / NT4;
+  p.n_full = B * H * p.full_groups;
+  p.n_items = p.n_full + (tiles % NT4 ? B * H : 0);
+  const int grid = std::min(p.n_items, num_sms());
+  COUNTR_CHECK_CUDA(launch_pdl(attention_fwd4_kernel<DH, kBf16>, dim3(grid), dim3(kThreads4), SM::kTotal, stream, tq, tkv, p));
+  return COUNTR_OK;
 }
 
 template <int DH, bool kBf16>
@@ -1095,6 +1489,19 @@ extern "C" int countr_attention_fwd(const void* qkv, void* out, float* lse, int 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(qkv && out, "null pointer");
   COUNTR_REQUIRE(B > 0 && L > 0 && H > 0, "bad shape B=%d L=%d H=%d", B, L, H);
+  // COUNTR_ATTN4: 0 = two-tile kernel everywhere, 1 (default) = four-tile kernel for head_dim 64 and for head_dim 32 at large
+  // batch, 2 = always.  (head_dim 32, B = 8, L = 576 measured slower, 60 vs 28 us: the 64-row remainder items of 128 heads pile up
+  // on the 20 CTAs that have no four-tile item.)
+  static int four = -1;
+  if (four < 0) {
+    const char* e = getenv("COUNTR_ATTN4");
+    four = e != nullptr ? atoi(e) : 1;
+  }
+  if (four && dh == 64) return bf16 ? launch_attention4<64, true>(qkv, out, lse, B, L, H, scale, stream)
+                                    : launch_attention4<64, false>(qkv, out, lse, B, L, H, scale, stream);
+  // head_dim 32: only when every CTA gets four-tile items anyway (B*H >= SMs: pre-training decoder, B = 128 inference)
+  if ((four >= 2 || (four == 1 && B * H * ((L + BQ - 1) / BQ / NT4) >= num_sms())) && dh == 32) return bf16 ? launch_attention4<32, true>(qkv, out, lse, B, L, H, scale, stream)
+                                    : launch_attention4<32, false>(qkv, out, lse, B, L, H, scale, stream);
   if (dh == 64) return bf16 ? launch_attention<64, true>(qkv, out, lse, B, L, H, scale, bf16, stream)
                             : launch_attention<64, false>(qkv, out, lse, B, L, H, scale, bf16, stream);
   if (dh == 32) return bf16 ? launch_attention<32, true>(qkv, out, lse, B, L, H, scale, bf16, stream)

@@ -26,7 +26,7 @@ def timeit(fn, reps=20):
     return best
 
 
-SHAPES = ((8, 576, 12, 64), (8, 576, 16, 32), (32, 288, 12, 64), (128, 576, 12, 64))
+SHAPES = ((8, 576, 12, 64), (8, 576, 16, 32), (32, 288, 12, 64), (128, 576, 12, 64), (32, 576, 16, 32), (128, 576, 16, 32))
 for B, L, H, dh in (SHAPES[:1] if os.environ.get("ATTN_ONE") else SHAPES):
     qkv = torch.randn(B, L, 3, H, dh, device=dev).half()
     out = torch.empty(B, L, H * dh, device=dev, dtype=torch.float16)
