@@ -545,6 +545,8 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   auto item_ntiles = [&](int item) { return min(NT4, tiles_total - NT4 * item_group(item)); };
 
   pdl_trigger();
+  ATR_INIT;
+  if (tid == 0) ATR(0);
   if (tid == 0) {
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_kv);
@@ -705,7 +707,9 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       for (int c = 0; c < nchunks; ++c) {
         const int valid = min(KC4, p.L - c * KC4);
         const int groups = (valid + 31) / 32;
+        if (warp == 0) ATR(16 + 8 * n_c);
         mbar_wait(s_full + t, n_c & 1);
+        if (warp == 0) ATR(17 + 8 * n_c);
         tc_fence_after();
         uint32_t r[2][32];
         tmem_ld_32x32b_x32(t_s, r[0]);
@@ -714,6 +718,7 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_free + t);
+        if (warp == 0) ATR(18 + 8 * n_c);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const int lim = valid - g * 32;
@@ -743,6 +748,7 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           m_run = m_cand;
         }
         bool rescaled = false;
+        if (warp == 0) ATR(19 + 8 * n_c);
         if (n_c > 0) {
           mbar_wait(p_free + t, (n_c - 1) & 1);
           tc_fence_after();
@@ -759,6 +765,7 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
             }
           }
         }
+        if (warp == 0) ATR(20 + 8 * n_c);
         const float2 sc2 = splat2(p.scale_log2), nm2 = splat2(-m_run);
         float2 ls2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
@@ -783,6 +790,7 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full + t);
+        if (warp == 0) ATR(21 + 8 * n_c);
         ++n_c;
       }
       mbar_wait(o_full + t, n_o & 1);

@@ -24,10 +24,12 @@ t = tr.cpu().tolist()
 t0 = t[0]
 rel = lambda v: v - t0 if v else -1
 print("softmax warp 0 (tile 0), per chunk: [before s_full wait, S ready, S in regs (s_free), max done, p_free ok, P written (p_full)]")
-for c in range(12):
+for c in range(20):
     v = [rel(x) for x in t[16 + 8 * c:16 + 8 * c + 6]]
     if v[1] >= 0:
         print(f"  chunk {c:2d}: {v}   wait S {v[1]-v[0]:5d}  load {v[2]-v[1]:5d}  max {v[3]-v[2]:5d}  wait PV {v[4]-v[3]:5d}  exp+store {v[5]-v[4]:5d}")
+if os.environ.get("COUNTR_ATTN4", "1") != "0":
+    sys.exit(0)
 print("MMA warp, per ring chunk j: [start, S(next) issued, p_full t0 ok, PV t0 issued, p_full t1 ok, PV t1 issued]")
 for j in range(12):
     v = [rel(x) for x in t[1024 + 8 * j:1024 + 8 * j + 6]]
