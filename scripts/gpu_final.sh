@@ -17,10 +17,9 @@ cap() {   # name, kernel regex, launch skip
 }
 cap r2_ncu_gn_bwd_reduce1 gn_relu_bwd_reduce_kernel 8
 cap r2_ncu_gn_bwd_reduce0 gn_relu_bwd_reduce_kernel 9
-cap r2_ncu_attn_fwd64 attention_fwd_kernel 28
 cap r2_ncu_grouped_colsum grouped_colsum_kernel 2
-for w in conv attn; do
-  timeout 200 ncu --set full --clock-control none --import-source on --launch-skip 4 --launch-count 1 -f -o gpurun_out/r2_ncu_prof_$w python scripts/prof_gemm.py $w > /dev/null 2>&1
-  python scripts/ncu_summary.py gpurun_out/r2_ncu_prof_$w.ncu-rep gpurun_out/r2_ncu_prof_$w.json > /dev/null 2>&1 && echo "captured $w"
-done
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel --launch-skip 3 --launch-count 1 -f -o gpurun_out/r2_conv_h3 python scripts/prof_gemm.py conv > /dev/null 2>&1
+python scripts/ncu_summary.py gpurun_out/r2_conv_h3.ncu-rep gpurun_out/r2_conv_h3_ncu_summary.json > /dev/null 2>&1 && echo "captured conv h3"
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:attention_fwd4 --launch-skip 3 --launch-count 1 -f -o gpurun_out/r2_ncu_attn_fwd4 python scripts/prof_gemm.py attn > /dev/null 2>&1
+python scripts/ncu_summary.py gpurun_out/r2_ncu_attn_fwd4.ncu-rep gpurun_out/r2_ncu_attn_fwd4.json > /dev/null 2>&1 && echo "captured attn fwd4"
 rm -f gpurun_out/*.ncu-rep
