@@ -45,6 +45,11 @@ SIGS = {
     "countr_aug_color_jitter": [P, P, P, P, I, I, I, P],
     "countr_aug_gaussian_blur": [P, P, P, P, I, I, I, I, I, P],
     "countr_aug_hflip": [P, P, P, I, I, I, I, P],
+    "countr_aug_mosaic": [P, I, I, I, P, P],
+    "countr_aug_mosaic_dots": [P, I, I, P, P, P],
+    "countr_density_filter": [P, P, P, I, I, I, P, I, F, P],
+    "countr_aug_affine": [P, P, I, I, I, P, P],
+    "countr_aug_affine_dots": [P, I, c_double, c_double, I, I, P, P, P],
     "countr_grouped_dw": [P, I, I, P],
     "countr_grouped_colsum": [P, I, P],
     "countr_density_from_dots": [P, P, I, I, c_double, c_double, I, I, I, I, I, I, P, I, F, P, P, P],

@@ -384,3 +384,222 @@ extern "C" int countr_aug_hflip(const float* in, float* out, const int32_t* flag
   COUNTR_CHECK_CUDA(cudaGetLastError());
   return COUNTR_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Mosaic collage (util/FSC147.py:183-262) and the affine warp with key points (:146-171).
+// ------------------------------------------------------------------------------------------
+namespace countr {
+namespace {
+
+struct MosaicArgs {
+  countr_mosaic_src src[4];
+  int rl, bl, half, C;
+};
+
+// tile t at (row r, column c) of its rl x rl resize: Resize((rl, rl))(TF.crop(image, top, left, length, length)), the same
+// bilinear arithmetic as crop_resize_kernel
+__device__ __forceinline__ float mosaic_tile(const countr_mosaic_src& s, int ch, int rl, int r, int c) {
+  const int n = s.length;
+  const float scale = static_cast<float>(n) / rl;
+  float ry = scale * (r + 0.5f) - 0.5f, rx = scale * (c + 0.5f) - 0.5f;
+  ry = ry < 0.f ? 0.f : ry;
+  rx = rx < 0.f ? 0.f : rx;
+  const int iy0 = min(static_cast<int>(ry), n - 1), ix0 = min(static_cast<int>(rx), n - 1);
+  const int iy1 = iy0 + (iy0 < n - 1 ? 1 : 0), ix1 = ix0 + (ix0 < n - 1 ? 1 : 0);
+  const float ly1 = fminf(fmaxf(ry - iy0, 0.f), 1.f), lx1 = fminf(fmaxf(rx - ix0, 0.f), 1.f);
+  const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const float* p = s.img + ch * s.sc + s.top * s.sh + s.left * s.sw;
+  const float a = p[iy0 * s.sh + ix0 * s.sw], b = p[iy0 * s.sh + ix1 * s.sw];
+  const float cq = p[iy1 * s.sh + ix0 * s.sw], d = p[iy1 * s.sh + ix1 * s.sw];
+  return ly0 * (lx0 * a + lx1 * b) + ly1 * (lx0 * cq + lx1 * d);
+}
+
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+
+// the reference's seam recurrence `far * (bl - i) / (2 bl) + near * (i + bl) / (2 bl)` in its fp32 operation order
+__device__ __forceinline__ float seam(float far_v, float near_v, int i, int bl) {
+  const float d = static_cast<float>(2 * bl);
+  return __fadd_rn(__fdiv_rn(__fmul_rn(far_v, static_cast<float>(bl - i)), d), __fdiv_rn(__fmul_rn(near_v, static_cast<float>(i + bl)), d));
+}
+
+// column `c` (tile coordinates, 0..rl) of the vertical strip built from tiles (2k, 2k+1) at collage row y   (:239-245 / :247-253)
+__device__ __forceinline__ float mosaic_strip(const MosaicArgs& a, int k, int ch, int y, int c) {
+  const countr_mosaic_src& top = a.src[2 * k];
+  const countr_mosaic_src& bot = a.src[2 * k + 1];
+  const int rl = a.rl, bl = a.bl, half = a.half;
+  float v;
+  if (y < half) {
+    v = mosaic_tile(top, ch, rl, bl + y, c);
+    const int i = half - 1 - y;
+    if (i < bl) v = seam(mosaic_tile(bot, ch, rl, bl - i, c), v, i, bl);
+  } else {
+    v = mosaic_tile(bot, ch, rl, bl + y - half, c);
+    const int i = y - half;
+    if (i < bl) v = seam(mosaic_tile(top, ch, rl, rl - 1 - bl + i, c), v, i, bl);
+  }
+  return clamp01(v);
+}
+
+__global__ void __launch_bounds__(256) mosaic_kernel(const MosaicArgs a, float* __restrict__ out) {
+  const int side = 2 * a.half;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.C * side * side) return;
+  const int x = idx % side, y = (idx / side) % side, ch = idx / (side * side);
+  const int rl = a.rl, bl = a.bl, half = a.half;
+  float v;
+  if (x < half) {                                                                       // :255-261
+    v = mosaic_strip(a, 0, ch, y, bl + x);
+    const int i = half - 1 - x;
+    if (i < bl) v = seam(mosaic_strip(a, 1, ch, y, bl - i), v, i, bl);
+  } else {
+    v = mosaic_strip(a, 1, ch, y, bl + x - half);
+    const int i = x - half;
+    if (i < bl) v = seam(mosaic_strip(a, 0, ch, y, rl - 1 - bl + i), v, i, bl);
+  }
+  out[idx] = clamp01(v);
+}
+
+// dot maps of the four tiles written straight into the collage canvas (:190-196, :228-232, :240, :248, :256)
+__global__ void __launch_bounds__(128) mosaic_dots_kernel(const MosaicArgs a, const double* __restrict__ dots, float* __restrict__ canvas) {
+  const int t = blockIdx.y;
+  const countr_mosaic_src& s = a.src[t];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.dot_count) return;
+  const double dx = dots[(static_cast<long long>(s.dot_begin) + i) * 2], dy = dots[(static_cast<long long>(s.dot_begin) + i) * 2 + 1];
+  const int py = min(s.H - 1, static_cast<int>(dy * s.scale_h)), px = min(s.W - 1, static_cast<int>(dx * s.scale_w));
+  if (py < s.top || py >= s.top + s.length || px < s.left || px >= s.left + s.length) return;
+  // int((p - start) * rl / length): a quotient of small integers, the float64 division cannot reach the next integer
+  const int r = min(a.rl - 1, (py - s.top) * a.rl / s.length), c = min(a.rl - 1, (px - s.left) * a.rl / s.length);
+  if (r < a.bl || r >= a.rl - a.bl || c < a.bl || c >= a.rl - a.bl) return;
+  const int side = 2 * a.half;
+  canvas[((t & 1) * a.half + r - a.bl) * side + (t >> 1) * a.half + c - a.bl] = 1.0f;
+}
+
+struct Affine6 { double m[6]; };
+
+// out(y, x) = bilinear sample of img at M^-1 (x, y), zero outside (constant border 0, order 1)
+__global__ void __launch_bounds__(256) affine_warp_kernel(const float* __restrict__ img, float* __restrict__ out, int C, int H, int W, const Affine6 inv) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * W) return;
+  const int x = idx % W, y = idx / W;
+  const double sx = inv.m[0] * x + inv.m[1] * y + inv.m[2], sy = inv.m[3] * x + inv.m[4] * y + inv.m[5];
+  const double fx = floor(sx), fy = floor(sy);
+  const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+  const float wx = static_cast<float>(sx - fx), wy = static_cast<float>(sy - fy);
+  const bool in_x0 = x0 >= 0 && x0 < W, in_x1 = x0 + 1 >= 0 && x0 + 1 < W, in_y0 = y0 >= 0 && y0 < H, in_y1 = y0 + 1 >= 0 && y0 + 1 < H;
+  const bool far_out = sx <= -1.0 || sx >= W || sy <= -1.0 || sy >= H;
+  for (int ch = 0; ch < C; ++ch) {
+    const float* p = img + static_cast<long long>(ch) * H * W;
+    float v = 0.f;
+    if (!far_out) {
+      const float a = in_y0 && in_x0 ? p[y0 * W + x0] : 0.f, b = in_y0 && in_x1 ? p[y0 * W + x0 + 1] : 0.f;
+      const float c = in_y1 && in_x0 ? p[(y0 + 1) * W + x0] : 0.f, d = in_y1 && in_x1 ? p[(y0 + 1) * W + x0 + 1] : 0.f;
+      v = (1.f - wy) * ((1.f - wx) * a + wx * b) + wy * ((1.f - wx) * c + wx * d);
+    }
+    out[static_cast<long long>(ch) * H * W + idx] = v;
+  }
+}
+
+// key points through the forward matrix, then the reference's dot map (:146-166): truncated coordinates, points that leave
+// the image are dropped
+__global__ void __launch_bounds__(128) affine_dots_kernel(const double* __restrict__ dots, int n, double scale_h, double scale_w, int H, int W,
+                                                          const Affine6 fwd, float* __restrict__ canvas) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double kx = min(W - 1, static_cast<int>(dots[2 * i] * scale_w)), ky = min(H - 1, static_cast<int>(dots[2 * i + 1] * scale_h));
+  const double ax = fwd.m[0] * kx + fwd.m[1] * ky + fwd.m[2], ay = fwd.m[3] * kx + fwd.m[4] * ky + fwd.m[5];
+  if (!(ax >= 0.0 && ax < W && ay >= 0.0 && ay < H)) return;                  // Keypoint.is_out_of_image
+  const int r = static_cast<int>(ay), c = static_cast<int>(ax);
+  if (r > H - 1 || c > W - 1) return;
+  canvas[r * W + c] = 1.0f;
+}
+
+bool mosaic_args(const countr_mosaic_src* src, int rl, int bl, int C, MosaicArgs* a, const char** why) {
+  a->rl = rl, a->bl = bl, a->half = rl - 2 * bl, a->C = C;
+  if (!src || C <= 0 || bl <= 0 || a->half <= 0 || bl >= a->half) { *why = "bad rl / bl"; return false; }
+  for (int t = 0; t < 4; ++t) {
+    const countr_mosaic_src& s = src[t];
+    if (!s.img || s.H <= 0 || s.W <= 0 || s.length <= 0 || s.top < 0 || s.left < 0 || s.top + s.length > s.H || s.left + s.length > s.W ||
+        s.dot_count < 0 || s.dot_begin < 0) {
+      *why = "a source crop leaves its image";
+      return false;
+    }
+    a->src[t] = s;
+  }
+  return true;
+}
+
+}  // namespace
+}  // namespace countr
+
+extern "C" int countr_aug_mosaic(const countr_mosaic_src* src, int rl, int bl, int C, float* out, countr_stream_t stream_) {
+  using namespace countr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MosaicArgs a;
+  const char* why = "";
+  COUNTR_REQUIRE(out && mosaic_args(src, rl, bl, C, &a, &why), "mosaic: %s (rl=%d bl=%d)", why, rl, bl);
+  const int total = C * 4 * a.half * a.half;
+  mosaic_kernel<<<(total + 255) / 256, 256, 0, stream>>>(a, out);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_aug_mosaic_dots(const countr_mosaic_src* src, int rl, int bl, const double* dots, float* canvas, countr_stream_t stream_) {
+  using namespace countr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MosaicArgs a;
+  const char* why = "";
+  COUNTR_REQUIRE(canvas && mosaic_args(src, rl, bl, 1, &a, &why), "mosaic dots: %s (rl=%d bl=%d)", why, rl, bl);
+  const int side = 2 * a.half;
+  COUNTR_CHECK_CUDA(cudaMemsetAsync(canvas, 0, sizeof(float) * side * side, stream));
+  int n_max = 0;
+  for (int t = 0; t < 4; ++t) n_max = std::max(n_max, a.src[t].dot_count);
+  if (n_max > 0) {
+    COUNTR_REQUIRE(dots, "null dots");
+    mosaic_dots_kernel<<<dim3((n_max + 127) / 128, 4), 128, 0, stream>>>(a, dots, canvas);
+  }
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_density_filter(const float* canvas, float* tmp, float* out, int B, int H, int W, const double* weights, int radius,
+                                     float gain, countr_stream_t stream_) {
+  using namespace countr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(canvas && tmp && out && weights && tmp != out && tmp != canvas, "null or aliased pointer");
+  COUNTR_REQUIRE(B > 0 && H > 0 && W > 0 && radius >= 0 && radius < H && radius < W && radius <= 512, "bad shape B=%d H=%d W=%d radius=%d", B, H, W,
+                 radius);
+  const long long total = static_cast<long long>(B) * H * W;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  const size_t smem = sizeof(double) * (radius + 1);
+  gauss_pass_kernel<<<blocks, 256, smem, stream>>>(canvas, tmp, weights, radius, B, H, W, 0, 1.0f);
+  gauss_pass_kernel<<<blocks, 256, smem, stream>>>(tmp, out, weights, radius, B, H, W, 1, gain);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_aug_affine(const float* img, float* out, int C, int H, int W, const double* inverse, countr_stream_t stream_) {
+  using namespace countr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(img && out && img != out && inverse && C > 0 && H > 0 && W > 0 && static_cast<long long>(H) * W < (1ll << 30), "bad arguments");
+  Affine6 m;
+  for (int i = 0; i < 6; ++i) m.m[i] = inverse[i];
+  affine_warp_kernel<<<(H * W + 255) / 256, 256, 0, stream>>>(img, out, C, H, W, m);
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}
+
+extern "C" int countr_aug_affine_dots(const double* dots, int n, double scale_h, double scale_w, int H, int W, const double* forward,
+                                      float* canvas, countr_stream_t stream_) {
+  using namespace countr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  COUNTR_REQUIRE(canvas && forward && n >= 0 && H > 0 && W > 0 && (n == 0 || dots), "bad arguments");
+  COUNTR_CHECK_CUDA(cudaMemsetAsync(canvas, 0, sizeof(float) * H * W, stream));
+  if (n > 0) {
+    Affine6 m;
+    for (int i = 0; i < 6; ++i) m.m[i] = forward[i];
+    affine_dots_kernel<<<(n + 127) / 128, 128, 0, stream>>>(dots, n, scale_h, scale_w, H, W, m, canvas);
+  }
+  COUNTR_CHECK_CUDA(cudaGetLastError());
+  return COUNTR_OK;
+}

@@ -396,7 +396,19 @@ int countr_rect_mass(const float* map, int H, int W, const int32_t* rects, int n
  *                            scratch: B doubles
  *   countr_aug_gaussian_blur torchvision GaussianBlur(kernel_size=(kx, ky)) with sigma[b] (reflect padding, :373); tmp: image-sized
  *   countr_aug_hflip         TF.hflip of the images whose flag is set, `planes` channels per image (image and density map, :176-180)
- * Not built: imgaug's Affine with keypoints (:146-171) and the mosaic collage (:183-262).
+ *   countr_aug_mosaic        the 2 x 2 self-/cross-image collage (:183-262): quadrant t (0 top-left, 1 bottom-left, 2 top-right,
+ *                            3 bottom-right) = Resize((rl, rl))(TF.crop(src[t].img, top, left, length, length)) with rl = 192 + 2 bl,
+ *                            rows/columns bl..rl-bl kept and the 2 bl-wide seams blended with the reference's recurrence and
+ *                            index offsets (:241-245, :257-261); out: fp32 [C][2(rl-2bl)][2(rl-2bl)].  `src` is a HOST array of 4.
+ *   countr_aug_mosaic_dots   the collage's dot map (:190-196, :228-232): dots [.][2] float64 (x, y) on the device, quadrant t uses
+ *                            dots[dot_begin .. dot_begin+dot_count) (count 0 for an image of another class); canvas [2(rl-2bl)]^2
+ *   countr_density_filter    scipy.ndimage.gaussian_filter + gain on an existing dot map (the tail of countr_density_from_dots, :265-269)
+ *   countr_aug_affine        bilinear (order 1), zero-border warp of fp32 [C][H][W] by the 2 x 3 matrix `inverse` (output pixel ->
+ *                            source position; HOST array of 6 doubles) — the image half of iaa.Affine (:151-159)
+ *   countr_aug_affine_dots   the key points through the 2 x 3 `forward` matrix and the reference's dot map of the survivors
+ *                            (:146-149, :162-166); canvas [H][W]
+ * imgaug (0.4.0, requirements.txt) is not installable here: the matrix composition in countr_b200/data.py:affine_matrix restates
+ * its published order and is NOT pinned against imgaug itself; cv2's 1/32-pixel coordinate quantisation is not reproduced.
  * ------------------------------------------------------------------------------------------ */
 int countr_aug_noise_clamp(const float* img, float* out, int64_t n, float stddev, uint64_t seed, countr_stream_t stream);
 int countr_aug_color_jitter(float* img, const int32_t* ops, const float* factors, double* scratch, int B, int H, int W,
@@ -404,6 +416,22 @@ int countr_aug_color_jitter(float* img, const int32_t* ops, const float* factors
 int countr_aug_gaussian_blur(const float* img, float* tmp, float* out, const float* sigma, int B, int H, int W, int kx, int ky,
                              countr_stream_t stream);
 int countr_aug_hflip(const float* in, float* out, const int32_t* flags, int B, int planes, int H, int W, countr_stream_t stream);
+typedef struct countr_mosaic_src {
+  const float* img;             /* fp32 [C][H][W] view of the resized source image of this quadrant (device) */
+  int64_t sc, sh, sw;           /* its element strides */
+  int32_t H, W;                 /* new_TH, new_TW */
+  int32_t top, left, length;    /* start_H, start_W, length of the square crop */
+  int32_t dot_begin, dot_count; /* this quadrant's annotated points */
+  int32_t pad_;
+  double scale_h, scale_w;      /* Tscale_factor_h / Tscale_factor_w */
+} countr_mosaic_src;
+int countr_aug_mosaic(const countr_mosaic_src* src, int rl, int bl, int C, float* out, countr_stream_t stream);
+int countr_aug_mosaic_dots(const countr_mosaic_src* src, int rl, int bl, const double* dots, float* canvas, countr_stream_t stream);
+int countr_density_filter(const float* canvas, float* tmp, float* out, int B, int H, int W, const double* weights, int radius, float gain,
+                          countr_stream_t stream);
+int countr_aug_affine(const float* img, float* out, int C, int H, int W, const double* inverse, countr_stream_t stream);
+int countr_aug_affine_dots(const double* dots, int n, double scale_h, double scale_w, int H, int W, const double* forward, float* canvas,
+                           countr_stream_t stream);
 
 #ifdef __cplusplus
 }
