@@ -58,6 +58,8 @@ def _declare(lib):
     lib.countr_set_sm_budget.restype = c_int32
     lib.countr_gemm.argtypes = [POINTER(GemmDesc), c_void_p]
     lib.countr_gemm.restype = c_int32
+    lib.countr_weight_refresh_blocks.argtypes = [c_int32, c_int64, c_int64]
+    lib.countr_weight_refresh_blocks.restype = c_int64
     from . import _sigs  # noqa: WPS433  (plain-argument entry points)
     _sigs.declare(lib)
 

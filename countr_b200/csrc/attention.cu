@@ -29,7 +29,10 @@ namespace countr {
 __device__ long long* g_attn_trace = nullptr;
 #define ATR_INIT long long* const atr_ = (g_attn_trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) ? g_attn_trace : nullptr
 #define ATR(slot) do { if (atr_ != nullptr && (slot) < 4096) atr_[(slot)] = clock64(); } while (0)
+// per-CTA begin / end stamps (globaltimer, ns) at [2048 + 2 * cta + which]
+#define ATR_CTA(which) do { if (g_attn_trace != nullptr && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_attn_trace[2048 + 2 * blockIdx.x + (which)] = static_cast<long long>(t_); } } while (0)
 #else
+#define ATR_CTA(which) do {} while (0)
 #define ATR_INIT do {} while (0)
 #define ATR(slot) do {} while (0)
 #endif
@@ -91,6 +94,22 @@ struct AttnArgs {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_v2f(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float2 ld_shared_v2f(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+// named barriers 1..8 pair the two softmax warps that share the rows of a split item (fwd4 kernel)
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -497,6 +516,7 @@ struct Attn4Args {
   int B, L, H;
   float scale_log2;
   int n_full, n_items, full_groups;     // items [0, n_full): four-tile groups (bh-major inside a group index), then the remainders
+  int split;                            // split one-tile items over two slots by key chunk
 };
 
 template <int DH, bool kBf16>
@@ -543,9 +563,13 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   auto item_bh = [&](int item) { return item < p.n_full ? item % BH : item - p.n_full; };
   auto item_group = [&](int item) { return item < p.n_full ? item / BH : p.full_groups; };
   auto item_ntiles = [&](int item) { return min(NT4, tiles_total - NT4 * item_group(item)); };
+  // a one-tile item would leave three quarters of the CTA idle and run its chunks strictly one after the other (S -> softmax ->
+  // P.V latency per chunk): it is split over two tile slots by key chunk (even / odd) and merged at the end
+  auto item_split = [&](int nt) { return p.split != 0 && nt == 1 && nchunks >= 2; };
 
   pdl_trigger();
   ATR_INIT;
+  ATR_CTA(0);
   if (tid == 0) ATR(0);
   if (tid == 0) {
     tma_prefetch_desc(&tma_q);
@@ -614,17 +638,18 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       const int item = cta_item(it);
       if (item < 0) break;
       const int nt = item_ntiles(item);
+      const bool split = item_split(nt);
       mbar_wait(q_full, it & 1);
       for (int c = 0; c < nchunks; ++c, ++j) {
         const int s = j % KS4;
         mbar_wait(k_full + s, static_cast<uint32_t>(j / KS4) & 1u);
 #pragma unroll
         for (int t = 0; t < NT4; ++t) {
-          if (t < nt) {
+          if (split ? t == (c & 1) : t < nt) {
             int& n_s = t == 0 ? n_s0 : t == 1 ? n_s1 : t == 2 ? n_s2 : n_s3;
             if (n_s > 0) mbar_wait(s_free + t, (n_s - 1) & 1);
             tc_fence_after();
-            const uint64_t a_desc = make_desc(sQ + t * SM::kQBytes, 16, kSboK, kLayout);
+            const uint64_t a_desc = make_desc(sQ + (split ? 0 : t) * SM::kQBytes, 16, kSboK, kLayout);
             const uint64_t b_desc = make_desc(sK + s * SM::kKBytes, 16, kSboK, kLayout);
             if (elect_one()) {
 #pragma unroll
@@ -632,7 +657,7 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
                 umma_f16_ss(tmem_base + 256 + t * KC4, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc_s,
                             k != 0);
               umma_commit(s_full + t);
-              if (t == nt - 1) {
+              if (split || t == nt - 1) {
                 umma_commit(k_empty + s);
                 if (c == nchunks - 1) umma_commit(q_empty);
               }
@@ -653,14 +678,16 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       const int item = cta_item(it);
       if (item < 0) break;
       const int nt = item_ntiles(item);
+      const bool split = item_split(nt);
       for (int c = 0; c < nchunks; ++c, ++j) {
         const int s = j % KS4;
         const int valid = min(KC4, p.L - c * KC4);
         const int ksteps = ((valid + 31) / 32) * 2;
+        const int c_own = split ? c >> 1 : c;            // chunks this slot has accumulated before this one
         mbar_wait(v_full + s, static_cast<uint32_t>(j / KS4) & 1u);
 #pragma unroll
         for (int t = 0; t < NT4; ++t) {
-          if (t < nt) {
+          if (split ? t == (c & 1) : t < nt) {
             int& n_p = t == 0 ? n_p0 : t == 1 ? n_p1 : t == 2 ? n_p2 : n_p3;
             mbar_wait(p_full + t, n_p & 1);
             tc_fence_after();
@@ -668,11 +695,11 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
               for (int k = 0; k < ksteps; ++k) {
                 const uint64_t a_desc = make_desc(sP + t * SM::kPBytes + k * 32, 16, 1024, 2u);
                 const uint64_t b_desc = make_desc(sV + s * SM::kKBytes + k * kVStep, 16, kSboK, kLayout);
-                umma_f16_ss(tmem_base + t * 64, a_desc, b_desc, idesc_o, (c | k) != 0);
+                umma_f16_ss(tmem_base + t * 64, a_desc, b_desc, idesc_o, (c_own | k) != 0);
               }
               umma_commit(p_free + t);
-              if (c == nchunks - 1) umma_commit(o_full + t);
-              if (t == nt - 1) umma_commit(v_empty + s);
+              if (split ? c >= nchunks - 2 : c == nchunks - 1) umma_commit(o_full + t);
+              if (split || t == nt - 1) umma_commit(v_empty + s);
             }
             __syncwarp();
             ++n_p;
@@ -686,15 +713,22 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t t_s = t_lane + 256 + t * KC4, t_o = t_lane + t * 64;
     const uint32_t prow = smem_u32(smem + SM::kOffP + t * SM::kPBytes + (row >> 3) * 1024 + (row & 7) * 128) | ((row & 7) << 4);
+    // hand-over buffers of a split item: O rows (fp32, 16-byte chunks XOR-swizzled by the row) in Q slots 2-3, (m, l) in P slot 3
+    const uint32_t xrow = smem_u32(smem + SM::kOffQ + 2 * SM::kQBytes) + row * (DH * 4);
+    const uint32_t xml = smem_u32(smem + SM::kOffP + 3 * SM::kPBytes) + row * 8;
+    bool xbuf_used = false;
     int n_c = 0, n_o = 0;
     for (int it = 0;; ++it) {
       const int item = cta_item(it);
       if (item < 0) break;
-      if (t >= item_ntiles(item)) continue;
+      const int nt = item_ntiles(item);
+      const bool split = item_split(nt);
+      if (t >= (split ? 2 : nt)) continue;
       const int bh = item_bh(item), h = bh % p.H, b = bh / p.H;
-      const int q0 = (NT4 * item_group(item) + t) * BQ;
+      const int q0 = (NT4 * item_group(item) + (split ? 0 : t)) * BQ;
+      const int c0 = split ? t : 0, cstep = split ? 2 : 1;      // a split item: this slot takes every other key chunk
       if (q0 + quarter * 32 >= p.L) {
-        for (int c = 0; c < nchunks; ++c, ++n_c) {
+        for (int c = c0; c < nchunks; c += cstep, ++n_c) {
           mbar_wait(s_full + t, n_c & 1);
           if (lane == 0) mbar_arrive(s_free + t);
           if (lane == 0) mbar_arrive(p_full + t);
@@ -704,7 +738,7 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         continue;
       }
       float m_run = -INFINITY, l_run = 0.f;
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = c0; c < nchunks; c += cstep) {
         const int valid = min(KC4, p.L - c * KC4);
         const int groups = (valid + 31) / 32;
         if (warp == 0) ATR(16 + 8 * n_c);
@@ -752,7 +786,7 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         if (n_c > 0) {
           mbar_wait(p_free + t, (n_c - 1) & 1);
           tc_fence_after();
-          if (c > 0 && __any_sync(0xffffffffu, corr != 1.f)) {
+          if (c != c0 && __any_sync(0xffffffffu, corr != 1.f)) {
             rescaled = true;
 #pragma unroll
             for (int d0 = 0; d0 < DH; d0 += 16) {
@@ -796,6 +830,36 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       mbar_wait(o_full + t, n_o & 1);
       ++n_o;
       tc_fence_after();
+      float f_own = 1.f, f_other = 0.f;
+      if (split) {
+        // the two slots hold partial softmax sums over the even / odd key chunks of the same rows: slot 1 hands its
+        // (m, l, O) over through shared memory (Q slots 2-3 and P slot 3 are idle in a one-tile item), slot 0 merges
+        if (t == 1) {
+          if (xbuf_used) named_bar_sync(5 + quarter, 64);          // slot 0 has read the previous item's hand-over
+          xbuf_used = true;
+#pragma unroll
+          for (int d0 = 0; d0 < DH; d0 += 16) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(t_o + d0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              st_shared_v4(xrow + ((((d0 >> 2) + v) ^ (row & (DH / 4 - 1))) << 4), make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]));
+          }
+          st_shared_v2f(xml, m_run, l_run);
+          tc_fence_before();
+          __threadfence_block();
+          named_bar_arrive(1 + quarter, 64);
+          continue;
+        }
+        named_bar_sync(1 + quarter, 64);
+        const float2 ml1 = ld_shared_v2f(xml);
+        const float m_all = fmaxf(m_run, ml1.x);
+        f_own = ex2_approx(m_run - m_all);
+        f_other = ex2_approx(ml1.x - m_all);
+        l_run = l_run * f_own + ml1.y * f_other;
+        m_run = m_all;
+      }
       const float inv_l = 1.f / l_run;
       const int q = q0 + row;
       uint16_t* orow = p.out + (static_cast<long long>(b) * p.L + q) * (p.H * DH) + h * DH;
@@ -804,6 +868,16 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         uint32_t o[16];
         tmem_ld_32x32b_x16(t_o + d0, o);
         tmem_ld_wait();
+        if (split) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const uint4 x = ld_shared_v4(xrow + ((((d0 >> 2) + v) ^ (row & (DH / 4 - 1))) << 4));
+            o[4 * v + 0] = __float_as_uint(__uint_as_float(o[4 * v + 0]) * f_own + __uint_as_float(x.x) * f_other);
+            o[4 * v + 1] = __float_as_uint(__uint_as_float(o[4 * v + 1]) * f_own + __uint_as_float(x.y) * f_other);
+            o[4 * v + 2] = __float_as_uint(__uint_as_float(o[4 * v + 2]) * f_own + __uint_as_float(x.z) * f_other);
+            o[4 * v + 3] = __float_as_uint(__uint_as_float(o[4 * v + 3]) * f_own + __uint_as_float(x.w) * f_other);
+          }
+        }
         if (q < p.L) {
           uint4 o0, o1;
           o0.x = pack2(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l, kBf16);
@@ -821,11 +895,16 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       if (p.lse != nullptr && q < p.L)
         p.lse[(static_cast<long long>(b) * p.H + h) * p.L + q] = (m_run + log2f(l_run)) * 0.69314718055994531f;
       tc_fence_before();
+      if (split && cta_item(it + 1) >= 0) {       // the next item of this CTA is a one-tile item too (they come last)
+        __threadfence_block();
+        named_bar_arrive(5 + quarter, 64);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  ATR_CTA(1);
   if (warp == kMmaWarp4) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -856,6 +935,8 @@ int launch_attention4(const void* qkv, void* out, float* lse, int B, int L, int 
   p.full_groups = tiles / NT4;
   p.n_full = B * H * p.full_groups;
   p.n_items = p.n_full + (tiles % NT4 ? B * H : 0);
+  static const int split_env = [] { const char* e = getenv("COUNTR_ATTN4_SPLIT"); return e ? atoi(e) : 1; }();
+  p.split = split_env;
   const int grid = std::min(p.n_items, num_sms());
   COUNTR_CHECK_CUDA(launch_pdl(attention_fwd4_kernel<DH, kBf16>, dim3(grid), dim3(kThreads4), SM::kTotal, stream, tq, tkv, p));
   return COUNTR_OK;

@@ -1095,8 +1095,8 @@ extern "C" int countr_window_blend(const void* outs, int dtype, const int32_t* s
 //                                                 kind 2  conv pack mode 0 (Cout = R, Cin = C): dst[co][tap][ci] = w[co][ci][tap]
 //                                                 kind 3  conv pack mode 1:                     dst[ci][tap][co] = w[co][ci][8 - tap]
 //   blk_prefix[e] = first block of entry e (n_entries + 1 values); 256 threads per block:
-//   kind 0: 2048 elements per block; kind 1: one 32 x 32 tile per block; kind 2: one (co, 128 ci) slab per block;
-//   kind 3: one 32 x 32 tile of w viewed as [Cout][Cin*9] per block.
+//   kind 0: 2048 elements per block; kind 1: one 64 x 64 tile per block; kind 2: one (co, 128 ci) slab per block;
+//   kind 3: one 64 x 64 tile of w viewed as [Cout][Cin*9] per block  (countr_weight_refresh_blocks gives the count).
 // ------------------------------------------------------------------------------------------
 namespace countr {
 namespace {
@@ -1106,18 +1106,61 @@ struct WREntry {
   long long kind, R, C, pad;
 };
 
-__global__ void __launch_bounds__(256) weight_refresh_kernel(const WREntry* __restrict__ entries, const int* __restrict__ blk_prefix,
-                                                             int n_entries, int bf16) {
-  __shared__ int s_e;
-  __shared__ float tile[32][33];
-  if (threadIdx.x == 0) {
-    int e = 0;
-    while (e + 1 < n_entries && static_cast<int>(blockIdx.x) >= blk_prefix[e + 1]) ++e;
-    s_e = e;
+// blocks of one entry (shared by the kernel's decode and by countr_weight_refresh_blocks, which the host plan calls)
+__host__ __device__ inline long long wr_blocks(long long kind, long long R, long long C) {
+  if (kind == 0) return (R * C + 2047) / 2048;
+  if (kind == 1) return ((R + 63) / 64) * ((C + 63) / 64);
+  if (kind == 2) return R * ((C + 127) / 128);
+  return ((R + 63) / 64) * ((9 * C + 63) / 64);
+}
+
+// 64 x 64 transpose tile of src viewed as [R][CC]: coalesced 128-byte row reads, 128-byte packed 16-bit row writes
+// (two consecutive r per thread).  dst row of source column c: dst_row(c) * R.
+template <bool kConvFlip>
+__device__ __forceinline__ void wr_transpose_tile(const float* __restrict__ src, uint16_t* __restrict__ dst, int R, int CC, int lb, int bf16,
+                                                  float (*tile)[65]) {
+  const int tiles_c = (CC + 63) / 64;
+  const int c0 = (lb % tiles_c) * 64, r0 = (lb / tiles_c) * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = ty; i < 64; i += 8) {
+    const int r = r0 + i;
+    const float* sp = src + static_cast<size_t>(r) * CC + c0;
+    tile[i][tx] = (r < R && c0 + tx < CC) ? sp[tx] : 0.f;
+    tile[i][tx + 32] = (r < R && c0 + tx + 32 < CC) ? sp[tx + 32] : 0.f;
   }
   __syncthreads();
-  const WREntry en = entries[s_e];
-  const int lb = blockIdx.x - blk_prefix[s_e];      // block index inside the entry
+  const bool even = (R & 1) == 0;
+#pragma unroll
+  for (int i = ty; i < 64; i += 8) {
+    const int c = c0 + i, r = r0 + 2 * tx;
+    if (c >= CC || r >= R) continue;
+    size_t row = static_cast<size_t>(c);
+    if (kConvFlip) {
+      const int ci = c / 9, tap = c - ci * 9;
+      row = static_cast<size_t>(ci) * 9 + (8 - tap);
+    }
+    uint16_t* dp = dst + row * R + r;
+    if (even) {
+      *reinterpret_cast<uint32_t*>(dp) = pack2(tile[2 * tx][i], tile[2 * tx + 1][i], bf16);
+    } else {
+      dp[0] = static_cast<uint16_t>(pack2(tile[2 * tx][i], 0.f, bf16) & 0xffffu);
+      if (r + 1 < R) dp[1] = static_cast<uint16_t>(pack2(tile[2 * tx + 1][i], 0.f, bf16) & 0xffffu);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) weight_refresh_kernel(const WREntry* __restrict__ entries, const int* __restrict__ blk_prefix,
+                                                             int n_entries, int bf16) {
+  __shared__ float tile[64][65];
+  // entry of this block: last e with blk_prefix[e] <= blockIdx.x (every thread runs the same 7-step search: broadcast loads)
+  int lo = 0, hi = n_entries - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (blk_prefix[mid] <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid - 1;
+  }
+  const WREntry en = entries[lo];
+  const int lb = blockIdx.x - blk_prefix[lo];      // block index inside the entry
   const int R = static_cast<int>(en.R), C = static_cast<int>(en.C);
   if (en.kind == 0) {
     const long long n = static_cast<long long>(R) * C;
@@ -1134,22 +1177,11 @@ __global__ void __launch_bounds__(256) weight_refresh_kernel(const WREntry* __re
       for (long long j = i; j < n && j < i + 8; ++j) en.dst[j] = static_cast<uint16_t>(pack2(en.src[j], 0.f, bf16) & 0xffffu);
     }
   } else if (en.kind == 1) {
-    const int tiles_c = (C + 31) / 32;
-    const int c0 = (lb % tiles_c) * 32, r0 = (lb / tiles_c) * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int i = ty; i < 32; i += 8) {
-      const int r = r0 + i, c = c0 + tx;
-      tile[i][tx] = (r < R && c < C) ? en.src[static_cast<size_t>(r) * C + c] : 0.f;
-    }
-    __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-      const int c = c0 + i, r = r0 + tx;
-      if (r < R && c < C) en.dst[static_cast<size_t>(c) * R + r] = static_cast<uint16_t>(pack2(tile[tx][i], 0.f, bf16) & 0xffffu);
-    }
+    wr_transpose_tile<false>(en.src, en.dst, R, C, lb, bf16, tile);
   } else if (en.kind == 2) {
     // mode 0: dst[co][tap][ci] = w[co][ci][tap].  Block = (co, 128 input channels): 1152 contiguous floats in, 9 rows of
     // 128 contiguous 16-bit values out (Cout = R, Cin = C).
-    __shared__ float cw[128 * 9];
+    float* cw = &tile[0][0];
     const int cblocks = (C + 127) / 128;
     const int co = lb / cblocks, ci0 = (lb % cblocks) * 128;
     const int nci = min(128, C - ci0);
@@ -1163,27 +1195,16 @@ __global__ void __launch_bounds__(256) weight_refresh_kernel(const WREntry* __re
     }
   } else {
     // mode 1: dst[ci][tap][co] = w[co][ci][8 - tap]: the transpose of w viewed as [Cout][Cin*9], with the 9 taps of every
-    // input channel written in reverse order.  Same 32 x 32 tiles as kind 1 (rows = co, columns = ci*9 + tap).
-    const int CC = C * 9;
-    const int tiles_c = (CC + 31) / 32;
-    const int c0 = (lb % tiles_c) * 32, r0 = (lb / tiles_c) * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int i = ty; i < 32; i += 8) {
-      const int r = r0 + i, c = c0 + tx;
-      tile[i][tx] = (r < R && c < CC) ? en.src[static_cast<size_t>(r) * CC + c] : 0.f;
-    }
-    __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-      const int c = c0 + i, r = r0 + tx;
-      if (r < R && c < CC) {
-        const int ci = c / 9, tap = c - ci * 9;
-        en.dst[(static_cast<size_t>(ci) * 9 + (8 - tap)) * R + r] = static_cast<uint16_t>(pack2(tile[tx][i], 0.f, bf16) & 0xffffu);
-      }
-    }
+    // input channel written in reverse order
+    wr_transpose_tile<true>(en.src, en.dst, R, C * 9, lb, bf16, tile);
   }
 }
 }  // namespace
 }  // namespace countr
+
+extern "C" int64_t countr_weight_refresh_blocks(int kind, int64_t R, int64_t C) {
+  return (kind < 0 || kind > 3 || R < 0 || C < 0) ? -1 : countr::wr_blocks(kind, R, C);
+}
 
 extern "C" int countr_weight_refresh(const void* entries, const int32_t* blk_prefix, int n_entries, int total_blocks, int bf16,
                                      countr_stream_t stream_) {

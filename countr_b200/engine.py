@@ -21,6 +21,7 @@ import weakref
 import torch
 
 from . import ops
+from ._lib import lib
 
 F16 = torch.float16
 F32 = torch.float32
@@ -117,9 +118,9 @@ class WeightCache:
             rows, prefix, nblk = [], [0], 0
             for src, dst, code, r, c in work:
                 rows += [src, dst, code, r, c, 0]
-                n = r * c
-                nblk += ((n + 2047) // 2048 if code == 0 else ((r + 31) // 32) * ((c + 31) // 32) if code == 1 else
-                         r * ((c + 127) // 128) if code == 2 else ((r + 31) // 32) * ((9 * c + 31) // 32))
+                nb = lib().countr_weight_refresh_blocks(code, r, c)
+                assert nb >= 0
+                nblk += nb
                 prefix.append(nblk)
             tab = (torch.tensor(rows, dtype=torch.int64, device=dev), torch.tensor(prefix, dtype=torch.int32, device=dev), len(work), nblk)
             if len(self._tables) > 64:

@@ -366,11 +366,12 @@ int countr_density_from_dots(const double* dots, const int32_t* counts, int B, i
 /* Batched refresh of the 16-bit operand copies of fp32 master weights (one launch per optimizer step instead of one per
  * tensor).  entries: device array of {const float* src; uint16* dst; int64 kind, R, C, pad} with kind 0 = cast of R*C
  * elements, 1 = cast + transpose [R][C] -> [C][R], 2 / 3 = countr_conv_weight_pack mode 0 / 1 with Cout = R, Cin = C;
- * blk_prefix[e] (n_entries + 1 values) = first 256-thread block of entry e: 2048 elements per block for kind 0, one 32x32
- * tile per block for kind 1, one (co, 128 input channels) slab per block for kind 2, one 32x32 tile of the filter viewed
- * as [Cout][Cin*9] per block for kind 3. */
+ * blk_prefix[e] (n_entries + 1 values) = first 256-thread block of entry e, entry e taking
+ * countr_weight_refresh_blocks(kind, R, C) blocks (2048 elements per block for kind 0, one 64x64 tile per block for kind 1,
+ * one (co, 128 input channels) slab per block for kind 2, one 64x64 tile of the filter viewed as [Cout][Cin*9] for kind 3). */
 int countr_weight_refresh(const void* entries, const int32_t* blk_prefix, int n_entries, int total_blocks, int bf16,
                           countr_stream_t stream);
+int64_t countr_weight_refresh_blocks(int kind, int64_t R, int64_t C);   /* host-only helper, -1 on bad arguments */
 
 /* Exemplar crops (util/FSC147.py:285-298, 343-351): out[b][s] = Resize((out_hw, out_hw))(img[b][:, y1:y2+1, x1:x2+1]) with
  * torchvision 0.14.1's tensor semantics (bilinear, align_corners=False, no antialias).  img: fp32, element strides

@@ -29,6 +29,16 @@ for c in range(20):
     if v[1] >= 0:
         print(f"  chunk {c:2d}: {v}   wait S {v[1]-v[0]:5d}  load {v[2]-v[1]:5d}  max {v[3]-v[2]:5d}  wait PV {v[4]-v[3]:5d}  exp+store {v[5]-v[4]:5d}")
 if os.environ.get("COUNTR_ATTN4", "1") != "0":
+    # per-CTA begin / end (globaltimer ns) of the four-tile kernel
+    spans = [(t[2048 + 2 * i], t[2048 + 2 * i + 1]) for i in range(148) if t[2048 + 2 * i]]
+    if spans:
+        g0 = min(a for a, _ in spans)
+        n_full = B * H * ((L + 127) // 128 // 4)
+        full = [(a - g0, b - g0) for a, b in spans[:n_full]]
+        rest = [(a - g0, b - g0) for a, b in spans[n_full:]]
+        print(f"CTA spans (ns): {len(full)} four-tile CTAs begin {min(a for a, _ in full)}..{max(a for a, _ in full)} end {min(b for _, b in full)}..{max(b for _, b in full)}")
+        if rest:
+            print(f"                {len(rest)} remainder CTAs begin {min(a for a, _ in rest)}..{max(a for a, _ in rest)} end {min(b for _, b in rest)}..{max(b for _, b in rest)}")
     sys.exit(0)
 print("MMA warp, per ring chunk j: [start, S(next) issued, p_full t0 ok, PV t0 issued, p_full t1 ok, PV t1 issued]")
 for j in range(12):

@@ -519,3 +519,28 @@ def test_conv_dw_and_linear_dw_cta_pair(cuda, pair):
     ops.gemm(a, b, c, M, N, K, lda=M, ldb=N, ldc=N, a_mn=True, b_mn=True, atomic=True, split_k=4, bn=256, pair=pair)
     torch.cuda.synchronize()
     assert_close(c, a.float().t() @ b.float(), 3e-5, f"linear dW pair={pair}")
+
+
+def test_weight_refresh_all_kinds_ragged_shapes(cuda):
+    """countr_weight_refresh: cast, transpose and both conv filter packings in one launch, on shapes that do not fill the 64 x 64
+    tiles / 128-channel slabs (odd row counts take the unpacked store path)."""
+    from countr_b200 import ops
+    from countr_b200.engine import WeightCache
+    g = torch.Generator().manual_seed(5)
+    mk = lambda *shape: torch.nn.Parameter(torch.randn(*shape, generator=g).to(cuda))  # noqa: E731
+    lin = [mk(512, 2048), mk(100, 70), mk(33, 65), mk(1, 7)]
+    conv = [mk(256, 512, 3, 3), mk(64, 3, 3, 3), mk(37, 21, 3, 3)]
+    wc = WeightCache()
+    plan = [(p, "w") for p in lin] + [(p, "wt") for p in lin] + [(p, "c0") for p in conv] + [(p, "c1") for p in conv]
+    before = ops.LAUNCHES[0]
+    assert wc.refresh_batch(plan) == len(plan)
+    assert ops.LAUNCHES[0] - before <= 1
+    for p in lin:
+        assert torch.equal(wc.w16(p), p.detach().half())
+        assert torch.equal(wc.w16_t(p), p.detach().t().contiguous().half())
+    for p in conv:
+        co, ci = p.shape[:2]
+        w = p.detach()
+        assert torch.equal(wc.conv16(p, 0).reshape(co, 9, ci), w.reshape(co, ci, 9).permute(0, 2, 1).contiguous().half())
+        flipped = w.reshape(co, ci, 9).flip(-1)                               # tap -> 8 - tap
+        assert torch.equal(wc.conv16(p, 1).reshape(ci, 9, co), flipped.permute(1, 2, 0).contiguous().half())
