@@ -7,6 +7,7 @@
 // All are HBM-bound: NHWC, 16-byte vector loads, per-block partial sums, one atomic per block.
 #include "../../include/countr_b200.h"
 #include "common.cuh"
+#include "tma.h"
 
 namespace countr {
 namespace {
@@ -254,6 +255,217 @@ __global__ void __launch_bounds__(256) gn_relu_bwd_reduce_kernel(
       const int cvv = threadIdx.x >> 3, which = threadIdx.x & 7;
       if ((cvv & 3) == 0 && which < 2) atomicAdd(gsum + (static_cast<long long>(b) * G + (cvv >> 2)) * 2 + which, static_cast<double>(v));
       if (MODE == 1 && cvv == 0 && which == 2) atomicAdd(db1, v);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm + ReLU backward, pass A for the up-sampled stages (mode 0 above), staged through shared memory.
+// The register-walking kernel above is latency-bound (one dependent round trip to L2 / HBM per row step, 16 warps per SM:
+// 1.9 TB/s at 96^2 -> 192^2).  Here a block owns 4 x 8 output pixels at a time; the 10 x 18 hi-res pixels they gather from
+// arrive as ten row-contiguous bulk copies (cp.async.bulk, 9 KB each, mbarrier completion) into one of two stages, so the next
+// tile's 92 KB are in flight while this one is reduced.  Blocks are persistent per image (the per-image group sums stay in
+// registers) and run the channel / group reductions once at the end.  16 warps: warp = (row pair, column) of the tile — with
+// 8 warps walking all four rows the kernel was bound by its own dependent ld.shared -> fma chains (2 warps per scheduler).
+// ------------------------------------------------------------------------------------------
+constexpr int GT_X = 8;
+constexpr int GT_COLS = 2 * GT_X + 2;
+constexpr uint32_t GT_PIX = kC * 2;                        // bytes of one pixel's channel vector
+constexpr uint32_t GT_PITCH = GT_COLS * GT_PIX;
+template <int GT_Y, int NS>
+struct GatherCfg {
+  static constexpr int kRows = 2 * GT_Y + 2;
+  static constexpr uint32_t kStage = kRows * GT_PITCH;
+  static constexpr uint32_t kSmem = NS * kStage + 64;
+};
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// d = a * w + c with a, w 16-bit and c, d fp32 in ONE instruction (FHFMA; PTX mixed-precision fma, sm_100): the conversion
+// of every gathered value (HADD2.F32) was a fifth of the instructions this kernel issued, and it is issue-bound
+template <bool kBf16>
+__device__ __forceinline__ float fma_mixed(uint32_t a16, uint16_t w16, float c) {
+  float d;
+  const uint16_t a = static_cast<uint16_t>(a16);
+  if (kBf16) asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(w16), "f"(c));
+  else asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(w16), "f"(c));
+  return d;
+}
+
+template <int GT_Y, int NS, bool kBf16>
+__global__ void __launch_bounds__(512, 1) gn_relu_bwd_gather_kernel(
+    const uint16_t* __restrict__ raw, const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const uint16_t* __restrict__ d_next, uint16_t* __restrict__ dyh, float* __restrict__ dgamma, float* __restrict__ dbeta,
+    double* __restrict__ gsum, int H, int W, int G, float eps) {
+  constexpr int bf16 = kBf16 ? 1 : 0;
+  constexpr uint32_t GT_STAGE = GatherCfg<GT_Y, NS>::kStage;
+  constexpr int RPW = GT_Y / 2;                      // rows per warp: warps 0-7 take the upper half of the tile, 8-15 the lower
+  extern __shared__ __align__(128) uint8_t gt_smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gt_smem + NS * GT_STAGE);
+  __shared__ float s_mean[8], s_rstd[8];
+  const int b = blockIdx.y;
+  const int HW = H * W;
+  const int cpg = kC / G;
+  if (threadIdx.x < G) {
+    const double cnt = static_cast<double>(HW) * cpg;
+    const double sm = stats[(static_cast<long long>(b) * G + threadIdx.x) * 2];
+    const double ss = stats[(static_cast<long long>(b) * G + threadIdx.x) * 2 + 1];
+    const double mean = sm / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0) var = 0;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = rsqrtf(static_cast<float>(var) + eps);
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) mbar_init(bars + i, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int cv = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c0 = cv * 8, g = c0 / cpg;
+  const float mean = s_mean[g], rstd = s_rstd[g];
+  float gam[8], bet[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gam[j] = gamma[c0 + j];
+    bet[j] = beta[c0 + j];
+  }
+  float R1[8], R2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) R1[j] = R2[j] = 0.f;
+  const uint16_t* rb = raw + static_cast<long long>(b) * HW * kC + c0;
+  uint16_t* ob = dyh + static_cast<long long>(b) * HW * kC + c0;
+  const uint16_t* nb = d_next + static_cast<long long>(b) * 4 * HW * kC;
+  const int ntx = (W + GT_X - 1) / GT_X, ntiles = ntx * ((H + GT_Y - 1) / GT_Y);
+
+  // hi-res window of tile t: rows hy0..hy1, columns hx0..hx1 (clamped at the borders like the taps)
+  auto window = [&](int t, int& y0, int& x0, int& hy0, int& hy1, int& hx0, int& hx1) {
+    y0 = (t / ntx) * GT_Y;
+    x0 = (t % ntx) * GT_X;
+    const int yl = min(H, y0 + GT_Y) - 1, xl = min(W, x0 + GT_X) - 1;
+    hy0 = max(2 * y0 - 1, 0), hy1 = min(2 * yl + 2, 2 * H - 1);
+    hx0 = max(2 * x0 - 1, 0), hx1 = min(2 * xl + 2, 2 * W - 1);
+  };
+  auto issue = [&](int t, int stage) {      // one thread
+    int y0, x0, hy0, hy1, hx0, hx1;
+    window(t, y0, x0, hy0, hy1, hx0, hx1);
+    const uint32_t row_bytes = static_cast<uint32_t>(hx1 - hx0 + 1) * GT_PIX;
+    fence_proxy_async_smem();              // the stage was read with ld.shared two tiles ago
+    mbar_arrive_expect_tx(bars + stage, row_bytes * static_cast<uint32_t>(hy1 - hy0 + 1));
+    const uint32_t dst = smem_u32(gt_smem) + stage * GT_STAGE;
+    for (int r = hy0; r <= hy1; ++r)
+      bulk_g2s(dst + (r - hy0) * GT_PITCH, nb + (static_cast<long long>(r) * (2 * W) + hx0) * kC, row_bytes, bars + stage);
+  };
+
+  int it = 0;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < NS - 1; ++k)
+      if (static_cast<int>(blockIdx.x + k * gridDim.x) < ntiles) issue(blockIdx.x + k * gridDim.x, k);
+  }
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const int stage = it % NS;
+    // NS - 1 tiles ahead, into the stage the previous iteration released
+    if (threadIdx.x == 0 && t + (NS - 1) * static_cast<int>(gridDim.x) < ntiles) issue(t + (NS - 1) * gridDim.x, (it + NS - 1) % NS);
+    int y0, x0, hy0, hy1, hx0, hx1;
+    window(t, y0, x0, hy0, hy1, hx0, hx1);
+    const int ix = x0 + (pl & 7);
+    const int ys = y0 + RPW * (pl >> 3);               // this warp's rows
+    const int y1 = min(H, y0 + GT_Y);
+    const bool active = ix < W && ys < y1;
+    // this thread's raw vectors do not depend on the staged tile: request them before waiting for it
+    uint4 xr[RPW];
+#pragma unroll
+    for (int k = 0; k < RPW; ++k)
+      xr[k] = (active && ys + k < y1) ? *reinterpret_cast<const uint4*>(rb + static_cast<long long>((ys + k) * W + ix) * kC) : make_uint4(0, 0, 0, 0);
+    mbar_wait(bars + stage, static_cast<uint32_t>(it / NS) & 1u);
+    if (active) {
+      int ox[4];
+      float wx[4];
+      up2_adjoint_taps(ix, W, ox, wx);
+      // taps without weight (image border) read a valid neighbour and multiply it by zero: no branches in the row loop
+      uint32_t off[4];
+      uint16_t wh[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        off[c] = static_cast<uint32_t>((wx[c] != 0.f ? ox[c] : ox[1]) - hx0) * GT_PIX;
+        wh[c] = static_cast<uint16_t>(pack2(wx[c], 0.f, bf16) & 0xffffu);         // 0, 0.25, 0.75, 1: exact in both formats
+      }
+      const uint8_t* st = gt_smem + stage * GT_STAGE + c0 * 2;
+      auto hrow = [&](int oy, float (&h)[8]) {
+        const uint8_t* rp = st + (oy - hy0) * GT_PITCH;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 u = *reinterpret_cast<const uint4*>(rp + off[c]);
+          const uint32_t w32[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            h[2 * i] = fma_mixed<kBf16>(w32[i] & 0xffffu, wh[c], c == 0 ? 0.f : h[2 * i]);
+            h[2 * i + 1] = fma_mixed<kBf16>(w32[i] >> 16, wh[c], c == 0 ? 0.f : h[2 * i + 1]);
+          }
+        }
+      };
+      float h0[8], h1[8], h2[8], h3[8];
+      hrow(max(2 * ys - 1, 0), h0);
+      hrow(2 * ys, h1);
+#pragma unroll
+      for (int k = 0; k < RPW; ++k) {
+        const int iy = ys + k;
+        if (iy < y1) {
+          hrow(2 * iy + 1, h2);
+          hrow(min(2 * iy + 2, 2 * H - 1), h3);
+          const float w0 = iy >= 1 ? 0.25f : 0.f, w1y = iy == 0 ? 1.f : 0.75f;
+          const float w2 = iy == H - 1 ? 1.f : 0.75f, w3 = iy <= H - 2 ? 0.25f : 0.f;
+          float x[8], dy[8];
+          unpack8(xr[k], x, bf16);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float dz = w0 * h0[j] + w1y * h1[j] + w2 * h2[j] + w3 * h3[j];
+            const float xh = (x[j] - mean) * rstd;
+            dy[j] = fmaf(xh, gam[j], bet[j]) > 0.f ? dz : 0.f;
+            R1[j] += dy[j];
+            R2[j] = fmaf(dy[j], xh, R2[j]);
+            h0[j] = h2[j];
+            h1[j] = h3[j];
+          }
+          *reinterpret_cast<uint4*>(ob + static_cast<long long>(iy * W + ix) * kC) = pack8(dy, bf16);
+        }
+      }
+    }
+    __syncthreads();          // everyone is done with this stage before the next iteration refills it
+  }
+
+  // channel sums over the 16 pixel lanes and the per-(image, group) sums, once per block; the stages are free now
+  float(*red)[kC + 8] = reinterpret_cast<float(*)[kC + 8]>(gt_smem);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s1 += gam[j] * R1[j];
+    s2 += gam[j] * R2[j];
+  }
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+  for (int q = 0; q < 3; ++q) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[pl][c0 + j] = q == 0 ? R2[j] : q == 1 ? R1[j] : 0.f;
+    if (q == 2) {
+      red[pl][c0] = s1; red[pl][c0 + 1] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x < kC) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v += red[k][threadIdx.x];
+      if (q == 0) atomicAdd(dgamma + threadIdx.x, v);
+      else if (q == 1) atomicAdd(dbeta + threadIdx.x, v);
+      else {
+        const int cvv = threadIdx.x >> 3, which = threadIdx.x & 7;
+        if ((cvv & 3) == 0 && which < 2) atomicAdd(gsum + (static_cast<long long>(b) * G + (cvv >> 2)) * 2 + which, static_cast<double>(v));
+      }
     }
     __syncthreads();
   }
@@ -771,7 +983,21 @@ extern "C" int countr_gn_relu_bwd_reduce(const void* raw, const double* stats, c
   COUNTR_REQUIRE(mode == 0 || (dmap && w1 && dw1 && db1), "1x1-conv mode needs dmap, w1, dw1, db1");
   dim3 grid;
   gn_grid(H * W, B, &grid);
-  if (mode == 0) {
+  static const int gather_env = [] { const char* e = getenv("COUNTR_GN_GATHER"); return e ? atoi(e) : 1; }();
+  if (mode == 0 && gather_env) {
+    auto launch = [&](auto kern, int ty, uint32_t smem, PerDeviceOnce& once) -> int {
+      if (once.need()) COUNTR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      const int ntiles = ((W + GT_X - 1) / GT_X) * ((H + ty - 1) / ty);
+      const int bpi = std::max(1, std::min(ntiles, num_sms() / B));       // persistent blocks per image
+      kern<<<dim3(bpi, B), 512, smem, stream>>>(reinterpret_cast<const uint16_t*>(raw), stats, gamma, beta, reinterpret_cast<const uint16_t*>(d_next),
+                                                reinterpret_cast<uint16_t*>(dyh), dgamma, dbeta, gsum, H, W, G, eps);
+      return COUNTR_OK;
+    };
+    static PerDeviceOnce once_f16, once_bf16;
+    const int rc = bf16 ? launch(gn_relu_bwd_gather_kernel<4, 2, true>, 4, GatherCfg<4, 2>::kSmem, once_bf16)
+                        : launch(gn_relu_bwd_gather_kernel<4, 2, false>, 4, GatherCfg<4, 2>::kSmem, once_f16);
+    if (rc) return rc;
+  } else if (mode == 0) {
     // strips of 8 columns x R rows; keep >= ~4 blocks per SM in flight
     const int nxt = (W + 7) / 8;
     int R = 8;

@@ -1,0 +1,31 @@
+"""Device time of the GroupNorm+ReLU backward reduce pass (up-sample adjoint gather) on the decoder-head shapes, B=8."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from countr_b200 import ops
+
+dev = torch.device("cuda:0")
+B, C, G = 8, 256, 8
+for H in ((96,) if os.environ.get("GN_ONE") else (24, 48, 96)):
+    raw = torch.randn(B, H, H, C, device=dev).half()
+    d_next = torch.randn(B, 2 * H, 2 * H, C, device=dev).half()
+    xg = raw.double().reshape(B, H * H, G, C // G)
+    stats = torch.stack([xg.sum((1, 3)), (xg * xg).sum((1, 3))], -1).contiguous()
+    gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+    dyh = torch.empty_like(raw)
+    dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    gsum = torch.zeros(B, G, 2, device=dev, dtype=torch.float64)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    f = lambda: ops.gn_relu_bwd_reduce(raw, stats, gamma, beta, dyh, dg, db, gsum, G, 1e-5, d_next=d_next)
+    for _ in range(3):
+        f()
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); f(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    mb = (raw.numel() * 2 * 2 + d_next.numel() * 2) / 1e6
+    print(f"gn_relu_bwd_reduce mode 0  {H}^2 -> {2*H}^2: {ts[len(ts)//2]:7.1f} us (cold L2)  {mb:6.1f} MB  {mb / ts[len(ts)//2]:5.2f} TB/s", flush=True)

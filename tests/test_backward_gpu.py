@@ -30,10 +30,12 @@ def test_upsample2x_bwd(cuda):
     assert_close(dx.reshape(2, -1), x.grad.reshape(2, -1), 1e-3, "up2 bwd f16")
 
 
-@pytest.mark.parametrize("mode", [0, 1])
-def test_gn_relu_backward(cuda, mode):
+@pytest.mark.parametrize("mode,B,H,W", [(0, 2, 24, 24), (1, 2, 24, 24), (0, 1, 30, 21), (0, 3, 5, 9), (0, 8, 48, 48), (0, 1, 96, 100)])
+def test_gn_relu_backward(cuda, mode, B, H, W):
+    """mode 0 (up-sample adjoint gather, shared-memory staged tiles): whole tiles, ragged tiles on both axes, maps smaller than a
+    tile, several tiles per persistent block; mode 1: the 1x1-conv head."""
     from countr_b200 import ops
-    B, H, W, C, G = 2, 24, 24, 256, 8
+    C, G = 256, 8
     raw = _rand16((B, H, W, C), cuda, seed=20, scale=2.0)
     gamma = (torch.randn(C, device=cuda) * 0.5 + 1).requires_grad_(True)
     beta = (torch.randn(C, device=cuda) * 0.3).requires_grad_(True)
