@@ -101,7 +101,7 @@ constexpr int kC = 256;
 //           dbeta = w R1, dgamma = w R2, dw1 = gamma R2 + beta R1   (relu(y) = y where the mask is 1)
 // and the group sums follow at the end as S1 = sum_c gamma_c dbeta_c, S2 = sum_c gamma_c dgamma_c.
 template <int MODE>
-__global__ void __launch_bounds__(256) gn_relu_bwd_reduce_kernel(
+__global__ void __launch_bounds__(256, MODE == 1 ? 3 : 2) gn_relu_bwd_reduce_kernel(
     const uint16_t* __restrict__ raw, const double* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ beta, const uint16_t* __restrict__ d_next, const float* __restrict__ dmap,
     const float* __restrict__ w1, uint16_t* __restrict__ dyh, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -883,38 +883,53 @@ __global__ void __launch_bounds__(256) inorm_pool_bwd_split_kernel(const uint16_
 // ------------------------------------------------------------------------------------------
 // decoder_proj1[0] weight gradient: dW[co][ci][ky][kx] += sum_{n,y,x} d_raw[n,y,x,co] * box[n,ci,y+ky-1,x+kx-1]
 // (Cin = 3 -> K = 27: a direct smem-tiled reduction, not a tensor-core shape)
-// block = 512 pixels of one sample in 4 sub-tiles of 128; smem holds the sub-tile transposed
+// block = 512 pixels of one sample in 4 tiles of 128 (fewer tiles per block means more atomics: slower); smem holds the tile transposed
 // ([tap][pixel] fp32, [co][pixel] fp16) so each thread (co = tid % 64, taps tid/64 + 4j) reads 4 pixels per LDS.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) exemplar_conv1_dw_kernel(const void* __restrict__ boxes, int dtype, long long sB, long long sK,
                                                                  long long sC, long long sH, long long sW,
                                                                  const uint16_t* __restrict__ d_raw, float* __restrict__ dw, int S,
-                                                                 int HW, int bf16) {
-  constexpr int PX = 128, SUB = 4;
+                                                                 int HW, int bf16, int SUB) {
+  constexpr int PX = 128;
   __shared__ __align__(16) float s_in[27][PX];
   __shared__ __align__(16) uint16_t s_d[64][PX + 4];
+  __shared__ float s_box[3][4][66];              // the PX / W (+2 halo) input rows of the tile, zero-padded columns -1 and W
   const int n = blockIdx.y;
   const int b = n / S, s = n % S;
   const int H = HW, W = HW;
+  const int rows = PX / W;                       // image rows per tile (the host checks W == 64: two rows)
   const int co = threadIdx.x & 63, kq = threadIdx.x >> 6;
   float acc[7];
 #pragma unroll
   for (int j = 0; j < 7; ++j) acc[j] = 0.f;
   for (int sub = 0; sub < SUB; ++sub) {
     const int p0 = (blockIdx.x * SUB + sub) * PX;
+    const int y0 = p0 / W;
+    __syncthreads();
+    // both fills are independent global loads (one round trip): the halo rows of the box and the 16-byte d_raw vectors
+    for (int i = threadIdx.x; i < 3 * (rows + 2) * 66; i += blockDim.x) {
+      const int xx = i % 66 - 1, r = (i / 66) % (rows + 2), ci = i / (66 * (rows + 2));
+      const int yy = y0 + r - 1;
+      float v = 0.f;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = load_any(boxes, b * sB + s * sK + ci * sC + yy * sH + xx * sW, dtype);
+      s_box[ci][r][xx + 1] = v;
+    }
+#pragma unroll
+    for (int i = threadIdx.x; i < PX * 8; i += 256) {
+      const int px = i >> 3, c8 = (i & 7) * 8;
+      const uint4 v = *reinterpret_cast<const uint4*>(d_raw + (static_cast<long long>(n) * H * W + p0 + px) * 64 + c8);
+      const uint32_t w32[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s_d[c8 + 2 * j][px] = static_cast<uint16_t>(w32[j] & 0xffffu);
+        s_d[c8 + 2 * j + 1][px] = static_cast<uint16_t>(w32[j] >> 16);
+      }
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < PX * 27; i += blockDim.x) {
       const int px = i % PX, k = i / PX;
       const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
-      const int pix = p0 + px;
-      const int yy = pix / W + ky - 1, xx = pix % W + kx - 1;
-      float v = 0.f;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = load_any(boxes, b * sB + s * sK + ci * sC + yy * sH + xx * sW, dtype);
-      s_in[k][px] = v;
-    }
-    for (int i = threadIdx.x; i < PX * 64; i += blockDim.x) {
-      const int c = i % 64, px = i / 64;
-      s_d[c][px] = d_raw[(static_cast<long long>(n) * H * W + p0 + px) * 64 + c];
+      s_in[k][px] = s_box[ci][px / W + ky][px % W + kx];
     }
     __syncthreads();
     for (int px = 0; px < PX; px += 4) {
@@ -1105,10 +1120,12 @@ extern "C" int countr_inorm_relu_pool_bwd(const void* raw, const float* mean, co
 extern "C" int countr_exemplar_conv1_dw(const void* boxes, int dtype, int64_t sB, int64_t sK, int64_t sC, int64_t sH, int64_t sW,
                                         const void* d_raw, float* dw, int B, int S, int HW, int bf16, countr_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  COUNTR_REQUIRE(boxes && d_raw && dw && (HW * HW) % 512 == 0, "bad arguments");
-  dim3 grid(HW * HW / 512, B * S);
+  static const int sub_env = [] { const char* e = getenv("COUNTR_CONV1_DW_SUB"); return e ? atoi(e) : 4; }();
+  const int sub = (sub_env == 2 || sub_env == 4) && (HW * HW) % (128 * sub_env) == 0 ? sub_env : 1;      // 128-pixel tiles per block
+  COUNTR_REQUIRE(boxes && d_raw && dw && HW == 64, "the stage-1 exemplar weight gradient is built for 64 x 64 boxes (got %d)", HW);
+  dim3 grid(HW * HW / (128 * sub), B * S);
   exemplar_conv1_dw_kernel<<<grid, 256, 0, stream>>>(boxes, dtype, sB, sK, sC, sH, sW, reinterpret_cast<const uint16_t*>(d_raw), dw, S,
-                                                     HW, bf16);
+                                                     HW, bf16, sub);
   COUNTR_CHECK_CUDA(cudaGetLastError());
   return COUNTR_OK;
 }

@@ -29,3 +29,29 @@ for H in ((96,) if os.environ.get("GN_ONE") else (24, 48, 96)):
     ts.sort()
     mb = (raw.numel() * 2 * 2 + d_next.numel() * 2) / 1e6
     print(f"gn_relu_bwd_reduce mode 0  {H}^2 -> {2*H}^2: {ts[len(ts)//2]:7.1f} us (cold L2)  {mb:6.1f} MB  {mb / ts[len(ts)//2]:5.2f} TB/s", flush=True)
+
+# mode 1: the 1x1-conv head at 192^2 (reads raw, writes dyh)
+H = 192
+raw = torch.randn(B, H, H, C, device=dev).half()
+xg = raw.double().reshape(B, H * H, G, C // G)
+stats = torch.stack([xg.sum((1, 3)), (xg * xg).sum((1, 3))], -1).contiguous()
+gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+dyh = torch.empty_like(raw)
+dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+gsum = torch.zeros(B, G, 2, device=dev, dtype=torch.float64)
+dmap = torch.randn(B, H, H, device=dev)
+w1, dw1, db1 = torch.randn(C, device=dev), torch.zeros(C, device=dev), torch.zeros(1, device=dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+f = lambda: ops.gn_relu_bwd_reduce(raw, stats, gamma, beta, dyh, dg, db, gsum, G, 1e-5, dmap=dmap, w1=w1, dw1=dw1, db1=db1)
+for _ in range(3):
+    f()
+ts = []
+for _ in range(10):
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); f(); e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1) * 1e3)
+ts.sort()
+mb = raw.numel() * 2 * 2 / 1e6
+print(f"gn_relu_bwd_reduce mode 1  {H}^2: {ts[len(ts)//2]:7.1f} us (cold L2)  {mb:6.1f} MB  {mb / ts[len(ts)//2]:5.2f} TB/s", flush=True)
