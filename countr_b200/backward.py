@@ -14,6 +14,8 @@ util/misc.py:266-270); which parameters receive a gradient follows models_mae_cr
 Parameter gradients are views into one flat fp32 arena (one memset, ready for a single
 all-reduce); they are returned to autograd, which accumulates them into `.grad` as usual.
 """
+import os
+
 import torch
 
 from . import ops
@@ -194,6 +196,7 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
         ops.zero_(dy32)
     dh = torch.empty(M, Dd, dtype=F32, device=dev)
     side = None
+    kv_done = None
     n_blocks = len(sv["blocks"])
     # Weight / bias gradients are leaves of the backward graph: the chain LayerNorm' -> dX GEMM -> attention' -> ... never
     # reads them.  They run on the side stream (one fork per producer, one join at the end), so the latency-bound
@@ -284,6 +287,11 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
             if eng.overlap_exemplar:
                 side = eng.side_stream(dev)
                 side.wait_stream(torch.cuda.current_stream())
+                if wstream is not None and defer:
+                    # the deferred weight-gradient jobs only need the k/v gradients that are already queued on the side
+                    # stream, not the exemplar-CNN backward behind them: the grouped launch at the end waits for this event
+                    kv_done = torch.cuda.Event()
+                    kv_done.record(side)
                 with torch.cuda.stream(side):
                     _exemplar_backward(m, sv, boxes, S, dy32, grads, wc, G)
             else:
@@ -315,10 +323,15 @@ def decoder_backward(eng, m, sv, boxes, grad_out):
     else:
         _dw_linear(g16, sv["lat16"], G(de.weight))
 
-    if side is not None or wstream is not None:
-        torch.cuda.current_stream().wait_stream(eng.side_stream(dev))     # join the exemplar-CNN backward and the k/v work
-    if defer:
+    if kv_done is not None and getattr(eng, "early_flush", os.environ.get("COUNTR_EARLY_FLUSH", "1") != "0"):
+        torch.cuda.current_stream().wait_event(kv_done)
         jobs.flush()
+        torch.cuda.current_stream().wait_stream(eng.side_stream(dev))     # join the exemplar-CNN backward
+    else:
+        if side is not None or wstream is not None:
+            torch.cuda.current_stream().wait_stream(eng.side_stream(dev))     # join the exemplar-CNN backward and the k/v work
+        if defer:
+            jobs.flush()
     keep.clear()
     # Every parameter that just received a gradient is about to be changed by an optimizer, and torch's version counter
     # cannot be relied on to say so (torch.optim.AdamW(fused=True) updates parameters without bumping `_version`, and so
