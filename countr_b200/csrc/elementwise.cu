@@ -286,15 +286,17 @@ __global__ void __launch_bounds__(256) gn_relu_up2_rows_kernel(const uint16_t* _
     bv[j] = sb[cv * 8 + j];
   }
   // hl / hr: the two horizontally blended output columns (2 ix, 2 ix + 1) of one normalised input row
-  auto blend_row = [&](int row, float (&hl)[8], float (&hr)[8]) {
+  auto load_row = [&](int row, uint4 (&u)[3]) {
     const uint16_t* rp = xb + static_cast<long long>(row) * W * C;
-    const uint4 u0 = *reinterpret_cast<const uint4*>(rp + static_cast<long long>(xl) * C);
-    const uint4 u1 = *reinterpret_cast<const uint4*>(rp + static_cast<long long>(ix) * C);
-    const uint4 u2 = *reinterpret_cast<const uint4*>(rp + static_cast<long long>(xr) * C);
+    u[0] = *reinterpret_cast<const uint4*>(rp + static_cast<long long>(xl) * C);
+    u[1] = *reinterpret_cast<const uint4*>(rp + static_cast<long long>(ix) * C);
+    u[2] = *reinterpret_cast<const uint4*>(rp + static_cast<long long>(xr) * C);
+  };
+  auto blend = [&](const uint4 (&u)[3], float (&hl)[8], float (&hr)[8]) {
     float a0[8], a1[8], a2[8];
-    unpack8(u0, a0, bf16);
-    unpack8(u1, a1, bf16);
-    unpack8(u2, a2, bf16);
+    unpack8(u[0], a0, bf16);
+    unpack8(u[1], a1, bf16);
+    unpack8(u[2], a2, bf16);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float v0 = fmaxf(fmaf(a0[j], av[j], bv[j]), 0.f), v1 = fmaxf(fmaf(a1[j], av[j], bv[j]), 0.f);
@@ -304,10 +306,18 @@ __global__ void __launch_bounds__(256) gn_relu_up2_rows_kernel(const uint16_t* _
     }
   };
   float hl0[8], hr0[8], hl1[8], hr1[8], hl2[8], hr2[8];
-  blend_row(max(y0 - 1, 0), hl0, hr0);
-  blend_row(y0, hl1, hr1);
+  uint4 ua[3], ub[3], un[3];
+  load_row(max(y0 - 1, 0), ua);
+  load_row(y0, ub);
+  load_row(min(y0 + 1, H - 1), un);             // the row the first iteration needs: three rows in flight at once
+  blend(ua, hl0, hr0);
+  blend(ub, hl1, hr1);
   for (int iy = y0; iy < y1; ++iy) {
-    blend_row(min(iy + 1, H - 1), hl2, hr2);
+    // one row of look-ahead: the loads of row iy + 2 are in flight while row iy's four output rows are blended and stored (the
+    // walk was one dependent L2 / HBM round trip per row step at 16 warps per SM)
+    uint4 uc[3] = {un[0], un[1], un[2]};
+    if (iy + 1 < y1) load_row(min(iy + 2, H - 1), un);
+    blend(uc, hl2, hr2);
     float o[8];
     uint16_t* yo = yb + (static_cast<long long>(2 * iy) * OW + 2 * ix) * C;
 #pragma unroll
