@@ -1,6 +1,7 @@
 """Per-kernel counts of the Blackwell-specific SASS mnemonics in the shipped library (evidence for profiles/):
 UTCHMMA (tcgen05.mma), LDTM / STTM (tcgen05.ld / st, tensor memory), UTMALDG / UTMASTG / UTMAREDG (TMA load / store / reduce-add),
-UTCBAR (tcgen05.commit -> mbarrier), SYNCS (mbarrier ops), plus the legacy tensor-core HMMA as a negative check.
+UTCBAR (tcgen05.commit -> mbarrier), SYNCS (mbarrier ops), UBLKCP (cp.async.bulk, non-tensor bulk copy), FHFMA (mixed-precision
+fma.rn.f32.f16 / .bf16), plus the legacy tensor-core HMMA as a negative check.
 
     python scripts/sass_summary.py [path/to/lib.so] > profiles/sass_summary.txt
 """
@@ -12,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "countr_b200", "lib", "libcountr_sm100.so")
-MNEMONICS = ["UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTMAPF", "UTCBAR", "SYNCS", "HMMA", "ELECT", "FFMA2", "MUFU"]
+MNEMONICS = ["UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTMAPF", "UTCBAR", "SYNCS", "HMMA", "ELECT", "FFMA2", "MUFU", "UBLKCP", "FHFMA"]
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
 arch = sorted(set(re.findall(r"arch = (sm_\w+)", out)))
 counts = collections.OrderedDict()
