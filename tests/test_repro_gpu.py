@@ -37,4 +37,5 @@ def test_step_is_reproducible_run_to_run(cuda):
     rel = (num / den) ** 0.5
     exact = sum(int(torch.equal(g1[k], g2[k])) for k in g1)
     print(f"\n[repro] gradients: relL2 between two runs {rel:.2e}; {exact}/{len(g1)} tensors bit-identical")
+    print("[repro] not bit-identical:", ", ".join(k for k in g1 if not torch.equal(g1[k], g2[k])))
     assert rel < 1e-5
