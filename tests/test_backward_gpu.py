@@ -30,10 +30,12 @@ def test_upsample2x_bwd(cuda):
     assert_close(dx.reshape(2, -1), x.grad.reshape(2, -1), 1e-3, "up2 bwd f16")
 
 
-@pytest.mark.parametrize("mode,B,H,W", [(0, 2, 24, 24), (1, 2, 24, 24), (0, 1, 30, 21), (0, 3, 5, 9), (0, 8, 48, 48), (0, 1, 96, 100)])
+@pytest.mark.parametrize("mode,B,H,W", [(0, 2, 24, 24), (1, 2, 24, 24), (0, 1, 30, 21), (0, 3, 5, 9), (0, 8, 48, 48), (0, 1, 96, 100),
+                                        (1, 1, 30, 21), (1, 8, 96, 96), (1, 3, 5, 9), (1, 2, 100, 100)])
 def test_gn_relu_backward(cuda, mode, B, H, W):
     """mode 0 (up-sample adjoint gather, shared-memory staged tiles): whole tiles, ragged tiles on both axes, maps smaller than a
-    tile, several tiles per persistent block; mode 1: the 1x1-conv head."""
+    tile, several tiles per persistent block; mode 1: the 1x1-conv head (64-pixel bulk-copy tiles: a ragged last tile, the stage ring
+    wrapping, a map below the staged kernel's minimum size)."""
     from countr_b200 import ops
     C, G = 256, 8
     raw = _rand16((B, H, W, C), cuda, seed=20, scale=2.0)
