@@ -4,6 +4,7 @@
 // job is to touch every activation exactly once between two tensor-core kernels.
 #include "../../include/countr_b200.h"
 #include "common.cuh"
+#include "tma.h"
 
 namespace countr {
 namespace {
@@ -337,6 +338,138 @@ __global__ void __launch_bounds__(256) gn_relu_up2_rows_kernel(const uint16_t* _
       hl0[j] = hl1[j]; hr0[j] = hr1[j];
       hl1[j] = hl2[j]; hr1[j] = hr2[j];
     }
+  }
+}
+
+// Shared-memory staged variant for C == 256 (the density head): persistent blocks per image; a tile = 8 x 8 input pixels ->
+// 16 x 16 output pixels, its 10 x 10 input window arrives as ten row-contiguous bulk copies (cp.async.bulk, mbarrier completion)
+// into one of three 51 KB stages, so two tiles are in flight while one is blended and stored.  The row-walking kernel above waits
+// for a global round trip per row step; here the walk reads shared memory only and the kernel runs at its store rate.
+constexpr int UT_X = 8, UT_Y = 8, UT_NS = 3, UT_C = 256;
+constexpr uint32_t UT_PIX = UT_C * 2, UT_PITCH = (UT_X + 2) * UT_PIX, UT_STAGE = (UT_Y + 2) * UT_PITCH;
+constexpr uint32_t UT_SMEM = UT_NS * UT_STAGE + 64 + 2 * UT_C * sizeof(float);
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(512, 1) gn_relu_up2_staged_kernel(const uint16_t* __restrict__ x, const double* __restrict__ stats,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                    uint16_t* __restrict__ y, int H, int W, int G, float eps, int bf16) {
+  constexpr int C = UT_C;
+  extern __shared__ __align__(128) uint8_t ut_smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ut_smem + UT_NS * UT_STAGE);
+  float* sa = reinterpret_cast<float*>(ut_smem + UT_NS * UT_STAGE + 64);
+  float* sb = sa + C;
+  const int b = blockIdx.y;
+  const int cpg = C / G;
+  const double cnt = static_cast<double>(H) * W * cpg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double s = stats[(static_cast<long long>(b) * G + g) * 2], ss = stats[(static_cast<long long>(b) * G + g) * 2 + 1];
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = rsqrtf(static_cast<float>(var) + eps);
+    const float a = rstd * gamma[c];
+    sa[c] = a;
+    sb[c] = beta[c] - static_cast<float>(mean) * a;
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < UT_NS; ++i) mbar_init(bars + i, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int cv = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  float av[8], bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    av[j] = sa[cv * 8 + j];
+    bv[j] = sb[cv * 8 + j];
+  }
+  const uint16_t* xb = x + static_cast<long long>(b) * H * W * C;
+  uint16_t* yb = y + static_cast<long long>(b) * 4 * H * W * C + cv * 8;
+  const int OW = 2 * W;
+  const int ntx = (W + UT_X - 1) / UT_X, ntiles = ntx * ((H + UT_Y - 1) / UT_Y);
+
+  auto window = [&](int t, int& y0, int& x0, int& wy0, int& wy1, int& wx0, int& wx1) {
+    y0 = (t / ntx) * UT_Y;
+    x0 = (t % ntx) * UT_X;
+    wy0 = max(y0 - 1, 0), wy1 = min(y0 + UT_Y, H - 1);
+    wx0 = max(x0 - 1, 0), wx1 = min(x0 + UT_X, W - 1);
+  };
+  auto issue = [&](int t, int stage) {      // one thread
+    int y0, x0, wy0, wy1, wx0, wx1;
+    window(t, y0, x0, wy0, wy1, wx0, wx1);
+    const uint32_t row_bytes = static_cast<uint32_t>(wx1 - wx0 + 1) * UT_PIX;
+    fence_proxy_async_smem();
+    mbar_arrive_expect_tx(bars + stage, row_bytes * static_cast<uint32_t>(wy1 - wy0 + 1));
+    const uint32_t dst = smem_u32(ut_smem) + stage * UT_STAGE;
+    for (int r = wy0; r <= wy1; ++r)
+      bulk_g2s(dst + (r - wy0) * UT_PITCH, xb + (static_cast<long long>(r) * W + wx0) * C, row_bytes, bars + stage);
+  };
+
+  int it = 0;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < UT_NS - 1; ++k)
+      if (static_cast<int>(blockIdx.x + k * gridDim.x) < ntiles) issue(blockIdx.x + k * gridDim.x, k);
+  }
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const int stage = it % UT_NS;
+    if (threadIdx.x == 0 && t + (UT_NS - 1) * static_cast<int>(gridDim.x) < ntiles) issue(t + (UT_NS - 1) * gridDim.x, (it + UT_NS - 1) % UT_NS);
+    int y0, x0, wy0, wy1, wx0, wx1;
+    window(t, y0, x0, wy0, wy1, wx0, wx1);
+    const int ix = x0 + (pl & 7);
+    const int ys = y0 + (UT_Y / 2) * (pl >> 3), ye = min(min(H, y0 + UT_Y), ys + UT_Y / 2);      // this warp's rows
+    mbar_wait(bars + stage, static_cast<uint32_t>(it / UT_NS) & 1u);
+    if (ix < W && ys < ye) {
+      const uint8_t* st = ut_smem + stage * UT_STAGE + cv * 16;
+      const uint32_t ol = static_cast<uint32_t>(max(ix - 1, 0) - wx0) * UT_PIX, oc = static_cast<uint32_t>(ix - wx0) * UT_PIX;
+      const uint32_t orr = static_cast<uint32_t>(min(ix + 1, W - 1) - wx0) * UT_PIX;
+      // hl / hr: the two horizontally blended output columns (2 ix, 2 ix + 1) of one normalised input row
+      auto blend = [&](int row, float (&hl)[8], float (&hr)[8]) {
+        const uint8_t* rp = st + (row - wy0) * UT_PITCH;
+        float a0[8], a1[8], a2[8];
+        unpack8(*reinterpret_cast<const uint4*>(rp + ol), a0, bf16);
+        unpack8(*reinterpret_cast<const uint4*>(rp + oc), a1, bf16);
+        unpack8(*reinterpret_cast<const uint4*>(rp + orr), a2, bf16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v0 = fmaxf(fmaf(a0[j], av[j], bv[j]), 0.f), v1 = fmaxf(fmaf(a1[j], av[j], bv[j]), 0.f);
+          const float v2 = fmaxf(fmaf(a2[j], av[j], bv[j]), 0.f);
+          hl[j] = 0.25f * v0 + 0.75f * v1;
+          hr[j] = 0.75f * v1 + 0.25f * v2;
+        }
+      };
+      float hl0[8], hr0[8], hl1[8], hr1[8], hl2[8], hr2[8];
+      blend(max(ys - 1, 0), hl0, hr0);
+      blend(ys, hl1, hr1);
+      for (int iy = ys; iy < ye; ++iy) {
+        blend(min(iy + 1, H - 1), hl2, hr2);
+        float o[8];
+        uint16_t* yo = yb + (static_cast<long long>(2 * iy) * OW + 2 * ix) * C;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.25f * hl0[j] + 0.75f * hl1[j];
+        *reinterpret_cast<uint4*>(yo) = pack8(o, bf16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.25f * hr0[j] + 0.75f * hr1[j];
+        *reinterpret_cast<uint4*>(yo + C) = pack8(o, bf16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.75f * hl1[j] + 0.25f * hl2[j];
+        *reinterpret_cast<uint4*>(yo + static_cast<long long>(OW) * C) = pack8(o, bf16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.75f * hr1[j] + 0.25f * hr2[j];
+        *reinterpret_cast<uint4*>(yo + static_cast<long long>(OW) * C + C) = pack8(o, bf16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          hl0[j] = hl1[j]; hr0[j] = hr1[j];
+          hl1[j] = hl2[j]; hr1[j] = hr2[j];
+        }
+      }
+    }
+    __syncthreads();          // everyone is done with this stage before the next iteration refills it
   }
 }
 
@@ -933,6 +1066,18 @@ extern "C" int countr_gn_relu_upsample2x(const void* x, const double* stats, con
   const long long cap = 148ll * 8 * 4;
   if (blocks * B > cap) blocks = (cap + B - 1) / B;
   if (blocks < 1) blocks = 1;
+  static const int staged_env = [] { const char* e = getenv("COUNTR_GN_UP2_STAGED"); return e ? atoi(e) : 1; }();
+  if (staged_env && C == UT_C && B <= 65535 && H * W >= 1024) {   // smaller maps: too few tiles to pipeline (24^2: 12.3 vs 11.0 us)
+    static PerDeviceOnce attr_once;
+    if (attr_once.need())
+      COUNTR_CHECK_CUDA(cudaFuncSetAttribute(gn_relu_up2_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UT_SMEM));
+    const int ntiles = ((W + UT_X - 1) / UT_X) * ((H + UT_Y - 1) / UT_Y);
+    const int bpi = std::max(1, std::min(ntiles, num_sms() / B));       // persistent blocks per image
+    gn_relu_up2_staged_kernel<<<dim3(bpi, B), 512, UT_SMEM, stream>>>(reinterpret_cast<const uint16_t*>(x), stats, gamma, beta,
+                                                                       reinterpret_cast<uint16_t*>(y), H, W, G, eps, bf16);
+    COUNTR_CHECK_CUDA(cudaGetLastError());
+    return COUNTR_OK;
+  }
   const int vecs_ = C / 8;
   if (vecs_ <= 256 && 256 % vecs_ == 0 && B <= 65535) {
     const int ppb = 256 / vecs_;                               // pixel columns per block

@@ -401,8 +401,10 @@ def test_casts_and_patchify(cuda):
         assert torch.equal(a, ref)
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 24, 24), (1, 96, 96)])
+@pytest.mark.parametrize("B,H,W", [(2, 24, 24), (1, 96, 96), (1, 40, 37), (3, 5, 9), (8, 48, 48), (2, 100, 100)])
 def test_gn_relu_upsample(cuda, B, H, W):
+    """Whole 8 x 8 tiles, ragged tiles on both axes, a map below the staged kernel's minimum size (row-walking kernel), several tiles per
+    persistent block with the three-stage ring wrapping."""
     from countr_b200 import ops
     C, G = 256, 8
     x = _rand16((B, H, W, C), cuda, seed=14, scale=2.0)
