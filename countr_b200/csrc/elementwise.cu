@@ -570,6 +570,101 @@ __global__ void __launch_bounds__(256) gn_relu_dot_kernel(const uint16_t* __rest
   }
 }
 
+// Staged variant for C == 256: the image's pixels are one contiguous stream; a tile = 64 pixels = one 32 KB bulk copy, four stages
+// per persistent block (three tiles in flight), 16 warps x 4 pixels per tile.
+constexpr int DT_PX = 64, DT_NS = 4;
+constexpr uint32_t DT_STAGE = DT_PX * UT_C * 2;
+constexpr uint32_t DT_SMEM = DT_NS * DT_STAGE + 64 + 3 * UT_C * sizeof(float);
+
+__global__ void __launch_bounds__(512, 1) gn_relu_dot_staged_kernel(const uint16_t* __restrict__ x, const double* __restrict__ stats,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                    const float* __restrict__ w, const float* __restrict__ bias,
+                                                                    float* __restrict__ out, int HW, int G, float eps, int bf16) {
+  constexpr int C = UT_C;
+  extern __shared__ __align__(128) uint8_t dt_smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dt_smem + DT_NS * DT_STAGE);
+  float* sa = reinterpret_cast<float*>(dt_smem + DT_NS * DT_STAGE + 64);
+  float* sb = sa + C;
+  float* sw = sb + C;
+  const int b = blockIdx.y;
+  const int cpg = C / G;
+  const double cnt = static_cast<double>(HW) * cpg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double s = stats[(static_cast<long long>(b) * G + g) * 2], ss = stats[(static_cast<long long>(b) * G + g) * 2 + 1];
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = rsqrtf(static_cast<float>(var) + eps);
+    const float a = rstd * gamma[c];
+    sa[c] = a;
+    sb[c] = beta[c] - static_cast<float>(mean) * a;
+    sw[c] = w[c];
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < DT_NS; ++i) mbar_init(bars + i, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float b0 = bias[0];
+  const int c0 = lane * 8;
+  float av[8], bv[8], wv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    av[j] = sa[c0 + j];
+    bv[j] = sb[c0 + j];
+    wv[j] = sw[c0 + j];
+  }
+  const uint16_t* xb = x + static_cast<long long>(b) * HW * C;
+  float* ob = out + static_cast<long long>(b) * HW;
+  const int ntiles = (HW + DT_PX - 1) / DT_PX;
+  auto issue = [&](int t, int stage) {      // one thread
+    const int npx = min(DT_PX, HW - t * DT_PX);
+    fence_proxy_async_smem();
+    mbar_arrive_expect_tx(bars + stage, static_cast<uint32_t>(npx) * C * 2);
+    const uint32_t dst = smem_u32(dt_smem) + stage * DT_STAGE;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(xb + static_cast<long long>(t) * DT_PX * C);
+    const uint32_t half = static_cast<uint32_t>(npx / 2) * C * 2, rest = static_cast<uint32_t>(npx) * C * 2 - half;
+    if (half) bulk_g2s(dst, src, half, bars + stage);
+    bulk_g2s(dst + half, src + half, rest, bars + stage);
+  };
+  int it = 0;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < DT_NS - 1; ++k)
+      if (static_cast<int>(blockIdx.x + k * gridDim.x) < ntiles) issue(blockIdx.x + k * gridDim.x, k);
+  }
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const int stage = it % DT_NS;
+    if (threadIdx.x == 0 && t + (DT_NS - 1) * static_cast<int>(gridDim.x) < ntiles) issue(t + (DT_NS - 1) * gridDim.x, (it + DT_NS - 1) % DT_NS);
+    const int p0 = t * DT_PX;
+    mbar_wait(bars + stage, static_cast<uint32_t>(it / DT_NS) & 1u);
+    const uint8_t* st = dt_smem + stage * DT_STAGE + c0 * 2;
+    float acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      // pixels past the end of a ragged last tile read stale shared memory; their results are not stored
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(st + (warp + 16 * u) * (C * 2)), f, bf16);
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a = fmaf(fmaxf(fmaf(f[j], av[j], bv[j]), 0.f), wv[j], a);
+      acc[u] = a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+    }
+    if (lane < 4) {
+      const int pk = p0 + warp + 16 * lane;
+      const float r = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+      if (pk < HW) ob[pk] = r + b0;
+    }
+    __syncthreads();
+  }
+}
+
 // bilinear x2 of a single-channel fp32 map [B][H][W] -> out (fp32 / fp16 / bf16) [B][2H][2W]
 __global__ void up2_f32_kernel(const float* __restrict__ x, void* __restrict__ y, int B, int H, int W, int out_dtype) {
   const int OW = 2 * W, OH = 2 * H;
@@ -1102,6 +1197,18 @@ extern "C" int countr_gn_relu_conv1x1(const void* x, const double* stats, const 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   COUNTR_REQUIRE(x && stats && gamma && beta && w && bias && out, "null pointer");
   COUNTR_REQUIRE(C % 8 == 0 && C % G == 0 && C <= 4096, "bad channel count %d / groups %d", C, G);
+  static const int staged_env = [] { const char* e = getenv("COUNTR_GN_DOT_STAGED"); return e ? atoi(e) : 1; }();
+  if (staged_env && C == UT_C && B <= 65535 && HW >= 4096) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need())
+      COUNTR_CHECK_CUDA(cudaFuncSetAttribute(gn_relu_dot_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
+    const int ntiles = (HW + DT_PX - 1) / DT_PX;
+    const int bpi = std::max(1, std::min(ntiles, num_sms() / B));
+    gn_relu_dot_staged_kernel<<<dim3(bpi, B), 512, DT_SMEM, stream>>>(reinterpret_cast<const uint16_t*>(x), stats, gamma, beta, w, bias, out,
+                                                                       HW, G, eps, bf16);
+    COUNTR_CHECK_CUDA(cudaGetLastError());
+    return COUNTR_OK;
+  }
   long long blocks = (HW + 31) / 32;
   const long long cap = 148ll * 8 * 2;
   if (blocks * B > cap) blocks = (cap + B - 1) / B;

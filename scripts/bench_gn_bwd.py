@@ -75,3 +75,24 @@ for H in ((96,) if os.environ.get("GN_ONE") else (24, 48, 96)):
     ts.sort()
     mb = (raw.numel() + y.numel()) * 2 / 1e6
     print(f"gn_relu_upsample2x  {H}^2 -> {2*H}^2: {ts[len(ts)//2]:7.1f} us (cold L2)  {mb:6.1f} MB  {mb / ts[len(ts)//2]:5.2f} TB/s", flush=True)
+
+# forward: GroupNorm + ReLU + 1x1 conv (decode_head3) at 192^2
+H = 192
+raw = torch.randn(B, H, H, C, device=dev).half()
+xg = raw.double().reshape(B, H * H, G, C // G)
+stats = torch.stack([xg.sum((1, 3)), (xg * xg).sum((1, 3))], -1).contiguous()
+d = torch.empty(B, H, H, device=dev)
+w1, bias1 = torch.randn(C, device=dev), torch.zeros(1, device=dev)
+f = lambda: ops.gn_relu_conv1x1(raw, stats, gamma, beta, w1, bias1, d, G, 1e-5)
+for _ in range(3):
+    f()
+ts = []
+for _ in range(10):
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); f(); e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1) * 1e3)
+ts.sort()
+mb = raw.numel() * 2 / 1e6
+print(f"gn_relu_conv1x1  {H}^2: {ts[len(ts)//2]:7.1f} us (cold L2)  {mb:6.1f} MB  {mb / ts[len(ts)//2]:5.2f} TB/s", flush=True)
