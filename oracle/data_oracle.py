@@ -3,7 +3,9 @@
 Follows util/FSC147.py:262-273 (ResizeTrainImage without augmentation: scatter on the resized canvas, crop the 384-wide
 window at `start`, `ndimage.gaussian_filter(sigma=(1, 1), order=0)`, * 60) and :326-331 (ResizeValImage: 384 x 384 canvas,
 `gaussian_filter(sigma=4, radius=7, order=0)`, * 60) line by line, with the same numpy / scipy calls the reference makes.
-util/FSC147.py itself cannot be imported here (imgaug / torchvision transforms pipeline), the arithmetic is all scipy's.
+Pinned against the reference itself: scripts/gen_golden_aug.py runs util/FSC147.py's own ResizeTrainImage / ResizeValImage
+(stand-ins for the absent cv2 / imgaug) and tests/test_reference_transforms.py checks these functions bit for bit against its
+outputs (tests/golden/fsc147_transforms.npz).  The affine step (imgaug) is the one piece that stays unpinned.
 """
 import numpy as np
 from scipy import ndimage
@@ -144,3 +146,27 @@ def affine_dot_canvas(dots, H, W, new_H, new_W, matrix):
         if int(ay) <= new_H - 1 and int(ax) <= new_W - 1 and not out_of_image:
             canvas[int(ay)][int(ax)] = 1
     return canvas
+
+
+# ---------------------------------------------------------------------------------------------- host-side resize (util/FSC147.py:102-126)
+def flex_resize(h, w, max_hw=384):
+    """ResizeTrainImage.flex_resize (util/FSC147.py:102-115): the smaller side to max_hw, or both rounded down to multiples of 16."""
+    if h < max_hw <= w or h <= w < max_hw:
+        new_h = max_hw
+        new_w = round(w * new_h / h)
+    elif w < max_hw <= h or w < h < max_hw:
+        new_w = max_hw
+        new_h = round(h * new_w / w)
+    else:
+        new_w = 16 * int(w / 16)
+        new_h = 16 * int(h / 16)
+    return new_h, new_w
+
+
+def resize_pil(arr_u8, new_hw):
+    """`TTensor(transforms.Resize((new_H, new_W))(image))` for a PIL image (util/FSC147.py:125-126, 324-325): PIL's antialiased
+    bilinear resize, then uint8 -> float32 / 255.  arr_u8: uint8 [H, W, 3].  Returns float32 torch [3, new_H, new_W]."""
+    import torch
+    from PIL import Image
+    img = Image.fromarray(arr_u8).resize((new_hw[1], new_hw[0]), Image.BILINEAR)
+    return torch.from_numpy(np.asarray(img).astype(np.float32) / 255.0).permute(2, 0, 1).contiguous()
