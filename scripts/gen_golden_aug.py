@@ -208,6 +208,53 @@ def main():
     for kk, v in image_sample(res["image"]).items():
         out["v_image_" + kk] = v
 
+    # --- case 5: the augmentation branch without collage (:133-180, :263-267): the Gaussian noise is replaced by zeros (the GPU path
+    # has its own generator), the affine is the identity stand-in; ColorJitter / GaussianBlur draws are logged
+    class _NoNoise:
+        def __getattr__(self, name):
+            return getattr(np.random, name)
+
+        def normal(self, loc, scale, size):
+            return np.zeros(size)
+
+    class _NP:
+        random = _NoNoise()
+
+        def __getattr__(self, name):
+            return getattr(np, name)
+
+    log = {}
+    cj, gb = ref.Augmentation.transforms
+    real_cj, real_gb = type(cj).get_params, type(gb).get_params
+
+    def cj_params(*a, **k):
+        r = real_cj(*a, **k)
+        log["jitter"] = ([int(i) for i in r[0]], [float(v) for v in r[1:]])
+        return r
+
+    def gb_params(*a, **k):
+        r = real_gb(*a, **k)
+        log["sigma"] = float(r)
+        return r
+
+    type(cj).get_params = staticmethod(cj_params)
+    type(gb).get_params = staticmethod(gb_params)
+    ref.np = _NP()
+    try:
+        res, ints, crops = run(ref.ResizeTrainImage, "a.png", [0.9, 0.7], 21, do_aug=True)
+    finally:
+        ref.np = np
+        type(cj).get_params, type(gb).get_params = staticmethod(real_cj), staticmethod(real_gb)
+    assert len(crops) == 1 and crops[0][2:] == (384, 384)
+    out["a_jitter_order"] = np.array(log["jitter"][0])
+    out["a_jitter_factors"] = np.array(log["jitter"][1])          # brightness, contrast, saturation, hue
+    out["a_sigma"] = np.float64(log["sigma"])
+    out["a_crop"] = np.array(crops[0][:2])
+    out["a_density"] = res["gt_density"].numpy()
+    for kk, v in image_sample(res["image"].float()).items():
+        out["a_image_" + kk] = v
+    print("case 5: jitter", log["jitter"], "sigma", log["sigma"], "crop", crops[0][:2], "objects", float(res["gt_density"].sum()) / 60)
+
     path = os.path.join(ROOT, "tests", "golden", "fsc147_transforms.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KB;", {k: getattr(v, "shape", v) for k, v in out.items() if k.startswith("m1_") or k.startswith("t_")})

@@ -124,3 +124,62 @@ def test_density_and_box_kernels_match_the_reference(cuda):
                              dtype=torch.int32, device=cuda)[None]
         got = data.crop_resize_boxes(r[None], rects)[0].cpu()
         assert torch.allclose(got, torch.from_numpy(g[key + "_boxes"]), rtol=0, atol=2e-6)
+
+
+def _aug_draws(g):
+    order = [int(v) for v in g["a_jitter_order"]]
+    by_fn = [float(v) for v in g["a_jitter_factors"]]                  # brightness, contrast, saturation, hue
+    top, left = (int(v) for v in g["a_crop"])
+    return order, by_fn, float(g["a_sigma"]), (top, left)
+
+
+def _robust_image_check(g, prefix, img):
+    """fp32 arithmetic against the reference's float64 pipeline; hue can pick the neighbouring sector at a boundary."""
+    s = _sample(np.asarray(img, dtype=np.float32))
+    for k in ("grid", "rows", "cols"):
+        diff = np.abs(s[k] - g[f"{prefix}_image_{k}"])
+        assert diff.mean() < 3e-6 and (diff > 1e-4).mean() < 1e-3, (prefix, k, diff.mean(), diff.max())
+
+
+def test_augmentation_branch_composition_matches_the_reference():
+    """util/FSC147.py:133-180, 263-269 run by the reference (zero noise, identity affine, logged ColorJitter / GaussianBlur / flip /
+    crop draws) against the same steps composed from torchvision's functional ops and the oracle's dot map, in fp32."""
+    tvF = pytest.importorskip("torchvision.transforms.functional")
+    g = np.load(GOLD)
+    order, by_fn, sigma, (top, left) = _aug_draws(g)
+    a = g["img_a"]
+    h, w = a.shape[:2]
+    nh, nw = D.flex_resize(h, w)
+    x = torch.clamp(D.resize_pil(a, (nh, nw)), 0, 1)
+    fns = [tvF.adjust_brightness, tvF.adjust_contrast, tvF.adjust_saturation, tvF.adjust_hue]
+    for fn in order:
+        x = fns[fn](x, by_fn[fn])
+    x = tvF.gaussian_blur(x, kernel_size=[7, 9], sigma=[sigma, sigma])
+    x = x.flip(-1)[:, top:top + 384, left:left + 384]
+    _robust_image_check(g, "a", x.numpy())
+    canvas = np.ascontiguousarray(D.affine_dot_canvas(g["dots_a"], h, w, nh, nw, np.eye(3))[:, ::-1])[top:top + 384, left:left + 384]
+    assert np.array_equal(D.filter_density(canvas), g["a_density"])
+
+
+@pytest.mark.gpu
+def test_train_transform_kernels_match_the_reference(cuda):
+    """countr_b200.data.train_transform (every pixel operation a kernel) against the reference's own augmentation branch."""
+    from countr_b200 import data
+    g = np.load(GOLD)
+    order, by_fn, sigma, crop = _aug_draws(g)
+    a = g["img_a"]
+    h, w = a.shape[:2]
+    nh, nw = D.flex_resize(h, w)
+    sh, sw = float(nh) / h, float(nw) / w
+    ra = D.resize_pil(a, (nh, nw)).to(cuda)
+    ops_t = torch.tensor(order, dtype=torch.int32).view(4, 1)
+    fac = torch.tensor([by_fn[fn] for fn in order], dtype=torch.float32).view(4, 1)
+    rects = torch.tensor([[int(int(b[0]) * sh), int(int(b[1]) * sw), int(int(b[2]) * sh), int(int(b[3]) * sw)] for b in g["boxes_a"]],
+                         dtype=torch.int32)
+    draws = dict(mosaic=None, noise_seed=0, jitter=(ops_t, fac), blur_sigma=torch.tensor([sigma]),
+                 affine=dict(rotate_deg=0.0, scale=1.0, shear_deg=0.0, translate_frac=(0.0, 0.0)), flip=True, crop=crop)
+    out = data.train_transform(ra, torch.from_numpy(g["dots_a"]).to(cuda), (sh, sw), rects, draws, noise_std=0.0)
+    _robust_image_check(g, "a", out["image"].cpu().numpy())
+    den = out["gt_density"].cpu().numpy()
+    assert np.allclose(den, g["a_density"], rtol=0, atol=1e-6), np.abs(den - g["a_density"]).max()
+    assert torch.allclose(out["boxes"].cpu(), torch.from_numpy(g["m1_boxes"]), rtol=0, atol=2e-6)      # same un-augmented crops (:286-288)
