@@ -5,7 +5,9 @@ normalisation).  Only tests/ may import this; the product path (countr_b200/infe
 `forward(imgs, boxes, shot_num) -> [N, 384, 384]` is the model under test on the CPU (oracle/countr_oracle.forward with
 the state dict bound).  torchvision is not needed: TF.crop is a slice and transforms.Resize((h, w)) on a float tensor is
 F.interpolate(mode="bilinear", align_corners=False) without antialiasing in the reference's torchvision 0.14.1 pin (up-scaling, so
-antialiasing would not matter either)."""
+antialiasing would not matter either).
+Pinned against the script itself: scripts/gen_golden_eval.py runs the reference's own TestData + main() and
+tests/test_reference_eval.py compares this restatement (and the CUDA path) with the counts it printed."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F

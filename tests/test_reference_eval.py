@@ -1,0 +1,73 @@
+"""The evaluation path pinned against the REFERENCE'S OWN script: tests/golden/eval_fewshot.npz holds the per-image counts that
+`FSC_test_cross(few-shot).py` itself (its TestData dataset and its main() loop: sliding window, 3 x 3 tiling for tiny exemplars,
+test-time normalisation) printed for three synthetic images with the seeded synthetic base-model weights — produced by
+scripts/gen_golden_eval.py.  The CPU test drives the oracle (oracle/infer_oracle.py + oracle/countr_oracle.py) over the two
+un-tiled images; the GPU test drives countr_b200.infer.evaluate_image over all three."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import data_oracle as D
+from oracle import synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "eval_fewshot.npz")
+
+
+def _inputs(g, key):
+    """TestData.__getitem__ (FSC_test_cross(few-shot).py:134-181): resized image, 64 x 64 exemplars, scaled boxes."""
+    arr = g["img_" + key]
+    H, W = arr.shape[:2]
+    new_H = 384
+    new_W = 16 * int((W / H * 384) / 16)
+    sw, sh = float(new_W) / W, float(new_H) / H
+    image = D.resize_pil(arr, (new_H, new_W))
+    rects = [[int(y1 * sh), int(x1 * sw), int(y2 * sh), int(x2 * sw)] for y1, x1, y2, x2 in g["boxes_" + key].tolist()]
+    boxes = D.crop_resize_boxes(image, rects)
+    return image[None], boxes[None], rects
+
+
+def _eval_state_dict():
+    cfg = synth.CONFIGS["base"]
+    sd = synth.make_state_dict(cfg, seed=0)
+    sd["decode_head3.3.bias"] = torch.full_like(sd["decode_head3.3.bias"], 0.5)      # scripts/gen_golden_eval.py:eval_state_dict
+    return cfg, sd
+
+
+def test_evaluation_oracle_matches_the_reference_script():
+    from oracle import countr_oracle as O
+    from oracle import infer_oracle as IO
+    g = np.load(GOLD)
+    cfg, sd = _eval_state_dict()
+    names = [str(n) for n in g["names"]]
+    for key in ("r", "p"):                        # one window / three overlapping windows; both take the normalisation branch
+        i = names.index(key + ".png")
+        assert not bool(g["tiled"][i])
+        samples, boxes, pos = _inputs(g, key)
+        with torch.no_grad():
+            cnt, _ = IO.evaluate_image(lambda im, bx, s: O.forward(sd, cfg, im.contiguous(), bx, s), samples, boxes, pos)
+            raw, _ = IO.evaluate_image(lambda im, bx, s: O.forward(sd, cfg, im.contiguous(), bx, s), samples, boxes, pos, normalization=False)
+        ref = float(g["pred_cnt"][i])
+        assert abs(cnt - ref) < 2e-4 * abs(ref), (key, cnt, ref)
+        assert raw > 5 * cnt                      # the mass under the exemplar boxes did rescale the count (e_cnt > 1.8, :353-359)
+
+
+@pytest.mark.gpu
+def test_evaluate_image_matches_the_reference_script(cuda):
+    from countr_b200.infer import evaluate_image, small_exemplar_count
+    from test_parity_gpu import build
+    g = np.load(GOLD)
+    m, _, _ = build("base", 0, cuda)
+    with torch.no_grad():
+        m.decode_head3[3].bias.fill_(0.5)
+    m.eval()
+    names = [str(n) for n in g["names"]]
+    for key in ("r", "p", "q"):
+        i = names.index(key + ".png")
+        samples, boxes, pos = _inputs(g, key)
+        assert (small_exemplar_count(pos) >= 1) == bool(g["tiled"][i])
+        cnt, _ = evaluate_image(m, samples.to(cuda), boxes.to(cuda), pos)
+        ref = float(g["pred_cnt"][i])
+        print(f"[eval vs reference script] {key}: {cnt.item():.4f} vs {ref:.4f} (tiled: {bool(g['tiled'][i])})")
+        assert abs(cnt.item() - ref) < 3e-3 * abs(ref), (key, cnt.item(), ref)
