@@ -138,6 +138,22 @@ def main():
     out["tiled"] = np.array(tiled)
     out["gt_cnt"] = np.array(gts)
     out["pred_cnt"] = np.array(pred, dtype=np.float64)
+    # ---- the zero-shot script on the same images: model(window, boxes, 0), no tiling (s_cnt >= 100 never holds), no normalisation
+    spec0 = importlib.util.spec_from_file_location("ref_zeroshot", os.path.join(REF, "FSC_test_cross(zero-shot).py"))
+    ref0 = importlib.util.module_from_spec(spec0)
+    spec0.loader.exec_module(ref0)
+    ref0.annotations, ref0.data_split, ref0.im_dir = annotations, {"test": list(images)}, im_dir
+    prints0 = []
+    ref0.print = lambda *a, **k: (prints0.append(" ".join(str(x) for x in a)), real_print(*a, **k))
+    args0 = ref0.get_args_parser().parse_args(["--device", "cpu", "--output_dir", os.path.join(tmp, "out0"), "--resume", "", "--no_pin_mem",
+                                               "--num_workers", "0"])
+    os.makedirs(args0.output_dir, exist_ok=True)
+    ref0.main(args0)
+    lines0 = [p for p in prints0 if "pred_cnt:" in p and "id:" in p]
+    assert len(lines0) == len(images), lines0
+    out["zs_names"] = np.array([ln.split("id: ")[1].strip() for ln in lines0])
+    out["zs_pred_cnt"] = np.array([float(ln.split("pred_cnt:")[1].split(",")[0]) for ln in lines0], dtype=np.float64)
+
     path = os.path.join(ROOT, "tests", "golden", "eval_fewshot.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KB", dict(zip(names, zip(pred, tiled))))

@@ -71,3 +71,35 @@ def test_evaluate_image_matches_the_reference_script(cuda):
         ref = float(g["pred_cnt"][i])
         print(f"[eval vs reference script] {key}: {cnt.item():.4f} vs {ref:.4f} (tiled: {bool(g['tiled'][i])})")
         assert abs(cnt.item() - ref) < 3e-3 * abs(ref), (key, cnt.item(), ref)
+
+
+def test_zero_shot_oracle_matches_the_reference_script():
+    """`FSC_test_cross(zero-shot).py`: model(window, boxes, 0) over the sliding window, no tiling, no normalisation."""
+    from oracle import countr_oracle as O
+    from oracle import infer_oracle as IO
+    g = np.load(GOLD)
+    cfg, sd = _eval_state_dict()
+    names = [str(n) for n in g["zs_names"]]
+    samples, _, _ = _inputs(g, "p")
+    with torch.no_grad():
+        den = IO.window_pass(lambda im, bx, s: O.forward(sd, cfg, im.contiguous(), bx, s), samples, torch.empty(1, 0), 0)
+    ref = float(g["zs_pred_cnt"][names.index("p.png")])
+    assert abs(float(den.sum() / 60) - ref) < 2e-4 * abs(ref)
+
+
+@pytest.mark.gpu
+def test_zero_shot_evaluation_matches_the_reference_script(cuda):
+    from countr_b200.infer import sliding_window_density
+    from test_parity_gpu import build
+    g = np.load(GOLD)
+    m, _, _ = build("base", 0, cuda)
+    with torch.no_grad():
+        m.decode_head3[3].bias.fill_(0.5)
+    m.eval()
+    names = [str(n) for n in g["zs_names"]]
+    for key in ("r", "p", "q"):
+        samples, _, _ = _inputs(g, key)
+        _, cnt = sliding_window_density(m, samples.to(cuda), torch.empty(1, 0, device=cuda), 0)
+        ref = float(g["zs_pred_cnt"][names.index(key + ".png")])
+        print(f"[zero-shot vs reference script] {key}: {cnt.item():.3f} vs {ref:.3f}")
+        assert abs(cnt.item() - ref) < 3e-3 * abs(ref), (key, cnt.item(), ref)
