@@ -83,8 +83,9 @@ def evaluate_image(model, samples, boxes, pos, shot_num=None, max_s_cnt=1, norma
     samples [1, 3, 384, W] fp32, boxes [1, K, 3, 64, 64] (or empty), pos: the K exemplar rectangles (y1, x1, y2, x2) in pixels.
     Returns (pred_cnt: 0-d device tensor, density map(s) [384, W] or [9, 384, W] fp32).
 
-    Reference quirks kept: with tiling the normalisation uses the LAST crop's density map (the loop variable the reference
-    reads after its loop), and demo.py counts only that last crop (its `pred_cnt =` sits after the loop)."""
+    Reference quirk kept: with tiling the normalisation uses the LAST crop's density map (the loop variable the reference reads
+    after its loop; the bottom-right crop in both scripts).  demo.py differs from the test script in the crop order (row by row),
+    in counting small exemplars over ALL boxes, and in passing the literal shot count 3."""
     dev = samples.device
     _, _, h, w = samples.shape
     K = boxes.shape[1] if boxes.dim() == 5 else 0
@@ -111,7 +112,7 @@ def evaluate_image(model, samples, boxes, pos, shot_num=None, max_s_cnt=1, norma
         density = torch.empty(9, h, w, dtype=torch.float32, device=dev)
         for k in range(9):
             _blend(outs[k * nw:(k + 1) * nw], st, nw, h, win, w, density[k])
-        pred = density.sum() / 60 if semantics == "test" else density[8].sum() / 60
+        pred = density.sum() / 60                    # both scripts add up all nine crops (demo.py:127, few-shot:320)
         last = density[8]
     else:
         batch = torch.stack([samples[0, :, :, s:s + win] for s in starts])

@@ -41,24 +41,32 @@ def window_pass(forward, image, boxes, shot_num):
     return density_map
 
 
-def evaluate_image(forward, samples, boxes, pos, max_s_cnt=1, normalization=True):
-    """:258-359.  Returns (pred_cnt float, list of density maps: one, or the nine crops' maps)."""
-    num_boxes = boxes.shape[1] if boxes.nelement() > 0 else 0
+def evaluate_image(forward, samples, boxes, pos, max_s_cnt=1, normalization=True, demo=False):
+    """:258-359 — or, with demo=True, demo.py:76-169 (run_one_image): small exemplars counted over ALL boxes, the literal shot
+    count 3, the nine crops taken row by row.  Returns (pred_cnt float, list of density maps: one, or the nine crops' maps)."""
+    num_boxes = 3 if demo else (boxes.shape[1] if boxes.nelement() > 0 else 0)
     _, _, h, w = samples.shape
     r_cnt = s_cnt = 0
     for rect in pos:
         r_cnt += 1
-        if r_cnt > 3:
+        if r_cnt > 3 and not demo:
             break
         if rect[2] - rect[0] < 10 and rect[3] - rect[1] < 10:
             s_cnt += 1
     if s_cnt >= max_s_cnt:
         crop = lambda top, left, hh, ww: samples[0][:, top:top + hh, left:left + ww]          # TF.crop, no padding needed  # noqa: E731
-        r_images = [crop(0, 0, int(h / 3), int(w / 3)), crop(int(h / 3), 0, int(h / 3), int(w / 3)),
-                    crop(0, int(w / 3), int(h / 3), int(w / 3)), crop(int(h / 3), int(w / 3), int(h / 3), int(w / 3)),
-                    crop(int(h * 2 / 3), 0, int(h / 3), int(w / 3)), crop(int(h * 2 / 3), int(w / 3), int(h / 3), int(w / 3)),
-                    crop(0, int(w * 2 / 3), int(h / 3), int(w / 3)), crop(int(h / 3), int(w * 2 / 3), int(h / 3), int(w / 3)),
-                    crop(int(h * 2 / 3), int(w * 2 / 3), int(h / 3), int(w / 3))]
+        if demo:                                                                                 # demo.py:86-94
+            r_images = [crop(0, 0, int(h / 3), int(w / 3)), crop(0, int(w / 3), int(h / 3), int(w / 3)),
+                        crop(0, int(w * 2 / 3), int(h / 3), int(w / 3)), crop(int(h / 3), 0, int(h / 3), int(w / 3)),
+                        crop(int(h / 3), int(w / 3), int(h / 3), int(w / 3)), crop(int(h / 3), int(w * 2 / 3), int(h / 3), int(w / 3)),
+                        crop(int(h * 2 / 3), 0, int(h / 3), int(w / 3)), crop(int(h * 2 / 3), int(w / 3), int(h / 3), int(w / 3)),
+                        crop(int(h * 2 / 3), int(w * 2 / 3), int(h / 3), int(w / 3))]
+        else:
+            r_images = [crop(0, 0, int(h / 3), int(w / 3)), crop(int(h / 3), 0, int(h / 3), int(w / 3)),
+                        crop(0, int(w / 3), int(h / 3), int(w / 3)), crop(int(h / 3), int(w / 3), int(h / 3), int(w / 3)),
+                        crop(int(h * 2 / 3), 0, int(h / 3), int(w / 3)), crop(int(h * 2 / 3), int(w / 3), int(h / 3), int(w / 3)),
+                        crop(0, int(w * 2 / 3), int(h / 3), int(w / 3)), crop(int(h / 3), int(w * 2 / 3), int(h / 3), int(w / 3)),
+                        crop(int(h * 2 / 3), int(w * 2 / 3), int(h / 3), int(w / 3))]
         pred_cnt = 0
         maps = []
         for r_image in r_images:

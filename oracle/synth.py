@@ -8,6 +8,8 @@ cannot hide.
 """
 import math
 
+import numpy as np
+
 import torch
 
 from . import countr_oracle as O
@@ -132,3 +134,16 @@ def weight_decay_groups(named_params, weight_decay):
             continue
         (no_decay if (p.ndim == 1 or n.endswith(".bias")) else decay).append(p)
     return [{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": weight_decay}]
+
+
+def smooth_image(h, w, seed):
+    """Smooth uint8 RGB test pattern (sums of sinusoids): deterministic, so large test images need not be stored in fixtures."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    img = np.zeros((h, w, 3))
+    for c in range(3):
+        for _ in range(4):
+            fy, fx, ph = rng.uniform(0.01, 0.12), rng.uniform(0.01, 0.12), rng.uniform(0, 6.28)
+            img[..., c] += rng.uniform(0.3, 1.0) * np.sin(fy * yy + fx * xx + ph)
+    img = (img - img.min()) / (img.max() - img.min())
+    return (img * 255).astype(np.uint8)

@@ -103,3 +103,52 @@ def test_zero_shot_evaluation_matches_the_reference_script(cuda):
         ref = float(g["zs_pred_cnt"][names.index(key + ".png")])
         print(f"[zero-shot vs reference script] {key}: {cnt.item():.3f} vs {ref:.3f}")
         assert abs(cnt.item() - ref) < 3e-3 * abs(ref), (key, cnt.item(), ref)
+
+
+DEMO_GOLD = os.path.join(os.path.dirname(__file__), "golden", "demo_counts.npz")
+DEMO_BBOXES = [[[136, 98], [173, 127]], [[209, 125], [242, 150]], [[212, 168], [258, 200]]]      # demo.py:52-56, (x, y) corners
+
+
+def _demo_inputs(h, w, seed):
+    """demo.py:34-73 (load_image) on the synthetic image the generator used."""
+    arr = synth.smooth_image(h, w, seed)
+    new_H = 384
+    new_W = 16 * int((w / h * 384) / 16)
+    sh, sw = float(new_H) / h, float(new_W) / w
+    image = D.resize_pil(arr, (new_H, new_W))
+    rects = [[int(b[0][1] * sh), int(b[0][0] * sw), int(b[1][1] * sh), int(b[1][0] * sw)] for b in DEMO_BBOXES]
+    return image[None], D.crop_resize_boxes(image, rects)[None], rects
+
+
+def test_demo_oracle_matches_demo_py():
+    """demo.py executed by scripts/gen_golden_demo.py (plain sliding-window case) against the oracle's demo mode."""
+    from oracle import countr_oracle as O
+    from oracle import infer_oracle as IO
+    g = np.load(DEMO_GOLD)
+    cfg, sd = _eval_state_dict()
+    h, w, seed = (int(v) for v in g["plain_hw_seed"])
+    samples, boxes, pos = _demo_inputs(h, w, seed)
+    with torch.no_grad():
+        cnt, maps = IO.evaluate_image(lambda im, bx, s: O.forward(sd, cfg, im.contiguous(), bx, s), samples, boxes, pos, demo=True)
+    assert len(maps) == 1
+    ref = float(g["plain_count"])
+    assert abs(cnt - ref) < 2e-4 * abs(ref), (cnt, ref)
+
+
+@pytest.mark.gpu
+def test_evaluate_image_demo_semantics_match_demo_py(cuda):
+    from countr_b200.infer import evaluate_image
+    from test_parity_gpu import build
+    g = np.load(DEMO_GOLD)
+    m, _, _ = build("base", 0, cuda)
+    with torch.no_grad():
+        m.decode_head3[3].bias.fill_(0.5)
+    m.eval()
+    for name, tiled in (("plain", False), ("tiled", True)):
+        h, w, seed = (int(v) for v in g[name + "_hw_seed"])
+        samples, boxes, pos = _demo_inputs(h, w, seed)
+        cnt, dens = evaluate_image(m, samples.to(cuda), boxes.to(cuda), pos, semantics="demo")
+        assert (dens.dim() == 3) == tiled
+        ref = float(g[name + "_count"])
+        print(f"[demo.py] {name}: {cnt.item():.4f} vs {ref:.4f}")
+        assert abs(cnt.item() - ref) < 3e-3 * abs(ref), (name, cnt.item(), ref)
