@@ -14,6 +14,7 @@ Loss scale, learning rate, found_inf and the step counter live in a device state
 with the host and a step captured in a CUDA graph follows the lr schedule and the dynamic loss scale.
 """
 import ctypes
+import math
 
 import numpy as np
 import torch
@@ -30,6 +31,15 @@ ST_SCALE, ST_GROWTH, ST_FOUND_INF, ST_GRAD_NORM, ST_LR, ST_STEP = range(6)
 
 def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def scheduled_lr(epoch, lr, min_lr=0.0, warmup_epochs=10, epochs=200):
+    """The learning rate the scripts set before every iteration (util/lr_sched.py:9-21, called with the fractional epoch
+    `data_iter_step / len(loader) + epoch`, FSC_finetune_cross.py:270-271): linear warm-up, then half a cosine down to min_lr.
+    Host arithmetic; feed the result to `FineTuner.set_lr` / `ArenaAdamW.set_lr`."""
+    if epoch < warmup_epochs:
+        return lr * epoch / warmup_epochs
+    return min_lr + (lr - min_lr) * 0.5 * (1.0 + math.cos(math.pi * (epoch - warmup_epochs) / (epochs - warmup_epochs)))
 
 
 class FineTuner:

@@ -66,3 +66,15 @@ def test_grad_arena_allreduce_world2():
             ret = mgr.dict()
             mp.spawn(_worker, args=(2, port, shots, ret), nprocs=2, join=True)
             assert ret[0] and ret[1], shots
+
+
+def test_scheduled_lr_matches_the_reference_schedule():
+    """countr_b200.train.scheduled_lr against util/lr_sched.py:adjust_learning_rate run by scripts/gen_golden_lr.py."""
+    import os
+    import numpy as np
+    from countr_b200.train import scheduled_lr
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lr_sched.npz"))
+    for name in ("finetune", "pretrain"):
+        lr, min_lr, warm, epochs = (float(v) for v in g[name + "_args"])
+        got = np.array([scheduled_lr(float(e), lr, min_lr, warm, epochs) for e in g[name + "_epochs"]])
+        assert np.array_equal(got, g[name + "_lr"])
