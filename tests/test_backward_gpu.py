@@ -286,3 +286,62 @@ def test_exemplar_cnn_gradients_with_matched_storage_rounding(cuda):
         # (different) ~1 % of the arg-max / ReLU decisions still flips; the stage-level kernels are checked
         # tightly (2e-3) on identical inputs in test_inorm_relu_pool_bwd / test_conv_weight_grads.
         assert e < 0.15, (n, e)
+
+
+def test_groupnorm_kernels_bf16(cuda):
+    """The bf16 switch of the staged GroupNorm kernels (forward up-sample and 1x1 head, backward gather and head reduce): the
+    mixed-precision FMA and the packers take a different instruction path than fp16."""
+    from countr_b200 import ops
+    bf = torch.bfloat16
+    B, C, G = 2, 256, 8
+
+    def stats_of(raw):
+        xg = raw.double().reshape(raw.shape[0], -1, G, C // G)
+        return torch.stack([xg.sum((1, 3)), (xg * xg).sum((1, 3))], -1).contiguous()
+
+    gamma0 = torch.randn(C, device=cuda) * 0.5 + 1
+    beta0 = torch.randn(C, device=cuda) * 0.3
+    # forward: up-sample (48^2 -> staged kernel) and 1x1 head (64^2 = 4096 pixels -> staged kernel)
+    x = _rand16((B, 48, 48, C), cuda, bf, seed=70, scale=2.0)
+    y = torch.empty(B, 96, 96, C, device=cuda, dtype=bf)
+    ops.gn_relu_upsample2x(x, stats_of(x), gamma0, beta0, y, G, 1e-5)
+    act = F.relu(F.group_norm(x.float().permute(0, 3, 1, 2), G, gamma0, beta0, 1e-5))
+    ref = F.interpolate(act, scale_factor=2, mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    assert_close(y.reshape(-1, C), ref.reshape(-1, C), 8e-3, "bf16 gn+relu+up2")
+    x2 = _rand16((B, 64, 64, C), cuda, bf, seed=71, scale=2.0)
+    w = torch.randn(C, device=cuda) * 0.1
+    bias = torch.randn(1, device=cuda)
+    d = torch.empty(B, 64, 64, device=cuda)
+    ops.gn_relu_conv1x1(x2, stats_of(x2), gamma0, beta0, w, bias, d, G, 1e-5)
+    act2 = F.relu(F.group_norm(x2.float().permute(0, 3, 1, 2), G, gamma0, beta0, 1e-5))
+    assert_close(d.reshape(B, -1), F.conv2d(act2, w.reshape(1, C, 1, 1), bias).reshape(B, -1), 1e-4, "bf16 gn+relu+1x1")
+    # backward, both modes
+    for mode, (H, W) in ((0, (24, 24)), (1, (24, 24))):
+        raw = _rand16((B, H, W, C), cuda, bf, seed=72 + mode, scale=2.0)
+        gamma = gamma0.clone().requires_grad_(True)
+        beta = beta0.clone().requires_grad_(True)
+        xin = raw.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+        z = F.relu(F.group_norm(xin, G, gamma, beta, 1e-5))
+        stats = stats_of(raw)
+        dyh = torch.empty_like(raw)
+        dgamma, dbeta = torch.zeros(C, device=cuda), torch.zeros(C, device=cuda)
+        gsum = torch.zeros(B, G, 2, device=cuda, dtype=torch.float64)
+        dbias = torch.zeros(C, device=cuda)
+        if mode == 0:
+            d_next = _rand16((B, 2 * H, 2 * W, C), cuda, bf, seed=80)
+            F.interpolate(z, scale_factor=2, mode="bilinear", align_corners=False).backward(d_next.float().permute(0, 3, 1, 2))
+            ops.gn_relu_bwd_reduce(raw, stats, gamma.detach(), beta.detach(), dyh, dgamma, dbeta, gsum, G, 1e-5, d_next=d_next)
+        else:
+            w1 = (torch.randn(C, device=cuda) * 0.1).requires_grad_(True)
+            b1 = torch.zeros(1, device=cuda, requires_grad=True)
+            dmap = torch.randn(B, H, W, device=cuda)
+            F.conv2d(z, w1.reshape(1, C, 1, 1), b1).squeeze(1).backward(dmap)
+            dw1, db1 = torch.zeros(C, device=cuda), torch.zeros(1, device=cuda)
+            ops.gn_relu_bwd_reduce(raw, stats, gamma.detach(), beta.detach(), dyh, dgamma, dbeta, gsum, G, 1e-5, dmap=dmap,
+                                   w1=w1.detach(), dw1=dw1, db1=db1)
+            assert_close(dw1[None], w1.grad[None], 2e-3, "bf16 dw1")
+        ops.gn_bwd_apply(raw, dyh, stats, gsum, gamma.detach(), dyh, dbias, G, 1e-5)
+        torch.cuda.synchronize()
+        assert_close(dyh.reshape(-1, C), xin.grad.permute(0, 2, 3, 1).reshape(-1, C), 1.5e-2, f"bf16 gn bwd dx mode {mode}")
+        assert_close(dgamma[None], gamma.grad[None], 1.5e-2, f"bf16 dgamma mode {mode}")
+        assert_close(dbeta[None], beta.grad[None], 1.5e-2, f"bf16 dbeta mode {mode}")
