@@ -159,3 +159,25 @@ def test_oracle_matches_reference_at_the_benchmarked_config():
     assert rel(lat.norm(dim=-1), g["latent_rownorm"][:2]) < 2e-5
     assert rel(pool, g["out_pool8"][:2]) < 2e-5
     assert rel(out.sum((1, 2)), g["out_sum"][:2]) < 2e-5
+
+
+def test_scaler_state_follows_torch_gradscaler():
+    """oracle/train_oracle.ScalerState (what the device-side loss-scale update of countr_b200.train is checked against) against
+    torch's own GradScaler — the class util/misc.py:260-287 wraps — over a sequence with overflow steps; the skipped updates too."""
+    from oracle import train_oracle as TO
+    p = torch.nn.Parameter(torch.ones(4))
+    opt = torch.optim.SGD([p], lr=0.1)
+    sc = torch.amp.GradScaler("cpu", init_scale=1024.0, growth_interval=3)
+    st = TO.ScalerState(1024.0, interval=3)
+    for bad in [0, 0, 0, 1, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0]:
+        before = p.detach().clone()
+        opt.zero_grad()
+        sc.scale((p * p).sum()).backward()
+        if bad:
+            p.grad[0] = float("inf")
+        sc.unscale_(opt)
+        sc.step(opt)
+        sc.update()
+        st.update(bool(bad))
+        assert sc.get_scale() == st.scale
+        assert torch.equal(p.detach(), before) == bool(bad)          # an overflow step leaves the parameters alone
