@@ -152,3 +152,43 @@ def test_evaluate_image_demo_semantics_match_demo_py(cuda):
         ref = float(g[name + "_count"])
         print(f"[demo.py] {name}: {cnt.item():.4f} vs {ref:.4f}")
         assert abs(cnt.item() - ref) < 3e-3 * abs(ref), (name, cnt.item(), ref)
+
+
+@pytest.mark.parametrize("w", [384, 400, 511, 512, 513, 576, 640, 700, 768, 896, 1000, 1152])
+def test_window_starts_follow_the_reference_loop(w):
+    """countr_b200.infer.window_starts against the window positions the reference's while-loop visits (:323-349), read back from the
+    oracle's literal restatement through a probe image whose pixel value is its column index."""
+    from countr_b200.infer import window_starts
+    from oracle import infer_oracle as IO
+    probe = torch.arange(w, dtype=torch.float32).expand(1, 3, 384, w).contiguous()
+    seen = []
+
+    def fake_forward(im, bx, s):
+        seen.append(int(im[0, 0, 0, 0].item()))
+        return torch.zeros(1, 384, 384)
+
+    IO.window_pass(fake_forward, probe, torch.empty(1, 0), 0)
+    assert window_starts(w) == seen
+
+
+@pytest.mark.parametrize("demo", [False, True])
+def test_tile_rects_follow_the_reference_crop_order(demo):
+    """countr_b200.infer.tile_rects against the order in which the scripts build their nine crops (few-shot :276-284 column by column,
+    demo.py:86-94 row by row): the probe's pixel value encodes (row, column), the blown-up crop keeps its top-left pixel."""
+    from countr_b200.infer import tile_rects
+    from oracle import infer_oracle as IO
+    h, w = 384, 500
+    probe = (torch.arange(h, dtype=torch.float32)[:, None] * 1000 + torch.arange(w, dtype=torch.float32)[None, :]).expand(1, 3, h, w).contiguous()
+    seen = []
+
+    def fake_forward(im, bx, s):
+        if im.shape[-1] == 384 and len(seen) < 9 * 2:
+            seen.append(float(im[0, 0, 0, 0].item()))
+        return torch.zeros(1, 384, 384)
+
+    tiny = [(10, 10, 15, 16), (50, 60, 120, 130), (200, 210, 300, 310)]           # one exemplar under 10 px: tiling
+    IO.evaluate_image(fake_forward, probe, torch.zeros(1, 3, 3, 64, 64), tiny, demo=demo)
+    firsts = seen[::2]                                                               # w = 500: two windows per crop, the first starts at column 0
+    rects = tile_rects(h, w, "demo" if demo else "test")
+    assert [(int(v // 1000), int(v % 1000)) for v in firsts] == [(t, l) for t, l, _, _ in rects]
+    assert all((ch, cw) == (int(h / 3), int(w / 3)) for _, _, ch, cw in rects)
