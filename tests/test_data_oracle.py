@@ -109,3 +109,30 @@ def test_crop_resize_kernel_matches_oracle(cuda):
     win = imgs.to(cuda)[:, :, :, 16:400]
     r2 = torch.tensor([[[10, 20, 57, 90]], [[0, 0, 383, 383]], [[30, 40, 33, 44]]], dtype=torch.int32, device=cuda)
     assert torch.equal(crop_resize_boxes(win, r2), crop_resize_boxes(win.contiguous(), r2))
+
+
+def test_host_side_draw_helpers():
+    """countr_b200.data host logic (no kernel calls): ColorJitter draws stay inside torchvision's ranges and use every function once;
+    the affine matrix composes centre -> scale -> shear -> rotate -> translate -> back."""
+    from countr_b200 import data
+    g = torch.Generator().manual_seed(0)
+    ops_t, fac = data.sample_color_jitter(64, generator=g)
+    assert ops_t.shape == (4, 64) and fac.shape == (4, 64)
+    assert all(sorted(ops_t[:, b].tolist()) == [0, 1, 2, 3] for b in range(64))
+    lo = {0: 0.75, 1: 0.85, 2: 0.85, 3: -0.15}
+    hi = {0: 1.25, 1: 1.15, 2: 1.15, 3: 0.15}
+    for j in range(4):
+        for b in range(64):
+            fn = int(ops_t[j, b])
+            assert lo[fn] <= float(fac[j, b]) <= hi[fn]
+    assert len({tuple(ops_t[:, b].tolist()) for b in range(64)}) > 4             # the order is drawn per image
+    H, W = 384, 512
+    assert np.allclose(data.affine_matrix(H, W), np.eye(3))
+    c = np.array([W / 2 - 0.5, H / 2 - 0.5, 1.0])
+    M = data.affine_matrix(H, W, rotate_deg=15, scale=1.2, shear_deg=-10, translate_frac=(0.1, -0.2))
+    assert np.allclose(M @ c, c + np.array([round(0.1 * W), round(-0.2 * H), 0.0]))   # the centre only moves by the translation
+    R = data.affine_matrix(H, W, rotate_deg=90)
+    p = R @ np.array([W / 2 - 0.5 + 10, H / 2 - 0.5, 1.0])                       # +x of the centre -> +y (clockwise on screen, y down)
+    assert np.allclose(p[:2], [W / 2 - 0.5, H / 2 - 0.5 + 10])
+    S = data.affine_matrix(H, W, scale=0.8)
+    assert np.allclose((S @ np.array([W / 2 - 0.5 + 10, H / 2 - 0.5 + 5, 1.0]))[:2], [W / 2 - 0.5 + 8, H / 2 - 0.5 + 4])
